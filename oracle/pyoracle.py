@@ -1,0 +1,166 @@
+"""ctypes view of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the product path (wumingpic_b200) never does.
+PARITY UNPINNED by reference goldens -- see oracle/oracle_common.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+
+def build(fast=False):
+    target = "liboracle_fast.so" if fast else "liboracle.so"
+    subprocess.run(["make", "-s", "-C", _HERE, target], check=True)
+    return os.path.join(_HERE, target)
+
+
+def lib(fast=False):
+    key = bool(fast)
+    if key not in _LIBS:
+        path = os.path.join(_HERE, "liboracle_fast.so" if fast else "liboracle.so")
+        src_newer = (not os.path.exists(path)) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(path)
+            for f in ("oracle3d.cpp", "oracle2d.cpp", "oracle_common.h"))
+        if src_newer:
+            path = build(fast)
+        L = C.CDLL(path)
+        dp = C.POINTER(C.c_double)
+        ip = C.POINTER(C.c_int)
+        for dim in ("3", "2"):
+            if not hasattr(L, f"orc{dim}_create"):
+                continue
+            getattr(L, f"orc{dim}_create").restype = C.c_void_p
+            getattr(L, f"orc{dim}_dptr").restype = dp
+            getattr(L, f"orc{dim}_iptr").restype = ip
+        L.orc3_create.argtypes = [C.c_int] * 6 + [C.c_double] * 4 + [dp, dp, C.c_int]
+        L.orc3_dptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc3_iptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc3_load_weibel.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 4 + [C.c_uint64]
+        for name in ("destroy", "particle_solv", "bc_particle_x", "bc_particle_yz", "sort_bucket", "step",
+                     "clear_error"):
+            getattr(L, "orc3_" + name).argtypes = [C.c_void_p]
+        L.orc3_field_fdtd_i.argtypes = [C.c_void_p, C.c_int]
+        L.orc3_nranks.argtypes = [C.c_void_p]
+        L.orc3_error.argtypes = [C.c_void_p]
+        L.orc3_rank_geom.argtypes = [C.c_void_p, C.c_int, ip]
+        L.orc3_set_xrange.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc3_cg_iterations.argtypes = [C.c_void_p, ip]
+        L.orc3_energy.argtypes = [C.c_void_p, dp]
+        L.orc3_gauss.argtypes = [C.c_void_p, C.c_int, dp]
+        _LIBS[key] = L
+    return _LIBS[key]
+
+
+def weibel_constants(n0, mass_ratio=1.0, sigma_e=0.0, omega_pe=0.1, c=1.0):
+    """q, r, b0 as in 3d/proj/weibel/app.f90:298-309."""
+    wpe = omega_pe
+    wge = omega_pe * np.sqrt(sigma_e)
+    wpi = wpe / np.sqrt(mass_ratio)
+    wgi = wge / mass_ratio
+    r = np.array([mass_ratio, 1.0])
+    q = np.array([+np.sqrt(r[0] / (4.0 * np.pi * n0)) * wpi, -np.sqrt(r[1] / (4.0 * np.pi * n0)) * wpe])
+    b0 = r[0] * c / q[0] * wgi
+    return q, r, b0
+
+
+class World3:
+    """In-process emulation of an nproc_j x nproc_k MPI run of the 3-D reference loop."""
+
+    def __init__(self, nx, ny, nz, np_cap, nproc_j=1, nproc_k=1, delx=1.0, delt=1.0, c=1.0, gfac=0.501,
+                 q=(1.0, -1.0), r=(1.0, 1.0), bc=0, fast=False):
+        self.L = lib(fast)
+        self.nx, self.ny, self.nz, self.np, self.ndim, self.nsp = nx, ny, nz, np_cap, 7, 2
+        self.q = np.ascontiguousarray(q, dtype=np.float64)
+        self.r = np.ascontiguousarray(r, dtype=np.float64)
+        self.delx, self.delt, self.c, self.gfac = delx, delt, c, gfac
+        dp = C.POINTER(C.c_double)
+        self.h = C.c_void_p(self.L.orc3_create(nx, ny, nz, np_cap, nproc_j, nproc_k, delx, delt, c, gfac,
+                                               self.q.ctypes.data_as(dp), self.r.ctypes.data_as(dp), bc))
+        self.nranks = self.L.orc3_nranks(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.orc3_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def geom(self, rank=0):
+        g = (C.c_int * 8)()
+        self.L.orc3_rank_geom(self.h, rank, g)
+        return dict(zip(("nys", "nye", "nzs", "nze", "jup", "jdown", "kup", "kdown"), list(g)))
+
+    # numpy views in Fortran index order (first index fastest): shapes reversed for C order
+    def _shape(self, rank, which):
+        g = self.geom(rank)
+        nyl, nzl = g["nye"] - g["nys"] + 1, g["nze"] - g["nzs"] + 1
+        if which in ("up", "gp"):
+            return (self.nsp, nzl, nyl, self.np, self.ndim)
+        if which in ("uf", "df"):
+            return (nzl + 4, nyl + 4, self.nx + 4, 6)
+        if which == "uj":
+            return (nzl + 4, nyl + 4, self.nx + 4, 3)
+        if which == "gkl":
+            return (nzl, nyl, self.nx, 3)
+        if which == "np2":
+            return (self.nsp, nzl, nyl)
+        if which == "cumcnt":
+            return (self.nsp, nzl, nyl, self.nx + 1)
+        raise KeyError(which)
+
+    def arr(self, which, rank=0):
+        shape = self._shape(rank, which)
+        if which in ("np2", "cumcnt"):
+            p = self.L.orc3_iptr(self.h, rank, 0 if which == "np2" else 1)
+        else:
+            p = self.L.orc3_dptr(self.h, rank, ("up", "gp", "uf", "df", "uj", "gkl").index(which))
+        return np.ctypeslib.as_array(p, shape=shape)
+
+    def load_weibel(self, n0, v_thi=0.1, v_the=0.1, t_ani=5.0, b0=0.0, seed=20240601):
+        self.L.orc3_load_weibel(self.h, n0, v_thi, v_the, t_ani, b0, seed)
+
+    def particle_solv(self):
+        self.L.orc3_particle_solv(self.h)
+
+    def field_fdtd_i(self, stage=0):
+        self.L.orc3_field_fdtd_i(self.h, stage)
+
+    def bc_particle_x(self):
+        self.L.orc3_bc_particle_x(self.h)
+
+    def bc_particle_yz(self):
+        self.L.orc3_bc_particle_yz(self.h)
+
+    def sort_bucket(self):
+        self.L.orc3_sort_bucket(self.h)
+
+    def step(self):
+        self.L.orc3_step(self.h)
+
+    def error(self):
+        return self.L.orc3_error(self.h)
+
+    def cg_iterations(self):
+        it = (C.c_int * 3)()
+        self.L.orc3_cg_iterations(self.h, it)
+        return list(it)
+
+    def energy(self):
+        e = (C.c_double * 4)()
+        self.L.orc3_energy(self.h, e)
+        return np.array(list(e))
+
+    def gauss(self, which=0):
+        e = (C.c_double * 2)()
+        self.L.orc3_gauss(self.h, which, e)
+        return e[0], e[1]
