@@ -1,0 +1,546 @@
+// wm_api.cu -- the C ABI of include/wuming_b200.h: context life cycle, host <-> device state
+// transfer in the reference's array layouts, and the per-procedure entry points that sequence the
+// kernels of wm_particles.cu / wm_fields.cu exactly like the reference's time loop
+// (3d/proj/weibel/app.f90:100-108).
+#include "wm_internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+int wm_comm_destroy(wm_ctx* ctx);
+
+namespace {
+thread_local std::string g_err;
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+int free_particles(wm_ctx* c) {
+  for (int k = 0; k < 6; ++k) {
+    if (c->A.c[k]) cudaFree(c->A.c[k]);
+    if (c->B.c[k]) cudaFree(c->B.c[k]);
+    c->A.c[k] = c->B.c[k] = nullptr;
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (c->id[k]) cudaFree(c->id[k]);
+    c->id[k] = nullptr;
+  }
+  c->cap = 0;
+  return WM_OK;
+}
+
+// make room for `need` particles (keeps no contents: callers refill)
+int reserve_particles(wm_ctx* c, size_t need) {
+  if (need <= c->cap) return WM_OK;
+  free_particles(c);
+  double factor = c->nranks > 1 ? 1.25 : 1.0;
+  if (const char* e = getenv("WM_CAP_FACTOR")) factor = atof(e);
+  size_t cap = (size_t)(need * factor) + 1024;
+  const int ncomp = c->g.ndim - 1;
+  for (int k = 0; k < ncomp; ++k) {
+    WM_CUDA(cudaMalloc(&c->A.c[k], cap * sizeof(double)));
+    WM_CUDA(cudaMalloc(&c->B.c[k], cap * sizeof(double)));
+  }
+  for (int k = 0; k < 2; ++k) WM_CUDA(cudaMalloc(&c->id[k], cap * sizeof(double)));
+  c->cap = cap;
+  return WM_OK;
+}
+
+int reserve_stage(wm_ctx* c, size_t elems) {
+  if (elems <= c->stage_elems) return WM_OK;
+  if (c->stage) cudaFree(c->stage);
+  c->stage = nullptr;
+  WM_CUDA(cudaMalloc(&c->stage, elems * sizeof(double)));
+  c->stage_elems = elems;
+  return WM_OK;
+}
+
+int check_flags(wm_ctx* c) {
+  int f = 0;
+  WM_CUDA(cudaMemcpyAsync(&f, c->flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  WM_CUDA(cudaStreamSynchronize(c->stream));
+  if (f & 1) {
+    wm_set_error("memory over (np2 > np)");
+    return WM_ERR_MEMORY_OVER;
+  }
+  if (f & 2) {
+    wm_set_error("a particle left the one-cell neighbourhood of its cell (|inc| > 1 or outside the slab)");
+    return WM_ERR_PARTICLE_LOST;
+  }
+  return WM_OK;
+}
+
+bool range_ok(const wm_ctx* c, int nxs, int nxe) {
+  return nxs >= c->g.nxgs && nxe <= c->g.nxge && nxs <= nxe;
+}
+}  // namespace
+
+void wm_set_error(const std::string& msg) { g_err = msg; }
+
+extern "C" {
+
+const char* wm_last_error(void) { return g_err.c_str(); }
+int wm_version(void) { return 100; }
+
+int wm_para_range(int n1, int n2, int isize, int irank, int* ns, int* ne) {
+  // 3d/common/mpi_set.f90:81-94
+  if (isize <= 0 || irank < 0 || irank >= isize || !ns || !ne) return WM_ERR_ARG;
+  int iwork1 = (n2 - n1 + 1) / isize;
+  int iwork2 = (n2 - n1 + 1) % isize;
+  *ns = irank * iwork1 + n1 + std::min(irank, iwork2);
+  *ne = *ns + iwork1 - 1;
+  if (iwork2 > irank) *ne = *ne + 1;
+  return WM_OK;
+}
+
+int wm_create(const wm_params* prm, wm_ctx** out) {
+  if (!prm || !out) return WM_ERR_ARG;
+  *out = nullptr;
+  const wm_params& p = *prm;
+  if (!((p.dim == 3 && p.ndim == 7) || (p.dim == 2 && p.ndim == 6)) || p.nsp != 2 || p.np <= 0) {
+    wm_set_error("wm_create: need (dim,ndim) = (3,7) or (2,6), nsp = 2, np > 0");
+    return WM_ERR_ARG;
+  }
+  if (p.nxge < p.nxgs || p.nye < p.nys || (p.dim == 3 && p.nze < p.nzs) || p.nproc_j < 1 || p.nproc_k < 1) {
+    wm_set_error("wm_create: empty index range");
+    return WM_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    wm_set_error("wm_create: no CUDA device (this backend has no CPU fallback)");
+    return WM_ERR_CUDA;
+  }
+  wm_ctx* c = new wm_ctx();
+  c->prm = p;
+  for (int k = 0; k < 6; ++k) c->A.c[k] = c->B.c[k] = nullptr;
+  if (p.device >= 0) {
+    c->device = p.device;
+  } else {
+    cudaGetDevice(&c->device);
+  }
+  WM_CUDA(cudaSetDevice(c->device));
+  WM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  Geo& g = c->g;
+  g.dim = p.dim; g.ndim = p.ndim; g.nsp = p.nsp; g.np = p.np;
+  g.nxgs = p.nxgs; g.nxge = p.nxge; g.nygs = p.nygs; g.nyge = p.nyge;
+  g.nys = p.nys; g.nye = p.nye;
+  if (p.dim == 3) { g.nzgs = p.nzgs; g.nzge = p.nzge; g.nzs = p.nzs; g.nze = p.nze; }
+  else { g.nzgs = g.nzge = g.nzs = g.nze = 0; }
+  g.nx = g.nxge - g.nxgs + 1; g.ny = g.nyge - g.nygs + 1; g.nz = p.dim == 3 ? g.nzge - g.nzgs + 1 : 1;
+  g.nyl = g.nye - g.nys + 1; g.nzl = p.dim == 3 ? g.nze - g.nzs + 1 : 1;
+  g.bx = g.nx + 4; g.by = g.nyl + 4; g.bz = p.dim == 3 ? g.nzl + 4 : 1;
+  g.npen = g.nsp * g.nyl * g.nzl;
+  g.bc = p.bc_kind;
+  g.delx = p.delx; g.delt = p.delt; g.c = p.c; g.gfac = p.gfac;
+  g.d_delx = 1.0 / p.delx; g.d_delt = 1.0 / p.delt;
+  for (int s = 0; s < 2; ++s) { g.q[s] = p.q[s]; g.r[s] = p.r[s]; }
+  // field__init: 3d/common/field.f90:57-63, 2d/common/field.f90:53-59
+  g.f1 = p.c * p.delt / p.delx;
+  g.f2 = p.gfac * g.f1 * g.f1;
+  g.f3 = 4.0 * kPi * p.delx / p.c;
+  g.f5 = std::pow(p.delx / (p.c * p.delt * p.gfac), 2);
+  g.f4 = (p.dim == 3 ? 6.0 : 4.0) + g.f5;
+  // mpi_set__init neighbour table (3d/common/mpi_set.f90:63-76), periodic in y and z
+  c->nranks = 1;  // until wm_comm_init
+  c->rank = p.rank_j * p.nproc_k + p.rank_k;
+  auto rk = [&](int j, int k) { return ((j + p.nproc_j) % p.nproc_j) * p.nproc_k + ((k + p.nproc_k) % p.nproc_k); };
+  c->rank_up[0] = rk(p.rank_j + 1, p.rank_k); c->rank_down[0] = rk(p.rank_j - 1, p.rank_k);
+  c->rank_up[1] = rk(p.rank_j, p.rank_k + 1); c->rank_down[1] = rk(p.rank_j, p.rank_k - 1);
+
+  const size_t nb = g.nbox();
+  WM_CUDA(cudaMalloc(&c->uf, nb * 6 * sizeof(double)));
+  WM_CUDA(cudaMalloc(&c->df, nb * 6 * sizeof(double)));
+  WM_CUDA(cudaMalloc(&c->tmpf, nb * 6 * sizeof(double)));
+  WM_CUDA(cudaMalloc(&c->uj, nb * 3 * sizeof(double)));
+  WM_CUDA(cudaMalloc(&c->gkl, nb * 3 * sizeof(double)));
+  double** cg[5] = {&c->phi, &c->pcg, &c->rcg, &c->bcg, &c->apcg};
+  for (auto pp : cg) {
+    WM_CUDA(cudaMalloc(pp, nb * sizeof(double)));
+    WM_CUDA(cudaMemsetAsync(*pp, 0, nb * sizeof(double), c->stream));
+  }
+  // field.f90:109-123: df, gkl, uj start at zero (df is the CG warm start)
+  WM_CUDA(cudaMemsetAsync(c->uf, 0, nb * 6 * sizeof(double), c->stream));
+  WM_CUDA(cudaMemsetAsync(c->df, 0, nb * 6 * sizeof(double), c->stream));
+  WM_CUDA(cudaMemsetAsync(c->tmpf, 0, nb * 6 * sizeof(double), c->stream));
+  WM_CUDA(cudaMemsetAsync(c->uj, 0, nb * 3 * sizeof(double), c->stream));
+  WM_CUDA(cudaMemsetAsync(c->gkl, 0, nb * 3 * sizeof(double), c->stream));
+  const size_t ncs = (size_t)g.npen * (g.nx + 1) + 1;
+  WM_CUDA(cudaMalloc(&c->cs, ncs * sizeof(int)));
+  WM_CUDA(cudaMalloc(&c->cs_new, ncs * sizeof(int)));
+  WM_CUDA(cudaMalloc(&c->cursor, ncs * sizeof(int)));
+  WM_CUDA(cudaMemsetAsync(c->cs, 0, ncs * sizeof(int), c->stream));
+  WM_CUDA(cudaMalloc(&c->np2, (size_t)g.npen * sizeof(int)));
+  WM_CUDA(cudaMalloc(&c->poff, ((size_t)g.npen + 1) * sizeof(int)));
+  WM_CUDA(cudaMemsetAsync(c->np2, 0, (size_t)g.npen * sizeof(int), c->stream));
+  WM_CUDA(cudaMemsetAsync(c->poff, 0, ((size_t)g.npen + 1) * sizeof(int), c->stream));
+  WM_CUDA(cudaMalloc(&c->flags, 4 * sizeof(int)));
+  WM_CUDA(cudaMemsetAsync(c->flags, 0, 4 * sizeof(int), c->stream));
+  WM_CUDA(cudaMalloc(&c->red, (4096 + 64) * sizeof(double)));
+  WM_CUDA(cudaMemsetAsync(c->red, 0, (4096 + 64) * sizeof(double), c->stream));
+  WM_CUDA(cudaMallocHost(&c->red_host, 64 * sizeof(double)));
+  c->hbuf_elems = (size_t)2 * 6 * g.bx * std::max(g.by, g.bz);
+  WM_CUDA(cudaMalloc(&c->hbuf[0], c->hbuf_elems * sizeof(double)));
+  WM_CUDA(cudaMalloc(&c->hbuf[2], c->hbuf_elems * sizeof(double)));
+  for (int e = 0; e < 8; ++e) WM_CUDA(cudaEventCreate(&c->ev[e]));
+  WM_CUDA(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return WM_OK;
+}
+
+int wm_destroy(wm_ctx* c) {
+  if (!c) return WM_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  wm_comm_destroy(c);
+  free_particles(c);
+  double* d[] = {c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
+                 c->hbuf[2], c->stage};
+  for (double* p : d) if (p) cudaFree(p);
+  int* ii[] = {c->cs, c->cs_new, c->cursor, c->np2, c->poff, c->flags};
+  for (int* p : ii) if (p) cudaFree(p);
+  if (c->scan_tmp) cudaFree(c->scan_tmp);
+  if (c->red_host) cudaFreeHost(c->red_host);
+  for (int e = 0; e < 8; ++e) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return WM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// state transfer
+// ---------------------------------------------------------------------------------------------
+int wm_upload(wm_ctx* c, const double* up, const int* np2, const int* cumcnt, const double* uf) {
+  if (!c) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  const Geo& g = c->g;
+  if (uf) WM_CUDA(cudaMemcpyAsync(c->uf, uf, g.nbox() * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (up) {
+    if (!np2 || !cumcnt) {
+      wm_set_error("wm_upload: up needs np2 and cumcnt");
+      return WM_ERR_ARG;
+    }
+    std::vector<int> poff(g.npen + 1, 0);
+    int maxcnt = 0;
+    for (int pen = 0; pen < g.npen; ++pen) {
+      if (np2[pen] < 0 || np2[pen] > g.np) {
+        wm_set_error("memory over (np2 > np)");
+        return WM_ERR_MEMORY_OVER;
+      }
+      poff[pen + 1] = poff[pen] + np2[pen];
+      maxcnt = std::max(maxcnt, np2[pen]);
+    }
+    c->ntot = poff[g.npen];
+    c->n_sp0 = poff[g.npen / g.nsp];
+    WM_TRY(reserve_particles(c, (size_t)c->ntot));
+    std::vector<int> cs((size_t)g.npen * (g.nx + 1) + 1);
+    for (int pen = 0; pen < g.npen; ++pen)
+      for (int i = 0; i <= g.nx; ++i) cs[(size_t)pen * (g.nx + 1) + i] = poff[pen] + cumcnt[(size_t)pen * (g.nx + 1) + i];
+    cs.back() = poff[g.npen];
+    WM_CUDA(cudaMemcpyAsync(c->cs, cs.data(), cs.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    WM_CUDA(cudaMemcpyAsync(c->np2, np2, (size_t)g.npen * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    WM_CUDA(cudaMemcpyAsync(c->poff, poff.data(), poff.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    WM_CUDA(cudaStreamSynchronize(c->stream));  // cs/poff are stack-owned host vectors
+    if (maxcnt > 0) {
+      const size_t per_pen = (size_t)maxcnt * g.ndim;
+      size_t want = std::min<size_t>(per_pen * g.npen, (size_t)32 << 20);
+      want = std::max(want, per_pen);
+      WM_TRY(reserve_stage(c, want));
+      const int chunk = (int)std::max<size_t>(1, c->stage_elems / per_pen);
+      for (int pen0 = 0; pen0 < g.npen; pen0 += chunk) {
+        const int n = std::min(chunk, g.npen - pen0);
+        WM_CUDA(cudaMemcpy2DAsync(c->stage, per_pen * sizeof(double), up + (size_t)pen0 * g.np * g.ndim,
+                                  (size_t)g.np * g.ndim * sizeof(double), per_pen * sizeof(double), n,
+                                  cudaMemcpyHostToDevice, c->stream));
+        WM_TRY(wm_k_aos_to_soa(c, c->stage, c->A, c->id[c->cid], pen0, n, maxcnt));
+      }
+    }
+    c->gp_valid = false;
+  }
+  WM_CUDA(cudaStreamSynchronize(c->stream));
+  return WM_OK;
+}
+
+int wm_download(wm_ctx* c, double* up, int* np2, int* cumcnt, double* uf, double* gp) {
+  if (!c) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  const Geo& g = c->g;
+  WM_TRY(check_flags(c));
+  if (uf) WM_CUDA(cudaMemcpyAsync(uf, c->uf, g.nbox() * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<int> h_np2(g.npen);
+  WM_CUDA(cudaMemcpyAsync(h_np2.data(), c->np2, (size_t)g.npen * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  WM_CUDA(cudaStreamSynchronize(c->stream));
+  int maxcnt = 0;
+  for (int v : h_np2) maxcnt = std::max(maxcnt, v);
+  if (np2) std::memcpy(np2, h_np2.data(), (size_t)g.npen * sizeof(int));
+  if (cumcnt) {
+    std::vector<int> cs((size_t)g.npen * (g.nx + 1));
+    WM_CUDA(cudaMemcpyAsync(cs.data(), c->cs, cs.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    WM_CUDA(cudaStreamSynchronize(c->stream));
+    for (int pen = 0; pen < g.npen; ++pen) {
+      const int base = cs[(size_t)pen * (g.nx + 1)];
+      for (int i = 0; i <= g.nx; ++i) cumcnt[(size_t)pen * (g.nx + 1) + i] = cs[(size_t)pen * (g.nx + 1) + i] - base;
+    }
+  }
+  for (int which = 0; which < 2; ++which) {
+    double* dst = which == 0 ? up : gp;
+    if (!dst || maxcnt == 0) continue;
+    if (which == 1 && !c->gp_valid) {
+      wm_set_error("wm_download: gp is only defined between particle__solv and bc__particle_yz");
+      return WM_ERR_STATE;
+    }
+    const size_t per_pen = (size_t)maxcnt * g.ndim;
+    size_t want = std::min<size_t>(per_pen * g.npen, (size_t)32 << 20);
+    want = std::max(want, per_pen);
+    WM_TRY(reserve_stage(c, want));
+    const int chunk = (int)std::max<size_t>(1, c->stage_elems / per_pen);
+    for (int pen0 = 0; pen0 < g.npen; pen0 += chunk) {
+      const int n = std::min(chunk, g.npen - pen0);
+      WM_TRY(wm_k_soa_to_aos(c, c->stage, which == 0 ? c->A : c->B, c->id[c->cid], pen0, n, maxcnt));
+      // only the first np2 records of a pencil are defined; rows are copied to the longest pencil
+      WM_CUDA(cudaMemcpy2DAsync(dst + (size_t)pen0 * g.np * g.ndim, (size_t)g.np * g.ndim * sizeof(double), c->stage,
+                                per_pen * sizeof(double), per_pen * sizeof(double), n, cudaMemcpyDeviceToHost,
+                                c->stream));
+    }
+  }
+  WM_CUDA(cudaStreamSynchronize(c->stream));
+  return WM_OK;
+}
+
+int wm_download_work(wm_ctx* c, int which, double* out) {
+  if (!c || !out) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  const Geo& g = c->g;
+  const size_t nb = g.nbox();
+  if (which == 0) {
+    WM_CUDA(cudaMemcpyAsync(out, c->uj, nb * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  } else if (which == 1) {
+    WM_CUDA(cudaMemcpyAsync(out, c->df, nb * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  } else if (which == 2) {
+    // gkl(3, nxgs:nxge, nys:nye, nzs:nze): the device keeps it on the box layout
+    std::vector<double> tmp(nb * 3);
+    WM_CUDA(cudaMemcpyAsync(tmp.data(), c->gkl, nb * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    WM_CUDA(cudaStreamSynchronize(c->stream));
+    size_t t = 0;
+    for (int k = g.nzs; k <= g.nze; ++k)
+      for (int j = g.nys; j <= g.nye; ++j)
+        for (int i = g.nxgs; i <= g.nxge; ++i)
+          for (int cc = 0; cc < 3; ++cc) out[t++] = tmp[g.box(i, j, k) * 3 + cc];
+  } else {
+    return WM_ERR_ARG;
+  }
+  WM_CUDA(cudaStreamSynchronize(c->stream));
+  return WM_OK;
+}
+
+int wm_upload_work(wm_ctx* c, int which, const double* in) {
+  if (!c || !in || which != 1) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  WM_CUDA(cudaMemcpyAsync(c->df, in, c->g.nbox() * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  WM_CUDA(cudaStreamSynchronize(c->stream));
+  return WM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the hot path, one entry per reference procedure
+// ---------------------------------------------------------------------------------------------
+int wm_particle_solv(wm_ctx* c, int nxs, int nxe) {
+  if (!c || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling particle__init()"); return WM_ERR_ARG; }
+  WM_CUDA(cudaSetDevice(c->device));
+  WM_TRY(wm_k_tmpf(c, nxs, nxe));
+  WM_TRY(wm_k_push(c, nxs, nxe));
+  c->gp_valid = true;
+  return WM_OK;
+}
+
+int wm_field_stage(wm_ctx* c, int nxs, int nxe, int stage) {
+  if (!c || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling field__init()"); return WM_ERR_ARG; }
+  WM_CUDA(cudaSetDevice(c->device));
+  switch (stage) {
+    case 1:
+      if (!c->gp_valid) { wm_set_error("field__fdtd_i needs the pushed particles (call particle__solv first)"); return WM_ERR_STATE; }
+      WM_TRY(wm_k_zero_uj(c, nxs, nxe));
+      return wm_k_deposit(c, nxs, nxe);
+    case 2: return wm_k_curre(c, nxs, nxe);
+    case 3: return wm_k_gkl(c, nxs, nxe);
+    case 4: return wm_k_cgm(c, nxs, nxe);
+    case 5: return wm_k_dfield(c, nxs, nxe);
+    case 6: return wm_k_de(c, nxs, nxe);
+    case 7: return wm_k_dfield(c, nxs, nxe);
+    case 8: return wm_k_update(c, nxs, nxe);
+  }
+  return WM_ERR_ARG;
+}
+
+int wm_field_fdtd_i(wm_ctx* c, int nxs, int nxe) {
+  for (int s = 1; s <= 8; ++s) WM_TRY(wm_field_stage(c, nxs, nxe, s));
+  return WM_OK;
+}
+
+int wm_bc_particle_x(wm_ctx* c, int nxs, int nxe) {
+  if (!c) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  if (!c->gp_valid) { wm_set_error("bc__particle_x acts on the pushed particles (call particle__solv first)"); return WM_ERR_STATE; }
+  return wm_k_bc_x(c, nxs, nxe, c->g.bc, 0.0);
+}
+
+int wm_bc_injection(wm_ctx* c, int nxs, int nxe, double u0) {
+  if (!c) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  if (!c->gp_valid) { wm_set_error("bc__injection acts on the pushed particles"); return WM_ERR_STATE; }
+  return wm_k_bc_x(c, nxs, nxe, WM_BC_SHOCK, u0);
+}
+
+int wm_bc_particle_yz(wm_ctx* c) {
+  if (!c) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  if (!c->gp_valid) { wm_set_error("bc__particle_yz acts on the pushed particles"); return WM_ERR_STATE; }
+  return wm_k_migrate(c);
+}
+
+int wm_sort_bucket(wm_ctx* c, int nxs, int nxe) {
+  if (!c || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling sort__init()"); return WM_ERR_ARG; }
+  WM_CUDA(cudaSetDevice(c->device));
+  if (!c->gp_valid) { wm_set_error("sort__bucket sorts the pushed particles"); return WM_ERR_STATE; }
+  WM_TRY(wm_k_sort(c, nxs, nxe));
+  c->gp_valid = false;
+  return WM_OK;
+}
+
+int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
+  if (!c || !range_ok(c, nxs, nxe)) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  for (int it = 0; it < nsteps; ++it) {
+    if (c->timing) WM_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    WM_TRY(wm_particle_solv(c, nxs, nxe));
+    if (c->timing) WM_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    if (order == WM_ORDER_RECONNECTION) WM_TRY(wm_bc_particle_x(c, nxs, nxe));
+    if (order == WM_ORDER_SHOCK) WM_TRY(wm_bc_injection(c, nxs, nxe, u0));
+    WM_TRY(wm_field_stage(c, nxs, nxe, 1));
+    if (c->timing) WM_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    for (int s = 2; s <= 8; ++s) WM_TRY(wm_field_stage(c, nxs, nxe, s));
+    if (c->timing) WM_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    if (order == WM_ORDER_WEIBEL) WM_TRY(wm_bc_particle_x(c, nxs, nxe));
+    WM_TRY(wm_bc_particle_yz(c));
+    WM_TRY(wm_sort_bucket(c, nxs, nxe));
+    if (c->timing) {
+      WM_CUDA(cudaEventRecord(c->ev[4], c->stream));
+      WM_CUDA(cudaEventSynchronize(c->ev[4]));
+      for (int e = 0; e < 4; ++e) cudaEventElapsedTime(&c->ms_phase[e], c->ev[e], c->ev[e + 1]);
+    }
+  }
+  return WM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer forms
+// ---------------------------------------------------------------------------------------------
+int wm_h_particle_solv(wm_ctx* c, double* gp, const double* up, const double* uf, const int* cumcnt, const int* np2,
+                       int nxs, int nxe) {
+  WM_TRY(wm_upload(c, up, np2, cumcnt, uf));
+  WM_TRY(wm_particle_solv(c, nxs, nxe));
+  return wm_download(c, nullptr, nullptr, nullptr, nullptr, gp);
+}
+
+int wm_h_field_fdtd_i(wm_ctx* c, double* uf, const double* up, const double* gp, const int* cumcnt, const int* np2,
+                      int nxs, int nxe) {
+  if (!c) return WM_ERR_ARG;
+  WM_TRY(wm_upload(c, up, np2, cumcnt, uf));
+  // gp arrives from the host as well: stage it into set B with the same pencil offsets
+  {
+    const Geo& g = c->g;
+    int maxcnt = 0;
+    for (int pen = 0; pen < g.npen; ++pen) maxcnt = std::max(maxcnt, np2[pen]);
+    if (maxcnt > 0) {
+      const size_t per_pen = (size_t)maxcnt * g.ndim;
+      const int chunk = (int)std::max<size_t>(1, c->stage_elems / per_pen);
+      for (int pen0 = 0; pen0 < g.npen; pen0 += chunk) {
+        const int n = std::min(chunk, g.npen - pen0);
+        WM_CUDA(cudaMemcpy2DAsync(c->stage, per_pen * sizeof(double), gp + (size_t)pen0 * g.np * g.ndim,
+                                  (size_t)g.np * g.ndim * sizeof(double), per_pen * sizeof(double), n,
+                                  cudaMemcpyHostToDevice, c->stream));
+        // the ID column of gp equals up's (particle.f90:227-231); it is written to the spare ID array
+        WM_TRY(wm_k_aos_to_soa(c, c->stage, c->B, c->id[1 - c->cid], pen0, n, maxcnt));
+      }
+    }
+    c->gp_valid = true;
+  }
+  WM_TRY(wm_field_fdtd_i(c, nxs, nxe));
+  return wm_download(c, nullptr, nullptr, nullptr, uf, nullptr);
+}
+
+int wm_h_step(wm_ctx* c, double* up, double* uf, int* np2, int* cumcnt, int nxs, int nxe, int order, double u0) {
+  WM_TRY(wm_upload(c, up, np2, cumcnt, uf));
+  WM_TRY(wm_step(c, nxs, nxe, order, u0, 1));
+  return wm_download(c, up, np2, cumcnt, uf, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostics
+// ---------------------------------------------------------------------------------------------
+int wm_load_weibel(wm_ctx* c, int n0, double v_thi, double v_the, double t_ani, double b0, unsigned long long seed) {
+  if (!c || n0 <= 0) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  const Geo& g = c->g;
+  if ((long long)n0 * g.nx > g.np) {
+    wm_set_error("Error: Too large number of particles");  // 3d/proj/weibel/app.f90:315-320
+    return WM_ERR_MEMORY_OVER;
+  }
+  c->ntot = (long long)n0 * g.nx * g.npen;
+  c->n_sp0 = c->ntot / g.nsp;
+  WM_TRY(reserve_particles(c, (size_t)c->ntot));
+  WM_TRY(wm_k_load_weibel(c, n0, v_thi, v_the, t_ani, b0, seed));
+  c->gp_valid = false;
+  return WM_OK;
+}
+
+int wm_energy(wm_ctx* c, double* out) {
+  if (!c || !out) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  return wm_k_energy(c, out);
+}
+
+int wm_gauss(wm_ctx* c, double* out) {
+  if (!c || !out) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  return wm_k_gauss(c, out);
+}
+
+int wm_get_stats(wm_ctx* c, wm_stats* out) {
+  if (!c || !out) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  const Geo& g = c->g;
+  std::vector<int> h(g.npen);
+  int f = 0;
+  WM_CUDA(cudaMemcpyAsync(h.data(), c->np2, (size_t)g.npen * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  WM_CUDA(cudaMemcpyAsync(&f, c->flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  WM_CUDA(cudaStreamSynchronize(c->stream));
+  for (int l = 0; l < 3; ++l) out->cg_iterations[l] = c->cg_ite[l];
+  out->n_particles = c->ntot;
+  out->max_np2 = 0;
+  for (int v : h) out->max_np2 = std::max(out->max_np2, v);
+  out->error_flags = f;
+  out->ms_push = c->ms_phase[0];
+  out->ms_deposit = c->ms_phase[1];
+  out->ms_field = c->ms_phase[2];
+  out->ms_sort = c->ms_phase[3];
+  return WM_OK;
+}
+
+int wm_sync(wm_ctx* c) {
+  if (!c) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  WM_CUDA(cudaStreamSynchronize(c->stream));
+  return check_flags(c);
+}
+
+int wm_set_timing(wm_ctx* c, int on) {
+  if (!c) return WM_ERR_ARG;
+  c->timing = on;
+  return WM_OK;
+}
+
+long long wm_launch_count(wm_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

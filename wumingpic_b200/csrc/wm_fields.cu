@@ -1,0 +1,593 @@
+// wm_fields.cu -- implicit FDTD Maxwell update on the device.
+//
+//   field__fdtd_i           3d/common/field.f90:70-208   [2d/common/field.f90:66-186]
+//   cgm                     3d/common/field.f90:409-560  [2d :319-461]
+//   boundary_periodic__curre / __dfield / __phi
+//                           3d/common/boundary_periodic.f90:676-978, 458-673, 981-1099
+//                           [2d/common/boundary_periodic.f90:357-508, 251-354, 511-568]
+//
+// All arrays live on the "box" layout of Geo (two ghost layers, component fastest), which is the
+// reference's own uf layout.  Every MPI_SENDRECV of the reference is one pack -> transport -> unpack
+// triple; the transport is a pointer hand-over when the neighbour is this rank (periodic wrap on a
+// single slab) and an NCCL send/recv pair otherwise (wm_comm.cu).  These kernels are HBM-bound
+// stencil sweeps over (nx+4)(nyl+4)(nzl+4) cells; they are sized one thread per cell with x fastest
+// so that every warp reads/writes contiguous rows.
+#include "wm_internal.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+// ---------------------------------------------------------------------------------------------
+// plane pack / unpack: `nl` consecutive planes starting at p0 along `axis` (1 = y, 2 = z), x range
+// [i0,i1], transverse range [t0,t1] (k for axis y, j for axis z), NC components.
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void k_pack(const double* __restrict__ arr, double* __restrict__ buf, Geo g, int axis, int p0, int nl,
+                       int i0, int i1, int t0, int t1) {
+  const int nxr = i1 - i0 + 1, ntr = t1 - t0 + 1;
+  const long long n = (long long)nl * nxr * ntr;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i = i0 + (int)(e % nxr);
+    long long rest = e / nxr;
+    int t = t0 + (int)(rest % ntr);
+    int l = (int)(rest / ntr);
+    int j = axis == 1 ? p0 + l : t;
+    int k = axis == 1 ? t : p0 + l;
+    const double* s = arr + g.box(i, j, k) * NC;
+    double* d = buf + e * NC;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) d[c] = s[c];
+  }
+}
+
+template <int NC, bool ADD>
+__global__ void k_unpack(double* __restrict__ arr, const double* __restrict__ buf, Geo g, int axis, int p0, int nl,
+                         int i0, int i1, int t0, int t1) {
+  const int nxr = i1 - i0 + 1, ntr = t1 - t0 + 1;
+  const long long n = (long long)nl * nxr * ntr;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i = i0 + (int)(e % nxr);
+    long long rest = e / nxr;
+    int t = t0 + (int)(rest % ntr);
+    int l = (int)(rest / ntr);
+    int j = axis == 1 ? p0 + l : t;
+    int k = axis == 1 ? t : p0 + l;
+    double* d = arr + g.box(i, j, k) * NC;
+    const double* s = buf + e * NC;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) d[c] = ADD ? d[c] + s[c] : s[c];
+  }
+}
+
+// One SENDRECV: planes [src_p0, src_p0+nl) are sent towards `down` (dir_down=1) or `up` and what
+// arrives is unpacked (copy or add) into planes [dst_p0, dst_p0+nl).
+template <int NC, bool ADD>
+int exchange(wm_ctx* ctx, double* arr, int axis, bool dir_down, int src_p0, int dst_p0, int nl, int i0, int i1,
+             int t0, int t1) {
+  const Geo& g = ctx->g;
+  const size_t n = (size_t)nl * (i1 - i0 + 1) * (t1 - t0 + 1) * NC;
+  if (n == 0) return WM_OK;
+  if (n > ctx->hbuf_elems) {
+    wm_set_error("halo buffer too small");
+    return WM_ERR_ARG;
+  }
+  double* snd = ctx->hbuf[0];
+  double* rcv = ctx->hbuf[2];
+  const int blocks = wm_blocks((long long)(n / NC), TPB);
+  k_pack<NC><<<blocks, TPB, 0, ctx->stream>>>(arr, snd, g, axis, src_p0, nl, i0, i1, t0, t1);
+  WM_LAUNCH_CHECK(ctx);
+  WM_TRY(wm_comm_sendrecv(ctx, axis, dir_down ? 1 : 0, snd, rcv, n));
+  const int peer = dir_down ? ctx->rank_down[axis - 1] : ctx->rank_up[axis - 1];
+  const double* in = (peer == ctx->rank) ? snd : rcv;
+  k_unpack<NC, ADD><<<blocks, TPB, 0, ctx->stream>>>(arr, in, g, axis, dst_p0, nl, i0, i1, t0, t1);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+// x-direction periodic operations over all (j,k) of the given transverse ranges
+template <int NC>
+__global__ void k_x_fold_add(double* __restrict__ arr, Geo g, int nxs, int nxe, int j0, int j1, int k0, int k1) {
+  // uj(nxe-1) += uj(nxs-2); uj(nxe) += uj(nxs-1); uj(nxs) += uj(nxe+1); uj(nxs+1) += uj(nxe+2)
+  // then ghosts <- interior (boundary_periodic.f90:965-976)
+  const int nj = j1 - j0 + 1, nk = k1 - k0 + 1;
+  const int n = nj * nk * NC;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    int c = e % NC;
+    int j = j0 + (e / NC) % nj;
+    int k = k0 + (e / NC) / nj;
+    double* row = arr + g.box(g.nxgs - 2, j, k) * NC + c;
+    auto X = [&](int i) -> double& { return row[(size_t)(i - (g.nxgs - 2)) * NC]; };
+    X(nxe - 1) = X(nxe - 1) + X(nxs - 2);
+    X(nxe) = X(nxe) + X(nxs - 1);
+    X(nxs) = X(nxs) + X(nxe + 1);
+    X(nxs + 1) = X(nxs + 1) + X(nxe + 2);
+    X(nxs - 2) = X(nxe - 1);
+    X(nxs - 1) = X(nxe);
+    X(nxe + 1) = X(nxs);
+    X(nxe + 2) = X(nxs + 1);
+  }
+}
+
+template <int NC>
+__global__ void k_x_copy(double* __restrict__ arr, Geo g, int nxs, int nxe, int nl, int j0, int j1, int k0, int k1) {
+  const int nj = j1 - j0 + 1, nk = k1 - k0 + 1;
+  const int n = nj * nk * NC;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    int c = e % NC;
+    int j = j0 + (e / NC) % nj;
+    int k = k0 + (e / NC) / nj;
+    double* row = arr + g.box(g.nxgs - 2, j, k) * NC + c;
+    auto X = [&](int i) -> double& { return row[(size_t)(i - (g.nxgs - 2)) * NC]; };
+    if (nl == 2) {
+      X(nxs - 2) = X(nxe - 1);
+      X(nxe + 2) = X(nxs + 1);
+    }
+    X(nxs - 1) = X(nxe);
+    X(nxe + 1) = X(nxs);
+  }
+}
+
+// one-layer periodic x fold of a scalar box array: a(nxe) += a(nxs-1); a(nxs) += a(nxe+1)
+__global__ void k_x_fold1(double* __restrict__ arr, Geo g, int nxs, int nxe, int j0, int j1, int k0, int k1) {
+  const int nj = j1 - j0 + 1, nk = k1 - k0 + 1;
+  const int n = nj * nk;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    int j = j0 + e % nj, k = k0 + e / nj;
+    double* row = arr + g.box(g.nxgs - 2, j, k);
+    auto X = [&](int i) -> double& { return row[i - (g.nxgs - 2)]; };
+    X(nxe) = X(nxe) + X(nxs - 1);
+    X(nxs) = X(nxs) + X(nxe + 1);
+  }
+}
+
+__global__ void k_zero_box(double* __restrict__ arr, Geo g, int nc, int i0, int i1) {
+  // zero x in [i0,i1] for all j,k of the box (field.f90:227-229)
+  const int nxr = i1 - i0 + 1;
+  const long long n = (long long)nxr * g.by * g.bz;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i = i0 + (int)(e % nxr);
+    long long jk = e / nxr;
+    double* d = arr + (jk * g.bx + (i - (g.nxgs - 2))) * nc;
+    for (int c = 0; c < nc; ++c) d[c] = 0.0;
+  }
+}
+
+// interior cell decode: e -> (i,j,k) with x fastest
+__device__ inline void cell_of(const Geo& g, long long e, int nxs, int nxr, int& i, int& j, int& k) {
+  i = nxs + (int)(e % nxr);
+  long long r = e / nxr;
+  j = g.nys + (int)(r % g.nyl);
+  k = g.nzs + (int)(r / g.nyl);
+}
+
+// K7: RHS of the implicit equation (field.f90:128-159; 2d field.f90:125-146)
+__global__ void k_gkl(const double* __restrict__ uf, const double* __restrict__ uj, double* __restrict__ gkl, Geo g,
+                      int nxs, int nxe) {
+  const int nxr = nxe - nxs + 1;
+  const long long n = (long long)nxr * g.nyl * g.nzl;
+  const double f1 = g.f1, f2 = g.f2, f3 = g.f3;
+  const size_t sx = 1, sy = g.bx, sz = (size_t)g.bx * g.by;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    cell_of(g, e, nxs, nxr, i, j, k);
+    const size_t o = g.box(i, j, k);
+    auto F = [&](int c, long long d) { return uf[(o + d) * 6 + (c - 1)]; };
+    auto J = [&](int c, long long d) { return uj[(o + d) * 3 + (c - 1)]; };
+    const long long mx = -(long long)sx, px = sx, my = -(long long)sy, py = sy, mz = -(long long)sz, pz = sz;
+    double g1, g2, g3;
+    if (g.dim == 3) {
+      g1 = +f2 * (+F(1, mz) + F(1, my) + F(1, mx) - 6.0 * F(1, 0) + F(1, px) + F(1, py) + F(1, pz)
+                  + f3 * (-J(3, my) + J(3, 0) + J(2, mz) - J(2, 0)))
+           - f1 * (-F(6, my) + F(6, 0) + F(5, mz) - F(5, 0));
+      g2 = +f2 * (+F(2, mz) + F(2, my) + F(2, mx) - 6.0 * F(2, 0) + F(2, px) + F(2, py) + F(2, pz)
+                  + f3 * (-J(1, mz) + J(1, 0) + J(3, mx) - J(3, 0)))
+           - f1 * (-F(4, mz) + F(4, 0) + F(6, mx) - F(6, 0));
+      g3 = +f2 * (+F(3, mz) + F(3, my) + F(3, mx) - 6.0 * F(3, 0) + F(3, px) + F(3, py) + F(3, pz)
+                  + f3 * (-J(2, mx) + J(2, 0) + J(1, my) - J(1, 0)))
+           - f1 * (-F(5, mx) + F(5, 0) + F(4, my) - F(4, 0));
+    } else {
+      g1 = +f2 * (+F(1, my) + F(1, mx) - 4.0 * F(1, 0) + F(1, px) + F(1, py) + f3 * (-J(3, my) + J(3, 0)))
+           - f1 * (-F(6, my) + F(6, 0));
+      g2 = +f2 * (+F(2, my) + F(2, mx) - 4.0 * F(2, 0) + F(2, px) + F(2, py) - f3 * (-J(3, mx) + J(3, 0)))
+           + f1 * (-F(6, mx) + F(6, 0));
+      g3 = +f2 * (+F(3, my) + F(3, mx) - 4.0 * F(3, 0) + F(3, px) + F(3, py)
+                  + f3 * (-J(2, mx) + J(2, 0) + J(1, my) - J(1, 0)))
+           - f1 * (-F(5, mx) + F(5, 0) + F(4, my) - F(4, 0));
+    }
+    double* out = gkl + o * 3;
+    out[0] = g1;
+    out[1] = g2;
+    out[2] = g3;
+  }
+}
+
+// K10: explicit dE (field.f90:167-191; 2d :154-171)
+__global__ void k_de(const double* __restrict__ uf, const double* __restrict__ uj, double* __restrict__ df, Geo g,
+                     int nxs, int nxe) {
+  const int nxr = nxe - nxs + 1;
+  const long long n = (long long)nxr * g.nyl * g.nzl;
+  const double f1 = g.f1, gfac = g.gfac;
+  const double fpd = 4.0 * kPi * g.delt;
+  const size_t sx = 1, sy = g.bx, sz = (size_t)g.bx * g.by;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    cell_of(g, e, nxs, nxr, i, j, k);
+    const size_t o = g.box(i, j, k);
+    auto F = [&](int c, size_t d) { return uf[(o + d) * 6 + (c - 1)]; };
+    auto D = [&](int c, size_t d) { return df[(o + d) * 6 + (c - 1)]; };
+    double e4, e5, e6;
+    if (g.dim == 3) {
+      e4 = +f1 * (+gfac * (-D(3, 0) + D(3, sy) + D(2, 0) - D(2, sz)) + (-F(3, 0) + F(3, sy) + F(2, 0) - F(2, sz)))
+           - fpd * uj[o * 3 + 0];
+      e5 = +f1 * (+gfac * (-D(1, 0) + D(1, sz) + D(3, 0) - D(3, sx)) + (-F(1, 0) + F(1, sz) + F(3, 0) - F(3, sx)))
+           - fpd * uj[o * 3 + 1];
+      e6 = +f1 * (+gfac * (-D(2, 0) + D(2, sx) + D(1, 0) - D(1, sy)) + (-F(2, 0) + F(2, sx) + F(1, 0) - F(1, sy)))
+           - fpd * uj[o * 3 + 2];
+    } else {
+      e4 = +f1 * (+gfac * (-D(3, 0) + D(3, sy)) + (-F(3, 0) + F(3, sy))) - fpd * uj[o * 3 + 0];
+      e5 = -f1 * (+gfac * (-D(3, 0) + D(3, sx)) + (-F(3, 0) + F(3, sx))) - fpd * uj[o * 3 + 1];
+      e6 = +f1 * (+gfac * (-D(2, 0) + D(2, sx) + D(1, 0) - D(1, sy)) + (-F(2, 0) + F(2, sx) + F(1, 0) - F(1, sy)))
+           - fpd * uj[o * 3 + 2];
+    }
+    df[o * 6 + 3] = e4;
+    df[o * 6 + 4] = e5;
+    df[o * 6 + 5] = e6;
+  }
+}
+
+// K11: uf += df over x in [nxs-2,nxe+2] and all j,k incl. ghosts (field.f90:196-206)
+__global__ void k_update(double* __restrict__ uf, const double* __restrict__ df, Geo g, int nxs, int nxe) {
+  const int nxr = (nxe + 2) - (nxs - 2) + 1;
+  const long long n = (long long)nxr * 6 * g.by * g.bz;
+  const int x0 = (nxs - 2) - (g.nxgs - 2);
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    long long row = e / (nxr * 6);
+    int w = (int)(e % (nxr * 6));
+    size_t a = ((size_t)row * g.bx + x0) * 6 + w;
+    uf[a] = uf[a] + df[a];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cgm kernels.  phi, p, r, b, ap are scalar box arrays.  Block partial sums go to `part`
+// (2 doubles per block) and are folded in a fixed order by k_fold, so results are deterministic.
+// ---------------------------------------------------------------------------------------------
+__device__ inline void block_sum2(double a, double b, double* part) {
+  __shared__ double sa[TPB / 32], sb[TPB / 32];
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, o);
+    b += __shfl_down_sync(0xffffffffu, b, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sa[w] = a; sb[w] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0, tb = 0;
+    for (int t = 0; t < TPB / 32; ++t) { ta += sa[t]; tb += sb[t]; }
+    part[2 * blockIdx.x] = ta;
+    part[2 * blockIdx.x + 1] = tb;
+  }
+}
+
+// out[o0], out[o1] = sums of the per-block partials (single block, fixed order)
+__global__ void k_fold(const double* __restrict__ part, int nblocks, double* __restrict__ out, int o0, int o1) {
+  __shared__ double sa[TPB], sb[TPB];
+  double a = 0, b = 0;
+  for (int t = threadIdx.x; t < nblocks; t += TPB) { a += part[2 * t]; b += part[2 * t + 1]; }
+  sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+  __syncthreads();
+  for (int s = TPB / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[o0] = sa[0]; if (o1 >= 0) out[o1] = sb[0]; }
+}
+
+// phi = db(l); b = f5*gkl(l); sum b^2   (field.f90:442-452)
+__global__ void k_cg_init(const double* __restrict__ df, const double* __restrict__ gkl, double* __restrict__ phi,
+                          double* __restrict__ b, double* __restrict__ part, Geo g, int nxs, int nxe, int l) {
+  const int nxr = nxe - nxs + 1;
+  const long long n = (long long)nxr * g.nyl * g.nzl;
+  double s = 0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    cell_of(g, e, nxs, nxr, i, j, k);
+    const size_t o = g.box(i, j, k);
+    phi[o] = df[o * 6 + l];
+    double bb = g.f5 * gkl[o * 3 + l];
+    b[o] = bb;
+    s = s + bb * bb;
+  }
+  block_sum2(s, 0.0, part);
+}
+
+// r = b + sum_neigh(phi) - f4*phi ; p = r ; sum r^2   (field.f90:460-473)
+__global__ void k_cg_r0(const double* __restrict__ phi, const double* __restrict__ b, double* __restrict__ r,
+                        double* __restrict__ p, double* __restrict__ part, Geo g, int nxs, int nxe) {
+  const int nxr = nxe - nxs + 1;
+  const long long n = (long long)nxr * g.nyl * g.nzl;
+  const size_t sy = g.bx, sz = (size_t)g.bx * g.by;
+  double s = 0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    cell_of(g, e, nxs, nxr, i, j, k);
+    const size_t o = g.box(i, j, k);
+    double rr;
+    if (g.dim == 3)
+      rr = b[o] + phi[o - sz] + phi[o - sy] + phi[o - 1] - g.f4 * phi[o] + phi[o + 1] + phi[o + sy] + phi[o + sz];
+    else
+      rr = b[o] + phi[o - sy] + phi[o - 1] - g.f4 * phi[o] + phi[o + 1] + phi[o + sy];
+    r[o] = rr;
+    p[o] = rr;
+    s = s + rr * rr;
+  }
+  block_sum2(s, 0.0, part);
+}
+
+// ap = f4*p - sum_neigh(p) ; sum r^2, sum p*ap   (field.f90:485-499)
+__global__ void k_cg_ap(const double* __restrict__ p, const double* __restrict__ r, double* __restrict__ ap,
+                        double* __restrict__ part, Geo g, int nxs, int nxe) {
+  const int nxr = nxe - nxs + 1;
+  const long long n = (long long)nxr * g.nyl * g.nzl;
+  const size_t sy = g.bx, sz = (size_t)g.bx * g.by;
+  double s1 = 0, s2 = 0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    cell_of(g, e, nxs, nxr, i, j, k);
+    const size_t o = g.box(i, j, k);
+    double a;
+    if (g.dim == 3)
+      a = -p[o - sz] - p[o - sy] - p[o - 1] + g.f4 * p[o] - p[o + 1] - p[o + sy] - p[o + sz];
+    else
+      a = -p[o - sy] - p[o - 1] + g.f4 * p[o] - p[o + 1] - p[o + sy];
+    ap[o] = a;
+    s1 = s1 + r[o] * r[o];
+    s2 = s2 + p[o] * a;
+  }
+  block_sum2(s1, s2, part);
+}
+
+// av = S[0]/S[1]; phi += av*p; r -= av*ap; sum r_new^2   (field.f90:507-518, 527-536)
+__global__ void k_cg_update(double* __restrict__ phi, double* __restrict__ r, const double* __restrict__ p,
+                            const double* __restrict__ ap, const double* __restrict__ S, double* __restrict__ part,
+                            Geo g, int nxs, int nxe) {
+  const int nxr = nxe - nxs + 1;
+  const long long n = (long long)nxr * g.nyl * g.nzl;
+  const double av = S[0] / S[1];
+  double s = 0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    cell_of(g, e, nxs, nxr, i, j, k);
+    const size_t o = g.box(i, j, k);
+    phi[o] = phi[o] + av * p[o];
+    double rn = r[o] - av * ap[o];
+    r[o] = rn;
+    s = s + rn * rn;
+  }
+  block_sum2(s, 0.0, part);
+}
+
+// bv = S[2]/S[0]; p = r + bv*p   (field.f90:539-549)
+__global__ void k_cg_p(double* __restrict__ p, const double* __restrict__ r, const double* __restrict__ S, Geo g,
+                       int nxs, int nxe) {
+  const int nxr = nxe - nxs + 1;
+  const long long n = (long long)nxr * g.nyl * g.nzl;
+  const double bv = S[2] / S[0];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    cell_of(g, e, nxs, nxr, i, j, k);
+    const size_t o = g.box(i, j, k);
+    p[o] = r[o] + bv * p[o];
+  }
+}
+
+// db(l) = phi   (field.f90:554-556)
+__global__ void k_cg_store(double* __restrict__ df, const double* __restrict__ phi, Geo g, int nxs, int nxe, int l) {
+  const int nxr = nxe - nxs + 1;
+  const long long n = (long long)nxr * g.nyl * g.nzl;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    cell_of(g, e, nxs, nxr, i, j, k);
+    const size_t o = g.box(i, j, k);
+    df[o * 6 + l] = phi[o];
+  }
+}
+
+int grid_for(long long n) {
+  long long b = (n + TPB - 1) / TPB;
+  const long long cap = 148LL * 8;  // persistent-style grid: 8 CTAs of 256 threads per SM
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// boundary_*__phi: one ghost layer of a scalar box array (boundary_periodic.f90:981-1099)
+int bc_phi(wm_ctx* ctx, double* a, int nxs, int nxe, int /*l*/) {
+  const Geo& g = ctx->g;
+  const int k0 = g.dim == 3 ? g.nzs : 0, k1 = g.dim == 3 ? g.nze : 0;
+  // y: row nys -> jdown's nye+1 ; row nye -> jup's nys-1   (i interior, k interior)
+  WM_TRY((exchange<1, false>(ctx, a, 1, true, g.nys, g.nye + 1, 1, nxs, nxe, k0, k1)));
+  WM_TRY((exchange<1, false>(ctx, a, 1, false, g.nye, g.nys - 1, 1, nxs, nxe, k0, k1)));
+  if (g.dim == 3) {
+    // z: plane nzs -> kdown's nze+1 ; plane nze -> kup's nzs-1   (j in [nys-1,nye+1])
+    WM_TRY((exchange<1, false>(ctx, a, 2, true, g.nzs, g.nze + 1, 1, nxs, nxe, g.nys - 1, g.nye + 1)));
+    WM_TRY((exchange<1, false>(ctx, a, 2, false, g.nze, g.nzs - 1, 1, nxs, nxe, g.nys - 1, g.nye + 1)));
+  }
+  // x periodic, one layer, over the ghost-extended transverse ranges
+  const int kk0 = g.dim == 3 ? g.nzs - 1 : 0, kk1 = g.dim == 3 ? g.nze + 1 : 0;
+  const int n = (g.nye - g.nys + 3) * (kk1 - kk0 + 1);
+  k_x_copy<1><<<wm_blocks(n, TPB), TPB, 0, ctx->stream>>>(a, g, nxs, nxe, 1, g.nys - 1, g.nye + 1, kk0, kk1);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+}  // namespace
+
+int wm_k_zero_uj(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const long long n = (long long)(nxe - nxs + 5) * g.by * g.bz;
+  k_zero_box<<<grid_for(n), TPB, 0, ctx->stream>>>(ctx->uj, g, 3, nxs - 2, nxe + 2);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+// boundary_periodic__curre (boundary_periodic.f90:676-978; 2d :357-508)
+int wm_k_curre(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  double* uj = ctx->uj;
+  if (g.dim == 3) {
+    // 1) y add, 2 layers, all k incl. ghosts
+    WM_TRY((exchange<3, true>(ctx, uj, 1, true, g.nys - 2, g.nye - 1, 2, nxs - 2, nxe + 2, g.nzs - 2, g.nze + 2)));
+    WM_TRY((exchange<3, true>(ctx, uj, 1, false, g.nye + 1, g.nys, 2, nxs - 2, nxe + 2, g.nzs - 2, g.nze + 2)));
+    // 2) z add, 2 layers, interior j only
+    WM_TRY((exchange<3, true>(ctx, uj, 2, true, g.nzs - 2, g.nze - 1, 2, nxs - 2, nxe + 2, g.nys, g.nye)));
+    WM_TRY((exchange<3, true>(ctx, uj, 2, false, g.nze + 1, g.nzs, 2, nxs - 2, nxe + 2, g.nys, g.nye)));
+    // 3) y copy-back, 1 layer, interior k
+    WM_TRY((exchange<3, false>(ctx, uj, 1, true, g.nys, g.nye + 1, 1, nxs - 2, nxe + 2, g.nzs, g.nze)));
+    WM_TRY((exchange<3, false>(ctx, uj, 1, false, g.nye, g.nys - 1, 1, nxs - 2, nxe + 2, g.nzs, g.nze)));
+    // 4) z copy-back, 1 layer, j in [nys-1,nye+1]
+    WM_TRY((exchange<3, false>(ctx, uj, 2, true, g.nzs, g.nze + 1, 1, nxs - 2, nxe + 2, g.nys - 1, g.nye + 1)));
+    WM_TRY((exchange<3, false>(ctx, uj, 2, false, g.nze, g.nzs - 1, 1, nxs - 2, nxe + 2, g.nys - 1, g.nye + 1)));
+  } else {
+    // 2-D: 2 layers add, then 2 layers copy-back (2d boundary_periodic.f90:357-508)
+    WM_TRY((exchange<3, true>(ctx, uj, 1, true, g.nys - 2, g.nye - 1, 2, nxs - 2, nxe + 2, 0, 0)));
+    WM_TRY((exchange<3, true>(ctx, uj, 1, false, g.nye + 1, g.nys, 2, nxs - 2, nxe + 2, 0, 0)));
+    WM_TRY((exchange<3, false>(ctx, uj, 1, true, g.nys, g.nye + 1, 2, nxs - 2, nxe + 2, 0, 0)));
+    WM_TRY((exchange<3, false>(ctx, uj, 1, false, g.nye - 1, g.nys - 2, 2, nxs - 2, nxe + 2, 0, 0)));
+  }
+  if (g.bc == WM_BC_PERIODIC) {
+    const int k0 = g.dim == 3 ? g.nzs - 2 : 0, k1 = g.dim == 3 ? g.nze + 2 : 0;
+    const int n = g.by * (k1 - k0 + 1) * 3;
+    k_x_fold_add<3><<<wm_blocks(n, TPB), TPB, 0, ctx->stream>>>(uj, g, nxs, nxe, g.nys - 2, g.nye + 2, k0, k1);
+    WM_LAUNCH_CHECK(ctx);
+  }
+  return WM_OK;
+}
+
+int wm_k_gkl(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const long long n = (long long)(nxe - nxs + 1) * g.nyl * g.nzl;
+  k_gkl<<<grid_for(n), TPB, 0, ctx->stream>>>(ctx->uf, ctx->uj, ctx->gkl, g, nxs, nxe);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+// boundary_periodic__dfield (boundary_periodic.f90:458-673; 2d :251-354)
+int wm_k_dfield(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  double* df = ctx->df;
+  const int k0 = g.dim == 3 ? g.nzs : 0, k1 = g.dim == 3 ? g.nze : 0;
+  WM_TRY((exchange<6, false>(ctx, df, 1, true, g.nys, g.nye + 1, 2, nxs, nxe, k0, k1)));
+  WM_TRY((exchange<6, false>(ctx, df, 1, false, g.nye - 1, g.nys - 2, 2, nxs, nxe, k0, k1)));
+  if (g.dim == 3) {
+    WM_TRY((exchange<6, false>(ctx, df, 2, true, g.nzs, g.nze + 1, 2, nxs, nxe, g.nys - 2, g.nye + 2)));
+    WM_TRY((exchange<6, false>(ctx, df, 2, false, g.nze - 1, g.nzs - 2, 2, nxs, nxe, g.nys - 2, g.nye + 2)));
+  }
+  if (g.bc == WM_BC_PERIODIC) {
+    const int kk0 = g.dim == 3 ? g.nzs - 2 : 0, kk1 = g.dim == 3 ? g.nze + 2 : 0;
+    const int n = g.by * (kk1 - kk0 + 1) * 6;
+    k_x_copy<6><<<wm_blocks(n, TPB), TPB, 0, ctx->stream>>>(df, g, nxs, nxe, 2, g.nys - 2, g.nye + 2, kk0, kk1);
+    WM_LAUNCH_CHECK(ctx);
+  }
+  return WM_OK;
+}
+
+int wm_k_de(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const long long n = (long long)(nxe - nxs + 1) * g.nyl * g.nzl;
+  k_de<<<grid_for(n), TPB, 0, ctx->stream>>>(ctx->uf, ctx->uj, ctx->df, g, nxs, nxe);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+int wm_k_update(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const long long n = (long long)(nxe - nxs + 5) * 6 * g.by * g.bz;
+  k_update<<<grid_for(n), TPB, 0, ctx->stream>>>(ctx->uf, ctx->df, g, nxs, nxe);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+// cgm (field.f90:409-560): host-driven loop, device-side scalars.  One 8-byte read-back per
+// iteration decides the `do while(sum_g > eps)` test; av, bv never leave the device.
+int wm_k_cgm(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const long long n = (long long)(nxe - nxs + 1) * g.nyl * g.nzl;
+  const int nb = grid_for(n);
+  double* part = ctx->red;           // 2*nb partials
+  double* S = ctx->red + 2 * 2048;   // S[0]=sumr S[1]=sum2 S[2]=sum1 S[3]=sum(b^2)
+  double* h = ctx->red_host;
+  const int ite_max = 100;
+  const double err = 1e-6;
+  cudaStream_t st = ctx->stream;
+  for (int l = 0; l < 3; ++l) {
+    int ite = 0;
+    k_cg_init<<<nb, TPB, 0, st>>>(ctx->df, ctx->gkl, ctx->phi, ctx->bcg, part, g, nxs, nxe, l);
+    WM_LAUNCH_CHECK(ctx);
+    k_fold<<<1, TPB, 0, st>>>(part, nb, S, 3, -1);
+    WM_LAUNCH_CHECK(ctx);
+    WM_TRY(wm_comm_allreduce_sum(ctx, S + 3, 1));
+    WM_TRY(bc_phi(ctx, ctx->phi, nxs, nxe, l + 1));
+    k_cg_r0<<<nb, TPB, 0, st>>>(ctx->phi, ctx->bcg, ctx->rcg, ctx->pcg, part, g, nxs, nxe);
+    WM_LAUNCH_CHECK(ctx);
+    k_fold<<<1, TPB, 0, st>>>(part, nb, S, 0, -1);
+    WM_LAUNCH_CHECK(ctx);
+    WM_TRY(wm_comm_allreduce_sum(ctx, S, 1));
+    WM_CUDA(cudaMemcpyAsync(h, S, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    WM_CUDA(cudaStreamSynchronize(st));
+    double sum_g = h[3];
+    const double eps = sqrt(sum_g) * err;
+    double sumr_g = h[0];
+    if (sqrt(sumr_g) > eps) {
+      while (sum_g > eps) {
+        ite = ite + 1;
+        WM_TRY(bc_phi(ctx, ctx->pcg, nxs, nxe, l + 1));
+        k_cg_ap<<<nb, TPB, 0, st>>>(ctx->pcg, ctx->rcg, ctx->apcg, part, g, nxs, nxe);
+        WM_LAUNCH_CHECK(ctx);
+        k_fold<<<1, TPB, 0, st>>>(part, nb, S, 0, 1);
+        WM_LAUNCH_CHECK(ctx);
+        WM_TRY(wm_comm_allreduce_sum(ctx, S, 2));
+        WM_CUDA(cudaMemcpyAsync(h, S, sizeof(double), cudaMemcpyDeviceToHost, st));
+        k_cg_update<<<nb, TPB, 0, st>>>(ctx->phi, ctx->rcg, ctx->pcg, ctx->apcg, S, part, g, nxs, nxe);
+        WM_LAUNCH_CHECK(ctx);
+        if (ite >= ite_max) {
+          WM_CUDA(cudaStreamSynchronize(st));
+          wm_set_error("********** stop at cgm after ite_max **********");
+          return WM_ERR_CG_ITEMAX;
+        }
+        k_fold<<<1, TPB, 0, st>>>(part, nb, S, 2, -1);
+        WM_LAUNCH_CHECK(ctx);
+        WM_TRY(wm_comm_allreduce_sum(ctx, S + 2, 1));
+        k_cg_p<<<nb, TPB, 0, st>>>(ctx->pcg, ctx->rcg, S, g, nxs, nxe);
+        WM_LAUNCH_CHECK(ctx);
+        WM_CUDA(cudaStreamSynchronize(st));
+        sumr_g = h[0];
+        sum_g = sqrt(sumr_g);
+      }
+    }
+    k_cg_store<<<nb, TPB, 0, st>>>(ctx->df, ctx->phi, g, nxs, nxe, l);
+    WM_LAUNCH_CHECK(ctx);
+    ctx->cg_ite[l] = ite;
+  }
+  return WM_OK;
+}
+
+// Diagnostic helper (Gauss check): fold the one-cell ghost layer of a scalar box array into the
+// owning cells -- the 1-layer analogue of boundary_periodic__curre's add phase (y, then z, then x).
+int wm_k_scalar_fold(wm_ctx* ctx, double* a, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const int k0 = g.dim == 3 ? g.nzs - 1 : 0, k1 = g.dim == 3 ? g.nze + 1 : 0;
+  WM_TRY((exchange<1, true>(ctx, a, 1, true, g.nys - 1, g.nye, 1, nxs - 1, nxe + 1, k0, k1)));
+  WM_TRY((exchange<1, true>(ctx, a, 1, false, g.nye + 1, g.nys, 1, nxs - 1, nxe + 1, k0, k1)));
+  if (g.dim == 3) {
+    WM_TRY((exchange<1, true>(ctx, a, 2, true, g.nzs - 1, g.nze, 1, nxs - 1, nxe + 1, g.nys, g.nye)));
+    WM_TRY((exchange<1, true>(ctx, a, 2, false, g.nze + 1, g.nzs, 1, nxs - 1, nxe + 1, g.nys, g.nye)));
+  }
+  if (g.bc == WM_BC_PERIODIC) {
+    const int kk0 = g.dim == 3 ? g.nzs : 0, kk1 = g.dim == 3 ? g.nze : 0;
+    const int n = g.nyl * (kk1 - kk0 + 1);
+    k_x_fold1<<<wm_blocks(n, TPB), TPB, 0, ctx->stream>>>(a, g, nxs, nxe, g.nys, g.nye, kk0, kk1);
+    WM_LAUNCH_CHECK(ctx);
+  }
+  return WM_OK;
+}

@@ -1,0 +1,147 @@
+// wm_internal.cuh -- shared declarations of the B200 backend (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/wuming_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// Device-side geometry: everything the kernels need, passed by value.
+// Box arrays (uf, df, uj, tmpf) keep the reference's layout (comp fastest, then x, y, z with two
+// ghost layers) so host <-> device transfers of uf are plain copies:
+//   box index of (i,j,k) = ((k-(nzs-2))*by + (j-(nys-2)))*bx + (i-(nxgs-2))
+// 2-D runs use nzl = 1, bz = 1 and k = 0 everywhere.
+// ---------------------------------------------------------------------------------------------
+struct Geo {
+  int dim, ndim, nsp, np;
+  int nxgs, nxge, nygs, nyge, nzgs, nzge, nys, nye, nzs, nze;
+  int nx, nyl, nzl;   // global x cells, local y / z cells
+  int ny, nz;         // global y / z cells
+  int bx, by, bz;     // box dims incl. ghosts
+  int npen;           // pencils on this rank over all species: nsp*nyl*nzl
+  int bc;
+  double delx, delt, c, gfac, d_delx, d_delt;
+  double q[2], r[2];
+  double f1, f2, f3, f4, f5;
+
+  __host__ __device__ inline size_t box(int i, int j, int k) const {
+    return ((size_t)(dim == 3 ? (k - (nzs - 2)) : 0) * by + (j - (nys - 2))) * bx + (i - (nxgs - 2));
+  }
+  __host__ __device__ inline size_t nbox() const { return (size_t)bx * by * bz; }
+  // pencil id of (j,k,isp) with isp 0-based: the order of the reference's np2(nys:nye,nzs:nze,nsp)
+  __host__ __device__ inline int pen(int j, int k, int isp) const {
+    return (isp * nzl + (dim == 3 ? (k - nzs) : 0)) * nyl + (j - nys);
+  }
+};
+
+// Particle store: structure of arrays, globally ordered by (species, k, j, i-cell).
+// Set A ("up") and set B ("gp") hold x,y,(z),ux,uy,uz; the 64-bit ID lives in its own ping-pong
+// pair because the push never reorders and so never touches it.
+struct Ptcl {
+  double* c[6];  // 3-D: x y z ux uy uz ; 2-D: x y ux uy uz (c[5] unused)
+};
+
+struct Halo;  // wm_halo.cu
+
+struct wm_ctx {
+  wm_params prm;
+  Geo g;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // particles
+  size_t cap = 0;      // capacity (particles) of each SoA array
+  long long ntot = 0;  // active particles
+  long long n_sp0 = 0; // particles of species 0 (they come first)
+  Ptcl A, B;
+  double* id[2] = {nullptr, nullptr};
+  int cid = 0;  // which id array goes with set A
+  // cell index: cs[pen*(nx+1) + (i-nxgs)] = absolute start of cell i of pencil pen; entry nx = pencil end
+  int* cs = nullptr;
+  int* cs_new = nullptr;   // histogram / scan target of the sort
+  int* cursor = nullptr;   // scatter cursors
+  int* np2 = nullptr;      // particles per pencil (npen)
+  int* poff = nullptr;     // pencil offsets (npen+1), absolute
+  int* flags = nullptr;    // sticky device error flags
+  void* scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
+  // fields
+  double *uf = nullptr, *df = nullptr, *uj = nullptr, *gkl = nullptr, *tmpf = nullptr;
+  // cg work arrays: phi, p (one ghost layer: (nx+2)(nyl+2)(nzl+2)), r, b, ap (interior)
+  double *phi = nullptr, *pcg = nullptr, *rcg = nullptr, *bcg = nullptr, *apcg = nullptr;
+  double* red = nullptr;        // reduction scratch (device)
+  double* red_host = nullptr;   // pinned
+  int cg_ite[3] = {0, 0, 0};
+  // halo buffers
+  double* hbuf[4] = {nullptr, nullptr, nullptr, nullptr};  // send lo, send hi, recv lo, recv hi
+  size_t hbuf_elems = 0;
+  // staging for host <-> device layout conversion
+  double* stage = nullptr;
+  size_t stage_elems = 0;
+  // state machine
+  bool gp_valid = false;     // set B holds the pushed state
+  bool keys_valid = false;   // migration pass done (histogram in cs_new)
+  bool df_zeroed = false;
+  // comm
+  void* nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+  int rank_up[2] = {0, 0}, rank_down[2] = {0, 0};  // [0]: y neighbours, [1]: z neighbours
+  // bookkeeping
+  long long launches = 0;
+  int timing = 0;
+  cudaEvent_t ev[8] = {};
+  float ms_phase[4] = {0, 0, 0, 0};
+};
+
+// error plumbing -------------------------------------------------------------------------------
+void wm_set_error(const std::string& msg);
+#define WM_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      wm_set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " at " + __FILE__ + \
+                   ":" + std::to_string(__LINE__));                                        \
+      return WM_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+#define WM_TRY(call)            \
+  do {                          \
+    int r__ = (call);           \
+    if (r__ != WM_OK) return r__; \
+  } while (0)
+#define WM_LAUNCH_CHECK(ctx)               \
+  do {                                     \
+    (ctx)->launches++;                     \
+    WM_CUDA(cudaGetLastError());           \
+  } while (0)
+
+static inline int wm_blocks(long long n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// sub-module entry points ------------------------------------------------------------------------
+// particles (wm_particles.cu)
+int wm_k_tmpf(wm_ctx* ctx, int nxs, int nxe);
+int wm_k_push(wm_ctx* ctx, int nxs, int nxe);
+int wm_k_deposit(wm_ctx* ctx, int nxs, int nxe);
+int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double u0);
+int wm_k_bc_x(wm_ctx* ctx, int nxs, int nxe, int kind, double u0);
+int wm_k_migrate(wm_ctx* ctx);
+int wm_k_sort(wm_ctx* ctx, int nxs, int nxe);
+int wm_k_energy(wm_ctx* ctx, double* out_host);
+int wm_k_gauss(wm_ctx* ctx, double* out_host);
+int wm_k_load_weibel(wm_ctx* ctx, int n0, double v_thi, double v_the, double t_ani, double b0, unsigned long long seed);
+int wm_k_aos_to_soa(wm_ctx* ctx, const double* stage, Ptcl dst, double* dst_id, int pen0, int npens, int maxcnt);
+int wm_k_soa_to_aos(wm_ctx* ctx, double* stage, Ptcl src, const double* src_id, int pen0, int npens, int maxcnt);
+int wm_k_cs_from_cumcnt(wm_ctx* ctx, const int* cumcnt_dev);
+int wm_k_cumcnt_from_cs(wm_ctx* ctx, int* cumcnt_dev);
+// fields (wm_fields.cu)
+int wm_k_zero_uj(wm_ctx* ctx, int nxs, int nxe);
+int wm_k_curre(wm_ctx* ctx, int nxs, int nxe);
+int wm_k_gkl(wm_ctx* ctx, int nxs, int nxe);
+int wm_k_cgm(wm_ctx* ctx, int nxs, int nxe);
+int wm_k_dfield(wm_ctx* ctx, int nxs, int nxe);
+int wm_k_de(wm_ctx* ctx, int nxs, int nxe);
+int wm_k_update(wm_ctx* ctx, int nxs, int nxe);
+// comm (wm_comm.cu)
+int wm_comm_sendrecv(wm_ctx* ctx, int axis, int dir_down, const double* snd, double* rcv, size_t n);
+int wm_comm_allreduce_sum(wm_ctx* ctx, double* dev_buf, int n);

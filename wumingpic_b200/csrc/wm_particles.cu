@@ -1,0 +1,559 @@
+// wm_particles.cu -- particle kernels: field staging, Buneman-Boris push, Esirkepov deposit,
+// x boundary, y/z re-binning and the cell-ordered counting sort.
+//
+//   particle__solv                3d/common/particle.f90:52-233   [2d/common/particle.f90:48-179]
+//   ele_cur                       3d/common/field.f90:211-406     [2d/common/field.f90:189-316]
+//   boundary_periodic__particle_x 3d/common/boundary_periodic.f90:68-101
+//   boundary_periodic__particle_yz                               :104-455
+//   sort__bucket                  3d/common/sort.f90:40-88
+//
+// Data layout: particles are a structure of arrays ordered by (species, k, j, x-cell); the cell
+// index `cs` plays the role of the reference's cumcnt (absolute offsets, nx+1 entries per pencil).
+// Each warp owns one cell at a time and its lanes walk that cell's particles, so every global
+// load/store is a contiguous 256-byte run and all lanes share the same 27-cell field stencil.
+#include "wm_internal.cuh"
+
+#include <cub/device/device_scan.cuh>
+
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ void shape3(double dh, double& sm, double& s0, double& sp) {
+  sm = 5e-1 * (5e-1 - dh) * (5e-1 - dh);
+  s0 = 7.5e-1 - dh * dh;
+  sp = 5e-1 * (5e-1 + dh) * (5e-1 + dh);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: fields at (i+1/2, j+1/2, k+1/2)   particle.f90:75-91 [2d :71-83]
+// ---------------------------------------------------------------------------------------------
+__global__ void k_tmpf(const double* __restrict__ uf, double* __restrict__ tmpf, Geo g, int nxs, int nxe) {
+  const int nxr = nxe - nxs + 3;
+  const int nyr = g.nyl + 2, nzr = g.dim == 3 ? g.nzl + 2 : 1;
+  const long long n = (long long)nxr * nyr * nzr;
+  const size_t sx = 6, sy = (size_t)g.bx * 6, sz = (size_t)g.bx * g.by * 6;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i = nxs - 1 + (int)(e % nxr);
+    long long r = e / nxr;
+    int j = g.nys - 1 + (int)(r % nyr);
+    int k = g.dim == 3 ? g.nzs - 1 + (int)(r / nyr) : 0;
+    const size_t o = g.box(i, j, k) * 6;
+    const double* u = uf + o;
+    double* t = tmpf + o;
+    if (g.dim == 3) {
+      t[0] = 2.5e-1 * (+u[0] + u[0 + sy] + u[0 + sz] + u[0 + sy + sz]);
+      t[1] = 2.5e-1 * (+u[1] + u[1 + sx] + u[1 + sz] + u[1 + sx + sz]);
+      t[2] = 2.5e-1 * (+u[2] + u[2 + sx] + u[2 + sy] + u[2 + sx + sy]);
+      t[3] = 5e-1 * (+u[3] + u[3 + sx]);
+      t[4] = 5e-1 * (+u[4] + u[4 + sy]);
+      t[5] = 5e-1 * (+u[5] + u[5 + sz]);
+    } else {
+      t[0] = 0.5 * (+u[0] + u[0 + sy]);
+      t[1] = 0.5 * (+u[1] + u[1 + sx]);
+      t[2] = 0.25 * (+u[2] + u[2 + sx] + u[2 + sy] + u[2 + sx + sy]);
+      t[3] = 0.5 * (+u[3] + u[3 + sx]);
+      t[4] = 0.5 * (+u[4] + u[4 + sy]);
+      t[5] = u[5];
+    }
+  }
+}
+
+// decode the c-th active cell (x fastest) -> (i,j,k)
+__device__ __forceinline__ void active_cell(const Geo& g, long long c, int nxs, int nxr, int& i, int& j, int& k) {
+  i = nxs + (int)(c % nxr);
+  long long r = c / nxr;
+  j = g.nys + (int)(r % g.nyl);
+  k = g.dim == 3 ? g.nzs + (int)(r / g.nyl) : 0;
+}
+
+// 27-point (9-point in 2-D) gather of the six staged field components, in the reference's
+// nesting: x-sum, then *shy summed over y, then *shz summed over z.
+template <int D>
+__device__ __forceinline__ void gather(const double* __restrict__ T, const Geo& g, const double sx[3],
+                                       const double sy[3], const double sz[3], double f[6]) {
+  const long long sY = (long long)g.bx * 6, sZ = (long long)g.bx * g.by * 6;
+  if (D == 3) {
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      double pl[6];
+#pragma unroll
+      for (int jj = 0; jj < 3; ++jj) {
+        const double* t = T + (kk - 1) * sZ + (jj - 1) * sY - 6;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          double row = +__ldg(t + c) * sx[0] + __ldg(t + 6 + c) * sx[1] + __ldg(t + 12 + c) * sx[2];
+          pl[c] = jj == 0 ? row * sy[0] : pl[c] + row * sy[jj];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) f[c] = kk == 0 ? pl[c] * sz[0] : f[c] + pl[c] * sz[kk];
+    }
+  } else {
+#pragma unroll
+    for (int jj = 0; jj < 3; ++jj) {
+      const double* t = T + (jj - 1) * sY - 6;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        double row = +__ldg(t + c) * sx[0] + __ldg(t + 6 + c) * sx[1] + __ldg(t + 12 + c) * sx[2];
+        f[c] = jj == 0 ? row * sy[0] : f[c] + row * sy[jj];
+      }
+    }
+  }
+}
+
+// Buneman-Boris update of one particle   particle.f90:186-217
+__device__ __forceinline__ void boris(const double f[6], double fac1, double fac2, double txxx, double c, double delt,
+                                      double& ux, double& uy, double& uz, double& gam_out) {
+  const double bpx = f[0], bpy = f[1], bpz = f[2], epx = f[3], epy = f[4], epz = f[5];
+  double uvm1 = ux + fac1 * epx;
+  double uvm2 = uy + fac1 * epy;
+  double uvm3 = uz + fac1 * epz;
+  double gam = sqrt(c * c + uvm1 * uvm1 + uvm2 * uvm2 + uvm3 * uvm3);
+  double igam = 1.0 / gam;
+  double fac1r = fac1 * igam;
+  double fac2r = fac2 / (gam + txxx * (bpx * bpx + bpy * bpy + bpz * bpz) * igam);
+  double uvm4 = uvm1 + fac1r * (+uvm2 * bpz - uvm3 * bpy);
+  double uvm5 = uvm2 + fac1r * (+uvm3 * bpx - uvm1 * bpz);
+  double uvm6 = uvm3 + fac1r * (+uvm1 * bpy - uvm2 * bpx);
+  uvm1 = uvm1 + fac2r * (+uvm5 * bpz - uvm6 * bpy);
+  uvm2 = uvm2 + fac2r * (+uvm6 * bpx - uvm4 * bpz);
+  uvm3 = uvm3 + fac2r * (+uvm4 * bpy - uvm5 * bpx);
+  ux = uvm1 + fac1 * epx;
+  uy = uvm2 + fac1 * epy;
+  uz = uvm3 + fac1 * epz;
+  gam_out = 1.0 / sqrt(1.0 + (+ux * ux + uy * uy + uz * uz) / (c * c));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: push.  One warp per cell, lanes over that cell's particles.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(TPB) k_push(Geo g, Ptcl A, Ptcl B, const int* __restrict__ cs,
+                                              const double* __restrict__ tmpf, int nxs, int nxe) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nxr = nxe - nxs + 1;
+  const long long ncell = (long long)nxr * g.nyl * g.nzl;
+  constexpr int U = D;  // index of ux in the SoA
+  for (long long cidx = warp; cidx < ncell; cidx += nwarps) {
+    int i, j, k;
+    active_cell(g, cidx, nxs, nxr, i, j, k);
+    const double* T = tmpf + g.box(i, j, k) * 6;
+    for (int isp = 0; isp < g.nsp; ++isp) {
+      const int* row = cs + (size_t)g.pen(j, k, isp) * (g.nx + 1) + (i - g.nxgs);
+      const int beg = row[0], end = row[1];
+      const double fac1 = g.q[isp] / g.r[isp] * 5e-1 * g.delt;
+      const double txxx = fac1 * fac1;
+      const double fac2 = g.q[isp] * g.delt / g.r[isp];
+      for (int p = beg + lane; p < end; p += 32) {
+        const double x = A.c[0][p], y = A.c[1][p];
+        const double z = D == 3 ? A.c[2][p] : 0.0;
+        double ux = A.c[U][p], uy = A.c[U + 1][p], uz = A.c[U + 2][p];
+        double sx[3], sy[3], sz[3] = {0, 1, 0};
+        shape3(x * g.d_delx - 5e-1 - i, sx[0], sx[1], sx[2]);
+        shape3(y * g.d_delx - 5e-1 - j, sy[0], sy[1], sy[2]);
+        if (D == 3) shape3(z * g.d_delx - 5e-1 - k, sz[0], sz[1], sz[2]);
+        double f[6];
+        gather<D>(T, g, sx, sy, sz, f);
+        double gam;
+        boris(f, fac1, fac2, txxx, g.c, g.delt, ux, uy, uz, gam);
+        B.c[U][p] = ux;
+        B.c[U + 1][p] = uy;
+        B.c[U + 2][p] = uz;
+        B.c[0][p] = x + ux * g.delt * gam;
+        B.c[1][p] = y + uy * g.delt * gam;
+        if (D == 3) B.c[2][p] = z + uz * g.delt * gam;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: Esirkepov deposit (v1: one particle per lane, non-zero W terms go straight to global RED.F64)
+// field.f90:252-396.  s0 is taken about the LOOP cell (from cs), s1 about int(x_new).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void s0ds(double xo, double xn, int cell, double d_delx, double s0[5], double ds[5],
+                                     int* flags) {
+  double dh = xo * d_delx - 5e-1 - cell;
+  s0[0] = 0.0;
+  shape3(dh, s0[1], s0[2], s0[3]);
+  s0[4] = 0.0;
+  int i2 = (int)(xn * d_delx);
+  dh = xn * d_delx - 5e-1 - i2;
+  int inc = i2 - cell;
+  if (inc < -1 || inc > 1) {
+    atomicOr(flags, 2);
+    inc = inc < 0 ? -1 : 1;
+  }
+  double s1_1, s1_2, s1_3;
+  shape3(dh, s1_1, s1_2, s1_3);
+  const double smo_1 = inc == -1 ? 1.0 : 0.0, smo_2 = inc == 0 ? 1.0 : 0.0, smo_3 = inc == 1 ? 1.0 : 0.0;
+  ds[0] = s1_1 * smo_1;
+  ds[1] = s1_1 * smo_2 + s1_2 * smo_1;
+  ds[2] = s1_2 * smo_2 + s1_3 * smo_1 + s1_1 * smo_3;
+  ds[3] = s1_3 * smo_2 + s1_2 * smo_3;
+  ds[4] = s1_3 * smo_3;
+#pragma unroll
+  for (int m = 0; m < 5; ++m) ds[m] = ds[m] - s0[m];
+}
+
+__device__ __forceinline__ void red_add(double* addr, double v) {
+  if (v != 0.0) atomicAdd(addr, v);
+}
+
+template <int D>
+__global__ void __launch_bounds__(TPB) k_deposit(Geo g, Ptcl A, Ptcl B, const int* __restrict__ cs,
+                                                 double* __restrict__ uj, int* flags, int nxs, int nxe) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nxr = nxe - nxs + 1;
+  const long long ncell = (long long)nxr * g.nyl * g.nzl;
+  const double fac = 1.0 / 3.0;
+  const long long sY = (long long)g.bx * 3, sZ = (long long)g.bx * g.by * 3;
+  for (long long cidx = warp; cidx < ncell; cidx += nwarps) {
+    int i, j, k;
+    active_cell(g, cidx, nxs, nxr, i, j, k);
+    double* J0 = uj + g.box(i, j, k) * 3;
+    for (int isp = 0; isp < g.nsp; ++isp) {
+      const int* row = cs + (size_t)g.pen(j, k, isp) * (g.nx + 1) + (i - g.nxgs);
+      const int beg = row[0], end = row[1];
+      const double qdxdt = g.q[isp] * g.delx * g.d_delt;
+      for (int p = beg + lane; p < end; p += 32) {
+        double s0x[5], s0y[5], dsx[5], dsy[5];
+        s0ds(A.c[0][p], B.c[0][p], i, g.d_delx, s0x, dsx, flags);
+        s0ds(A.c[1][p], B.c[1][p], j, g.d_delx, s0y, dsy, flags);
+        if (D == 3) {
+          double s0z[5], dsz[5];
+          s0ds(A.c[2][p], B.c[2][p], k, g.d_delx, s0z, dsz, flags);
+#pragma unroll
+          for (int kp = 0; kp < 5; ++kp) {
+#pragma unroll
+            for (int jp = 0; jp < 5; ++jp) {
+              // pjx(ip, jp, kp)
+              double dstmp = ((s0y[jp] + 5e-1 * dsy[jp]) * s0z[kp] + (5e-1 * s0y[jp] + fac * dsy[jp]) * dsz[kp]) * qdxdt;
+              double* Jx = J0 + (kp - 2) * sZ + (jp - 2) * sY;
+              double pj = -dsx[0] * dstmp;
+              red_add(Jx + (-1) * 3 + 0, pj);
+              pj = pj - dsx[1] * dstmp;
+              red_add(Jx + 0 * 3 + 0, pj);
+              pj = pj - dsx[2] * dstmp;
+              red_add(Jx + 1 * 3 + 0, pj);
+              pj = pj - dsx[3] * dstmp;
+              red_add(Jx + 2 * 3 + 0, pj);
+              // pjy(run, ip=jp, kp): x offset = jp-2, y offset = run, z offset = kp-2
+              dstmp = ((s0x[jp] + 5e-1 * dsx[jp]) * s0z[kp] + (5e-1 * s0x[jp] + fac * dsx[jp]) * dsz[kp]) * qdxdt;
+              double* Jy = J0 + (kp - 2) * sZ + (jp - 2) * 3 + 1;
+              pj = -dsy[0] * dstmp;
+              red_add(Jy + (-1) * sY, pj);
+              pj = pj - dsy[1] * dstmp;
+              red_add(Jy, pj);
+              pj = pj - dsy[2] * dstmp;
+              red_add(Jy + sY, pj);
+              pj = pj - dsy[3] * dstmp;
+              red_add(Jy + 2 * sY, pj);
+              // pjz(run, ip=jp, jp=kp): x offset = jp-2, y offset = kp-2, z offset = run
+              dstmp = ((s0x[jp] + 5e-1 * dsx[jp]) * s0y[kp] + (5e-1 * s0x[jp] + fac * dsx[jp]) * dsy[kp]) * qdxdt;
+              double* Jz = J0 + (kp - 2) * sY + (jp - 2) * 3 + 2;
+              pj = -dsz[0] * dstmp;
+              red_add(Jz + (-1) * sZ, pj);
+              pj = pj - dsz[1] * dstmp;
+              red_add(Jz, pj);
+              pj = pj - dsz[2] * dstmp;
+              red_add(Jz + sZ, pj);
+              pj = pj - dsz[3] * dstmp;
+              red_add(Jz + 2 * sZ, pj);
+            }
+          }
+        } else {
+          // 2-D (2d/common/field.f90:270-298): Jx, Jy by 2-D Esirkepov, Jz = q*vz*(S0S0 + ...)
+          const double ux = B.c[2][p], uy = B.c[3][p], uz = B.c[4][p];
+          const double gvz = uz / sqrt(1.0 + (+ux * ux + uy * uy + uz * uz) / (g.c * g.c));
+          const double qq = g.q[isp];
+#pragma unroll
+          for (int jp = 0; jp < 5; ++jp) {
+            double pj = 0.0;
+            double* Jx = J0 + (jp - 2) * sY;
+#pragma unroll
+            for (int ip = 0; ip < 4; ++ip) {
+              pj = pj - qq * g.delx * g.d_delt * dsx[ip] * (s0y[jp] + 0.5 * dsy[jp]);
+              red_add(Jx + (ip - 1) * 3 + 0, pj);
+            }
+          }
+#pragma unroll
+          for (int ip = 0; ip < 5; ++ip) {
+            double pj = 0.0;
+            double* Jy = J0 + (ip - 2) * 3 + 1;
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+              pj = pj - qq * g.delx * g.d_delt * dsy[jp] * (s0x[ip] + 0.5 * dsx[ip]);
+              red_add(Jy + (jp - 1) * sY, pj);
+            }
+          }
+#pragma unroll
+          for (int jp = 0; jp < 5; ++jp)
+#pragma unroll
+            for (int ip = 0; ip < 5; ++ip)
+              red_add(J0 + (jp - 2) * sY + (ip - 2) * 3 + 2,
+                      qq * gvz * (+s0x[ip] * s0y[jp] + 0.5 * dsx[ip] * s0y[jp] + 0.5 * s0x[ip] * dsy[jp]
+                                  + fac * dsx[ip] * dsy[jp]));
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K12: x boundary on the pushed set   boundary_periodic.f90:68-101
+// ---------------------------------------------------------------------------------------------
+__global__ void k_bc_x_periodic(Geo g, double* __restrict__ x, long long n) {
+  const double len = (g.nxge - g.nxgs + 1) * g.delx;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    double xx = x[p];
+    int ipos = (int)(xx * g.d_delx);
+    if (ipos < g.nxgs) x[p] = xx + len;
+    else if (ipos >= g.nxge + 1) x[p] = xx - len;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K13 + K14: y/z periodic wrap, destination cell, histogram; then scan and scatter.
+// The reference re-bins into pencils (boundary_periodic.f90:152-185) and then counting-sorts each
+// pencil in x (sort.f90:55-86); on the device both are one global counting sort whose key is
+// (species, k, j, i).  Only the per-cell particle SETS are defined by the reference (the order
+// inside a cell depends on OpenMP lock order there, on atomic order here).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ int dest_slot(const Geo& g, double x, double y, double z, int isp, int nxs, int nxe,
+                                         int* flags) {
+  // Positions were wrapped by the boundary kernels.  A wrap can round onto the upper edge exactly
+  // (x == (nxge+1)*delx); the reference keeps such a particle in the last cell/pencil (its pencil
+  // was fixed before the wrap, boundary_periodic.f90:156-178), so that one case is clamped silently.
+  int i = (int)x;  // sort.f90:65 (no d_delx)
+  int jpos = (int)(y * g.d_delx);
+  int kpos = D == 3 ? (int)(z * g.d_delx) : 0;
+  if (i == nxe + 1) i = nxe;
+  if (jpos == g.nye + 1 && g.nye == g.nyge) jpos = g.nye;
+  if (D == 3 && kpos == g.nze + 1 && g.nze == g.nzge) kpos = g.nze;
+  bool bad = (i < nxs) | (i > nxe) | (jpos < g.nys) | (jpos > g.nye);
+  if (D == 3) bad |= (kpos < g.nzs) | (kpos > g.nze);
+  if (bad) {
+    atomicOr(flags, 2);
+    i = min(max(i, nxs), nxe);
+    jpos = min(max(jpos, g.nys), g.nye);
+    if (D == 3) kpos = min(max(kpos, g.nzs), g.nze);
+  }
+  return g.pen(jpos, kpos, isp) * (g.nx + 1) + (i - g.nxgs);
+}
+
+// boundary_periodic__particle_yz, coordinate part (boundary_periodic.f90:156-171): periodic wrap of y (and z)
+template <int D>
+__global__ void k_wrap_yz(Geo g, Ptcl B, long long n) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    double y = B.c[1][p];
+    int jpos = (int)(y * g.d_delx);
+    if (jpos <= g.nygs - 1) B.c[1][p] = y + (g.nyge - g.nygs + 1) * g.delx;
+    else if (jpos >= g.nyge + 1) B.c[1][p] = y - (g.nyge - g.nygs + 1) * g.delx;
+    if (D == 3) {
+      double z = B.c[2][p];
+      int kpos = (int)(z * g.d_delx);
+      if (kpos <= g.nzgs - 1) B.c[2][p] = z + (g.nzge - g.nzgs + 1) * g.delx;
+      else if (kpos >= g.nzge + 1) B.c[2][p] = z - (g.nzge - g.nzgs + 1) * g.delx;
+    }
+  }
+}
+
+template <int D>
+__global__ void k_hist(Geo g, Ptcl B, long long n, long long n_sp0, int* __restrict__ hist, int* flags, int nxs, int nxe) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    int slot = dest_slot<D>(g, B.c[0][p], B.c[1][p], D == 3 ? B.c[2][p] : 0.0, p < n_sp0 ? 0 : 1, nxs, nxe, flags);
+    atomicAdd(hist + slot, 1);
+  }
+}
+
+template <int D>
+__global__ void k_scatter(Geo g, Ptcl B, Ptcl A, const double* __restrict__ id_in, double* __restrict__ id_out,
+                          long long n, long long n_sp0, int* __restrict__ cursor, int* flags, int nxs, int nxe) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    double x = B.c[0][p], y = B.c[1][p], z = D == 3 ? B.c[2][p] : 0.0;
+    int slot = dest_slot<D>(g, x, y, z, p < n_sp0 ? 0 : 1, nxs, nxe, flags);
+    int d = atomicAdd(cursor + slot, 1);
+    A.c[0][d] = x;
+    A.c[1][d] = y;
+    if (D == 3) A.c[2][d] = z;
+    A.c[D][d] = B.c[D][p];
+    A.c[D + 1][d] = B.c[D + 1][p];
+    A.c[D + 2][d] = B.c[D + 2][p];
+    id_out[d] = id_in[p];
+  }
+}
+
+__global__ void k_np2_from_cs(Geo g, const int* __restrict__ cs, int* __restrict__ np2, int* flags) {
+  for (int pen = blockIdx.x * blockDim.x + threadIdx.x; pen < g.npen; pen += gridDim.x * blockDim.x) {
+    const int* row = cs + (size_t)pen * (g.nx + 1);
+    int n = row[g.nx] - row[0];
+    np2[pen] = n;
+    if (n > g.np) atomicOr(flags, 1);  // "memory over (np2 > np)"
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host <-> device layout conversion: the reference's padded AoS pencils <-> SoA
+// stage holds [pencil][slot < maxcnt][ndim]
+// ---------------------------------------------------------------------------------------------
+__global__ void k_aos_to_soa(Geo g, const double* __restrict__ stage, Ptcl dst, double* __restrict__ dst_id,
+                             const int* __restrict__ poff, const int* __restrict__ np2, int pen0, int npens, int maxcnt) {
+  const long long n = (long long)npens * maxcnt;
+  const int nd = g.ndim;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int pl = (int)(e / maxcnt), ii = (int)(e % maxcnt);
+    int pen = pen0 + pl;
+    if (ii >= np2[pen]) continue;
+    const double* s = stage + e * nd;
+    size_t d = (size_t)poff[pen] + ii;
+    for (int c = 0; c < nd - 1; ++c) dst.c[c][d] = s[c];
+    dst_id[d] = s[nd - 1];
+  }
+}
+
+__global__ void k_soa_to_aos(Geo g, double* __restrict__ stage, Ptcl src, const double* __restrict__ src_id,
+                             const int* __restrict__ poff, const int* __restrict__ np2, int pen0, int npens, int maxcnt) {
+  const long long n = (long long)npens * maxcnt;
+  const int nd = g.ndim;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int pl = (int)(e / maxcnt), ii = (int)(e % maxcnt);
+    int pen = pen0 + pl;
+    if (ii >= np2[pen]) continue;
+    double* s = stage + e * nd;
+    size_t d = (size_t)poff[pen] + ii;
+    for (int c = 0; c < nd - 1; ++c) s[c] = src.c[c][d];
+    s[nd - 1] = src_id[d];
+  }
+}
+
+__global__ void k_poff_from_cs(Geo g, const int* __restrict__ cs, int* __restrict__ poff) {
+  for (int pen = blockIdx.x * blockDim.x + threadIdx.x; pen <= g.npen; pen += gridDim.x * blockDim.x)
+    poff[pen] = pen < g.npen ? cs[(size_t)pen * (g.nx + 1)] : cs[(size_t)(g.npen - 1) * (g.nx + 1) + g.nx];
+}
+
+int grid_for(long long n) {
+  long long b = (n + TPB - 1) / TPB;
+  const long long cap = 148LL * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+
+int wm_k_tmpf(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const long long n = (long long)(nxe - nxs + 3) * (g.nyl + 2) * (g.dim == 3 ? g.nzl + 2 : 1);
+  k_tmpf<<<grid_for(n), TPB, 0, ctx->stream>>>(ctx->uf, ctx->tmpf, g, nxs, nxe);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+int wm_k_push(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const long long ncell = (long long)(nxe - nxs + 1) * g.nyl * g.nzl;
+  const int blocks = (int)std::min<long long>((ncell * 32 + TPB - 1) / TPB, 148LL * 8);
+  if (g.dim == 3)
+    k_push<3><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->tmpf, nxs, nxe);
+  else
+    k_push<2><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->tmpf, nxs, nxe);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+int wm_k_deposit(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const long long ncell = (long long)(nxe - nxs + 1) * g.nyl * g.nzl;
+  const int blocks = (int)std::min<long long>((ncell * 32 + TPB - 1) / TPB, 148LL * 8);
+  if (g.dim == 3)
+    k_deposit<3><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->uj, ctx->flags, nxs, nxe);
+  else
+    k_deposit<2><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->uj, ctx->flags, nxs, nxe);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+int wm_k_bc_x(wm_ctx* ctx, int /*nxs*/, int /*nxe*/, int kind, double /*u0*/) {
+  const Geo& g = ctx->g;
+  if (kind != WM_BC_PERIODIC) {
+    wm_set_error("x boundary kind not implemented yet");
+    return WM_ERR_ARG;
+  }
+  if (ctx->ntot == 0) return WM_OK;
+  k_bc_x_periodic<<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B.c[0], ctx->ntot);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+int wm_k_migrate(wm_ctx* ctx) {
+  const Geo& g = ctx->g;
+  if (ctx->ntot == 0) return WM_OK;
+  if (g.dim == 3)
+    k_wrap_yz<3><<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B, ctx->ntot);
+  else
+    k_wrap_yz<2><<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B, ctx->ntot);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const size_t ncs = (size_t)g.npen * (g.nx + 1);
+  const long long n0 = ctx->n_sp0;
+  WM_CUDA(cudaMemsetAsync(ctx->cs_new, 0, (ncs + 1) * sizeof(int), ctx->stream));
+  if (ctx->ntot > 0) {
+    if (g.dim == 3)
+      k_hist<3><<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B, ctx->ntot, n0, ctx->cs_new, ctx->flags, nxs, nxe);
+    else
+      k_hist<2><<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B, ctx->ntot, n0, ctx->cs_new, ctx->flags, nxs, nxe);
+    WM_LAUNCH_CHECK(ctx);
+  }
+  // exclusive scan of the histogram -> absolute cell starts (the new cumcnt)
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->cs_new, ctx->cs_new, (int)ncs, ctx->stream);
+  if (need > ctx->scan_tmp_bytes) {
+    if (ctx->scan_tmp) cudaFree(ctx->scan_tmp);
+    WM_CUDA(cudaMalloc(&ctx->scan_tmp, need));
+    ctx->scan_tmp_bytes = need;
+  }
+  WM_CUDA(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp, need, ctx->cs_new, ctx->cs_new, (int)ncs, ctx->stream));
+  ctx->launches += 2;
+  WM_CUDA(cudaMemcpyAsync(ctx->cursor, ctx->cs_new, ncs * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ctx->ntot > 0) {
+    if (g.dim == 3)
+      k_scatter<3><<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B, ctx->A, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
+                                                                 ctx->ntot, n0, ctx->cursor, ctx->flags, nxs, nxe);
+    else
+      k_scatter<2><<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B, ctx->A, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
+                                                                 ctx->ntot, n0, ctx->cursor, ctx->flags, nxs, nxe);
+    WM_LAUNCH_CHECK(ctx);
+  }
+  std::swap(ctx->cs, ctx->cs_new);
+  ctx->cid = 1 - ctx->cid;
+  k_np2_from_cs<<<wm_blocks(g.npen, TPB), TPB, 0, ctx->stream>>>(g, ctx->cs, ctx->np2, ctx->flags);
+  WM_LAUNCH_CHECK(ctx);
+  k_poff_from_cs<<<wm_blocks(g.npen + 1, TPB), TPB, 0, ctx->stream>>>(g, ctx->cs, ctx->poff);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+int wm_k_aos_to_soa(wm_ctx* ctx, const double* stage, Ptcl dst, double* dst_id, int pen0, int npens, int maxcnt) {
+  const long long n = (long long)npens * maxcnt;
+  if (n == 0) return WM_OK;
+  k_aos_to_soa<<<grid_for(n), TPB, 0, ctx->stream>>>(ctx->g, stage, dst, dst_id, ctx->poff, ctx->np2, pen0, npens, maxcnt);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+int wm_k_soa_to_aos(wm_ctx* ctx, double* stage, Ptcl src, const double* src_id, int pen0, int npens, int maxcnt) {
+  const long long n = (long long)npens * maxcnt;
+  if (n == 0) return WM_OK;
+  k_soa_to_aos<<<grid_for(n), TPB, 0, ctx->stream>>>(ctx->g, stage, src, src_id, ctx->poff, ctx->np2, pen0, npens, maxcnt);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
