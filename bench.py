@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of the whole PIC step (push + deposit + field solve + boundary/migration
++ sort) on N B200s of one node, plus the roofline of the dominant kernel, the CPU baseline and the
+end-to-end (host-buffer) number.  Contract: see the repo's task description; one JSON line on rank 0.
+
+  python bench.py [--gpus N --steps K --warmup W]          this backend (N > 1: launched by torchrun)
+  python bench.py --impl reference [--steps K --warmup W]  the reference's CPU algorithm (oracle port) on host cores
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): 3-D Weibel, uniform Maxwellian pair plasma,
+256 x 256 x 64 cells per GPU, 64 particles per cell and species (536.9 M particles per GPU), z-slabs
+across GPUs (weak scaling: nz = 64 N).  Inputs are synthetic (device-side Philox Maxwellian load).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-updates/sec (push+deposit+solve+migrate+sort), 3-D Weibel"
+UNIT = "particle-updates/s"
+BYTES_PER_UPDATE_STEP = 224       # 4 * ndim * 8 B (push r+w, sort r+w), 3-D
+BYTES_PER_UPDATE_PUSH = 112       # the push(+deposit) launch: read up + write gp, 2 * ndim * 8 B
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=256)
+    ap.add_argument("--ny", type=int, default=256)
+    ap.add_argument("--nz", type=int, default=64, help="z cells PER GPU")
+    ap.add_argument("--ppc", type=int, default=64, help="particles per cell and species")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-nz", type=int, default=4, help="z cells of the bounded CPU sample")
+    ap.add_argument("--unfused", action="store_true", help="time the per-procedure kernels instead of the fused step")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline(args, steps=2, warmup=1):
+    """The oracle (a C++ port of the reference loop nests, -O3 -march=native -fopenmp) on the host cores,
+    on a bounded sample of the same workload: same nx, ny, ppc and physics, only nz reduced."""
+    from oracle.pyoracle import World3, weibel_constants
+    import numpy as np
+    nx, ny, nz, n0 = args.nx, args.ny, args.cpu_nz, args.ppc
+    q, r, _ = weibel_constants(n0)
+    w = World3(nx, ny, nz, int(n0 * nx * 1.5), q=q, r=r, fast=True)
+    w.load_weibel(n0)
+    npart = int(w.arr("np2").sum())
+    for _ in range(warmup):
+        w.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        w.step()
+    dt = time.perf_counter() - t0
+    assert w.error() == 0
+    cores = len(os.sched_getaffinity(0))
+    w.close()
+    return {"value": npart * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"3-D Weibel {nx}x{ny}x{nz}, {n0} ppc x 2 species = {npart} particles, {steps} steps "
+                      f"({dt:.1f} s) with OMP threads = {cores}; oracle = C++ restatement of the Fortran loop nests "
+                      "(no Fortran compiler / MPI in this image)",
+            "seconds": dt, "ms_per_step": dt / steps * 1e3, "particles": npart}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"3-D Weibel {args.nx}x{args.ny}x{args.nz} cells/GPU, {args.ppc} ppc x 2 species; "
+                                   f"CPU arm runs the bounded sample nz={args.cpu_nz}",
+                       "parallelism": f"openmp{cb['cores']}"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import wumingpic_b200 as wm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    nx, ny, n0 = args.nx, args.ny, args.ppc
+    nz_glob = args.nz * world                           # weak scaling: z-slabs, per-GPU work fixed
+    lay = wm.SlabLayout(2, ny + 1, 2, nz_glob + 1, 1, world, rank)
+    q, r, _ = wm.weibel_constants(n0)
+    np_cap = int(n0 * nx * 1.25)
+    b = wm.Backend(3, np_cap, 2, nx + 1, 2, ny + 1, 2, nz_glob + 1, nys=lay.nys, nye=lay.nye, nzs=lay.nzs, nze=lay.nze,
+                   q=q, r=r, nproc_j=1, nproc_k=world, rank_j=0, rank_k=rank, device=local_rank)
+    if world > 1:
+        box = [b.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        b.comm_init(world, rank, box[0])
+    b.load_weibel(n0)
+    b.sync()
+    npart_rank = b.stats()["n_particles"]
+    npart = npart_rank * world
+    stream = torch.cuda.ExternalStream(b.stream(), device=torch.device("cuda", local_rank))
+    order = wm.backend.WM_ORDER_WEIBEL
+    step = (lambda n: b.step_unfused(2, nx + 1, n)) if args.unfused and hasattr(b, "step_unfused") else \
+           (lambda n: b.step(2, nx + 1, n, order))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steady state: W warm-up steps, then exactly K timed steps --------------------
+    step(args.warmup)
+    b.sync()
+    b.set_timing(True)
+    launches0 = b.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    step(args.steps)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = b.launch_count() - launches0
+    st = b.stats()
+    b.set_timing(False)
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = npart * args.steps / (ms * 1e-3)
+    res, rho = b.gauss()
+
+    # ---- roofline of the dominant kernel (push+deposit), timed live with CUDA events on the library stream ----
+    peak, peak_src = measured_peak()
+    k_ms = (st["ms_push"] + st["ms_deposit"]) / max(1, st["timed_steps"])
+    achieved = npart_rank * BYTES_PER_UPDATE_PUSH / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("push_deposit_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "push+deposit", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": npart_rank * BYTES_PER_UPDATE_PUSH,
+                "kernel_ms": k_ms,
+                "step": {"bytes_per_update": BYTES_PER_UPDATE_STEP,
+                         "achieved": npart_rank * BYTES_PER_UPDATE_STEP / (ms_per_step * 1e-3) / 1e9,
+                         "frac": npart_rank * BYTES_PER_UPDATE_STEP / (ms_per_step * 1e-3) / 1e9 / peak},
+                "phases_ms": {k: st[k] / max(1, st["timed_steps"]) for k in ("ms_push", "ms_deposit", "ms_field", "ms_sort")}}
+
+    # ---- end to end through the host-buffer C ABI call: pinned host state in, one step, host state out ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            shp = b.shapes()
+            up_t = torch.empty(shp["up"], dtype=torch.float64).pin_memory()
+            uf_t = torch.empty(shp["uf"], dtype=torch.float64).pin_memory()
+            up, uf = up_t.numpy(), uf_t.numpy()
+            np2, cc = b.empty("np2"), b.empty("cumcnt")
+            b.download(up, np2, cc, uf)
+            h2d = int(np2.sum()) * 7 * 8 + uf.nbytes + np2.nbytes + cc.nbytes
+            d2h = h2d
+            b.h_step(up, uf, np2, cc, 2, nx + 1, order)           # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                b.h_step(up, uf, np2, cc, 2, nx + 1, order)
+            barrier()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            e2e = {"value": npart * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+                   "how": "wm_h_step: full particle+field state H2D from pinned host arrays in the reference layout, "
+                          "one step, full state D2H, every step (worst-case drop-in; a driver that only syncs at its "
+                          "output cadence runs at `value`)"}
+            del up_t, uf_t
+        except Exception as ex:  # noqa: BLE001
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "error": f"{type(ex).__name__}: {ex}"}
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cb = cpu_baseline(args)
+            cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:  # noqa: BLE001
+            cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"3-D Weibel {nx}x{ny}x{args.nz} cells/GPU, {n0} ppc x 2 species "
+                                       f"({npart_rank} particles/GPU), periodic, cfl=1, gfac=0.501",
+                           "parallelism": f"z-slabs x{world}",
+                           "l2": "inputs (particle arrays, >= 30 GB) far exceed the 126 MB L2; no flush needed",
+                           "particles": npart, "path": "per-procedure kernels" if args.unfused else "wm_step"},
+                "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "checks": {"gauss_residual": res, "max_4pi_rho": rho, "cg_iterations": st["cg_iterations"],
+                           "error_flags": st["error_flags"]}}
+        print(json.dumps(line), flush=True)
+    b.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

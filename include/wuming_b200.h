@@ -72,7 +72,9 @@ typedef struct wm_stats {
   long long n_particles;   /* active particles on this rank */
   int max_np2;             /* fullest pencil */
   int error_flags;         /* sticky device-side flags: bit0 memory over, bit1 particle lost, bit2 cg ite_max */
-  double ms_push, ms_deposit, ms_field, ms_sort;  /* CUDA-event time of the last step's phases (0 if not measured) */
+  int timed_steps;         /* steps accumulated in the ms_* sums since wm_set_timing(ctx, 1) */
+  double ms_push, ms_deposit, ms_field, ms_sort;  /* CUDA-event time of the phases, SUMMED over timed_steps
+                                                     (fused path: ms_push = fused push+deposit kernel, ms_deposit = 0) */
 } wm_stats;
 
 const char* wm_last_error(void);
@@ -136,8 +138,10 @@ int wm_energy(wm_ctx* ctx, double* out);
 int wm_gauss(wm_ctx* ctx, double* out);
 int wm_get_stats(wm_ctx* ctx, wm_stats* out);
 int wm_sync(wm_ctx* ctx);
-/* CUDA-event timing of phases inside wm_step: 0 off, 1 on */
+/* CUDA-event timing of phases inside wm_step: 0 off, 1 on (resets the sums) */
 int wm_set_timing(wm_ctx* ctx, int on);
+/* the cudaStream_t every kernel of this context is launched on (so that callers can record their own events on it) */
+void* wm_stream(wm_ctx* ctx);
 /* number of kernels this library launched since wm_create (bench.py's gpu_launches) */
 long long wm_launch_count(wm_ctx* ctx);
 

@@ -43,7 +43,7 @@ class _Params(C.Structure):
 
 class _Stats(C.Structure):
     _fields_ = [("cg_iterations", C.c_int * 3), ("n_particles", C.c_longlong), ("max_np2", C.c_int),
-                ("error_flags", C.c_int), ("ms_push", C.c_double), ("ms_deposit", C.c_double),
+                ("error_flags", C.c_int), ("timed_steps", C.c_int), ("ms_push", C.c_double), ("ms_deposit", C.c_double),
                 ("ms_field", C.c_double), ("ms_sort", C.c_double)]
 
 
@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     "wm_upload", "wm_download", "wm_download_work", "wm_upload_work", "wm_particle_solv", "wm_field_fdtd_i", "wm_field_stage",
     "wm_bc_particle_x", "wm_bc_injection", "wm_bc_particle_yz", "wm_sort_bucket", "wm_step",
     "wm_h_particle_solv", "wm_h_field_fdtd_i", "wm_h_step", "wm_load_weibel", "wm_energy", "wm_gauss",
-    "wm_get_stats", "wm_sync", "wm_set_timing", "wm_launch_count",
+    "wm_get_stats", "wm_sync", "wm_set_timing", "wm_launch_count", "wm_stream",
 ]
 
 
@@ -98,6 +98,8 @@ def load_library():
         L.wm_set_timing.argtypes = [vp, C.c_int]
         L.wm_launch_count.argtypes = [vp]
         L.wm_launch_count.restype = C.c_longlong
+        L.wm_stream.argtypes = [vp]
+        L.wm_stream.restype = C.c_void_p
         _LIB = L
     return _LIB
 
@@ -286,7 +288,7 @@ class Backend:
         s = _Stats()
         self._ck(self.L.wm_get_stats(self.h, C.byref(s)))
         return {"cg_iterations": list(s.cg_iterations), "n_particles": s.n_particles, "max_np2": s.max_np2,
-                "error_flags": s.error_flags, "ms_push": s.ms_push, "ms_deposit": s.ms_deposit,
+                "error_flags": s.error_flags, "timed_steps": s.timed_steps, "ms_push": s.ms_push, "ms_deposit": s.ms_deposit,
                 "ms_field": s.ms_field, "ms_sort": s.ms_sort}
 
     def sync(self):
@@ -297,3 +299,7 @@ class Backend:
 
     def launch_count(self):
         return self.L.wm_launch_count(self.h)
+
+    def stream(self):
+        """raw cudaStream_t of this context (wrap with torch.cuda.ExternalStream to record events on it)"""
+        return self.L.wm_stream(self.h)

@@ -427,7 +427,11 @@ int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
     if (c->timing) {
       WM_CUDA(cudaEventRecord(c->ev[4], c->stream));
       WM_CUDA(cudaEventSynchronize(c->ev[4]));
-      for (int e = 0; e < 4; ++e) cudaEventElapsedTime(&c->ms_phase[e], c->ev[e], c->ev[e + 1]);
+      for (int e = 0; e < 4; ++e) {
+        cudaEventElapsedTime(&c->ms_phase[e], c->ev[e], c->ev[e + 1]);
+        c->ms_sum[e] += c->ms_phase[e];
+      }
+      c->timed_steps++;
     }
   }
   return WM_OK;
@@ -521,10 +525,11 @@ int wm_get_stats(wm_ctx* c, wm_stats* out) {
   out->max_np2 = 0;
   for (int v : h) out->max_np2 = std::max(out->max_np2, v);
   out->error_flags = f;
-  out->ms_push = c->ms_phase[0];
-  out->ms_deposit = c->ms_phase[1];
-  out->ms_field = c->ms_phase[2];
-  out->ms_sort = c->ms_phase[3];
+  out->timed_steps = c->timed_steps;
+  out->ms_push = c->ms_sum[0];
+  out->ms_deposit = c->ms_sum[1];
+  out->ms_field = c->ms_sum[2];
+  out->ms_sort = c->ms_sum[3];
   return WM_OK;
 }
 
@@ -538,9 +543,12 @@ int wm_sync(wm_ctx* c) {
 int wm_set_timing(wm_ctx* c, int on) {
   if (!c) return WM_ERR_ARG;
   c->timing = on;
+  for (int e = 0; e < 4; ++e) c->ms_sum[e] = 0;
+  c->timed_steps = 0;
   return WM_OK;
 }
 
 long long wm_launch_count(wm_ctx* c) { return c ? c->launches : 0; }
+void* wm_stream(wm_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 }  // extern "C"

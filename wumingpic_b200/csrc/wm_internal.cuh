@@ -92,6 +92,8 @@ struct wm_ctx {
   int timing = 0;
   cudaEvent_t ev[8] = {};
   float ms_phase[4] = {0, 0, 0, 0};
+  double ms_sum[4] = {0, 0, 0, 0};
+  int timed_steps = 0;
 };
 
 // error plumbing -------------------------------------------------------------------------------
