@@ -119,6 +119,9 @@ int wm_sort_bucket(wm_ctx* ctx, int nxs, int nxe);      /* sort__bucket         
 
 /* nsteps whole time steps with the fused push+deposit kernel (benchmark path); `order` = WM_ORDER_* */
 int wm_step(wm_ctx* ctx, int nxs, int nxe, int order, double u0, int nsteps);
+/* 1 (default): wm_step uses the fused push+deposit kernel and the deterministic sort where available;
+ * 0: wm_step calls the per-procedure kernels, exactly like a driver calling the five entry points above */
+int wm_set_fused(wm_ctx* ctx, int on);
 
 /* -- host-buffer forms with the reference's own argument lists (upload, run, download) ---------- */
 int wm_h_particle_solv(wm_ctx* ctx, double* gp, const double* up, const double* uf, const int* cumcnt,

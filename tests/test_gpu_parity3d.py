@@ -103,9 +103,13 @@ def test_boundary_migration_sort_exact(pair):
     assert moved == int(np2.sum())
 
 
-def test_multistep_drift_and_invariants():
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "per-procedure"])
+def test_multistep_drift_and_invariants(fused):
+    """Whole steps against the oracle, through wm_step's fused kernel + deterministic sort and through the
+    per-procedure kernels (what a driver calling the five entry points runs)."""
     w = make_world3(NX, NY, NZ, N0)
     b = backend_for(w)
+    b.set_fused(fused)
     upload_from_world(b, w)
     ntot = int(w.arr("np2").sum())
     e0 = b.energy()
@@ -136,6 +140,40 @@ def test_multistep_drift_and_invariants():
             worst = max(worst, np.abs(rg[:, :6] - rr[:, :6]).max())
     assert worst < 1e-9, worst
     np.testing.assert_allclose(b.energy(), w.energy(), rtol=1e-9)
+    b.close()
+
+
+def test_fused_path_is_deterministic():
+    """The fused path's sort is a stable, atomic-free scatter: two runs from the same state give bit-identical
+    particle arrays (J sums still use global RED.F64 whose order may differ, so fields agree to round-off)."""
+    outs = []
+    w = make_world3(NX, NY, NZ, N0, steps=1)    # one host state (the OpenMP oracle itself is not bit-reproducible)
+    for rep in range(2):
+        b = backend_for(w)
+        upload_from_world(b, w)
+        b.step(2, NX + 1, 1)
+        up, np2, cc = b.empty("up"), b.empty("np2"), b.empty("cumcnt")
+        b.download(up, np2, cc)
+        outs.append((up[active_mask(np2, w.np)].view(np.int64).copy(), np2.copy(), cc.copy()))
+        b.close()
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    assert np.array_equal(outs[0][0], outs[1][0])
+
+
+def test_odd_grid_fused():
+    """nx not a multiple of the 16-cell CTA group, tiny ny/nz (every cell touches the periodic wrap)."""
+    w = make_world3(21, 3, 4, 5, steps=1)
+    b = backend_for(w)
+    upload_from_world(b, w)
+    for _ in range(3):
+        w.step()
+        b.step(2, 22, 1)
+    uf, np2 = b.empty("uf"), b.empty("np2")
+    b.download(uf=uf, np2=np2)
+    assert np.array_equal(np2, w.arr("np2"))
+    assert rel_err(uf, w.arr("uf")) < 1e-9
+    res, rho = b.gauss()
+    assert res < 1e-13 * max(rho, 1.0)
     b.close()
 
 

@@ -51,7 +51,7 @@ class _Stats(C.Structure):
 ABI_SYMBOLS = [
     "wm_last_error", "wm_version", "wm_para_range", "wm_create", "wm_destroy", "wm_comm_unique_id", "wm_comm_init",
     "wm_upload", "wm_download", "wm_download_work", "wm_upload_work", "wm_particle_solv", "wm_field_fdtd_i", "wm_field_stage",
-    "wm_bc_particle_x", "wm_bc_injection", "wm_bc_particle_yz", "wm_sort_bucket", "wm_step",
+    "wm_bc_particle_x", "wm_bc_injection", "wm_bc_particle_yz", "wm_sort_bucket", "wm_step", "wm_set_fused",
     "wm_h_particle_solv", "wm_h_field_fdtd_i", "wm_h_step", "wm_load_weibel", "wm_energy", "wm_gauss",
     "wm_get_stats", "wm_sync", "wm_set_timing", "wm_launch_count", "wm_stream",
 ]
@@ -87,6 +87,7 @@ def load_library():
         L.wm_bc_injection.argtypes = [vp, C.c_int, C.c_int, C.c_double]
         L.wm_bc_particle_yz.argtypes = [vp]
         L.wm_step.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
+        L.wm_set_fused.argtypes = [vp, C.c_int]
         L.wm_h_particle_solv.argtypes = [vp, dp, dp, dp, ip, ip, C.c_int, C.c_int]
         L.wm_h_field_fdtd_i.argtypes = [vp, dp, dp, dp, ip, ip, C.c_int, C.c_int]
         L.wm_h_step.argtypes = [vp, dp, dp, ip, ip, C.c_int, C.c_int, C.c_int, C.c_double]
@@ -259,6 +260,9 @@ class Backend:
 
     def step(self, nxs, nxe, nsteps=1, order=WM_ORDER_WEIBEL, u0=0.0):
         self._ck(self.L.wm_step(self.h, nxs, nxe, order, u0, nsteps))
+
+    def set_fused(self, on=True):
+        self._ck(self.L.wm_set_fused(self.h, 1 if on else 0))
 
     # -- host-buffer forms (the reference's own argument lists) -----------------------------------
     def h_particle__solv(self, gp, up, uf, cumcnt, np2, nxs, nxe):

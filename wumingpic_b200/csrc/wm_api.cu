@@ -198,7 +198,8 @@ int wm_destroy(wm_ctx* c) {
   double* d[] = {c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
                  c->hbuf[2], c->stage};
   for (double* p : d) if (p) cudaFree(p);
-  int* ii[] = {c->cs, c->cs_new, c->cursor, c->np2, c->poff, c->flags};
+  int* ii[] = {c->cs, c->cs_new, c->cursor, c->np2, c->poff, c->flags, c->cnt27};
+  if (c->dst_off) cudaFree(c->dst_off);
   for (int* p : ii) if (p) cudaFree(p);
   if (c->scan_tmp) cudaFree(c->scan_tmp);
   if (c->red_host) cudaFreeHost(c->red_host);
@@ -411,19 +412,34 @@ int wm_sort_bucket(wm_ctx* c, int nxs, int nxe) {
 int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
   if (!c || !range_ok(c, nxs, nxe)) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
+  const bool fused = c->use_fused && c->g.dim == 3 && c->g.bc == WM_BC_PERIODIC && order == WM_ORDER_WEIBEL &&
+                     c->nranks == 1;
   for (int it = 0; it < nsteps; ++it) {
     if (c->timing) WM_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    WM_TRY(wm_particle_solv(c, nxs, nxe));
-    if (c->timing) WM_CUDA(cudaEventRecord(c->ev[1], c->stream));
-    if (order == WM_ORDER_RECONNECTION) WM_TRY(wm_bc_particle_x(c, nxs, nxe));
-    if (order == WM_ORDER_SHOCK) WM_TRY(wm_bc_injection(c, nxs, nxe, u0));
-    WM_TRY(wm_field_stage(c, nxs, nxe, 1));
-    if (c->timing) WM_CUDA(cudaEventRecord(c->ev[2], c->stream));
-    for (int s = 2; s <= 8; ++s) WM_TRY(wm_field_stage(c, nxs, nxe, s));
-    if (c->timing) WM_CUDA(cudaEventRecord(c->ev[3], c->stream));
-    if (order == WM_ORDER_WEIBEL) WM_TRY(wm_bc_particle_x(c, nxs, nxe));
-    WM_TRY(wm_bc_particle_yz(c));
-    WM_TRY(wm_sort_bucket(c, nxs, nxe));
+    if (fused) {
+      // K1, then ONE kernel for push + boundaries + deposit + destination counting (wm_fused.cu)
+      WM_TRY(wm_k_tmpf(c, nxs, nxe));
+      WM_TRY(wm_k_zero_uj(c, nxs, nxe));
+      WM_TRY(wm_k_push_deposit_fused(c, nxs, nxe, order, u0));
+      c->gp_valid = true;
+      if (c->timing) { WM_CUDA(cudaEventRecord(c->ev[1], c->stream)); WM_CUDA(cudaEventRecord(c->ev[2], c->stream)); }
+      for (int s = 2; s <= 8; ++s) WM_TRY(wm_field_stage(c, nxs, nxe, s));
+      if (c->timing) WM_CUDA(cudaEventRecord(c->ev[3], c->stream));
+      WM_TRY(wm_k_sort_fused(c, nxs, nxe));
+      c->gp_valid = false;
+    } else {
+      WM_TRY(wm_particle_solv(c, nxs, nxe));
+      if (c->timing) WM_CUDA(cudaEventRecord(c->ev[1], c->stream));
+      if (order == WM_ORDER_RECONNECTION) WM_TRY(wm_bc_particle_x(c, nxs, nxe));
+      if (order == WM_ORDER_SHOCK) WM_TRY(wm_bc_injection(c, nxs, nxe, u0));
+      WM_TRY(wm_field_stage(c, nxs, nxe, 1));
+      if (c->timing) WM_CUDA(cudaEventRecord(c->ev[2], c->stream));
+      for (int s = 2; s <= 8; ++s) WM_TRY(wm_field_stage(c, nxs, nxe, s));
+      if (c->timing) WM_CUDA(cudaEventRecord(c->ev[3], c->stream));
+      if (order == WM_ORDER_WEIBEL) WM_TRY(wm_bc_particle_x(c, nxs, nxe));
+      WM_TRY(wm_bc_particle_yz(c));
+      WM_TRY(wm_sort_bucket(c, nxs, nxe));
+    }
     if (c->timing) {
       WM_CUDA(cudaEventRecord(c->ev[4], c->stream));
       WM_CUDA(cudaEventSynchronize(c->ev[4]));
@@ -434,6 +450,12 @@ int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
       c->timed_steps++;
     }
   }
+  return WM_OK;
+}
+
+int wm_set_fused(wm_ctx* c, int on) {
+  if (!c) return WM_ERR_ARG;
+  c->use_fused = on;
   return WM_OK;
 }
 

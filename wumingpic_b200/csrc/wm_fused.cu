@@ -1,0 +1,509 @@
+// wm_fused.cu -- the benchmark hot path: ONE kernel for K1-gather + Boris push + x/y/z boundary +
+// Esirkepov deposit + destination-cell counting, followed by a deterministic stable counting sort.
+//
+//   particle__solv   3d/common/particle.f90:93-225      ele_cur  3d/common/field.f90:238-404
+//   bc__particle_x   3d/common/boundary_periodic.f90:68-101
+//   bc__particle_yz  :104-455 (coordinate wrap + re-binning)    sort__bucket  3d/common/sort.f90:55-86
+//
+// Why this shape (measured on B200):
+//   * fp64 atomicAdd on shared memory is an ATOMS.CAS spin loop on sm_100a and warp shuffles issue at one
+//     warp-instruction per clock per SM, so neither smem atomics nor shuffle reductions can carry the
+//     ~300 current contributions per particle.  Instead the deposit is turned inside out:
+//       phase A  one PARTICLE per thread: gather (field tile in smem, loaded by TMA bulk copies), Boris,
+//                move, boundary wrap, and the 1-D Esirkepov factors (prefix sums c, pairs (S0,DS)) written
+//                to a shared-memory record;
+//       phase B  one OUTPUT STRIP per thread: (cell, component, transverse index) owns 4x5 current values
+//                in REGISTERS and walks the records of its cell: acc[r][kp] += c[r] * (A*S0[kp] + B*DS[kp]).
+//     No atomics and no shuffles on the per-particle path; each strip ends with <= 20 RED.F64 to global J.
+//   * a CTA owns 16 consecutive x cells of one (j,k) pencil: their particles are one contiguous run of the
+//     cell-sorted SoA (coalesced 128-byte loads per half-warp) and share an 18x3x3 field tile.
+//   * the kernel also counts, per source cell, how many particles go to each of the 27 neighbour cells.
+//     |dx| < c dt <= 1 cell, so that count matrix is all the sort needs: destination offsets follow from a
+//     per-cell prefix over the 27 sources and ranks from the (stable) order inside the source cell, which
+//     makes the scatter atomic-free and the particle order -- hence every later sum -- deterministic.
+#include "wm_internal.cuh"
+
+#include <cub/device/device_scan.cuh>
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int G = 16;         // cells per CTA
+constexpr int SLOTS = 16;     // particles per cell and batch
+constexpr int NF = 21;        // double2 fields per particle record
+constexpr int CSTR = 17;      // slot stride between cells (bank spreading)
+constexpr int FSTR = 273;     // double2 stride between record fields (== 1 mod 8)
+constexpr int TILE_X = G + 2;
+constexpr int TILE_ROW = TILE_X * 6;  // doubles per (jj,kk) row of the field tile
+
+struct __align__(16) Smem {
+  double tile[9 * TILE_ROW];          // tmpf for cells i0-1..i0+16, j-1..j+1, k-1..k+1
+  double2 rec[NF * FSTR];             // per-particle deposit factors, field-major
+  int beg[2][G + 1];                  // cs row segments of both species
+  int cnt27[2][27][G];                // destination-offset counts per (species, offset, cell)
+  int nbatch;
+  unsigned long long bar;             // mbarrier for the TMA bulk copies
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ void shape3(double dh, double& sm, double& s0, double& sp) {
+  sm = 5e-1 * (5e-1 - dh) * (5e-1 - dh);
+  s0 = 7.5e-1 - dh * dh;
+  sp = 5e-1 * (5e-1 + dh) * (5e-1 + dh);
+}
+
+// S0 (about the loop cell) and DS = S1 - S0 (S1 about int(x_new)) on the 5-point stencil, field.f90:255-325
+__device__ __forceinline__ int s0ds(double xo, double xn, int cell, double d_delx, double s0[5], double ds[5],
+                                    int* flags) {
+  double dh = xo * d_delx - 5e-1 - cell;
+  s0[0] = 0.0;
+  shape3(dh, s0[1], s0[2], s0[3]);
+  s0[4] = 0.0;
+  int i2 = (int)(xn * d_delx);
+  dh = xn * d_delx - 5e-1 - i2;
+  int inc = i2 - cell;
+  if (inc < -1 || inc > 1) {
+    atomicOr(flags, 2);
+    inc = inc < 0 ? -1 : 1;
+  }
+  double a, b, c;
+  shape3(dh, a, b, c);
+  ds[0] = inc == -1 ? a : 0.0;
+  ds[1] = inc == -1 ? b : (inc == 0 ? a : 0.0);
+  ds[2] = inc == -1 ? c : (inc == 0 ? b : a);
+  ds[3] = inc == 0 ? c : (inc == 1 ? b : 0.0);
+  ds[4] = inc == 1 ? c : 0.0;
+#pragma unroll
+  for (int m = 0; m < 5; ++m) ds[m] = ds[m] - s0[m];
+  return inc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused push + boundary + deposit + destination counting (3-D)
+//   ORDER 0 (Weibel/beam): deposit sees the un-wrapped new position, the periodic x wrap follows
+// ---------------------------------------------------------------------------------------------
+template <int ORDER>
+__global__ void __launch_bounds__(TPB, 2)
+k_fused3(Geo g, Ptcl A, Ptcl B, const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj,
+         int* __restrict__ cnt27, unsigned char* __restrict__ dst_off, int* flags, int nxs, int nxe, int ngx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  const int t = threadIdx.x;
+  // group -> (i0, j, k)
+  const int gx = blockIdx.x % ngx;
+  const int jk = blockIdx.x / ngx;
+  const int j = g.nys + jk % g.nyl, k = g.nzs + jk / g.nyl;
+  const int i0 = nxs + gx * G;
+  const int ncg = min(G, nxe - i0 + 1);  // cells in this group
+
+  if (t == 0) mbar_init(&S.bar, 1);
+  if (t < 2 * (G + 1)) {
+    const int isp = t / (G + 1), ii = t % (G + 1);
+    const int* row = cs + (size_t)g.pen(j, k, isp) * (g.nx + 1) + (i0 - g.nxgs);
+    S.beg[isp][ii] = row[min(ii, ncg)];
+  }
+  for (int e = t; e < 2 * 27 * G; e += TPB) (&S.cnt27[0][0][0])[e] = 0;
+  __syncthreads();
+  if (t == 0) {
+    // field tile by TMA bulk copies: 9 rows of (ncg+2) cells x 6 doubles (48 B per cell keeps 16-B alignment)
+    const uint32_t row_bytes = (uint32_t)(ncg + 2) * 48u;
+    mbar_expect_tx(&S.bar, 9u * row_bytes);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int jj = r % 3 - 1, kk = r / 3 - 1;
+      tma_bulk_g2s(&S.tile[r * TILE_ROW], tmpf + g.box(i0 - 1, j + jj, k + kk) * 6, row_bytes, &S.bar);
+    }
+    int mx = 0;
+    for (int c = 0; c < ncg; ++c)
+      mx = max(mx, (S.beg[0][c + 1] - S.beg[0][c]) + (S.beg[1][c + 1] - S.beg[1][c]));
+    S.nbatch = (mx + SLOTS - 1) / SLOTS;
+  }
+  __syncthreads();
+  const int nbatch = S.nbatch;
+
+  // phase-A identity: (cell, slot); phase-B identity: (cell, component, transverse index m)
+  const int ca = t >> 4, sa = t & 15;
+  const int cb = t >> 4, hb = t & 15;
+  const int comp = hb / 5, mb = hb % 5;
+  const bool b_active = hb < 15 && cb < ncg;
+  const int n0a = ca < ncg ? S.beg[0][ca + 1] - S.beg[0][ca] : 0;
+  const int n1a = ca < ncg ? S.beg[1][ca + 1] - S.beg[1][ca] : 0;
+  const int ncb = cb < ncg ? (S.beg[0][cb + 1] - S.beg[0][cb]) + (S.beg[1][cb + 1] - S.beg[1][cb]) : 0;
+
+  double acc[20];
+#pragma unroll
+  for (int e = 0; e < 20; ++e) acc[e] = 0.0;
+
+  // record field indices: 0..5 = c prefix sums (x01 x23 y01 y23 z01 z23), 6+5a+m = (S0,DS)[m] of axis a
+  const int f_c = 2 * comp;
+  const int ax1 = comp == 0 ? 1 : 0;              // first transverse axis (A,B): y for Jx, x for Jy and Jz
+  const int ax2 = comp == 2 ? 1 : 2;              // second transverse axis: z for Jx and Jy, y for Jz
+  const double fac = 1.0 / 3.0;
+  const int ia = i0 + ca;
+  const double len_x = (g.nxge - g.nxgs + 1) * g.delx;
+  const double len_y = (g.nyge - g.nygs + 1) * g.delx;
+  const double len_z = (g.nzge - g.nzgs + 1) * g.delx;
+
+  mbar_wait(&S.bar, 0);
+
+  for (int batch = 0; batch < nbatch; ++batch) {
+    // ------------------------------ phase A ------------------------------
+    {
+      const int idx = batch * SLOTS + sa;
+      int p = -1, isp = 0;
+      if (idx < n0a) { p = S.beg[0][ca] + idx; }
+      else if (idx < n0a + n1a) { p = S.beg[1][ca] + (idx - n0a); isp = 1; }
+      if (p >= 0) {
+        const double x = A.c[0][p], y = A.c[1][p], z = A.c[2][p];
+        double ux = A.c[3][p], uy = A.c[4][p], uz = A.c[5][p];
+        double sx[3], sy[3], sz[3];
+        shape3(x * g.d_delx - 5e-1 - ia, sx[0], sx[1], sx[2]);
+        shape3(y * g.d_delx - 5e-1 - j, sy[0], sy[1], sy[2]);
+        shape3(z * g.d_delx - 5e-1 - k, sz[0], sz[1], sz[2]);
+        // gather from the smem tile, reference nesting (x-sum, *shy, *shz)  particle.f90:126-184
+        double f[6];
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+          double pl[6];
+#pragma unroll
+          for (int jj = 0; jj < 3; ++jj) {
+            const double2* tr = reinterpret_cast<const double2*>(&S.tile[(kk * 3 + jj) * TILE_ROW + ca * 6]);
+            double v[18];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) { double2 d = tr[e]; v[2 * e] = d.x; v[2 * e + 1] = d.y; }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+              double row = +v[c] * sx[0] + v[6 + c] * sx[1] + v[12 + c] * sx[2];
+              pl[c] = jj == 0 ? row * sy[0] : pl[c] + row * sy[jj];
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 6; ++c) f[c] = kk == 0 ? pl[c] * sz[0] : f[c] + pl[c] * sz[kk];
+        }
+        // Buneman-Boris  particle.f90:186-217
+        const double fac1 = g.q[isp] / g.r[isp] * 5e-1 * g.delt;
+        const double txxx = fac1 * fac1;
+        const double fac2 = g.q[isp] * g.delt / g.r[isp];
+        double xn, yn, zn;
+        {
+          const double bpx = f[0], bpy = f[1], bpz = f[2], epx = f[3], epy = f[4], epz = f[5];
+          double uvm1 = ux + fac1 * epx, uvm2 = uy + fac1 * epy, uvm3 = uz + fac1 * epz;
+          double gam = sqrt(g.c * g.c + uvm1 * uvm1 + uvm2 * uvm2 + uvm3 * uvm3);
+          double igam = 1.0 / gam;
+          double fac1r = fac1 * igam;
+          double fac2r = fac2 / (gam + txxx * (bpx * bpx + bpy * bpy + bpz * bpz) * igam);
+          double uvm4 = uvm1 + fac1r * (+uvm2 * bpz - uvm3 * bpy);
+          double uvm5 = uvm2 + fac1r * (+uvm3 * bpx - uvm1 * bpz);
+          double uvm6 = uvm3 + fac1r * (+uvm1 * bpy - uvm2 * bpx);
+          uvm1 = uvm1 + fac2r * (+uvm5 * bpz - uvm6 * bpy);
+          uvm2 = uvm2 + fac2r * (+uvm6 * bpx - uvm4 * bpz);
+          uvm3 = uvm3 + fac2r * (+uvm4 * bpy - uvm5 * bpx);
+          ux = uvm1 + fac1 * epx;
+          uy = uvm2 + fac1 * epy;
+          uz = uvm3 + fac1 * epz;
+          gam = 1.0 / sqrt(1.0 + (+ux * ux + uy * uy + uz * uz) / (g.c * g.c));
+          xn = x + ux * g.delt * gam;
+          yn = y + uy * g.delt * gam;
+          zn = z + uz * g.delt * gam;
+        }
+        // Esirkepov 1-D factors -> record
+        const double qdxdt = g.q[isp] * g.delx * g.d_delt;
+        const int slot = ca * CSTR + sa;
+        int inc[3];
+        {
+          const double xo[3] = {x, y, z}, xnw[3] = {xn, yn, zn};
+          const int cell[3] = {ia, j, k};
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            double s0[5], ds[5];
+            inc[a] = s0ds(xo[a], xnw[a], cell[a], g.d_delx, s0, ds, flags);
+            const double c0 = -ds[0] * qdxdt;
+            const double c1 = c0 - ds[1] * qdxdt;
+            const double c2 = c1 - ds[2] * qdxdt;
+            const double c3 = c2 - ds[3] * qdxdt;
+            S.rec[(2 * a) * FSTR + slot] = make_double2(c0, c1);
+            S.rec[(2 * a + 1) * FSTR + slot] = make_double2(c2, c3);
+#pragma unroll
+            for (int m = 0; m < 5; ++m) S.rec[(6 + 5 * a + m) * FSTR + slot] = make_double2(s0[m], ds[m]);
+          }
+        }
+        // boundaries: periodic x (boundary_periodic.f90:86-92) and periodic y,z wrap of the coordinate (:161-171).
+        // The destination cell is fixed by the pre-wrap integer cell, as in the reference.
+        {
+          int ipos = (int)(xn * g.d_delx);
+          if (ipos < g.nxgs) xn = xn + len_x;
+          else if (ipos >= g.nxge + 1) xn = xn - len_x;
+          int jpos = (int)(yn * g.d_delx);
+          if (jpos <= g.nygs - 1) yn = yn + len_y;
+          else if (jpos >= g.nyge + 1) yn = yn - len_y;
+          int kpos = (int)(zn * g.d_delx);
+          if (kpos <= g.nzgs - 1) zn = zn + len_z;
+          else if (kpos >= g.nzge + 1) zn = zn - len_z;
+        }
+        B.c[0][p] = xn; B.c[1][p] = yn; B.c[2][p] = zn;
+        B.c[3][p] = ux; B.c[4][p] = uy; B.c[5][p] = uz;
+        const int o = (inc[0] + 1) + 3 * (inc[1] + 1) + 9 * (inc[2] + 1);
+        dst_off[p] = (unsigned char)o;
+        atomicAdd(&S.cnt27[isp][o][ca], 1);
+      }
+    }
+    __syncthreads();
+    // ------------------------------ phase B ------------------------------
+    if (b_active) {
+      const int nv = min(SLOTS, ncb - batch * SLOTS);
+      for (int s = 0; s < nv; ++s) {
+        const int slot = cb * CSTR + s;
+        const double2 c01 = S.rec[f_c * FSTR + slot];
+        const double2 c23 = S.rec[(f_c + 1) * FSTR + slot];
+        const double2 p1 = S.rec[(6 + 5 * ax1 + mb) * FSTR + slot];
+        const double Av = p1.x + 5e-1 * p1.y;
+        const double Bv = 5e-1 * p1.x + fac * p1.y;
+#pragma unroll
+        for (int kp = 0; kp < 5; ++kp) {
+          const double2 p2 = S.rec[(6 + 5 * ax2 + kp) * FSTR + slot];
+          const double D = (kp == 0 || kp == 4) ? Bv * p2.y : Av * p2.x + Bv * p2.y;
+          acc[0 * 5 + kp] += c01.x * D;
+          acc[1 * 5 + kp] += c01.y * D;
+          acc[2 * 5 + kp] += c23.x * D;
+          acc[3 * 5 + kp] += c23.y * D;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- flush: current strips -> global J (RED.F64, zeros skipped), counts -> cnt27 -----------------
+  if (b_active) {
+    const int ib = i0 + cb;
+    const long long sY = (long long)g.bx * 3, sZ = (long long)g.bx * g.by * 3;
+    double* J0 = uj + g.box(ib, j, k) * 3 + comp;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int kp = 0; kp < 5; ++kp) {
+        const double v = acc[r * 5 + kp];
+        if (v != 0.0) {
+          long long off;
+          if (comp == 0) off = (r - 1) * 3 + (mb - 2) * sY + (kp - 2) * sZ;        // Jx(i+r-1, j+jp-2, k+kp-2)
+          else if (comp == 1) off = (mb - 2) * 3 + (r - 1) * sY + (kp - 2) * sZ;   // Jy(i+ip-2, j+r-1, k+kp-2)
+          else off = (mb - 2) * 3 + (kp - 2) * sY + (r - 1) * sZ;                  // Jz(i+ip-2, j+jp-2, k+r-1)
+          atomicAdd(J0 + off, v);
+        }
+      }
+  }
+  {
+    const size_t ncell = (size_t)g.nx * g.nyl * g.nzl;
+    const size_t cell0 = ((size_t)(k - g.nzs) * g.nyl + (j - g.nys)) * g.nx + (i0 - g.nxgs);
+    for (int e = t; e < 2 * 27 * G; e += TPB) {
+      const int c = e % G, o = (e / G) % 27, isp = e / (G * 27);
+      if (c < ncg) cnt27[((size_t)o * 2 + isp) * ncell + cell0 + c] = S.cnt27[isp][o][c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic counting sort from the 27-offset counts
+// ---------------------------------------------------------------------------------------------
+// destination cell of source cell (i,j,k) and offset o, periodic in all three directions (one slab)
+__device__ __forceinline__ bool neighbour_src(const Geo& g, int i, int j, int k, int o, int nxs, int nxe, size_t& src) {
+  // source S such that S + off(o) == (i,j,k)
+  int di = o % 3 - 1, dj = (o / 3) % 3 - 1, dk = o / 9 - 1;
+  int si = i - di, sj = j - dj, sk = k - dk;
+  if (si < g.nxgs) si += g.nx; else if (si > g.nxge) si -= g.nx;
+  if (sj < g.nygs) sj += g.ny; else if (sj > g.nyge) sj -= g.ny;
+  if (sk < g.nzgs) sk += g.nz; else if (sk > g.nzge) sk -= g.nz;
+  if (si < nxs || si > nxe) return false;
+  src = ((size_t)(sk - g.nzs) * g.nyl + (sj - g.nys)) * g.nx + (si - g.nxgs);
+  return true;
+}
+
+// per destination cell: exclusive prefix over its 27 sources (in place: counts -> offsets), total -> hist
+__global__ void k_offsets3(Geo g, int* __restrict__ cnt27, int* __restrict__ hist, int nxs, int nxe) {
+  const size_t ncell = (size_t)g.nx * g.nyl * g.nzl;
+  const size_t n = ncell * 2;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int isp = (int)(e / ncell);
+    const size_t cell = e % ncell;
+    const int i = g.nxgs + (int)(cell % g.nx);
+    const int j = g.nys + (int)((cell / g.nx) % g.nyl);
+    const int k = g.nzs + (int)(cell / ((size_t)g.nx * g.nyl));
+    int run = 0;
+    if (i >= nxs && i <= nxe) {
+#pragma unroll 1
+      for (int o = 0; o < 27; ++o) {
+        size_t src;
+        if (!neighbour_src(g, i, j, k, o, nxs, nxe, src)) continue;
+        int* pc = cnt27 + ((size_t)o * 2 + isp) * ncell + src;
+        const int c = *pc;
+        *pc = run;
+        run += c;
+      }
+    }
+    hist[(size_t)g.pen(j, k, isp) * (g.nx + 1) + (i - g.nxgs)] = run;
+  }
+}
+
+// one warp per source cell and species: stable scatter B -> A
+__global__ void __launch_bounds__(TPB) k_scatter3(Geo g, Ptcl B, Ptcl A, const double* __restrict__ id_in,
+                                                  double* __restrict__ id_out, const int* __restrict__ cs,
+                                                  const int* __restrict__ cs_new, const int* __restrict__ off27,
+                                                  const unsigned char* __restrict__ dst_off, int nxs, int nxe) {
+  __shared__ int s_base[TPB / 32][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nxr = nxe - nxs + 1;
+  const size_t ncell = (size_t)g.nx * g.nyl * g.nzl;
+  const long long nwork = (long long)nxr * g.nyl * g.nzl * 2;
+  for (long long w = warp; w < nwork; w += nwarps) {
+    const int isp = (int)(w / ((long long)nxr * g.nyl * g.nzl));
+    const long long c = w % ((long long)nxr * g.nyl * g.nzl);
+    const int i = nxs + (int)(c % nxr);
+    const int j = g.nys + (int)((c / nxr) % g.nyl);
+    const int k = g.nzs + (int)(c / ((long long)nxr * g.nyl));
+    const int* row = cs + (size_t)g.pen(j, k, isp) * (g.nx + 1) + (i - g.nxgs);
+    const int beg = row[0], end = row[1];
+    if (beg == end) continue;
+    const size_t src = ((size_t)(k - g.nzs) * g.nyl + (j - g.nys)) * g.nx + (i - g.nxgs);
+    __syncwarp();
+    if (lane < 27) {
+      // destination cell of offset `lane`, periodic wrap
+      int di = lane % 3 - 1, dj = (lane / 3) % 3 - 1, dk = lane / 9 - 1;
+      int ti = i + di, tj = j + dj, tk = k + dk;
+      if (ti < g.nxgs) ti += g.nx; else if (ti > g.nxge) ti -= g.nx;
+      if (tj < g.nygs) tj += g.ny; else if (tj > g.nyge) tj -= g.ny;
+      if (tk < g.nzgs) tk += g.nz; else if (tk > g.nzge) tk -= g.nz;
+      s_base[wib][lane] = cs_new[(size_t)g.pen(tj, tk, isp) * (g.nx + 1) + (ti - g.nxgs)]
+                          + off27[((size_t)lane * 2 + isp) * ncell + src];
+    }
+    __syncwarp();
+    for (int p0 = beg; p0 < end; p0 += 32) {
+      const int p = p0 + lane;
+      const bool act = p < end;
+      const int o = act ? dst_off[p] : 31;
+      const unsigned mask = __match_any_sync(0xffffffffu, o);
+      const int rank = __popc(mask & ((1u << lane) - 1u));
+      int d = 0;
+      if (act) d = s_base[wib][o] + rank;
+      __syncwarp();
+      if (act && rank == 0) s_base[wib][o] += __popc(mask);   // group leader advances the cursor
+      __syncwarp();
+      if (act) {
+        A.c[0][d] = B.c[0][p]; A.c[1][d] = B.c[1][p]; A.c[2][d] = B.c[2][p];
+        A.c[3][d] = B.c[3][p]; A.c[4][d] = B.c[4][p]; A.c[5][d] = B.c[5][p];
+        id_out[d] = id_in[p];
+      }
+    }
+  }
+}
+
+__global__ void k_np2_poff(Geo g, const int* __restrict__ cs, int* __restrict__ np2, int* __restrict__ poff, int* flags) {
+  for (int pen = blockIdx.x * blockDim.x + threadIdx.x; pen <= g.npen; pen += gridDim.x * blockDim.x) {
+    if (pen < g.npen) {
+      const int* row = cs + (size_t)pen * (g.nx + 1);
+      int n = row[g.nx] - row[0];
+      np2[pen] = n;
+      poff[pen] = row[0];
+      if (n > g.np) atomicOr(flags, 1);
+    } else {
+      poff[pen] = cs[(size_t)(g.npen - 1) * (g.nx + 1) + g.nx];
+    }
+  }
+}
+
+}  // namespace
+
+int wm_fused_smem_bytes() { return (int)sizeof(Smem); }
+
+int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double /*u0*/) {
+  const Geo& g = ctx->g;
+  if (g.dim != 3 || order != WM_ORDER_WEIBEL || g.bc != WM_BC_PERIODIC) {
+    wm_set_error("fused path: only 3-D periodic (Weibel order) so far");
+    return WM_ERR_ARG;
+  }
+  const size_t ncell = (size_t)g.nx * g.nyl * g.nzl;
+  if (!ctx->cnt27) {
+    WM_CUDA(cudaMalloc(&ctx->cnt27, ncell * 2 * 27 * sizeof(int)));
+    WM_CUDA(cudaMemsetAsync(ctx->cnt27, 0, ncell * 2 * 27 * sizeof(int), ctx->stream));
+  }
+  if (ctx->dst_off_cap < ctx->cap) {
+    if (ctx->dst_off) cudaFree(ctx->dst_off);
+    WM_CUDA(cudaMalloc(&ctx->dst_off, ctx->cap));
+    ctx->dst_off_cap = ctx->cap;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    WM_CUDA(cudaFuncSetAttribute(k_fused3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    attr_set = true;
+  }
+  const int ngx = (nxe - nxs + 1 + G - 1) / G;
+  const int blocks = ngx * g.nyl * g.nzl;
+  k_fused3<0><<<blocks, TPB, sizeof(Smem), ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->tmpf, ctx->uj, ctx->cnt27,
+                                                           ctx->dst_off, ctx->flags, nxs, nxe, ngx);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+// sort that follows the fused kernel: offsets -> scan -> stable scatter
+int wm_k_sort_fused(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const size_t ncs = (size_t)g.npen * (g.nx + 1);
+  const size_t ncell = (size_t)g.nx * g.nyl * g.nzl;
+  WM_CUDA(cudaMemsetAsync(ctx->cs_new, 0, (ncs + 1) * sizeof(int), ctx->stream));
+  {
+    const long long n = (long long)ncell * 2;
+    const int blocks = (int)std::min<long long>((n + TPB - 1) / TPB, 148LL * 16);
+    k_offsets3<<<blocks, TPB, 0, ctx->stream>>>(g, ctx->cnt27, ctx->cs_new, nxs, nxe);
+    WM_LAUNCH_CHECK(ctx);
+  }
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->cs_new, ctx->cs_new, (int)ncs, ctx->stream);
+  if (need > ctx->scan_tmp_bytes) {
+    if (ctx->scan_tmp) cudaFree(ctx->scan_tmp);
+    WM_CUDA(cudaMalloc(&ctx->scan_tmp, need));
+    ctx->scan_tmp_bytes = need;
+  }
+  WM_CUDA(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp, need, ctx->cs_new, ctx->cs_new, (int)ncs, ctx->stream));
+  ctx->launches += 2;
+  if (ctx->ntot > 0) {
+    const long long nwork = (long long)(nxe - nxs + 1) * g.nyl * g.nzl * 2;
+    const int blocks = (int)std::min<long long>((nwork * 32 + TPB - 1) / TPB, 148LL * 8);
+    k_scatter3<<<blocks, TPB, 0, ctx->stream>>>(g, ctx->B, ctx->A, ctx->id[ctx->cid], ctx->id[1 - ctx->cid], ctx->cs,
+                                                ctx->cs_new, ctx->cnt27, ctx->dst_off, nxs, nxe);
+    WM_LAUNCH_CHECK(ctx);
+  }
+  std::swap(ctx->cs, ctx->cs_new);
+  ctx->cid = 1 - ctx->cid;
+  k_np2_poff<<<wm_blocks(g.npen + 1, TPB), TPB, 0, ctx->stream>>>(g, ctx->cs, ctx->np2, ctx->poff, ctx->flags);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}

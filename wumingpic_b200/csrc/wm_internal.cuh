@@ -64,6 +64,10 @@ struct wm_ctx {
   int* np2 = nullptr;      // particles per pencil (npen)
   int* poff = nullptr;     // pencil offsets (npen+1), absolute
   int* flags = nullptr;    // sticky device error flags
+  int* cnt27 = nullptr;    // fused path: per (offset, species, source cell) counts -> offsets
+  unsigned char* dst_off = nullptr;  // fused path: destination offset (0..26) of every pushed particle
+  size_t dst_off_cap = 0;
+  int use_fused = 1;
   void* scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
   // fields
@@ -126,6 +130,7 @@ int wm_k_tmpf(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_push(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_deposit(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double u0);
+int wm_k_sort_fused(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_bc_x(wm_ctx* ctx, int nxs, int nxe, int kind, double u0);
 int wm_k_migrate(wm_ctx* ctx);
 int wm_k_sort(wm_ctx* ctx, int nxs, int nxe);
