@@ -1,0 +1,78 @@
+"""Multi-GPU parity check, launched by torchrun (one rank per GPU, NCCL):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multigpu_check.py [--fused 0|1] [--steps 6]
+
+Every rank builds the SAME in-process oracle world with nproc_k = WORLD_SIZE z-slabs (the oracle emulates the
+MPI ranks of the reference, 3d/common/mpi_set.f90:45-76, and its MPI_SENDRECV / MPI_ALLREDUCE call sites), uploads
+its own slab to its GPU, steps both, and compares its slab: np2 / cumcnt / per-cell particle records (IDs bit-exact),
+uf, and the Gauss residual.  Exit code 0 = parity."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--fused", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--nx", type=int, default=16)
+    ap.add_argument("--ny", type=int, default=12)
+    ap.add_argument("--nz", type=int, default=10)
+    ap.add_argument("--n0", type=int, default=8)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from tests.util import backend_for, canonical_cells, make_world3, rel_err, upload_from_world
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = make_world3(args.nx, args.ny, args.nz, args.n0, steps=2, nproc_k=world)
+    b = backend_for(w, rank=rank, device=local, nproc_k=world)
+    box = [b.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    b.comm_init(world, rank, box[0])
+    b.set_fused(bool(args.fused))
+    upload_from_world(b, w, rank)
+    ntot0 = sum(int(w.arr("np2", r).sum()) for r in range(world))
+    worst_uf = 0.0
+    for it in range(args.steps):
+        w.step()
+        b.step(2, args.nx + 1, 1)
+        uf = b.empty("uf")
+        b.download(uf=uf)
+        worst_uf = max(worst_uf, rel_err(uf, w.arr("uf", rank)))
+        res, rho = b.gauss()
+        assert res < 1e-13 * max(rho, 1.0), f"rank {rank}: Gauss residual {res} at step {it}"
+    assert w.error() == 0
+    up, np2, cc = b.empty("up"), b.empty("np2"), b.empty("cumcnt")
+    b.download(up, np2, cc)
+    assert np.array_equal(np2, w.arr("np2", rank)), f"rank {rank}: np2 differs"
+    assert np.array_equal(cc, w.arr("cumcnt", rank)), f"rank {rank}: cumcnt differs"
+    worst = 0.0
+    for (cg, rg), (cr, rr) in zip(canonical_cells(up, np2, cc),
+                                  canonical_cells(w.arr("up", rank), w.arr("np2", rank), w.arr("cumcnt", rank))):
+        assert np.array_equal(cg, cr)
+        assert np.array_equal(rg[:, 6].view(np.int64), rr[:, 6].view(np.int64)), f"rank {rank}: particle ID sets differ"
+        if len(rg):
+            worst = max(worst, np.abs(rg[:, :6] - rr[:, :6]).max())
+    assert worst < 1e-9 and worst_uf < 1e-8, (worst, worst_uf)
+    n = torch.tensor([b.stats()["n_particles"]], device="cuda", dtype=torch.int64)
+    dist.all_reduce(n)
+    assert int(n.item()) == ntot0, "global particle count not conserved"
+    assert b.stats()["error_flags"] == 0
+    print(f"rank {rank}/{world} ok: fused={args.fused} np2/cumcnt/IDs exact, max|dx| {worst:.2e}, uf rel {worst_uf:.2e}",
+          flush=True)
+    b.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

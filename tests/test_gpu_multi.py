@@ -1,0 +1,29 @@
+"""Multi-GPU (z-slab) parity through NCCL: runs tests/multigpu_check.py under torchrun when the box has >= 2 GPUs.
+On a 1-GPU box the test is skipped (NCCL cannot place two ranks on one device); the slab logic itself is also
+covered without GPUs by tests/test_mpi_set_gloo.py and by the oracle's multi-rank tests."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("fused", [1, 0], ids=["fused", "per-procedure"])
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_slab_parity(nranks, fused):
+    if _ngpu() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29520 + nranks + fused),
+           os.path.join(ROOT, "tests", "multigpu_check.py"), "--fused", str(fused), "--nz", "12"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok: ") == nranks

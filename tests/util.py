@@ -14,13 +14,14 @@ def make_world3(nx, ny, nz, n0, steps=0, nproc_j=1, nproc_k=1, np_factor=3, seed
     return w
 
 
-def backend_for(world, rank=0, device=-1):
-    """A CUDA Backend with the geometry of one oracle rank."""
+def backend_for(world, rank=0, device=-1, nproc_j=1, nproc_k=1):
+    """A CUDA Backend with the geometry of one oracle rank (rank = rank_j * nproc_k + rank_k, mpi_set.f90:45-60)."""
     import wumingpic_b200 as wm
     g = world.geom(rank)
     return wm.Backend(3, world.np, 2, world.nx + 1, 2, world.ny + 1, 2, world.nz + 1, nys=g["nys"], nye=g["nye"],
                       nzs=g["nzs"], nze=g["nze"], delx=world.delx, delt=world.delt, c=world.c, gfac=world.gfac,
-                      q=world.q, r=world.r, device=device)
+                      q=world.q, r=world.r, device=device, nproc_j=nproc_j, nproc_k=nproc_k,
+                      rank_j=rank // nproc_k, rank_k=rank % nproc_k)
 
 
 def upload_from_world(b, world, rank=0):

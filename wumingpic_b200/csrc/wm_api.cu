@@ -132,6 +132,9 @@ int wm_create(const wm_params* prm, wm_ctx** out) {
   g.nyl = g.nye - g.nys + 1; g.nzl = p.dim == 3 ? g.nze - g.nzs + 1 : 1;
   g.bx = g.nx + 4; g.by = g.nyl + 4; g.bz = p.dim == 3 ? g.nzl + 4 : 1;
   g.npen = g.nsp * g.nyl * g.nzl;
+  g.multi = 0;                              // set by wm_comm_init when the slab-axis neighbours are other ranks
+  g.ngrow = p.dim == 3 ? g.nyl : 1;
+  g.nrows = g.npen;
   g.bc = p.bc_kind;
   g.delx = p.delx; g.delt = p.delt; g.c = p.c; g.gfac = p.gfac;
   g.d_delx = 1.0 / p.delx; g.d_delt = 1.0 / p.delt;
@@ -143,6 +146,8 @@ int wm_create(const wm_params* prm, wm_ctx** out) {
   g.f5 = std::pow(p.delx / (p.c * p.delt * p.gfac), 2);
   g.f4 = (p.dim == 3 ? 6.0 : 4.0) + g.f5;
   // mpi_set__init neighbour table (3d/common/mpi_set.f90:63-76), periodic in y and z
+  c->last_nxs = g.nxgs;
+  c->last_nxe = g.nxge;
   c->nranks = 1;  // until wm_comm_init
   c->rank = p.rank_j * p.nproc_k + p.rank_k;
   auto rk = [&](int j, int k) { return ((j + p.nproc_j) % p.nproc_j) * p.nproc_k + ((k + p.nproc_k) % p.nproc_k); };
@@ -166,11 +171,17 @@ int wm_create(const wm_params* prm, wm_ctx** out) {
   WM_CUDA(cudaMemsetAsync(c->tmpf, 0, nb * 6 * sizeof(double), c->stream));
   WM_CUDA(cudaMemsetAsync(c->uj, 0, nb * 3 * sizeof(double), c->stream));
   WM_CUDA(cudaMemsetAsync(c->gkl, 0, nb * 3 * sizeof(double), c->stream));
-  const size_t ncs = (size_t)g.npen * (g.nx + 1) + 1;
+  // cell index rows: npen local pencils + the ghost rows of a slab run (wm_sort.cu), nx+1 entries each, + grand total
+  const size_t ncs = ((size_t)g.npen + 2 * g.nsp * g.ngrow) * (g.nx + 1) + 1;
   WM_CUDA(cudaMalloc(&c->cs, ncs * sizeof(int)));
   WM_CUDA(cudaMalloc(&c->cs_new, ncs * sizeof(int)));
-  WM_CUDA(cudaMalloc(&c->cursor, ncs * sizeof(int)));
   WM_CUDA(cudaMemsetAsync(c->cs, 0, ncs * sizeof(int), c->stream));
+  WM_CUDA(cudaMemsetAsync(c->cs_new, 0, ncs * sizeof(int), c->stream));
+  const size_t ninc = (size_t)2 * g.nsp * g.ngrow * (g.nx + 1) + 1;
+  WM_CUDA(cudaMalloc(&c->inc, ninc * sizeof(int)));
+  WM_CUDA(cudaMalloc(&c->inc_off, ninc * sizeof(int)));
+  WM_CUDA(cudaMalloc(&c->totals, 8 * sizeof(int)));
+  WM_CUDA(cudaMemsetAsync(c->inc, 0, ninc * sizeof(int), c->stream));
   WM_CUDA(cudaMalloc(&c->np2, (size_t)g.npen * sizeof(int)));
   WM_CUDA(cudaMalloc(&c->poff, ((size_t)g.npen + 1) * sizeof(int)));
   WM_CUDA(cudaMemsetAsync(c->np2, 0, (size_t)g.npen * sizeof(int), c->stream));
@@ -198,7 +209,7 @@ int wm_destroy(wm_ctx* c) {
   double* d[] = {c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
                  c->hbuf[2], c->stage};
   for (double* p : d) if (p) cudaFree(p);
-  int* ii[] = {c->cs, c->cs_new, c->cursor, c->np2, c->poff, c->flags, c->cnt27};
+  int* ii[] = {c->cs, c->cs_new, c->np2, c->poff, c->flags, c->cnt27, c->inc, c->inc_off, c->totals};
   if (c->dst_off) cudaFree(c->dst_off);
   for (int* p : ii) if (p) cudaFree(p);
   if (c->scan_tmp) cudaFree(c->scan_tmp);
@@ -239,6 +250,7 @@ int wm_upload(wm_ctx* c, const double* up, const int* np2, const int* cumcnt, co
     for (int pen = 0; pen < g.npen; ++pen)
       for (int i = 0; i <= g.nx; ++i) cs[(size_t)pen * (g.nx + 1) + i] = poff[pen] + cumcnt[(size_t)pen * (g.nx + 1) + i];
     cs.back() = poff[g.npen];
+    c->keys_valid = false;
     WM_CUDA(cudaMemcpyAsync(c->cs, cs.data(), cs.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     WM_CUDA(cudaMemcpyAsync(c->np2, np2, (size_t)g.npen * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     WM_CUDA(cudaMemcpyAsync(c->poff, poff.data(), poff.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -287,7 +299,7 @@ int wm_download(wm_ctx* c, double* up, int* np2, int* cumcnt, double* uf, double
   for (int which = 0; which < 2; ++which) {
     double* dst = which == 0 ? up : gp;
     if (!dst || maxcnt == 0) continue;
-    if (which == 1 && !c->gp_valid) {
+    if (which == 1 && (!c->gp_valid || c->keys_valid)) {
       wm_set_error("wm_download: gp is only defined between particle__solv and bc__particle_yz");
       return WM_ERR_STATE;
     }
@@ -352,15 +364,23 @@ int wm_particle_solv(wm_ctx* c, int nxs, int nxe) {
   WM_TRY(wm_k_tmpf(c, nxs, nxe));
   WM_TRY(wm_k_push(c, nxs, nxe));
   c->gp_valid = true;
+  c->keys_valid = false;
+  c->last_nxs = nxs;
+  c->last_nxe = nxe;
   return WM_OK;
 }
 
 int wm_field_stage(wm_ctx* c, int nxs, int nxe, int stage) {
   if (!c || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling field__init()"); return WM_ERR_ARG; }
   WM_CUDA(cudaSetDevice(c->device));
+  c->last_nxs = nxs;
+  c->last_nxe = nxe;
   switch (stage) {
     case 1:
-      if (!c->gp_valid) { wm_set_error("field__fdtd_i needs the pushed particles (call particle__solv first)"); return WM_ERR_STATE; }
+      if (!c->gp_valid || c->keys_valid) {
+        wm_set_error("field__fdtd_i needs the pushed particles: call it after particle__solv and before bc__particle_y[z]");
+        return WM_ERR_STATE;
+      }
       WM_TRY(wm_k_zero_uj(c, nxs, nxe));
       return wm_k_deposit(c, nxs, nxe);
     case 2: return wm_k_curre(c, nxs, nxe);
@@ -397,23 +417,27 @@ int wm_bc_particle_yz(wm_ctx* c) {
   if (!c) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
   if (!c->gp_valid) { wm_set_error("bc__particle_yz acts on the pushed particles"); return WM_ERR_STATE; }
-  return wm_k_migrate(c);
+  // re-binning is classification here; the movers travel inside sort__bucket's scatter (wm_sort.cu)
+  WM_TRY(wm_k_classify(c, c->last_nxs, c->last_nxe));
+  c->keys_valid = true;
+  return WM_OK;
 }
 
 int wm_sort_bucket(wm_ctx* c, int nxs, int nxe) {
   if (!c || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling sort__init()"); return WM_ERR_ARG; }
   WM_CUDA(cudaSetDevice(c->device));
   if (!c->gp_valid) { wm_set_error("sort__bucket sorts the pushed particles"); return WM_ERR_STATE; }
+  if (!c->keys_valid) WM_TRY(wm_k_classify(c, nxs, nxe));
   WM_TRY(wm_k_sort(c, nxs, nxe));
   c->gp_valid = false;
+  c->keys_valid = false;
   return WM_OK;
 }
 
 int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
   if (!c || !range_ok(c, nxs, nxe)) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
-  const bool fused = c->use_fused && c->g.dim == 3 && c->g.bc == WM_BC_PERIODIC && order == WM_ORDER_WEIBEL &&
-                     c->nranks == 1;
+  const bool fused = c->use_fused && c->g.dim == 3 && c->g.bc == WM_BC_PERIODIC && order == WM_ORDER_WEIBEL;
   for (int it = 0; it < nsteps; ++it) {
     if (c->timing) WM_CUDA(cudaEventRecord(c->ev[0], c->stream));
     if (fused) {
@@ -425,8 +449,9 @@ int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
       if (c->timing) { WM_CUDA(cudaEventRecord(c->ev[1], c->stream)); WM_CUDA(cudaEventRecord(c->ev[2], c->stream)); }
       for (int s = 2; s <= 8; ++s) WM_TRY(wm_field_stage(c, nxs, nxe, s));
       if (c->timing) WM_CUDA(cudaEventRecord(c->ev[3], c->stream));
-      WM_TRY(wm_k_sort_fused(c, nxs, nxe));
+      WM_TRY(wm_k_sort(c, nxs, nxe));
       c->gp_valid = false;
+      c->keys_valid = false;
     } else {
       WM_TRY(wm_particle_solv(c, nxs, nxe));
       if (c->timing) WM_CUDA(cudaEventRecord(c->ev[1], c->stream));
@@ -452,6 +477,18 @@ int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
   }
   return WM_OK;
 }
+
+}  // extern "C"
+
+// called by wm_comm_init once the communicator exists: the slab-axis neighbours are other ranks from now on
+int wm_enable_slab_migration(wm_ctx* c) {
+  Geo& g = c->g;
+  g.multi = 1;
+  g.nrows = g.npen + 2 * g.nsp * g.ngrow;
+  return WM_OK;
+}
+
+extern "C" {
 
 int wm_set_fused(wm_ctx* c, int on) {
   if (!c) return WM_ERR_ARG;

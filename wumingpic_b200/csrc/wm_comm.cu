@@ -15,7 +15,7 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat64 = 8 };
+enum { ncclInt8 = 0, ncclFloat64 = 8 };
 enum { ncclSum = 0 };
 
 struct NcclApi {
@@ -86,6 +86,11 @@ extern "C" int wm_comm_init(wm_ctx* ctx, int nranks, int rank, const char* id_by
     wm_set_error("rank does not match rank_j*nproc_k + rank_k");
     return WM_ERR_ARG;
   }
+  if (nranks > 1 && ((ctx->g.dim == 3 && ctx->prm.nproc_j != 1) || (ctx->g.dim == 2 && ctx->prm.nproc_k != 1))) {
+    wm_set_error("decompose along the last axis only (z-slabs in 3-D: nproc_j = 1; y-slabs in 2-D): on NVSwitch every "
+                 "GPU pair has full bandwidth, so 1-D slabs replace the reference's 2-D rank grid");
+    return WM_ERR_ARG;
+  }
   ctx->nranks = nranks;
   ctx->rank = rank;
   if (nranks == 1) return WM_OK;
@@ -100,7 +105,7 @@ extern "C" int wm_comm_init(wm_ctx* ctx, int nranks, int rank, const char* id_by
   WM_CUDA(cudaSetDevice(ctx->device));
   WM_NCCL(a.CommInitRank(&comm, nranks, id, rank));
   ctx->nccl_comm = comm;
-  return WM_OK;
+  return wm_enable_slab_migration(ctx);
 }
 
 int wm_comm_destroy(wm_ctx* ctx) {
@@ -126,6 +131,30 @@ int wm_comm_sendrecv(wm_ctx* ctx, int axis, int dir_down, const double* snd, dou
   WM_NCCL(a.Send(snd, n, ncclFloat64, to, comm, ctx->stream));
   WM_NCCL(a.Recv(rcv, n, ncclFloat64, from, comm, ctx->stream));
   WM_NCCL(a.GroupEnd());
+  return WM_OK;
+}
+
+// Grouped point-to-point messages (byte counts) for the migration phases of wm_sort.cu: everything between
+// begin and end is one ncclGroup, i.e. one fused transfer kernel over NVLink.
+int wm_comm_group_begin(wm_ctx* ctx) {
+  if (!ctx->nccl_comm) {
+    wm_set_error("multi-rank exchange requested but wm_comm_init was not called");
+    return WM_ERR_ARG;
+  }
+  WM_NCCL(api().GroupStart());
+  return WM_OK;
+}
+int wm_comm_group_end(wm_ctx* ctx) {
+  WM_NCCL(api().GroupEnd());
+  ctx->launches++;
+  return WM_OK;
+}
+int wm_comm_send(wm_ctx* ctx, int peer, const void* buf, size_t bytes) {
+  WM_NCCL(api().Send(buf, bytes, ncclInt8, peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  return WM_OK;
+}
+int wm_comm_recv(wm_ctx* ctx, int peer, void* buf, size_t bytes) {
+  WM_NCCL(api().Recv(buf, bytes, ncclInt8, peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
   return WM_OK;
 }
 

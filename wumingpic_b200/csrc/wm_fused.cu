@@ -21,9 +21,7 @@
 //     |dx| < c dt <= 1 cell, so that count matrix is all the sort needs: destination offsets follow from a
 //     per-cell prefix over the 27 sources and ranks from the (stable) order inside the source cell, which
 //     makes the scatter atomic-free and the particle order -- hence every later sum -- deterministic.
-#include "wm_internal.cuh"
-
-#include <cub/device/device_scan.cuh>
+#include "wm_cells.cuh"
 
 namespace {
 
@@ -113,15 +111,18 @@ __device__ __forceinline__ int s0ds(double xo, double xn, int cell, double d_del
 // ---------------------------------------------------------------------------------------------
 template <int ORDER>
 __global__ void __launch_bounds__(TPB, 2)
-k_fused3(Geo g, Ptcl A, Ptcl B, const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj,
-         int* __restrict__ cnt27, unsigned char* __restrict__ dst_off, int* flags, int nxs, int nxe, int ngx) {
+k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __restrict__ id_out,
+         const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj, int* __restrict__ cnt,
+         int* __restrict__ hist, unsigned char* __restrict__ dst_off, int* flags, int nxs, int nxe, int ngx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int t = threadIdx.x;
   // group -> (i0, j, k)
+  // block order: j-strips of 8 rows, then k, then the rows of the strip, x groups fastest -- the order wm_sort.cu
+  // walks too, so that a CTA's neighbours in y and z run within a few MB of it (J RED traffic stays in L2)
   const int gx = blockIdx.x % ngx;
-  const int jk = blockIdx.x / ngx;
-  const int j = g.nys + jk % g.nyl, k = g.nzs + jk / g.nyl;
+  int j, k;
+  wm_strip_pencil(g, blockIdx.x / ngx, j, k);
   const int i0 = nxs + gx * G;
   const int ncg = min(G, nxe - i0 + 1);  // cells in this group
 
@@ -175,6 +176,7 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const int* __restrict__ cs, const double* __rest
 
   mbar_wait(&S.bar, 0);
 
+  int ns0 = 0, nl0 = 0, ns1 = 0, nl1 = 0;   // stayers / leavers of this thread's cell written so far, per species
   for (int batch = 0; batch < nbatch; ++batch) {
     // ------------------------------ phase A ------------------------------
     {
@@ -182,9 +184,12 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const int* __restrict__ cs, const double* __rest
       int p = -1, isp = 0;
       if (idx < n0a) { p = S.beg[0][ca] + idx; }
       else if (idx < n0a + n1a) { p = S.beg[1][ca] + (idx - n0a); isp = 1; }
+      double xn = 0, yn = 0, zn = 0, ux = 0, uy = 0, uz = 0, idv = 0;
+      int o = 13;
       if (p >= 0) {
         const double x = A.c[0][p], y = A.c[1][p], z = A.c[2][p];
-        double ux = A.c[3][p], uy = A.c[4][p], uz = A.c[5][p];
+        ux = A.c[3][p]; uy = A.c[4][p]; uz = A.c[5][p];
+        idv = id_in[p];
         double sx[3], sy[3], sz[3];
         shape3(x * g.d_delx - 5e-1 - ia, sx[0], sx[1], sx[2]);
         shape3(y * g.d_delx - 5e-1 - j, sy[0], sy[1], sy[2]);
@@ -213,7 +218,6 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const int* __restrict__ cs, const double* __rest
         const double fac1 = g.q[isp] / g.r[isp] * 5e-1 * g.delt;
         const double txxx = fac1 * fac1;
         const double fac2 = g.q[isp] * g.delt / g.r[isp];
-        double xn, yn, zn;
         {
           const double bpx = f[0], bpy = f[1], bpz = f[2], epx = f[3], epy = f[4], epz = f[5];
           double uvm1 = ux + fac1 * epx, uvm2 = uy + fac1 * epy, uvm3 = uz + fac1 * epz;
@@ -269,11 +273,28 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const int* __restrict__ cs, const double* __rest
           if (kpos <= g.nzgs - 1) zn = zn + len_z;
           else if (kpos >= g.nzge + 1) zn = zn - len_z;
         }
-        B.c[0][p] = xn; B.c[1][p] = yn; B.c[2][p] = zn;
-        B.c[3][p] = ux; B.c[4][p] = uy; B.c[5][p] = uz;
-        const int o = (inc[0] + 1) + 3 * (inc[1] + 1) + 9 * (inc[2] + 1);
-        dst_off[p] = (unsigned char)o;
+        o = (inc[0] + 1) + 3 * (inc[1] + 1) + 9 * (inc[2] + 1);
         atomicAdd(&S.cnt27[isp][o][ca], 1);
+      }
+      // two-ended write of the pushed set inside the source cell: stayers packed at the front, leavers at the back
+      // (what wm_sort.cu's gather expects).  The 16 lanes of a half-warp share the cell; ranks come from ballots.
+      {
+        const unsigned lane = t & 31u;
+        const unsigned half = 0xffffu << (lane & 16u);
+        const unsigned lower = half & ((1u << lane) - 1u);
+        const bool v0 = p >= 0 && isp == 0, v1 = p >= 0 && isp == 1, st = o == 13;
+        const unsigned bs0 = __ballot_sync(0xffffffffu, v0 && st) & half, bl0 = __ballot_sync(0xffffffffu, v0 && !st) & half;
+        const unsigned bs1 = __ballot_sync(0xffffffffu, v1 && st) & half, bl1 = __ballot_sync(0xffffffffu, v1 && !st) & half;
+        if (p >= 0) {
+          int pw;
+          if (isp == 0) pw = st ? S.beg[0][ca] + ns0 + __popc(bs0 & lower) : S.beg[0][ca + 1] - 1 - (nl0 + __popc(bl0 & lower));
+          else          pw = st ? S.beg[1][ca] + ns1 + __popc(bs1 & lower) : S.beg[1][ca + 1] - 1 - (nl1 + __popc(bl1 & lower));
+          B.c[0][pw] = xn; B.c[1][pw] = yn; B.c[2][pw] = zn;
+          B.c[3][pw] = ux; B.c[4][pw] = uy; B.c[5][pw] = uz;
+          id_out[pw] = idv;
+          if (!st) dst_off[pw] = (unsigned char)o;
+        }
+        ns0 += __popc(bs0); nl0 += __popc(bl0); ns1 += __popc(bs1); nl1 += __popc(bl1);
       }
     }
     __syncthreads();
@@ -320,122 +341,21 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const int* __restrict__ cs, const double* __rest
         }
       }
   }
+  // ---- re-binning information for the sort: one count line per (cell, species), group sizes -> histogram ----
   {
-    const size_t ncell = (size_t)g.nx * g.nyl * g.nzl;
-    const size_t cell0 = ((size_t)(k - g.nzs) * g.nyl + (j - g.nys)) * g.nx + (i0 - g.nxgs);
+    const size_t cell0 = wm_cell_index(g, i0, j, k);
+    for (int e = t; e < G * 2 * WM_CNT_LINE; e += TPB) {
+      const int o = e % WM_CNT_LINE, isp = (e / WM_CNT_LINE) % 2, c = e / (2 * WM_CNT_LINE);
+      if (c < ncg) cnt[cell0 * 2 * WM_CNT_LINE + e] = o < 27 ? S.cnt27[isp][o][c] : 0;
+    }
     for (int e = t; e < 2 * 27 * G; e += TPB) {
       const int c = e % G, o = (e / G) % 27, isp = e / (G * 27);
-      if (c < ncg) cnt27[((size_t)o * 2 + isp) * ncell + cell0 + c] = S.cnt27[isp][o][c];
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// deterministic counting sort from the 27-offset counts
-// ---------------------------------------------------------------------------------------------
-// destination cell of source cell (i,j,k) and offset o, periodic in all three directions (one slab)
-__device__ __forceinline__ bool neighbour_src(const Geo& g, int i, int j, int k, int o, int nxs, int nxe, size_t& src) {
-  // source S such that S + off(o) == (i,j,k)
-  int di = o % 3 - 1, dj = (o / 3) % 3 - 1, dk = o / 9 - 1;
-  int si = i - di, sj = j - dj, sk = k - dk;
-  if (si < g.nxgs) si += g.nx; else if (si > g.nxge) si -= g.nx;
-  if (sj < g.nygs) sj += g.ny; else if (sj > g.nyge) sj -= g.ny;
-  if (sk < g.nzgs) sk += g.nz; else if (sk > g.nzge) sk -= g.nz;
-  if (si < nxs || si > nxe) return false;
-  src = ((size_t)(sk - g.nzs) * g.nyl + (sj - g.nys)) * g.nx + (si - g.nxgs);
-  return true;
-}
-
-// per destination cell: exclusive prefix over its 27 sources (in place: counts -> offsets), total -> hist
-__global__ void k_offsets3(Geo g, int* __restrict__ cnt27, int* __restrict__ hist, int nxs, int nxe) {
-  const size_t ncell = (size_t)g.nx * g.nyl * g.nzl;
-  const size_t n = ncell * 2;
-  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-    const int isp = (int)(e / ncell);
-    const size_t cell = e % ncell;
-    const int i = g.nxgs + (int)(cell % g.nx);
-    const int j = g.nys + (int)((cell / g.nx) % g.nyl);
-    const int k = g.nzs + (int)(cell / ((size_t)g.nx * g.nyl));
-    int run = 0;
-    if (i >= nxs && i <= nxe) {
-#pragma unroll 1
-      for (int o = 0; o < 27; ++o) {
-        size_t src;
-        if (!neighbour_src(g, i, j, k, o, nxs, nxe, src)) continue;
-        int* pc = cnt27 + ((size_t)o * 2 + isp) * ncell + src;
-        const int c = *pc;
-        *pc = run;
-        run += c;
+      const int n = c < ncg ? S.cnt27[isp][o][c] : 0;
+      if (n > 0) {
+        int drow, ti;
+        if (wm_dest_of(g, i0 + c, j, k, o, isp, nxs, nxe, drow, ti)) atomicAdd(hist + (size_t)drow * (g.nx + 1) + (ti - g.nxgs), n);
+        else atomicOr(flags, 2);
       }
-    }
-    hist[(size_t)g.pen(j, k, isp) * (g.nx + 1) + (i - g.nxgs)] = run;
-  }
-}
-
-// one warp per source cell and species: stable scatter B -> A
-__global__ void __launch_bounds__(TPB) k_scatter3(Geo g, Ptcl B, Ptcl A, const double* __restrict__ id_in,
-                                                  double* __restrict__ id_out, const int* __restrict__ cs,
-                                                  const int* __restrict__ cs_new, const int* __restrict__ off27,
-                                                  const unsigned char* __restrict__ dst_off, int nxs, int nxe) {
-  __shared__ int s_base[TPB / 32][32];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int nxr = nxe - nxs + 1;
-  const size_t ncell = (size_t)g.nx * g.nyl * g.nzl;
-  const long long nwork = (long long)nxr * g.nyl * g.nzl * 2;
-  for (long long w = warp; w < nwork; w += nwarps) {
-    const int isp = (int)(w / ((long long)nxr * g.nyl * g.nzl));
-    const long long c = w % ((long long)nxr * g.nyl * g.nzl);
-    const int i = nxs + (int)(c % nxr);
-    const int j = g.nys + (int)((c / nxr) % g.nyl);
-    const int k = g.nzs + (int)(c / ((long long)nxr * g.nyl));
-    const int* row = cs + (size_t)g.pen(j, k, isp) * (g.nx + 1) + (i - g.nxgs);
-    const int beg = row[0], end = row[1];
-    if (beg == end) continue;
-    const size_t src = ((size_t)(k - g.nzs) * g.nyl + (j - g.nys)) * g.nx + (i - g.nxgs);
-    __syncwarp();
-    if (lane < 27) {
-      // destination cell of offset `lane`, periodic wrap
-      int di = lane % 3 - 1, dj = (lane / 3) % 3 - 1, dk = lane / 9 - 1;
-      int ti = i + di, tj = j + dj, tk = k + dk;
-      if (ti < g.nxgs) ti += g.nx; else if (ti > g.nxge) ti -= g.nx;
-      if (tj < g.nygs) tj += g.ny; else if (tj > g.nyge) tj -= g.ny;
-      if (tk < g.nzgs) tk += g.nz; else if (tk > g.nzge) tk -= g.nz;
-      s_base[wib][lane] = cs_new[(size_t)g.pen(tj, tk, isp) * (g.nx + 1) + (ti - g.nxgs)]
-                          + off27[((size_t)lane * 2 + isp) * ncell + src];
-    }
-    __syncwarp();
-    for (int p0 = beg; p0 < end; p0 += 32) {
-      const int p = p0 + lane;
-      const bool act = p < end;
-      const int o = act ? dst_off[p] : 31;
-      const unsigned mask = __match_any_sync(0xffffffffu, o);
-      const int rank = __popc(mask & ((1u << lane) - 1u));
-      int d = 0;
-      if (act) d = s_base[wib][o] + rank;
-      __syncwarp();
-      if (act && rank == 0) s_base[wib][o] += __popc(mask);   // group leader advances the cursor
-      __syncwarp();
-      if (act) {
-        A.c[0][d] = B.c[0][p]; A.c[1][d] = B.c[1][p]; A.c[2][d] = B.c[2][p];
-        A.c[3][d] = B.c[3][p]; A.c[4][d] = B.c[4][p]; A.c[5][d] = B.c[5][p];
-        id_out[d] = id_in[p];
-      }
-    }
-  }
-}
-
-__global__ void k_np2_poff(Geo g, const int* __restrict__ cs, int* __restrict__ np2, int* __restrict__ poff, int* flags) {
-  for (int pen = blockIdx.x * blockDim.x + threadIdx.x; pen <= g.npen; pen += gridDim.x * blockDim.x) {
-    if (pen < g.npen) {
-      const int* row = cs + (size_t)pen * (g.nx + 1);
-      int n = row[g.nx] - row[0];
-      np2[pen] = n;
-      poff[pen] = row[0];
-      if (n > g.np) atomicOr(flags, 1);
-    } else {
-      poff[pen] = cs[(size_t)(g.npen - 1) * (g.nx + 1) + g.nx];
     }
   }
 }
@@ -450,16 +370,7 @@ int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double /*u
     wm_set_error("fused path: only 3-D periodic (Weibel order) so far");
     return WM_ERR_ARG;
   }
-  const size_t ncell = (size_t)g.nx * g.nyl * g.nzl;
-  if (!ctx->cnt27) {
-    WM_CUDA(cudaMalloc(&ctx->cnt27, ncell * 2 * 27 * sizeof(int)));
-    WM_CUDA(cudaMemsetAsync(ctx->cnt27, 0, ncell * 2 * 27 * sizeof(int), ctx->stream));
-  }
-  if (ctx->dst_off_cap < ctx->cap) {
-    if (ctx->dst_off) cudaFree(ctx->dst_off);
-    WM_CUDA(cudaMalloc(&ctx->dst_off, ctx->cap));
-    ctx->dst_off_cap = ctx->cap;
-  }
+  WM_TRY(wm_sort_prepare(ctx));
   static bool attr_set = false;
   if (!attr_set) {
     WM_CUDA(cudaFuncSetAttribute(k_fused3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
@@ -467,43 +378,10 @@ int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double /*u
   }
   const int ngx = (nxe - nxs + 1 + G - 1) / G;
   const int blocks = ngx * g.nyl * g.nzl;
-  k_fused3<0><<<blocks, TPB, sizeof(Smem), ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->tmpf, ctx->uj, ctx->cnt27,
-                                                           ctx->dst_off, ctx->flags, nxs, nxe, ngx);
+  k_fused3<0><<<blocks, TPB, sizeof(Smem), ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid], ctx->cs,
+                                                           ctx->tmpf, ctx->uj, ctx->cnt27, ctx->cs_new, ctx->dst_off,
+                                                           ctx->flags, nxs, nxe, ngx);
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
 }
 
-// sort that follows the fused kernel: offsets -> scan -> stable scatter
-int wm_k_sort_fused(wm_ctx* ctx, int nxs, int nxe) {
-  const Geo& g = ctx->g;
-  const size_t ncs = (size_t)g.npen * (g.nx + 1);
-  const size_t ncell = (size_t)g.nx * g.nyl * g.nzl;
-  WM_CUDA(cudaMemsetAsync(ctx->cs_new, 0, (ncs + 1) * sizeof(int), ctx->stream));
-  {
-    const long long n = (long long)ncell * 2;
-    const int blocks = (int)std::min<long long>((n + TPB - 1) / TPB, 148LL * 16);
-    k_offsets3<<<blocks, TPB, 0, ctx->stream>>>(g, ctx->cnt27, ctx->cs_new, nxs, nxe);
-    WM_LAUNCH_CHECK(ctx);
-  }
-  size_t need = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->cs_new, ctx->cs_new, (int)ncs, ctx->stream);
-  if (need > ctx->scan_tmp_bytes) {
-    if (ctx->scan_tmp) cudaFree(ctx->scan_tmp);
-    WM_CUDA(cudaMalloc(&ctx->scan_tmp, need));
-    ctx->scan_tmp_bytes = need;
-  }
-  WM_CUDA(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp, need, ctx->cs_new, ctx->cs_new, (int)ncs, ctx->stream));
-  ctx->launches += 2;
-  if (ctx->ntot > 0) {
-    const long long nwork = (long long)(nxe - nxs + 1) * g.nyl * g.nzl * 2;
-    const int blocks = (int)std::min<long long>((nwork * 32 + TPB - 1) / TPB, 148LL * 8);
-    k_scatter3<<<blocks, TPB, 0, ctx->stream>>>(g, ctx->B, ctx->A, ctx->id[ctx->cid], ctx->id[1 - ctx->cid], ctx->cs,
-                                                ctx->cs_new, ctx->cnt27, ctx->dst_off, nxs, nxe);
-    WM_LAUNCH_CHECK(ctx);
-  }
-  std::swap(ctx->cs, ctx->cs_new);
-  ctx->cid = 1 - ctx->cid;
-  k_np2_poff<<<wm_blocks(g.npen + 1, TPB), TPB, 0, ctx->stream>>>(g, ctx->cs, ctx->np2, ctx->poff, ctx->flags);
-  WM_LAUNCH_CHECK(ctx);
-  return WM_OK;
-}

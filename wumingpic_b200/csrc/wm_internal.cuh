@@ -21,6 +21,9 @@ struct Geo {
   int ny, nz;         // global y / z cells
   int bx, by, bz;     // box dims incl. ghosts
   int npen;           // pencils on this rank over all species: nsp*nyl*nzl
+  int multi;          // 1: the slab-axis neighbours (z in 3-D, y in 2-D) are other ranks -> ghost destination rows
+  int ngrow;          // pencils per ghost plane and species (nyl in 3-D, 1 in 2-D)
+  int nrows;          // destination rows of the sort: npen local + (multi ? 2*nsp*ngrow ghost rows : 0)
   int bc;
   double delx, delt, c, gfac, d_delx, d_delt;
   double q[2], r[2];
@@ -43,8 +46,6 @@ struct Ptcl {
   double* c[6];  // 3-D: x y z ux uy uz ; 2-D: x y ux uy uz (c[5] unused)
 };
 
-struct Halo;  // wm_halo.cu
-
 struct wm_ctx {
   wm_params prm;
   Geo g;
@@ -60,12 +61,14 @@ struct wm_ctx {
   // cell index: cs[pen*(nx+1) + (i-nxgs)] = absolute start of cell i of pencil pen; entry nx = pencil end
   int* cs = nullptr;
   int* cs_new = nullptr;   // histogram / scan target of the sort
-  int* cursor = nullptr;   // scatter cursors
   int* np2 = nullptr;      // particles per pencil (npen)
   int* poff = nullptr;     // pencil offsets (npen+1), absolute
   int* flags = nullptr;    // sticky device error flags
-  int* cnt27 = nullptr;    // fused path: per (offset, species, source cell) counts -> offsets
-  unsigned char* dst_off = nullptr;  // fused path: destination offset (0..26) of every pushed particle
+  int* cnt27 = nullptr;    // per (offset, species, source cell) counts -> offsets (wm_sort.cu)
+  unsigned char* dst_off = nullptr;  // destination offset (0..26) of every pushed particle
+  int* inc = nullptr;      // multi-rank: arrivals per edge-plane cell announced by the neighbours [side][isp][t][0..nx]
+  int* inc_off = nullptr;  // exclusive scan of inc (+ total)
+  int* totals = nullptr;   // device copy of the six per-step totals (k_totals)
   size_t dst_off_cap = 0;
   int use_fused = 1;
   void* scan_tmp = nullptr;
@@ -86,7 +89,7 @@ struct wm_ctx {
   // state machine
   bool gp_valid = false;     // set B holds the pushed state
   bool keys_valid = false;   // migration pass done (histogram in cs_new)
-  bool df_zeroed = false;
+  int last_nxs = 0, last_nxe = 0;  // x range of the last particle__solv (bc__particle_y[z] has no range argument)
   // comm
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
@@ -130,10 +133,12 @@ int wm_k_tmpf(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_push(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_deposit(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double u0);
-int wm_k_sort_fused(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_bc_x(wm_ctx* ctx, int nxs, int nxe, int kind, double u0);
-int wm_k_migrate(wm_ctx* ctx);
+// sort / migration (wm_sort.cu)
+int wm_sort_prepare(wm_ctx* ctx);
+int wm_k_classify(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_sort(wm_ctx* ctx, int nxs, int nxe);
+int wm_enable_slab_migration(wm_ctx* ctx);
 int wm_k_energy(wm_ctx* ctx, double* out_host);
 int wm_k_gauss(wm_ctx* ctx, double* out_host);
 int wm_k_load_weibel(wm_ctx* ctx, int n0, double v_thi, double v_the, double t_ani, double b0, unsigned long long seed);
@@ -152,3 +157,7 @@ int wm_k_update(wm_ctx* ctx, int nxs, int nxe);
 // comm (wm_comm.cu)
 int wm_comm_sendrecv(wm_ctx* ctx, int axis, int dir_down, const double* snd, double* rcv, size_t n);
 int wm_comm_allreduce_sum(wm_ctx* ctx, double* dev_buf, int n);
+int wm_comm_group_begin(wm_ctx* ctx);
+int wm_comm_group_end(wm_ctx* ctx);
+int wm_comm_send(wm_ctx* ctx, int peer, const void* buf, size_t bytes);
+int wm_comm_recv(wm_ctx* ctx, int peer, void* buf, size_t bytes);

@@ -1,5 +1,5 @@
 // wm_particles.cu -- particle kernels: field staging, Buneman-Boris push, Esirkepov deposit,
-// x boundary, y/z re-binning and the cell-ordered counting sort.
+// x boundary.  (y/z re-binning, migration and the cell-ordered sort live in wm_sort.cu.)
 //
 //   particle__solv                3d/common/particle.f90:52-233   [2d/common/particle.f90:48-179]
 //   ele_cur                       3d/common/field.f90:211-406     [2d/common/field.f90:189-316]
@@ -12,8 +12,6 @@
 // Each warp owns one cell at a time and its lanes walk that cell's particles, so every global
 // load/store is a contiguous 256-byte run and all lanes share the same 27-cell field stencil.
 #include "wm_internal.cuh"
-
-#include <cub/device/device_scan.cuh>
 
 namespace {
 
@@ -319,87 +317,6 @@ __global__ void k_bc_x_periodic(Geo g, double* __restrict__ x, long long n) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K13 + K14: y/z periodic wrap, destination cell, histogram; then scan and scatter.
-// The reference re-bins into pencils (boundary_periodic.f90:152-185) and then counting-sorts each
-// pencil in x (sort.f90:55-86); on the device both are one global counting sort whose key is
-// (species, k, j, i).  Only the per-cell particle SETS are defined by the reference (the order
-// inside a cell depends on OpenMP lock order there, on atomic order here).
-// ---------------------------------------------------------------------------------------------
-template <int D>
-__device__ __forceinline__ int dest_slot(const Geo& g, double x, double y, double z, int isp, int nxs, int nxe,
-                                         int* flags) {
-  // Positions were wrapped by the boundary kernels.  A wrap can round onto the upper edge exactly
-  // (x == (nxge+1)*delx); the reference keeps such a particle in the last cell/pencil (its pencil
-  // was fixed before the wrap, boundary_periodic.f90:156-178), so that one case is clamped silently.
-  int i = (int)x;  // sort.f90:65 (no d_delx)
-  int jpos = (int)(y * g.d_delx);
-  int kpos = D == 3 ? (int)(z * g.d_delx) : 0;
-  if (i == nxe + 1) i = nxe;
-  if (jpos == g.nye + 1 && g.nye == g.nyge) jpos = g.nye;
-  if (D == 3 && kpos == g.nze + 1 && g.nze == g.nzge) kpos = g.nze;
-  bool bad = (i < nxs) | (i > nxe) | (jpos < g.nys) | (jpos > g.nye);
-  if (D == 3) bad |= (kpos < g.nzs) | (kpos > g.nze);
-  if (bad) {
-    atomicOr(flags, 2);
-    i = min(max(i, nxs), nxe);
-    jpos = min(max(jpos, g.nys), g.nye);
-    if (D == 3) kpos = min(max(kpos, g.nzs), g.nze);
-  }
-  return g.pen(jpos, kpos, isp) * (g.nx + 1) + (i - g.nxgs);
-}
-
-// boundary_periodic__particle_yz, coordinate part (boundary_periodic.f90:156-171): periodic wrap of y (and z)
-template <int D>
-__global__ void k_wrap_yz(Geo g, Ptcl B, long long n) {
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
-    double y = B.c[1][p];
-    int jpos = (int)(y * g.d_delx);
-    if (jpos <= g.nygs - 1) B.c[1][p] = y + (g.nyge - g.nygs + 1) * g.delx;
-    else if (jpos >= g.nyge + 1) B.c[1][p] = y - (g.nyge - g.nygs + 1) * g.delx;
-    if (D == 3) {
-      double z = B.c[2][p];
-      int kpos = (int)(z * g.d_delx);
-      if (kpos <= g.nzgs - 1) B.c[2][p] = z + (g.nzge - g.nzgs + 1) * g.delx;
-      else if (kpos >= g.nzge + 1) B.c[2][p] = z - (g.nzge - g.nzgs + 1) * g.delx;
-    }
-  }
-}
-
-template <int D>
-__global__ void k_hist(Geo g, Ptcl B, long long n, long long n_sp0, int* __restrict__ hist, int* flags, int nxs, int nxe) {
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
-    int slot = dest_slot<D>(g, B.c[0][p], B.c[1][p], D == 3 ? B.c[2][p] : 0.0, p < n_sp0 ? 0 : 1, nxs, nxe, flags);
-    atomicAdd(hist + slot, 1);
-  }
-}
-
-template <int D>
-__global__ void k_scatter(Geo g, Ptcl B, Ptcl A, const double* __restrict__ id_in, double* __restrict__ id_out,
-                          long long n, long long n_sp0, int* __restrict__ cursor, int* flags, int nxs, int nxe) {
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
-    double x = B.c[0][p], y = B.c[1][p], z = D == 3 ? B.c[2][p] : 0.0;
-    int slot = dest_slot<D>(g, x, y, z, p < n_sp0 ? 0 : 1, nxs, nxe, flags);
-    int d = atomicAdd(cursor + slot, 1);
-    A.c[0][d] = x;
-    A.c[1][d] = y;
-    if (D == 3) A.c[2][d] = z;
-    A.c[D][d] = B.c[D][p];
-    A.c[D + 1][d] = B.c[D + 1][p];
-    A.c[D + 2][d] = B.c[D + 2][p];
-    id_out[d] = id_in[p];
-  }
-}
-
-__global__ void k_np2_from_cs(Geo g, const int* __restrict__ cs, int* __restrict__ np2, int* flags) {
-  for (int pen = blockIdx.x * blockDim.x + threadIdx.x; pen < g.npen; pen += gridDim.x * blockDim.x) {
-    const int* row = cs + (size_t)pen * (g.nx + 1);
-    int n = row[g.nx] - row[0];
-    np2[pen] = n;
-    if (n > g.np) atomicOr(flags, 1);  // "memory over (np2 > np)"
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // host <-> device layout conversion: the reference's padded AoS pencils <-> SoA
 // stage holds [pencil][slot < maxcnt][ndim]
 // ---------------------------------------------------------------------------------------------
@@ -431,11 +348,6 @@ __global__ void k_soa_to_aos(Geo g, double* __restrict__ stage, Ptcl src, const 
     for (int c = 0; c < nd - 1; ++c) s[c] = src.c[c][d];
     s[nd - 1] = src_id[d];
   }
-}
-
-__global__ void k_poff_from_cs(Geo g, const int* __restrict__ cs, int* __restrict__ poff) {
-  for (int pen = blockIdx.x * blockDim.x + threadIdx.x; pen <= g.npen; pen += gridDim.x * blockDim.x)
-    poff[pen] = pen < g.npen ? cs[(size_t)pen * (g.nx + 1)] : cs[(size_t)(g.npen - 1) * (g.nx + 1) + g.nx];
 }
 
 int grid_for(long long n) {
@@ -486,58 +398,6 @@ int wm_k_bc_x(wm_ctx* ctx, int /*nxs*/, int /*nxe*/, int kind, double /*u0*/) {
   }
   if (ctx->ntot == 0) return WM_OK;
   k_bc_x_periodic<<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B.c[0], ctx->ntot);
-  WM_LAUNCH_CHECK(ctx);
-  return WM_OK;
-}
-
-int wm_k_migrate(wm_ctx* ctx) {
-  const Geo& g = ctx->g;
-  if (ctx->ntot == 0) return WM_OK;
-  if (g.dim == 3)
-    k_wrap_yz<3><<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B, ctx->ntot);
-  else
-    k_wrap_yz<2><<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B, ctx->ntot);
-  WM_LAUNCH_CHECK(ctx);
-  return WM_OK;
-}
-
-int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
-  const Geo& g = ctx->g;
-  const size_t ncs = (size_t)g.npen * (g.nx + 1);
-  const long long n0 = ctx->n_sp0;
-  WM_CUDA(cudaMemsetAsync(ctx->cs_new, 0, (ncs + 1) * sizeof(int), ctx->stream));
-  if (ctx->ntot > 0) {
-    if (g.dim == 3)
-      k_hist<3><<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B, ctx->ntot, n0, ctx->cs_new, ctx->flags, nxs, nxe);
-    else
-      k_hist<2><<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B, ctx->ntot, n0, ctx->cs_new, ctx->flags, nxs, nxe);
-    WM_LAUNCH_CHECK(ctx);
-  }
-  // exclusive scan of the histogram -> absolute cell starts (the new cumcnt)
-  size_t need = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->cs_new, ctx->cs_new, (int)ncs, ctx->stream);
-  if (need > ctx->scan_tmp_bytes) {
-    if (ctx->scan_tmp) cudaFree(ctx->scan_tmp);
-    WM_CUDA(cudaMalloc(&ctx->scan_tmp, need));
-    ctx->scan_tmp_bytes = need;
-  }
-  WM_CUDA(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp, need, ctx->cs_new, ctx->cs_new, (int)ncs, ctx->stream));
-  ctx->launches += 2;
-  WM_CUDA(cudaMemcpyAsync(ctx->cursor, ctx->cs_new, ncs * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
-  if (ctx->ntot > 0) {
-    if (g.dim == 3)
-      k_scatter<3><<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B, ctx->A, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
-                                                                 ctx->ntot, n0, ctx->cursor, ctx->flags, nxs, nxe);
-    else
-      k_scatter<2><<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B, ctx->A, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
-                                                                 ctx->ntot, n0, ctx->cursor, ctx->flags, nxs, nxe);
-    WM_LAUNCH_CHECK(ctx);
-  }
-  std::swap(ctx->cs, ctx->cs_new);
-  ctx->cid = 1 - ctx->cid;
-  k_np2_from_cs<<<wm_blocks(g.npen, TPB), TPB, 0, ctx->stream>>>(g, ctx->cs, ctx->np2, ctx->flags);
-  WM_LAUNCH_CHECK(ctx);
-  k_poff_from_cs<<<wm_blocks(g.npen + 1, TPB), TPB, 0, ctx->stream>>>(g, ctx->cs, ctx->poff);
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
 }

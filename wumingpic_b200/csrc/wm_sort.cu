@@ -1,0 +1,567 @@
+// wm_sort.cu -- particle re-binning, inter-GPU migration and the cell-ordered sort, as ONE deterministic
+// counting sort keyed by (species, k, j, i):
+//
+//   boundary_*__particle_y[z]  3d/common/boundary_periodic.f90:104-455  [2d :99-248]
+//   sort__bucket               3d/common/sort.f90:40-88                 [2d/common/sort.f90:36-82]
+//
+// The reference moves a particle at most one cell per step in every direction (it assumes so at
+// boundary_periodic.f90:152-185: movers go to pencil jpos,kpos in [nys-1,nye+1] x [nzs-1,nze+1]).  So the whole
+// re-binning is described by one byte per particle -- the destination offset o = (di+1) + 3(dj+1) + 9(dk+1)
+// relative to its source cell -- and a 27 x ncell count matrix.  From those:
+//   producers   the fused push kernel (wm_fused.cu) or k_classify below write the pushed set B "two-ended" inside every
+//               source cell -- stayers packed at the front, leavers at the back with their offset byte -- one count
+//               line per (cell, species), and add each group's size to the histogram of its destination cell
+//               (integer RED; this is the histogram sort.f90:62-69 builds with a per-pencil loop);
+//   scan        exclusive sum over all cells = the new cumcnt (sort.f90:71-74), as absolute offsets;
+//   k_gather    per DESTINATION run of 8 cells (one CTA): prefix over the <= 27 source groups of each of its cells,
+//               block copy of the stayers, ballot-ranked pick of the arrivals out of the leaver zones of the <= 90
+//               source cells around it, staged in shared memory and written with full sectors.  No atomics on the
+//               data path; the order inside every cell is deterministic:
+//               [local sources by offset, each in zone order][arrivals from the low neighbour][from the high one].
+// Multi-GPU (slabs along the last axis: z in 3-D, y in 2-D; the reference's rank grid with nproc_j = 1): cells one
+// layer outside the slab are extra destination rows ("ghost rows") of the same sort, placed behind the local
+// particles.  Their per-cell counts travel first (the reference's count message, boundary_periodic.f90:192,243), are
+// added to the receiver's histogram before its scan, and the payload (the ghost rows of the 6 coordinate arrays and
+// the ID array, already sorted by destination cell) follows while the local scatter runs; k_insert drops each
+// arriving cell group into the slots reserved at the end of its cell.  The bulk particles are read once and
+// written once per step; only movers across a slab face make a second trip.
+#include "wm_cells.cuh"
+
+#include <algorithm>
+#include <cub/device/device_scan.cuh>
+
+namespace {
+
+constexpr int TPB = 256;
+
+// ---------------------------------------------------------------------------------------------
+// boundary_*__particle_y[z] on the pushed set (per-procedure path): movers are the particles with
+// int(y/delx) != j or int(z/delx) != k (boundary_periodic.f90:152-160); their coordinate is wrapped by the
+// GLOBAL periodic condition (:161-171).  x was wrapped/reflected by bc__particle_x; sort__bucket's key is int(x)
+// (sort.f90:65).  One warp per (cell, species); the classified set is written two-ended into P (the dead old set).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(TPB) k_classify(Geo g, Ptcl B, Ptcl P, const double* __restrict__ id_in,
+                                                  double* __restrict__ id_out, const int* __restrict__ cs,
+                                                  int* __restrict__ cnt, int* __restrict__ hist,
+                                                  unsigned char* __restrict__ dst_off, int* flags, int nxs, int nxe) {
+  __shared__ int s_cnt[TPB / 32][32];
+  constexpr int NC = D == 3 ? 6 : 5;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nxr = nxe - nxs + 1;
+  const int npl = g.nyl * g.nzl;
+  const long long per_sp = (long long)nxr * npl;
+  const double len_y = (g.nyge - g.nygs + 1) * g.delx, len_z = (g.nzge - g.nzgs + 1) * g.delx;
+  for (long long w = warp; w < per_sp * 2; w += nwarps) {
+    const int isp = (int)(w / per_sp);
+    const long long wi = w % per_sp;
+    int j, k;
+    wm_strip_pencil(g, (int)(wi / nxr), j, k);
+    const int i = nxs + (int)(wi % nxr);
+    const int* row = cs + (size_t)g.pen(j, k, isp) * (g.nx + 1) + (i - g.nxgs);
+    const int beg = row[0], end = row[1];
+    s_cnt[wib][lane] = 0;
+    __syncwarp();
+    int nfront = 0, nback = 0;
+    for (int p0 = beg; p0 < end; p0 += 32) {
+      const int p = p0 + lane;
+      const bool act = p < end;
+      double v[NC], idv = 0.0;
+      int o = 13;
+      if (act) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) v[c] = B.c[c][p];
+        idv = id_in[p];
+        int ix = (int)v[0];                          // sort.f90:65: no d_delx
+        if (ix == nxe + 1) ix = nxe;                 // a periodic wrap that rounded onto the upper edge stays in the last cell
+        int di = ix - i;
+        if (di > 1) di -= g.nx; else if (di < -1) di += g.nx;
+        const int jpos = (int)(v[1] * g.d_delx);
+        int dj = jpos - j, dk = 0;
+        if (jpos <= g.nygs - 1) v[1] = D == 2 ? __dadd_rd(v[1], len_y) : v[1] + len_y;
+        else if (jpos >= g.nyge + 1) v[1] = D == 2 ? __dadd_rd(v[1], -len_y) : v[1] - len_y;
+        if (D == 3) {
+          const int kpos = (int)(v[2] * g.d_delx);
+          dk = kpos - k;
+          if (kpos <= g.nzgs - 1) v[2] = v[2] + len_z;
+          else if (kpos >= g.nzge + 1) v[2] = v[2] - len_z;
+        }
+        if (di < -1 || di > 1 || dj < -1 || dj > 1 || dk < -1 || dk > 1) {
+          atomicOr(flags, 2);
+          di = max(-1, min(1, di)); dj = max(-1, min(1, dj)); dk = max(-1, min(1, dk));
+        }
+        o = (di + 1) + 3 * (dj + 1) + 9 * (dk + 1);
+        atomicAdd(&s_cnt[wib][o], 1);
+      }
+      const unsigned ms = __ballot_sync(0xffffffffu, act && o == 13);
+      const unsigned ml = __ballot_sync(0xffffffffu, act && o != 13);
+      if (act) {
+        const unsigned lower = (1u << lane) - 1u;
+        const int pos = o == 13 ? beg + nfront + __popc(ms & lower) : end - 1 - (nback + __popc(ml & lower));
+#pragma unroll
+        for (int c = 0; c < NC; ++c) P.c[c][pos] = v[c];
+        id_out[pos] = idv;
+        dst_off[pos] = (unsigned char)o;
+      }
+      nfront += __popc(ms);
+      nback += __popc(ml);
+    }
+    __syncwarp();
+    const size_t cell = wm_cell_index(g, i, j, k);
+    const int c = lane < 27 ? s_cnt[wib][lane] : 0;
+    cnt[(cell * 2 + isp) * WM_CNT_LINE + lane] = c;
+    if (c > 0) {
+      int drow, ti;
+      if (wm_dest_of(g, i, j, k, lane, isp, nxs, nxe, drow, ti)) atomicAdd(hist + (size_t)drow * (g.nx + 1) + (ti - g.nxgs), c);
+      else atomicOr(flags, 2);
+    }
+    __syncwarp();
+  }
+}
+
+// hist(edge-plane cell) += arrivals announced by the neighbours; inc = [side][isp][t][0..nx]
+__global__ void k_add_incoming(Geo g, const int* __restrict__ inc, int* __restrict__ hist) {
+  const int per_side = g.nsp * g.ngrow * (g.nx + 1);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 2 * per_side; e += gridDim.x * blockDim.x) {
+    const int side = e / per_side, r = e % per_side;
+    const int ii = r % (g.nx + 1), t = (r / (g.nx + 1)) % g.ngrow, isp = r / ((g.nx + 1) * g.ngrow);
+    if (ii == g.nx) continue;
+    const int c = inc[e];
+    if (c == 0) continue;
+    int j, k;
+    if (g.dim == 3) { j = g.nys + t; k = side == 0 ? g.nzs : g.nze; }
+    else { j = side == 0 ? g.nys : g.nye; k = 0; }
+    atomicAdd(hist + (size_t)g.pen(j, k, isp) * (g.nx + 1) + ii, c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_gather: the data movement of the sort, destination-centric (see the file header).
+// (A source-centric scatter writes 10-20 partial 32-byte sectors per cell and array, and every partial-sector
+//  write miss costs a DRAM sector fill: measured 2.1x read / 1.5x write amplification, profiles/r01_sort.md.)
+// ---------------------------------------------------------------------------------------------
+constexpr int GD = 8;       // destination cells per CTA
+constexpr int CAP = 768;    // tile capacity in particles; the (rare) overflow of a dense run goes straight to global
+constexpr int MAXSLOT = (GD + 2) * 9;
+
+struct Slot { int beg, end, obase, pos[3]; };   // leaver zone of one source cell; run position per di, or -1
+
+// source cell (si,sj,sk) of destination (i, virtual j, virtual k) and offset o; need_dl: required slab-axis offset of
+// a ghost row's sources, 2 = any (local rows)
+__device__ __forceinline__ bool src_of(const Geo& g, int i, int j, int k, int need_dl, int o, int nxs, int nxe, int& si,
+                                       int& sj, int& sk) {
+  const int di = o % 3 - 1, dj = (o / 3) % 3 - 1, dk = o / 9 - 1;
+  if (g.dim == 2 && dk != 0) return false;
+  const int dl = g.dim == 3 ? dk : dj;
+  if (need_dl != 2 && dl != need_dl) return false;
+  si = i - di; sj = j - dj; sk = k - dk;
+  if (g.bc == WM_BC_PERIODIC) si = wm_unwrap(si, g.nxgs, g.nxge, g.nx);
+  if (si < nxs || si > nxe) return false;
+  if (g.dim == 3) {
+    sj = wm_unwrap(sj, g.nys, g.nye, g.nyl);
+    if (sk < g.nzs || sk > g.nze) {
+      if (g.multi) return false;                 // that source lives on the neighbour rank
+      sk = wm_unwrap(sk, g.nzs, g.nze, g.nzl);
+    }
+  } else {
+    sk = 0;
+    if (sj < g.nys || sj > g.nye) {
+      if (g.multi) return false;
+      sj = wm_unwrap(sj, g.nys, g.nye, g.nyl);
+    }
+  }
+  return true;
+}
+
+template <int D>
+__global__ void __launch_bounds__(TPB) k_gather(Geo g, Ptcl B, Ptcl A, const double* __restrict__ id_in,
+                                                double* __restrict__ id_out, const int* __restrict__ cs,
+                                                const int* __restrict__ cs_new, const int* __restrict__ cnt,
+                                                const unsigned char* __restrict__ dst_off, int nxs, int nxe, int ngx) {
+  constexpr int NC = D == 3 ? 6 : 5;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* tile = reinterpret_cast<double*>(smem_raw);                 // [NC+1][CAP], laid out like the output run
+  int* s_new = reinterpret_cast<int*>(tile + (NC + 1) * CAP);         // [GD+1] new cell starts of the run
+  int* s_P = s_new + GD + 1;                                          // [GD][28] group sizes -> exclusive prefix per cell
+  int* s_stay = s_P + GD * 28;                                        // [GD][2] source start of the stayers, count
+  int* s_cur = s_stay + GD * 2;                                       // [warps][4] running position per di of a slot
+  Slot* s_slot = reinterpret_cast<Slot*>(s_cur + 4 * (TPB / 32));     // [MAXSLOT]
+  const int t = threadIdx.x, lane = t & 31, wib = t >> 5;
+  // ---- which destination run: local rows in strip order, ghost rows last; x groups fastest ----
+  const int gx = blockIdx.x % ngx;
+  const int wrow = blockIdx.x / ngx;
+  const int npl = g.nyl * g.nzl;
+  int isp, j, k, row, need_dl = 2;
+  if (wrow < g.npen) {
+    isp = wrow / npl;
+    wm_strip_pencil(g, wrow % npl, j, k);
+    row = g.pen(j, k, isp);
+  } else {
+    row = wrow;
+    const int r = row - g.npen;
+    const int side = r / (g.nsp * g.ngrow);
+    isp = (r / g.ngrow) % g.nsp;
+    const int tt = r % g.ngrow;
+    need_dl = side == 0 ? -1 : 1;
+    if (D == 3) { j = g.nys + tt; k = side == 0 ? g.nzs - 1 : g.nze + 1; }
+    else { j = side == 0 ? g.nys - 1 : g.nye + 1; k = 0; }
+  }
+  const int ia = nxs + gx * GD;
+  const int ncg = min(GD, nxe - ia + 1);
+  if (t <= GD) s_new[t] = cs_new[(size_t)row * (g.nx + 1) + (ia - g.nxgs) + min(t, ncg)];
+  // ---- group sizes of every destination cell of the run ----
+  if (t < GD * 27) {
+    const int d = t / 27, o = t % 27;
+    int c = 0, si, sj, sk;
+    if (d < ncg && src_of(g, ia + d, j, k, need_dl, o, nxs, nxe, si, sj, sk))
+      c = cnt[(wm_cell_index(g, si, sj, sk) * 2 + isp) * WM_CNT_LINE + o];
+    s_P[d * 28 + o] = c;
+  }
+  __syncthreads();
+  const int base = s_new[0];
+  const int ntile = s_new[ncg] - base;
+  if (ntile == 0) return;
+  if (t < ncg) {
+    int run = 0;
+    for (int o = 0; o < 27; ++o) {
+      const int c = s_P[t * 28 + o];
+      s_P[t * 28 + o] = run;
+      run += c;
+      if (o == 13) s_stay[2 * t + 1] = need_dl == 2 ? c : 0;
+    }
+    s_stay[2 * t] = need_dl == 2 ? cs[(size_t)row * (g.nx + 1) + (ia + t - g.nxgs)] : 0;
+  }
+  __syncthreads();
+  // ---- source slots: unwrapped x in [ia-1, ia+ncg], pencil offsets (sj,sk); only the leaver zone is scanned ----
+  const int nsx = ncg + 2;
+  const int nslot = nsx * (D == 3 ? 9 : 3);
+  if (t < nslot) {
+    const int sx = ia - 1 + t % nsx;
+    const int sjk = t / nsx;
+    const int sj = sjk % 3 - 1, sk = D == 3 ? sjk / 3 - 1 : 0;
+    Slot sl;
+    sl.beg = sl.end = 0;
+    sl.obase = 3 * (1 - sj) + 9 * (1 - sk);                             // offsets with dj = -sj, dk = -sk: obase + (di+1)
+    // the slot's particles need offset (di, -sj, -sk) with sx + di inside the run; the source must be reachable
+    int si, pj, pk;
+    const int o_mid = sl.obase + 1;                                     // di = 0 representative for the pencil part of src_of
+    bool ok = src_of(g, sx, j, k, need_dl, o_mid, nxs - 1, nxe + 1, si, pj, pk);   // x handled below (sx is unwrapped)
+    si = sx;
+    if (g.bc == WM_BC_PERIODIC) si = wm_unwrap(si, g.nxgs, g.nxge, g.nx);
+    if (si < nxs || si > nxe) ok = false;
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int d = sx + (r - 1) - ia;
+      int v = -1;
+      if (ok && d >= 0 && d < ncg && !(sl.obase + r == 13)) v = (s_new[d] - base) + s_P[d * 28 + sl.obase + r];
+      sl.pos[r] = v;
+      any = any || v >= 0;
+    }
+    if (ok && any) {
+      const size_t sc = wm_cell_index(g, si, pj, pk);
+      const int* crow = cs + (size_t)g.pen(pj, pk, isp) * (g.nx + 1) + (si - g.nxgs);
+      sl.beg = crow[0] + cnt[(sc * 2 + isp) * WM_CNT_LINE + 13];
+      sl.end = crow[1];
+    }
+    s_slot[t] = sl;
+  }
+  __syncthreads();
+  // ---- stayers: block copies ----
+  for (int d = wib; d < ncg; d += TPB / 32) {
+    const int sb = s_stay[2 * d], n = s_stay[2 * d + 1];
+    const int dp = (s_new[d] - base) + s_P[d * 28 + 13];
+    for (int e = lane; e < n; e += 32) {
+      const int pos = dp + e;
+      if (pos < CAP) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) tile[c * CAP + pos] = B.c[c][sb + e];
+        tile[NC * CAP + pos] = id_in[sb + e];
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) A.c[c][base + pos] = B.c[c][sb + e];
+        id_out[base + pos] = id_in[sb + e];
+      }
+    }
+  }
+  // ---- arrivals: ballot-ranked pick out of the leaver zones ----
+  for (int q = wib; q < nslot; q += TPB / 32) {
+    const int beg = s_slot[q].beg, end = s_slot[q].end;
+    if (beg >= end) continue;                                           // warp-uniform
+    const int obase = s_slot[q].obase;
+    __syncwarp();
+    if (lane < 3) s_cur[wib * 4 + lane] = s_slot[q].pos[lane];
+    __syncwarp();
+    for (int p0 = beg; p0 < end; p0 += 32) {
+      const int p = p0 + lane;
+      int key = 3;                                                      // 0..2: di+1 of a particle we take; 3: not ours
+      if (p < end) {
+        const int r = (int)dst_off[p] - obase;
+        if (r >= 0 && r < 3 && s_cur[wib * 4 + r] >= 0) key = r;
+      }
+      const unsigned m0 = __ballot_sync(0xffffffffu, key == 0);
+      const unsigned m1 = __ballot_sync(0xffffffffu, key == 1);
+      const unsigned m2 = __ballot_sync(0xffffffffu, key == 2);
+      const unsigned mine = key == 0 ? m0 : (key == 1 ? m1 : m2);
+      int pos = -1;
+      if (key < 3) pos = s_cur[wib * 4 + key] + __popc(mine & ((1u << lane) - 1u));
+      __syncwarp();
+      if (lane < 3) s_cur[wib * 4 + lane] += __popc(lane == 0 ? m0 : (lane == 1 ? m1 : m2));
+      __syncwarp();
+      if (pos >= 0) {
+        if (pos < CAP) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) tile[c * CAP + pos] = B.c[c][p];
+          tile[NC * CAP + pos] = id_in[p];
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) A.c[c][base + pos] = B.c[c][p];
+          id_out[base + pos] = id_in[p];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int nw = min(ntile, CAP);
+  for (int e = t; e < nw; e += TPB) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) A.c[c][base + e] = tile[c * CAP + e];
+    id_out[base + e] = tile[NC * CAP + e];
+  }
+}
+
+// arrivals: recv (in B / the spare ID array) holds [from the low neighbour | from the high neighbour], each sorted by
+// destination cell with the counts `inc` and exclusive offsets `inc_off`.  One warp per arriving cell group.
+template <int D>
+__global__ void __launch_bounds__(TPB) k_insert(Geo g, Ptcl R, const double* __restrict__ rid, Ptcl A,
+                                                double* __restrict__ id_out, const int* __restrict__ inc,
+                                                const int* __restrict__ inc_off, const int* __restrict__ cs_new) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+  const int per_side = g.nsp * g.ngrow * (g.nx + 1);
+  constexpr int NC = D == 3 ? 6 : 5;
+  const bool same_plane = g.dim == 3 ? g.nzs == g.nze : g.nys == g.nye;
+  for (int e = warp; e < 2 * per_side; e += nwarps) {
+    const int n = inc[e];
+    if (n == 0) continue;
+    const int side = e / per_side, r = e % per_side;
+    const int ii = r % (g.nx + 1), t = (r / (g.nx + 1)) % g.ngrow, isp = r / ((g.nx + 1) * g.ngrow);
+    int j, k;
+    if (g.dim == 3) { j = g.nys + t; k = side == 0 ? g.nzs : g.nze; }
+    else { j = side == 0 ? g.nys : g.nye; k = 0; }
+    const int cell_end = cs_new[(size_t)g.pen(j, k, isp) * (g.nx + 1) + ii + 1];
+    int dst = cell_end - n;
+    if (side == 0 && same_plane) dst -= inc[per_side + r];   // the high neighbour's arrivals come last
+    const int src = inc_off[e];
+    for (int q = lane; q < n; q += 32) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) A.c[c][dst + q] = R.c[c][src + q];
+      id_out[dst + q] = rid[src + q];
+    }
+  }
+}
+
+// `expect` >= 0: the population the sort must conserve (single rank); a mismatch means a particle pointed outside the
+// domain (|displacement| > one cell, or through a wall) and no destination claimed it
+__global__ void k_np2_poff(Geo g, const int* __restrict__ cs, int* __restrict__ np2, int* __restrict__ poff, int* flags,
+                           long long expect) {
+  for (int pen = blockIdx.x * blockDim.x + threadIdx.x; pen <= g.npen; pen += gridDim.x * blockDim.x) {
+    if (pen < g.npen) {
+      const int* row = cs + (size_t)pen * (g.nx + 1);
+      int n = row[g.nx] - row[0];
+      np2[pen] = n;
+      poff[pen] = row[0];
+      if (n > g.np) atomicOr(flags, 1);   // "memory over (np2 > np)"  boundary_periodic.f90:435-438
+    } else {
+      const int total = cs[(size_t)g.npen * (g.nx + 1)];
+      poff[pen] = total;
+      if (expect >= 0 && total != expect) atomicOr(flags, 2);
+    }
+  }
+}
+
+// totals the host needs in multi-rank mode: [0] local particles, [1] species-1 start, [2..3] ghost sends lo/hi,
+// [4..5] arrivals lo/hi
+__global__ void k_totals(Geo g, const int* __restrict__ cs_new, const int* __restrict__ inc_off, int* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int w = g.nx + 1;
+  const int g0 = cs_new[(size_t)g.npen * w];
+  const int g1 = cs_new[(size_t)(g.npen + g.nsp * g.ngrow) * w];
+  const int gend = cs_new[(size_t)g.nrows * w];
+  const int per_side = g.nsp * g.ngrow * w;
+  out[0] = g0;
+  out[1] = cs_new[(size_t)(g.npen / g.nsp) * w];
+  out[2] = g1 - g0;
+  out[3] = gend - g1;
+  out[4] = inc_off[per_side];
+  out[5] = inc_off[2 * per_side] - inc_off[per_side];
+}
+
+int grid_for(long long n) {
+  long long b = (n + TPB - 1) / TPB;
+  const long long cap = 148LL * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+int ensure_sort_buffers(wm_ctx* ctx) {
+  const Geo& g = ctx->g;
+  const size_t ncell = (size_t)g.nx * g.nyl * g.nzl;
+  if (!ctx->cnt27) {
+    WM_CUDA(cudaMalloc(&ctx->cnt27, ncell * 2 * WM_CNT_LINE * sizeof(int)));
+    WM_CUDA(cudaMemsetAsync(ctx->cnt27, 0, ncell * 2 * WM_CNT_LINE * sizeof(int), ctx->stream));
+  }
+  if (ctx->dst_off_cap < ctx->cap) {
+    if (ctx->dst_off) cudaFree(ctx->dst_off);
+    ctx->dst_off = nullptr;
+    WM_CUDA(cudaMalloc(&ctx->dst_off, ctx->cap));
+    ctx->dst_off_cap = ctx->cap;
+  }
+  return WM_OK;
+}
+
+int scan_ints(wm_ctx* ctx, int* data, size_t n) {
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, data, data, (int)n, ctx->stream);
+  if (need > ctx->scan_tmp_bytes) {
+    if (ctx->scan_tmp) cudaFree(ctx->scan_tmp);
+    ctx->scan_tmp = nullptr;
+    WM_CUDA(cudaMalloc(&ctx->scan_tmp, need));
+    ctx->scan_tmp_bytes = need;
+  }
+  WM_CUDA(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp, need, data, data, (int)n, ctx->stream));
+  ctx->launches += 2;
+  return WM_OK;
+}
+
+}  // namespace
+
+// called by the producers (fused push kernel, k_classify) before they accumulate the histogram
+int wm_sort_prepare(wm_ctx* ctx) {
+  WM_TRY(ensure_sort_buffers(ctx));
+  const size_t ncs = (size_t)ctx->g.nrows * (ctx->g.nx + 1);
+  WM_CUDA(cudaMemsetAsync(ctx->cs_new, 0, (ncs + 1) * sizeof(int), ctx->stream));
+  return WM_OK;
+}
+
+// boundary_*__particle_y[z]: classification + coordinate wrap of the pushed set (per-procedure path).  The classified
+// copy is written into the storage of the old sorted set (dead after the deposit); the two sets then swap names.
+int wm_k_classify(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  WM_TRY(wm_sort_prepare(ctx));
+  const long long nwork = (long long)(nxe - nxs + 1) * g.nyl * g.nzl * 2;
+  const int blocks = (int)std::min<long long>((nwork * 32 + TPB - 1) / TPB, 148LL * 8);
+  if (g.dim == 3)
+    k_classify<3><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->B, ctx->A, ctx->id[ctx->cid], ctx->id[1 - ctx->cid], ctx->cs,
+                                                   ctx->cnt27, ctx->cs_new, ctx->dst_off, ctx->flags, nxs, nxe);
+  else
+    k_classify<2><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->B, ctx->A, ctx->id[ctx->cid], ctx->id[1 - ctx->cid], ctx->cs,
+                                                   ctx->cnt27, ctx->cs_new, ctx->dst_off, ctx->flags, nxs, nxe);
+  WM_LAUNCH_CHECK(ctx);
+  std::swap(ctx->A, ctx->B);   // B = classified pushed set, A = free for the sorted output
+  return WM_OK;
+}
+
+// sort__bucket (+ the migration half of bc__particle_y[z]): needs dst_off / cnt27 of the pushed set B
+int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  cudaStream_t st = ctx->stream;
+  const int w = g.nx + 1;
+  const size_t ncs = (size_t)g.nrows * w;
+  const int per_side = g.nsp * g.ngrow * w;
+  // on entry: B / id[1-cid] hold the pushed set two-ended per source cell, cnt27 the count lines and cs_new the
+  // destination histogram (all written by the fused push kernel or by k_classify)
+  int tot[6] = {0, 0, 0, 0, 0, 0};
+  if (g.multi) {
+    // count message: my low ghost rows -> down neighbour (arrive in its high plane), high ghost rows -> up neighbour
+    int* ghost_lo = ctx->cs_new + (size_t)g.npen * w;
+    int* ghost_hi = ghost_lo + per_side;
+    const int ax = g.dim == 3 ? 1 : 0;
+    WM_TRY(wm_comm_group_begin(ctx));
+    WM_TRY(wm_comm_send(ctx, ctx->rank_down[ax], ghost_lo, (size_t)per_side * sizeof(int)));
+    WM_TRY(wm_comm_recv(ctx, ctx->rank_up[ax], ctx->inc + per_side, (size_t)per_side * sizeof(int)));
+    WM_TRY(wm_comm_send(ctx, ctx->rank_up[ax], ghost_hi, (size_t)per_side * sizeof(int)));
+    WM_TRY(wm_comm_recv(ctx, ctx->rank_down[ax], ctx->inc, (size_t)per_side * sizeof(int)));
+    WM_TRY(wm_comm_group_end(ctx));
+    k_add_incoming<<<grid_for(2 * per_side), TPB, 0, st>>>(g, ctx->inc, ctx->cs_new);
+    WM_LAUNCH_CHECK(ctx);
+    WM_CUDA(cudaMemcpyAsync(ctx->inc_off, ctx->inc, (size_t)2 * per_side * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    WM_CUDA(cudaMemsetAsync(ctx->inc_off + 2 * per_side, 0, sizeof(int), st));
+    WM_TRY(scan_ints(ctx, ctx->inc_off, (size_t)2 * per_side + 1));
+  }
+  WM_TRY(scan_ints(ctx, ctx->cs_new, ncs + 1));
+  if (g.multi) {
+    k_totals<<<1, 32, 0, st>>>(g, ctx->cs_new, ctx->inc_off, ctx->totals);
+    WM_LAUNCH_CHECK(ctx);
+    WM_CUDA(cudaMemcpyAsync(tot, ctx->totals, sizeof(tot), cudaMemcpyDeviceToHost, st));
+    WM_CUDA(cudaStreamSynchronize(st));
+    const size_t need = (size_t)tot[0] + tot[2] + tot[3];
+    if (need > ctx->cap || (size_t)tot[4] + tot[5] > ctx->cap) {
+      wm_set_error("particle arrays too small for the migrated population (raise WM_CAP_FACTOR)");
+      return WM_ERR_MEMORY_OVER;
+    }
+  }
+  const int old_cid = 1 - ctx->cid;   // the producers moved the IDs along with the particles into the spare array
+  {
+    const int ngx = (nxe - nxs + 1 + GD - 1) / GD;
+    const int blocks = g.nrows * ngx;
+    const size_t nint = (GD + 1) + GD * 28 + GD * 2 + 4 * (TPB / 32);
+    const size_t smem3 = (size_t)7 * CAP * sizeof(double) + nint * sizeof(int) + MAXSLOT * sizeof(Slot);
+    const size_t smem2 = (size_t)6 * CAP * sizeof(double) + nint * sizeof(int) + MAXSLOT * sizeof(Slot);
+    static bool attr_set = false;
+    if (!attr_set) {
+      WM_CUDA(cudaFuncSetAttribute(k_gather<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+      WM_CUDA(cudaFuncSetAttribute(k_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      attr_set = true;
+    }
+    if (g.dim == 3)
+      k_gather<3><<<blocks, TPB, smem3, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs, ctx->cs_new,
+                                              ctx->cnt27, ctx->dst_off, nxs, nxe, ngx);
+    else
+      k_gather<2><<<blocks, TPB, smem2, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs, ctx->cs_new,
+                                              ctx->cnt27, ctx->dst_off, nxs, nxe, ngx);
+    WM_LAUNCH_CHECK(ctx);
+  }
+  if (g.multi) {
+    // payload: ghost rows of A (behind the local particles) -> neighbours; arrivals land in B / the old ID array,
+    // which are free once the scatter has read them (stream order)
+    const int ax = g.dim == 3 ? 1 : 0;
+    const int ncomp = g.ndim - 1;
+    const size_t lo0 = (size_t)tot[0], hi0 = (size_t)tot[0] + tot[2];
+    WM_TRY(wm_comm_group_begin(ctx));
+    for (int c = 0; c <= ncomp; ++c) {
+      const double* src = c < ncomp ? ctx->A.c[c] : ctx->id[1 - old_cid];
+      double* dst = c < ncomp ? ctx->B.c[c] : ctx->id[old_cid];
+      WM_TRY(wm_comm_send(ctx, ctx->rank_down[ax], src + lo0, (size_t)tot[2] * sizeof(double)));
+      WM_TRY(wm_comm_recv(ctx, ctx->rank_up[ax], dst + tot[4], (size_t)tot[5] * sizeof(double)));
+      WM_TRY(wm_comm_send(ctx, ctx->rank_up[ax], src + hi0, (size_t)tot[3] * sizeof(double)));
+      WM_TRY(wm_comm_recv(ctx, ctx->rank_down[ax], dst, (size_t)tot[4] * sizeof(double)));
+    }
+    WM_TRY(wm_comm_group_end(ctx));
+    if (tot[4] + tot[5] > 0) {
+      const int blocks = std::min(wm_blocks((long long)2 * per_side * 32, TPB), 148 * 8);
+      if (g.dim == 3)
+        k_insert<3><<<blocks, TPB, 0, st>>>(g, ctx->B, ctx->id[old_cid], ctx->A, ctx->id[1 - old_cid], ctx->inc, ctx->inc_off,
+                                            ctx->cs_new);
+      else
+        k_insert<2><<<blocks, TPB, 0, st>>>(g, ctx->B, ctx->id[old_cid], ctx->A, ctx->id[1 - old_cid], ctx->inc, ctx->inc_off,
+                                            ctx->cs_new);
+      WM_LAUNCH_CHECK(ctx);
+    }
+    const long long kept = (long long)tot[0] - tot[4] - tot[5] + tot[2] + tot[3];
+    if (kept != ctx->ntot) {
+      wm_set_error("a particle left the one-cell neighbourhood of its cell (no destination cell claimed it)");
+      return WM_ERR_PARTICLE_LOST;
+    }
+    ctx->ntot = tot[0];
+    ctx->n_sp0 = tot[1];
+  }
+  std::swap(ctx->cs, ctx->cs_new);
+  ctx->cid = 1 - old_cid;
+  k_np2_poff<<<wm_blocks(g.npen + 1, TPB), TPB, 0, st>>>(g, ctx->cs, ctx->np2, ctx->poff, ctx->flags,
+                                                           g.multi ? -1LL : ctx->ntot);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
