@@ -65,6 +65,10 @@ int check_flags(wm_ctx* c) {
     wm_set_error("memory over (np2 > np)");
     return WM_ERR_MEMORY_OVER;
   }
+  if (f & 4) {
+    wm_set_error("********** stop at cgm after ite_max **********");
+    return WM_ERR_CG_ITEMAX;
+  }
   if (f & 2) {
     wm_set_error("a particle left the one-cell neighbourhood of its cell (|inc| > 1 or outside the slab)");
     return WM_ERR_PARTICLE_LOST;
@@ -160,7 +164,7 @@ int wm_create(const wm_params* prm, wm_ctx** out) {
   WM_CUDA(cudaMalloc(&c->tmpf, nb * 6 * sizeof(double)));
   WM_CUDA(cudaMalloc(&c->uj, nb * 3 * sizeof(double)));
   WM_CUDA(cudaMalloc(&c->gkl, nb * 3 * sizeof(double)));
-  double** cg[5] = {&c->phi, &c->pcg, &c->rcg, &c->bcg, &c->apcg};
+  double** cg[6] = {&c->phi, &c->pcg, &c->rcg, &c->bcg, &c->apcg, &c->pcg2};
   for (auto pp : cg) {
     WM_CUDA(cudaMalloc(pp, nb * sizeof(double)));
     WM_CUDA(cudaMemsetAsync(*pp, 0, nb * sizeof(double), c->stream));
@@ -180,7 +184,8 @@ int wm_create(const wm_params* prm, wm_ctx** out) {
   const size_t ninc = (size_t)2 * g.nsp * g.ngrow * (g.nx + 1) + 1;
   WM_CUDA(cudaMalloc(&c->inc, ninc * sizeof(int)));
   WM_CUDA(cudaMalloc(&c->inc_off, ninc * sizeof(int)));
-  WM_CUDA(cudaMalloc(&c->totals, 8 * sizeof(int)));
+  WM_CUDA(cudaMalloc(&c->totals, 16 * sizeof(int)));
+  WM_CUDA(cudaMemsetAsync(c->totals, 0, 16 * sizeof(int), c->stream));
   WM_CUDA(cudaMemsetAsync(c->inc, 0, ninc * sizeof(int), c->stream));
   WM_CUDA(cudaMalloc(&c->np2, (size_t)g.npen * sizeof(int)));
   WM_CUDA(cudaMalloc(&c->poff, ((size_t)g.npen + 1) * sizeof(int)));
@@ -206,7 +211,7 @@ int wm_destroy(wm_ctx* c) {
   cudaStreamSynchronize(c->stream);
   wm_comm_destroy(c);
   free_particles(c);
-  double* d[] = {c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
+  double* d[] = {c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->pcg2, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
                  c->hbuf[2], c->stage};
   for (double* p : d) if (p) cudaFree(p);
   int* ii[] = {c->cs, c->cs_new, c->np2, c->poff, c->flags, c->cnt27, c->inc, c->inc_off, c->totals};
@@ -578,6 +583,8 @@ int wm_get_stats(wm_ctx* c, wm_stats* out) {
   int f = 0;
   WM_CUDA(cudaMemcpyAsync(h.data(), c->np2, (size_t)g.npen * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   WM_CUDA(cudaMemcpyAsync(&f, c->flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (c->cg_ite_on_device)
+    WM_CUDA(cudaMemcpyAsync(c->cg_ite, c->totals + 6, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   WM_CUDA(cudaStreamSynchronize(c->stream));
   for (int l = 0; l < 3; ++l) out->cg_iterations[l] = c->cg_ite[l];
   out->n_particles = c->ntot;

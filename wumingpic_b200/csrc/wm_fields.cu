@@ -14,6 +14,12 @@
 // so that every warp reads/writes contiguous rows.
 #include "wm_internal.cuh"
 
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cstdlib>
+
+namespace cg = cooperative_groups;
+
 namespace {
 
 constexpr int TPB = 256;
@@ -395,6 +401,158 @@ __global__ void k_cg_store(double* __restrict__ df, const double* __restrict__ p
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// cgm as ONE persistent cooperative kernel (single rank, periodic): all three components, all
+// iterations, no host round trip.  Control flow is field.f90:437-558 verbatim, including
+// the reference's stop rule quirks; the periodic ghost fill of boundary_periodic__phi becomes index
+// wrapping.  Dot products: per-block partials in a fixed order, then EVERY block folds all partials in the
+// same fixed order after a grid sync, so all blocks take the same branch and results are deterministic.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_fold(double v, double* sh) {
+  // fixed-order tree over the block; every thread returns the total
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0;
+#pragma unroll
+  for (int q = 0; q < TPB / 32; ++q) t += sh[q];
+  return t;
+}
+
+// two-value grid reduction with ONE grid sync: the partial buffers ping-pong (a block can be at most one
+// reduction ahead of the slowest block, because it cannot pass the next sync alone)
+__device__ __forceinline__ void grid_sum2(cg::grid_group& grid, double a, double b, double* part, int& red_idx, double* sh,
+                                          double& ta, double& tb) {
+  a = block_fold(a, sh);
+  b = block_fold(b, sh);
+  double* buf = part + (size_t)(red_idx & 1) * 2 * gridDim.x;
+  red_idx++;
+  if (threadIdx.x == 0) { buf[2 * blockIdx.x] = a; buf[2 * blockIdx.x + 1] = b; }
+  grid.sync();
+  double x = 0, y = 0;
+  for (int q = threadIdx.x; q < (int)gridDim.x; q += TPB) { x += __ldcg(buf + 2 * q); y += __ldcg(buf + 2 * q + 1); }
+  ta = block_fold(x, sh);
+  tb = block_fold(y, sh);
+}
+
+__device__ __forceinline__ void cell_of32(const Geo& g, int e, int nxs, int nxr, int& i, int& j, int& k) {
+  i = nxs + e % nxr;
+  const int r = e / nxr;
+  j = g.nys + r % g.nyl;
+  k = g.nzs + r / g.nyl;
+}
+
+__global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const double* __restrict__ gkl,
+                                                  double* __restrict__ phi, double* p0, double* p1, double* __restrict__ r,
+                                                  double* __restrict__ b, double* __restrict__ ap, double* __restrict__ part,
+                                                  int* __restrict__ ite_out, int* flags, Geo g, int nxs, int nxe) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[TPB / 32];
+  const int nxr = nxe - nxs + 1;
+  const int n = nxr * g.nyl * g.nzl;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const long long sy = g.bx, sz = (long long)g.bx * g.by;
+  const double err = 1e-6;
+  const int ite_max = 100;
+  const bool d3 = g.dim == 3;
+  int red_idx = 0;
+  // neighbours with periodic wrap inside [nxs,nxe] x [nys,nye] x [nzs,nze]
+#define WM_NBR(e)                                                                     \
+  int i, j, k;                                                                        \
+  cell_of32(g, e, nxs, nxr, i, j, k);                                                 \
+  const long long o = (long long)g.box(i, j, k);                                      \
+  const long long xm = i == nxs ? o + (nxr - 1) : o - 1, xp = i == nxe ? o - (nxr - 1) : o + 1;              \
+  const long long ym = j == g.nys ? o + (g.nyl - 1) * sy : o - sy, yp = j == g.nye ? o - (g.nyl - 1) * sy : o + sy; \
+  const long long zm = !d3 ? o : (k == g.nzs ? o + (g.nzl - 1) * sz : o - sz);                                \
+  const long long zp = !d3 ? o : (k == g.nze ? o - (g.nzl - 1) * sz : o + sz);
+  for (int l = 0; l < 3; ++l) {
+    int ite = 0;
+    double s = 0, dummy;
+    double* pold = p0;   // the search direction of the previous iteration (complete)
+    double* pnew = p1;
+    for (int e = tid; e < n; e += nth) {
+      int i, j, k;
+      cell_of32(g, e, nxs, nxr, i, j, k);
+      const size_t o = g.box(i, j, k);
+      phi[o] = df[o * 6 + l];
+      const double bb = g.f5 * gkl[o * 3 + l];
+      b[o] = bb;
+      s = s + bb * bb;
+    }
+    double sum_g;
+    grid_sum2(grid, s, 0.0, part, red_idx, sh, sum_g, dummy);      // its sync also orders phi before the stencil below
+    const double eps = sqrt(sum_g) * err;
+    s = 0;
+    for (int e = tid; e < n; e += nth) {
+      WM_NBR(e)
+      double rr;
+      if (d3) rr = b[o] + phi[zm] + phi[ym] + phi[xm] - g.f4 * phi[o] + phi[xp] + phi[yp] + phi[zp];
+      else rr = b[o] + phi[ym] + phi[xm] - g.f4 * phi[o] + phi[xp] + phi[yp];
+      r[o] = rr;
+      pold[o] = rr;
+      s = s + rr * rr;
+    }
+    double sumr_g;
+    grid_sum2(grid, s, 0.0, part, red_idx, sh, sumr_g, dummy);
+    if (sqrt(sumr_g) > eps) {
+      double bv = 0.0;   // first iteration: p = r
+      while (sum_g > eps) {
+        ite = ite + 1;
+        // p = r + bv*p (field.f90:539-549 of the previous iteration) is evaluated on the fly at the seven stencil
+        // points with the same fma everywhere, so no separate sweep / grid sync is needed for it
+        double s1 = 0, s2 = 0;
+        for (int e = tid; e < n; e += nth) {
+          WM_NBR(e)
+#define WM_P(x) fma(bv, pold[x], r[x])
+          const double pc = WM_P(o);
+          double a;
+          if (d3) a = -WM_P(zm) - WM_P(ym) - WM_P(xm) + g.f4 * pc - WM_P(xp) - WM_P(yp) - WM_P(zp);
+          else a = -WM_P(ym) - WM_P(xm) + g.f4 * pc - WM_P(xp) - WM_P(yp);
+#undef WM_P
+          pnew[o] = pc;
+          ap[o] = a;
+          s1 = s1 + r[o] * r[o];
+          s2 = s2 + pc * a;
+        }
+        double sum2_g;
+        grid_sum2(grid, s1, s2, part, red_idx, sh, sumr_g, sum2_g);
+        const double av = sumr_g / sum2_g;
+        s = 0;
+        for (int e = tid; e < n; e += nth) {
+          int i, j, k;
+          cell_of32(g, e, nxs, nxr, i, j, k);
+          const size_t o = g.box(i, j, k);
+          phi[o] = phi[o] + av * pnew[o];
+          const double rn = r[o] - av * ap[o];
+          r[o] = rn;
+          s = s + rn * rn;
+        }
+        sum_g = sqrt(sumr_g);
+        if (ite >= ite_max) {
+          if (tid == 0) atomicOr(flags, 4);   // "stop at cgm after ite_max"  field.f90:522-525
+          break;
+        }
+        double sum1_g;
+        grid_sum2(grid, s, 0.0, part, red_idx, sh, sum1_g, dummy);   // its sync completes r and pnew for the next stencil
+        bv = sum1_g / sumr_g;
+        double* tsw = pold; pold = pnew; pnew = tsw;
+      }
+    }
+    grid.sync();   // every block is past the stencil reads of phi / r before df and the next component's phi are written
+    for (int e = tid; e < n; e += nth) {
+      int i, j, k;
+      cell_of32(g, e, nxs, nxr, i, j, k);
+      const size_t o = g.box(i, j, k);
+      df[o * 6 + l] = phi[o];
+    }
+    if (tid == 0) ite_out[l] = ite;
+    grid.sync();
+  }
+#undef WM_NBR
+}
+
 int grid_for(long long n) {
   long long b = (n + TPB - 1) / TPB;
   const long long cap = 148LL * 8;  // persistent-style grid: 8 CTAs of 256 threads per SM
@@ -513,6 +671,27 @@ int wm_k_update(wm_ctx* ctx, int nxs, int nxe) {
 int wm_k_cgm(wm_ctx* ctx, int nxs, int nxe) {
   const Geo& g = ctx->g;
   const long long n = (long long)(nxe - nxs + 1) * g.nyl * g.nzl;
+  static const bool no_coop = getenv("WM_CG_HOSTLOOP") != nullptr;
+  if (ctx->nranks == 1 && g.bc == WM_BC_PERIODIC && !no_coop && n < (1LL << 30)) {
+    // single rank, periodic: the whole solve is one cooperative launch
+    static int per_sm = 0;
+    if (per_sm == 0) WM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cgm_coop, TPB, 0));
+    int nsm = 0;
+    WM_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+    int nb = (int)std::min<long long>((long long)nsm * per_sm, (n + TPB - 1) / TPB);
+    nb = std::max(1, std::min(nb, 1024));   // 2 ping-pong partial buffers of 2*nb doubles in ctx->red
+    double *df = ctx->df, *gkl = ctx->gkl, *phi = ctx->phi, *p = ctx->pcg, *p2 = ctx->pcg2, *r = ctx->rcg, *b = ctx->bcg, *ap = ctx->apcg;
+    double* part = ctx->red;
+    int* ite_dev = ctx->totals + 6;
+    int* flags = ctx->flags;
+    Geo gg = g;
+    void* args[] = {&df, &gkl, &phi, &p, &p2, &r, &b, &ap, &part, &ite_dev, &flags, &gg, &nxs, &nxe};
+    WM_CUDA(cudaLaunchCooperativeKernel((void*)k_cgm_coop, dim3(nb), dim3(TPB), args, 0, ctx->stream));
+    ctx->launches++;
+    ctx->cg_ite_on_device = true;
+    return WM_OK;
+  }
+  ctx->cg_ite_on_device = false;
   const int nb = grid_for(n);
   double* part = ctx->red;           // 2*nb partials
   double* S = ctx->red + 2 * 2048;   // S[0]=sumr S[1]=sum2 S[2]=sum1 S[3]=sum(b^2)

@@ -23,23 +23,26 @@
 //     makes the scatter atomic-free and the particle order -- hence every later sum -- deterministic.
 #include "wm_cells.cuh"
 
+#include <cstdlib>
+
 namespace {
 
-constexpr int TPB = 256;
-constexpr int G = 16;         // cells per CTA
+// G = cells per CTA (template parameter): 16 threads per cell, so a CTA has 16*G threads.  G = 8 gives four
+// 128-thread CTAs per SM in different phases of their batch loop (better overlap of phase-A load latency with
+// phase-B math than two 256-thread CTAs); G = 16 halves the field-tile halo overhead.
 constexpr int SLOTS = 16;     // particles per cell and batch
 constexpr int NF = 21;        // double2 fields per particle record
 constexpr int CSTR = 17;      // slot stride between cells (bank spreading)
-constexpr int FSTR = 273;     // double2 stride between record fields (== 1 mod 8)
-constexpr int TILE_X = G + 2;
-constexpr int TILE_ROW = TILE_X * 6;  // doubles per (jj,kk) row of the field tile
 
+template <int G>
 struct __align__(16) Smem {
+  static constexpr int FSTR = G * CSTR + 1;   // double2 stride between record fields (== 1 mod 8)
+  static constexpr int TILE_X = G + 2;
+  static constexpr int TILE_ROW = TILE_X * 6; // doubles per (jj,kk) row of the field tile
   double tile[9 * TILE_ROW];          // tmpf for cells i0-1..i0+16, j-1..j+1, k-1..k+1
   double2 rec[NF * FSTR];             // per-particle deposit factors, field-major
   int beg[2][G + 1];                  // cs row segments of both species
   int cnt27[2][27][G];                // destination-offset counts per (species, offset, cell)
-  int nbatch;
   unsigned long long bar;             // mbarrier for the TMA bulk copies
 };
 
@@ -109,13 +112,15 @@ __device__ __forceinline__ int s0ds(double xo, double xn, int cell, double d_del
 // fused push + boundary + deposit + destination counting (3-D)
 //   ORDER 0 (Weibel/beam): deposit sees the un-wrapped new position, the periodic x wrap follows
 // ---------------------------------------------------------------------------------------------
-template <int ORDER>
-__global__ void __launch_bounds__(TPB, 2)
+template <int ORDER, int G>
+__global__ void __launch_bounds__(16 * G, 32 / G)
 k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __restrict__ id_out,
          const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj, int* __restrict__ cnt,
          int* __restrict__ hist, unsigned char* __restrict__ dst_off, int* flags, int nxs, int nxe, int ngx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  using SM = Smem<G>;
+  constexpr int TPB = 16 * G, FSTR = SM::FSTR, TILE_ROW = SM::TILE_ROW;
+  SM& S = *reinterpret_cast<SM*>(smem_raw);
   const int t = threadIdx.x;
   // group -> (i0, j, k)
   // block order: j-strips of 8 rows, then k, then the rows of the strip, x groups fastest -- the order wm_sort.cu
@@ -143,13 +148,7 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
       const int jj = r % 3 - 1, kk = r / 3 - 1;
       tma_bulk_g2s(&S.tile[r * TILE_ROW], tmpf + g.box(i0 - 1, j + jj, k + kk) * 6, row_bytes, &S.bar);
     }
-    int mx = 0;
-    for (int c = 0; c < ncg; ++c)
-      mx = max(mx, (S.beg[0][c + 1] - S.beg[0][c]) + (S.beg[1][c + 1] - S.beg[1][c]));
-    S.nbatch = (mx + SLOTS - 1) / SLOTS;
   }
-  __syncthreads();
-  const int nbatch = S.nbatch;
 
   // phase-A identity: (cell, slot); phase-B identity: (cell, component, transverse index m)
   const int ca = t >> 4, sa = t & 15;
@@ -159,6 +158,10 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
   const int n0a = ca < ncg ? S.beg[0][ca + 1] - S.beg[0][ca] : 0;
   const int n1a = ca < ncg ? S.beg[1][ca + 1] - S.beg[1][ca] : 0;
   const int ncb = cb < ncg ? (S.beg[0][cb + 1] - S.beg[0][cb]) + (S.beg[1][cb + 1] - S.beg[1][cb]) : 0;
+  // A cell's records are written (phase A) and consumed (phase B) by the same half-warp, so the two phases only need
+  // warp-level synchronisation: every warp walks the batches of its own two cells at its own pace, and the phase-A
+  // load latency of one warp overlaps the phase-B math of the others.
+  const int nbatch = (max(ncb, __shfl_xor_sync(0xffffffffu, ncb, 16)) + SLOTS - 1) / SLOTS;
 
   double acc[20];
 #pragma unroll
@@ -169,6 +172,7 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
   const int ax1 = comp == 0 ? 1 : 0;              // first transverse axis (A,B): y for Jx, x for Jy and Jz
   const int ax2 = comp == 2 ? 1 : 2;              // second transverse axis: z for Jx and Jy, y for Jz
   const double fac = 1.0 / 3.0;
+  const double inv_c2 = 1.0 / (g.c * g.c);
   const int ia = i0 + ca;
   const double len_x = (g.nxge - g.nxgs + 1) * g.delx;
   const double len_y = (g.nyge - g.nygs + 1) * g.delx;
@@ -221,8 +225,11 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
         {
           const double bpx = f[0], bpy = f[1], bpz = f[2], epx = f[3], epy = f[4], epz = f[5];
           double uvm1 = ux + fac1 * epx, uvm2 = uy + fac1 * epy, uvm3 = uz + fac1 * epz;
-          double gam = sqrt(g.c * g.c + uvm1 * uvm1 + uvm2 * uvm2 + uvm3 * uvm3);
-          double igam = 1.0 / gam;
+          // gam = sqrt(q), igam = 1/gam through one rsqrt (two roundings instead of a correctly rounded sqrt and a
+          // division: ~1e-16 relative, far inside the 1e-13 push tolerance; saves ~20 fp64 issue slots per particle)
+          const double qg = g.c * g.c + uvm1 * uvm1 + uvm2 * uvm2 + uvm3 * uvm3;
+          double igam = rsqrt(qg);
+          double gam = qg * igam;
           double fac1r = fac1 * igam;
           double fac2r = fac2 / (gam + txxx * (bpx * bpx + bpy * bpy + bpz * bpz) * igam);
           double uvm4 = uvm1 + fac1r * (+uvm2 * bpz - uvm3 * bpy);
@@ -234,7 +241,7 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
           ux = uvm1 + fac1 * epx;
           uy = uvm2 + fac1 * epy;
           uz = uvm3 + fac1 * epz;
-          gam = 1.0 / sqrt(1.0 + (+ux * ux + uy * uy + uz * uz) / (g.c * g.c));
+          gam = rsqrt(1.0 + (+ux * ux + uy * uy + uz * uz) * inv_c2);
           xn = x + ux * g.delt * gam;
           yn = y + uy * g.delt * gam;
           zn = z + uz * g.delt * gam;
@@ -297,7 +304,7 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
         ns0 += __popc(bs0); nl0 += __popc(bl0); ns1 += __popc(bs1); nl1 += __popc(bl1);
       }
     }
-    __syncthreads();
+    __syncwarp();
     // ------------------------------ phase B ------------------------------
     if (b_active) {
       const int nv = min(SLOTS, ncb - batch * SLOTS);
@@ -319,7 +326,7 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
         }
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
 
   // ---- flush: current strips -> global J (RED.F64, zeros skipped), counts -> cnt27 -----------------
@@ -342,6 +349,7 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
       }
   }
   // ---- re-binning information for the sort: one count line per (cell, species), group sizes -> histogram ----
+  __syncthreads();   // S.cnt27 was accumulated by all warps
   {
     const size_t cell0 = wm_cell_index(g, i0, j, k);
     for (int e = t; e < G * 2 * WM_CNT_LINE; e += TPB) {
@@ -360,9 +368,24 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
   }
 }
 
-}  // namespace
+template <int G>
+int launch_fused(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WM_CUDA(cudaFuncSetAttribute(k_fused3<0, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<G>)));
+    attr_set = true;
+  }
+  const int ngx = (nxe - nxs + 1 + G - 1) / G;
+  const int blocks = ngx * g.nyl * g.nzl;
+  k_fused3<0, G><<<blocks, 16 * G, sizeof(Smem<G>), ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
+                                                                  ctx->cs, ctx->tmpf, ctx->uj, ctx->cnt27, ctx->cs_new,
+                                                                  ctx->dst_off, ctx->flags, nxs, nxe, ngx);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
 
-int wm_fused_smem_bytes() { return (int)sizeof(Smem); }
+}  // namespace
 
 int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double /*u0*/) {
   const Geo& g = ctx->g;
@@ -371,17 +394,6 @@ int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double /*u
     return WM_ERR_ARG;
   }
   WM_TRY(wm_sort_prepare(ctx));
-  static bool attr_set = false;
-  if (!attr_set) {
-    WM_CUDA(cudaFuncSetAttribute(k_fused3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    attr_set = true;
-  }
-  const int ngx = (nxe - nxs + 1 + G - 1) / G;
-  const int blocks = ngx * g.nyl * g.nzl;
-  k_fused3<0><<<blocks, TPB, sizeof(Smem), ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid], ctx->cs,
-                                                           ctx->tmpf, ctx->uj, ctx->cnt27, ctx->cs_new, ctx->dst_off,
-                                                           ctx->flags, nxs, nxe, ngx);
-  WM_LAUNCH_CHECK(ctx);
-  return WM_OK;
+  static const int cells_per_cta = [] { const char* e = getenv("WM_FUSED_G"); return e ? atoi(e) : 8; }();
+  return cells_per_cta == 16 ? launch_fused<16>(ctx, nxs, nxe) : launch_fused<8>(ctx, nxs, nxe);
 }
-

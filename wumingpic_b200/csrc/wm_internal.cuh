@@ -76,10 +76,12 @@ struct wm_ctx {
   // fields
   double *uf = nullptr, *df = nullptr, *uj = nullptr, *gkl = nullptr, *tmpf = nullptr;
   // cg work arrays: phi, p (one ghost layer: (nx+2)(nyl+2)(nzl+2)), r, b, ap (interior)
+  double *pcg2 = nullptr;  // second search-direction buffer of the cooperative cgm
   double *phi = nullptr, *pcg = nullptr, *rcg = nullptr, *bcg = nullptr, *apcg = nullptr;
   double* red = nullptr;        // reduction scratch (device)
   double* red_host = nullptr;   // pinned
   int cg_ite[3] = {0, 0, 0};
+  bool cg_ite_on_device = false;   // the cooperative cgm leaves its iteration counts in totals[6..8]
   // halo buffers
   double* hbuf[4] = {nullptr, nullptr, nullptr, nullptr};  // send lo, send hi, recv lo, recv hi
   size_t hbuf_elems = 0;

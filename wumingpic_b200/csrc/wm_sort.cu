@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(TPB) k_gather(Geo g, Ptcl B, Ptcl A, const dou
   int* s_new = reinterpret_cast<int*>(tile + (NC + 1) * CAP);         // [GD+1] new cell starts of the run
   int* s_P = s_new + GD + 1;                                          // [GD][28] group sizes -> exclusive prefix per cell
   int* s_stay = s_P + GD * 28;                                        // [GD][2] source start of the stayers, count
-  int* s_cur = s_stay + GD * 2;                                       // [warps][4] running position per di of a slot
-  Slot* s_slot = reinterpret_cast<Slot*>(s_cur + 4 * (TPB / 32));     // [MAXSLOT]
+  int* s_list = s_stay + GD * 2;                                      // [MAXSLOT+1] live slots, count
+  Slot* s_slot = reinterpret_cast<Slot*>(s_list + MAXSLOT + 1);       // [MAXSLOT]
   const int t = threadIdx.x, lane = t & 31, wib = t >> 5;
   // ---- which destination run: local rows in strip order, ghost rows last; x groups fastest ----
   const int gx = blockIdx.x % ngx;
@@ -269,6 +269,20 @@ __global__ void __launch_bounds__(TPB) k_gather(Geo g, Ptcl B, Ptcl A, const dou
     s_slot[t] = sl;
   }
   __syncthreads();
+  // compact list of the slots that have something to scan (one warp, ballot compaction)
+  if (wib == 0) {
+    int n = 0;
+    for (int q0 = 0; q0 < nslot; q0 += 32) {
+      const int q = q0 + lane;
+      const bool live = q < nslot && s_slot[q].beg < s_slot[q].end;
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      if (live) s_list[n + __popc(m & ((1u << lane) - 1u))] = q;
+      n += __popc(m);
+    }
+    if (lane == 0) s_list[MAXSLOT] = n;
+  }
+  __syncthreads();
+  const int nlist = s_list[MAXSLOT];
   // ---- stayers: block copies ----
   for (int d = wib; d < ncg; d += TPB / 32) {
     const int sb = s_stay[2 * d], n = s_stay[2 * d + 1];
@@ -286,30 +300,24 @@ __global__ void __launch_bounds__(TPB) k_gather(Geo g, Ptcl B, Ptcl A, const dou
       }
     }
   }
-  // ---- arrivals: ballot-ranked pick out of the leaver zones ----
-  for (int q = wib; q < nslot; q += TPB / 32) {
-    const int beg = s_slot[q].beg, end = s_slot[q].end;
-    if (beg >= end) continue;                                           // warp-uniform
-    const int obase = s_slot[q].obase;
-    __syncwarp();
-    if (lane < 3) s_cur[wib * 4 + lane] = s_slot[q].pos[lane];
-    __syncwarp();
-    for (int p0 = beg; p0 < end; p0 += 32) {
+  // ---- arrivals: ballot-ranked pick out of the leaver zones (cursors live in registers, warp-uniform) ----
+  for (int q = wib; q < nlist; q += TPB / 32) {
+    const Slot& sl = s_slot[s_list[q]];
+    const int end = sl.end, obase = sl.obase;
+    int c0 = sl.pos[0], c1 = sl.pos[1], c2 = sl.pos[2];
+    for (int p0 = sl.beg; p0 < end; p0 += 32) {
       const int p = p0 + lane;
-      int key = 3;                                                      // 0..2: di+1 of a particle we take; 3: not ours
-      if (p < end) {
-        const int r = (int)dst_off[p] - obase;
-        if (r >= 0 && r < 3 && s_cur[wib * 4 + r] >= 0) key = r;
-      }
-      const unsigned m0 = __ballot_sync(0xffffffffu, key == 0);
-      const unsigned m1 = __ballot_sync(0xffffffffu, key == 1);
-      const unsigned m2 = __ballot_sync(0xffffffffu, key == 2);
-      const unsigned mine = key == 0 ? m0 : (key == 1 ? m1 : m2);
+      int r = -1;
+      if (p < end) r = (int)dst_off[p] - obase;
+      const unsigned m0 = __ballot_sync(0xffffffffu, r == 0 && c0 >= 0);
+      const unsigned m1 = __ballot_sync(0xffffffffu, r == 1 && c1 >= 0);
+      const unsigned m2 = __ballot_sync(0xffffffffu, r == 2 && c2 >= 0);
+      const unsigned lower = (1u << lane) - 1u;
       int pos = -1;
-      if (key < 3) pos = s_cur[wib * 4 + key] + __popc(mine & ((1u << lane) - 1u));
-      __syncwarp();
-      if (lane < 3) s_cur[wib * 4 + lane] += __popc(lane == 0 ? m0 : (lane == 1 ? m1 : m2));
-      __syncwarp();
+      if (r == 0 && c0 >= 0) pos = c0 + __popc(m0 & lower);
+      else if (r == 1 && c1 >= 0) pos = c1 + __popc(m1 & lower);
+      else if (r == 2 && c2 >= 0) pos = c2 + __popc(m2 & lower);
+      c0 += __popc(m0); c1 += __popc(m1); c2 += __popc(m2);
       if (pos >= 0) {
         if (pos < CAP) {
 #pragma unroll
@@ -507,7 +515,7 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
   {
     const int ngx = (nxe - nxs + 1 + GD - 1) / GD;
     const int blocks = g.nrows * ngx;
-    const size_t nint = (GD + 1) + GD * 28 + GD * 2 + 4 * (TPB / 32);
+    const size_t nint = (GD + 1) + GD * 28 + GD * 2 + MAXSLOT + 1;
     const size_t smem3 = (size_t)7 * CAP * sizeof(double) + nint * sizeof(int) + MAXSLOT * sizeof(Slot);
     const size_t smem2 = (size_t)6 * CAP * sizeof(double) + nint * sizeof(int) + MAXSLOT * sizeof(Slot);
     static bool attr_set = false;
