@@ -15,6 +15,9 @@
 //   boundary_periodic__dfield                                   :458-673
 //   boundary_periodic__curre                                    :676-978
 //   boundary_periodic__phi                                      :981-1099
+//   boundary_reconnection__*       3d/proj/reconnection/boundary_reconnection.f90:69-110 (particle_x), :672-682 (dfield x rule),
+//                                  :689-978 (curre: no x treatment), :1094-1116 (phi x rule)
+//   boundary_shock__*              3d/proj/shock/boundary_shock.f90:424-469 (injection), :674-686 (dfield), :1086-1108 (phi)
 //   mpi_set (rank table, slabs)   3d/common/mpi_set.f90:21-97
 //   time loop                     3d/proj/weibel/app.f90:100-108
 //   Weibel initial load           3d/proj/weibel/app.f90:298-338, 391-504
@@ -46,7 +49,7 @@ struct World3 {
   int nxgs = 2, nxge = 0, nygs = 2, nyge = 0, nzgs = 2, nzge = 0;
   int nxs = 0, nxe = 0;
   int nproc_j = 1, nproc_k = 1;
-  int bc = 0;  // 0 periodic
+  int bc = 0;  // 0 periodic, 1 reconnection walls, 2 shock walls
   double delx = 1, delt = 1, c = 1, gfac = 0.501, d_delx = 1, d_delt = 1;
   double q[2] = {0, 0}, r[2] = {1, 1};
   double f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
@@ -462,7 +465,8 @@ void bc_curre(World3& w) {
           for (int i = nxs - 2; i <= nxe + 2; ++i)
             for (int cc = 1; cc <= 3; ++cc) R.uj[R.i3(cc, i, j, R.nzs - 1)] = b[t++];
       });
-  // 5) x periodic fold + copy-back over all j,k incl. ghosts (:965-976)
+  // 5) x periodic fold + copy-back over all j,k incl. ghosts (:965-976); the wall modules do nothing in x
+  if (w.bc != 0) return;
   for (Rank3& R : w.ranks) {
     for (int k = R.nzs - 2; k <= R.nze + 2; ++k)
       for (int j = R.nys - 2; j <= R.nye + 2; ++j)
@@ -534,23 +538,39 @@ void bc_dfield(World3& w) {
   };
   sendrecv<double>(w, TO_KDOWN, pack_z(0, false), unpack_z(+1, true));
   sendrecv<double>(w, TO_KUP, pack_z(-1, true), unpack_z(-2, false));
-  // x periodic copy, all j,k incl. ghosts (:665-670)
+  // x periodic copy, all j,k incl. ghosts (:665-670); walls: 3d/proj/reconnection/boundary_reconnection.f90:672-682,
+  // 3d/proj/shock/boundary_shock.f90:674-686
   for (Rank3& R : w.ranks)
     for (int k = R.nzs - 2; k <= R.nze + 2; ++k)
-      for (int j = R.nys - 2; j <= R.nye + 2; ++j)
-        for (int cc = 1; cc <= 6; ++cc) {
-          R.df[R.i6(cc, nxs - 2, j, k)] = R.df[R.i6(cc, nxe - 1, j, k)];
-          R.df[R.i6(cc, nxs - 1, j, k)] = R.df[R.i6(cc, nxe, j, k)];
-          R.df[R.i6(cc, nxe + 1, j, k)] = R.df[R.i6(cc, nxs, j, k)];
-          R.df[R.i6(cc, nxe + 2, j, k)] = R.df[R.i6(cc, nxs + 1, j, k)];
+      for (int j = R.nys - 2; j <= R.nye + 2; ++j) {
+        auto D = [&](int cc, int i) -> double& { return R.df[R.i6(cc, i, j, k)]; };
+        if (w.bc == 0) {
+          for (int cc = 1; cc <= 6; ++cc) {
+            D(cc, nxs - 2) = D(cc, nxe - 1);
+            D(cc, nxs - 1) = D(cc, nxe);
+            D(cc, nxe + 1) = D(cc, nxs);
+            D(cc, nxe + 2) = D(cc, nxs + 1);
+          }
+        } else {
+          D(1, nxs - 1) = -D(1, nxs);
+          for (int cc = 2; cc <= 4; ++cc) D(cc, nxs - 1) = D(cc, nxs + 1);
+          for (int cc = 5; cc <= 6; ++cc) D(cc, nxs - 1) = -D(cc, nxs);
+          if (w.bc == 1) {
+            D(1, nxe) = -D(1, nxe - 1);
+            for (int cc = 2; cc <= 4; ++cc) D(cc, nxe + 1) = D(cc, nxe - 1);
+            for (int cc = 5; cc <= 6; ++cc) D(cc, nxe) = -D(cc, nxe - 1);
+          } else {
+            for (int cc = 1; cc <= 6; ++cc) D(cc, nxe + 1) = 0.0;
+          }
         }
+      }
 }
 
 // ---------------------------------------------------------------------------
 // boundary_periodic__phi -- 3d/common/boundary_periodic.f90:981-1099
 // `sel` picks cg.phi (0) or cg.p (1).
 // ---------------------------------------------------------------------------
-void bc_phi(World3& w, std::vector<Cg3>& cg, int sel, int /*l*/) {
+void bc_phi(World3& w, std::vector<Cg3>& cg, int sel, int l) {
   const int nxs = w.nxs, nxe = w.nxe;
   auto A = [&](Rank3& R) -> std::vector<double>& { return sel == 0 ? cg[R.rank].phi : cg[R.rank].p; };
   auto I = [&](Rank3& R, int i, int j, int k) { return cg[R.rank].i1(i, j, k); };
@@ -594,11 +614,21 @@ void bc_phi(World3& w, std::vector<Cg3>& cg, int sel, int /*l*/) {
         for (int j = R.nys - 1; j <= R.nye + 1; ++j)
           for (int i = nxs; i <= nxe; ++i) A(R)[I(R, i, j, R.nzs - 1)] = b[t++];
       });
+  // x: periodic (:1091-1096) or the wall rule of component l (boundary_reconnection.f90:1094-1116, boundary_shock.f90:1086-1108)
   for (Rank3& R : w.ranks)
     for (int k = R.nzs - 1; k <= R.nze + 1; ++k)
       for (int j = R.nys - 1; j <= R.nye + 1; ++j) {
-        A(R)[I(R, nxs - 1, j, k)] = A(R)[I(R, nxe, j, k)];
-        A(R)[I(R, nxe + 1, j, k)] = A(R)[I(R, nxs, j, k)];
+        std::vector<double>& a = A(R);
+        if (w.bc == 0) {
+          a[I(R, nxs - 1, j, k)] = a[I(R, nxe, j, k)];
+          a[I(R, nxe + 1, j, k)] = a[I(R, nxs, j, k)];
+        } else if (l == 1) {
+          a[I(R, nxs - 1, j, k)] = -a[I(R, nxs, j, k)];
+          a[I(R, nxe + 1, j, k)] = w.bc == 1 ? -a[I(R, nxe - 2, j, k)] : 0.0;
+        } else {
+          a[I(R, nxs - 1, j, k)] = a[I(R, nxs + 1, j, k)];
+          a[I(R, nxe + 1, j, k)] = w.bc == 1 ? a[I(R, nxe - 1, j, k)] : 0.0;
+        }
       }
 }
 
@@ -828,8 +858,53 @@ void bc_particle_x(World3& w, Rank3& R, std::vector<double>& up) {
   }
 }
 
+// boundary_reconnection__particle_x -- 3d/proj/reconnection/boundary_reconnection.f90:69-110 (reflecting walls)
+void bc_particle_x_reflect(World3& w, Rank3& R, std::vector<double>& up) {
+  const int nxs = w.nxs, nxe = w.nxe;
+  for (int isp = 1; isp <= w.nsp; ++isp)
+    for (int k = R.nzs; k <= R.nze; ++k)
+      for (int j = R.nys; j <= R.nye; ++j) {
+        const int n = R.np2[R.in2(j, k, isp)];
+        for (int ii = 1; ii <= n; ++ii) {
+          double* u = &up[R.ip(1, ii, j, k, isp)];
+          const int ipos = (int)(u[0] / w.delx);
+          if (ipos < nxs + 1) {
+            u[0] = 2.0 * (nxs + 1) * w.delx - u[0];
+            u[3] = -u[3]; u[4] = -u[4]; u[5] = -u[5];
+          } else if (ipos >= nxe - 1) {
+            u[0] = 2.0 * (nxe - 1) * w.delx - u[0];
+            u[3] = -u[3]; u[4] = -u[4]; u[5] = -u[5];
+          }
+        }
+      }
+}
+
+// boundary_shock__injection -- 3d/proj/shock/boundary_shock.f90:424-469
+void bc_injection(World3& w, Rank3& R, std::vector<double>& up, double u0) {
+  const int nxs = w.nxs, nxe = w.nxe;
+  const double xend = nxe * w.delx + u0 / std::sqrt(1.0 + (u0 * u0) / (w.c * w.c)) * w.delt;
+  for (int isp = 1; isp <= w.nsp; ++isp)
+    for (int k = R.nzs; k <= R.nze; ++k)
+      for (int j = R.nys; j <= R.nye; ++j) {
+        const int n = R.np2[R.in2(j, k, isp)];
+        for (int ii = 1; ii <= n; ++ii) {
+          double* u = &up[R.ip(1, ii, j, k, isp)];
+          const int ipos = (int)(u[0] * w.d_delx);
+          if (ipos < nxs + 1) {
+            u[0] = 2.0 * (nxs + 1) * w.delx - u[0];
+            u[3] = -u[3]; u[4] = -u[4]; u[5] = -u[5];
+          } else if (u[0] > xend) {
+            u[0] = 2.0 * xend - u[0];
+            u[3] = 2.0 * u0 - u[3];
+            u[4] = -u[4]; u[5] = -u[5];
+          }
+        }
+      }
+}
+
 // ---------------------------------------------------------------------------
 // boundary_periodic__particle_yz -- 3d/common/boundary_periodic.f90:104-455
+// (boundary_reconnection__particle_yz and boundary_shock__particle_yz are verbatim copies of it)
 // Serial per rank (the reference's arrival order under OpenMP locks is racy;
 // the serial order k-outer / j / ii is one admissible outcome).
 // ---------------------------------------------------------------------------
@@ -1003,12 +1078,15 @@ void sort_bucket(World3& w, Rank3& R, std::vector<double>& dst, const std::vecto
   }
 }
 
-// one time step in the Weibel/beam order -- 3d/proj/weibel/app.f90:100-108
-void step(World3& w) {
+// one time step; order 0: Weibel/beam (3d/proj/weibel/app.f90:100-108), 1: reconnection (3d/proj/reconnection/app.f90:103-108),
+// 2: shock without the driver's inject/relocate (3d/proj/shock/app.f90, same call order as 2d/proj/shock/app.f90:112-118)
+void step(World3& w, int order = 0, double u0 = 0.0) {
   for (Rank3& R : w.ranks) particle_solv(w, R, R.gp, R.up);
+  if (order == 1) for (Rank3& R : w.ranks) bc_particle_x_reflect(w, R, R.gp);
+  if (order == 2) for (Rank3& R : w.ranks) bc_injection(w, R, R.gp, u0);
   field_fdtd_i(w, 0);
   if (w.err) return;
-  for (Rank3& R : w.ranks) bc_particle_x(w, R, R.gp);
+  if (order == 0) for (Rank3& R : w.ranks) bc_particle_x(w, R, R.gp);
   bc_particle_yz(w, 0);
   if (w.err) return;
   for (Rank3& R : w.ranks) sort_bucket(w, R, R.up, R.gp);
@@ -1102,6 +1180,9 @@ void orc3_bc_particle_x(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ra
 void orc3_bc_particle_yz(void* h) { bc_particle_yz(*(World3*)h, 0); }
 void orc3_sort_bucket(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) sort_bucket(w, R, R.up, R.gp); }
 void orc3_step(void* h) { step(*(World3*)h); }
+void orc3_step_order(void* h, int order, double u0) { step(*(World3*)h, order, u0); }
+void orc3_bc_particle_x_reflect(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) bc_particle_x_reflect(w, R, R.gp); }
+void orc3_bc_injection(void* h, double u0) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) bc_injection(w, R, R.gp, u0); }
 
 // ---------------------------------------------------------------------------
 // Deterministic Weibel load -- 3d/proj/weibel/app.f90:311-338 (np2, cumcnt),
@@ -1212,8 +1293,10 @@ void orc3_gauss(void* h, int which, double* out) {
             }
             for (int c = -1; c <= 1; ++c)
               for (int b = -1; b <= 1; ++b)
-                for (int a = -1; a <= 1; ++a)
+                for (int a = -1; a <= 1; ++a) {
+                  if (w.bc != 0 && (c3[0] + a < w.nxgs || c3[0] + a > w.nxge)) continue;
                   rho[G(c3[0] + a, c3[1] + b, c3[2] + c)] += w.q[isp - 1] * s[0][a + 1] * s[1][b + 1] * s[2][c + 1];
+                }
           }
     for (int k = R.nzs; k <= R.nze; ++k)
       for (int j = R.nys; j <= R.nye; ++j)
@@ -1224,9 +1307,11 @@ void orc3_gauss(void* h, int which, double* out) {
         }
   }
   double res = 0, mx = 0;
+  // walls: only the cells nxs+1 .. nxe-2 that no wall rule touches
+  const int i_lo = w.bc == 0 ? w.nxgs : w.nxs + 1, i_hi = w.bc == 0 ? w.nxge : w.nxe - 2;
   for (int k = w.nzgs; k <= w.nzge; ++k)
     for (int j = w.nygs; j <= w.nyge; ++j)
-      for (int i = w.nxgs; i <= w.nxge; ++i) {
+      for (int i = i_lo; i <= i_hi; ++i) {
         double div = ex[G(i + 1, j, k)] - ex[G(i, j, k)] + ey[G(i, j + 1, k)] - ey[G(i, j, k)] + ez[G(i, j, k + 1)] - ez[G(i, j, k)];
         double rr = 4.0 * kPi * w.delx * rho[G(i, j, k)];
         res = std::max(res, std::fabs(div - rr));

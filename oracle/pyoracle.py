@@ -46,6 +46,9 @@ def lib(fast=False):
                      "clear_error"):
             getattr(L, "orc3_" + name).argtypes = [C.c_void_p]
         L.orc3_field_fdtd_i.argtypes = [C.c_void_p, C.c_int]
+        L.orc3_step_order.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.orc3_bc_particle_x_reflect.argtypes = [C.c_void_p]
+        L.orc3_bc_injection.argtypes = [C.c_void_p, C.c_double]
         L.orc3_nranks.argtypes = [C.c_void_p]
         L.orc3_error.argtypes = [C.c_void_p]
         L.orc3_rank_geom.argtypes = [C.c_void_p, C.c_int, ip]
@@ -53,6 +56,23 @@ def lib(fast=False):
         L.orc3_cg_iterations.argtypes = [C.c_void_p, ip]
         L.orc3_energy.argtypes = [C.c_void_p, dp]
         L.orc3_gauss.argtypes = [C.c_void_p, C.c_int, dp]
+        L.orc2_create.argtypes = [C.c_int] * 4 + [C.c_double] * 4 + [dp, dp, C.c_int]
+        L.orc2_dptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc2_iptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc2_load_weibel.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 4 + [C.c_uint64]
+        for name in ("destroy", "particle_solv", "bc_particle_y", "sort_bucket", "clear_error"):
+            getattr(L, "orc2_" + name).argtypes = [C.c_void_p]
+        L.orc2_bc_particle_x.argtypes = [C.c_void_p, C.c_int]
+        L.orc2_bc_injection.argtypes = [C.c_void_p, C.c_double]
+        L.orc2_step.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.orc2_field_fdtd_i.argtypes = [C.c_void_p, C.c_int]
+        L.orc2_nranks.argtypes = [C.c_void_p]
+        L.orc2_error.argtypes = [C.c_void_p]
+        L.orc2_rank_geom.argtypes = [C.c_void_p, C.c_int, ip]
+        L.orc2_set_xrange.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc2_cg_iterations.argtypes = [C.c_void_p, ip]
+        L.orc2_energy.argtypes = [C.c_void_p, dp]
+        L.orc2_gauss.argtypes = [C.c_void_p, C.c_int, dp]
         _LIBS[key] = L
     return _LIBS[key]
 
@@ -75,7 +95,7 @@ class World3:
     def __init__(self, nx, ny, nz, np_cap, nproc_j=1, nproc_k=1, delx=1.0, delt=1.0, c=1.0, gfac=0.501,
                  q=(1.0, -1.0), r=(1.0, 1.0), bc=0, fast=False):
         self.L = lib(fast)
-        self.nx, self.ny, self.nz, self.np, self.ndim, self.nsp = nx, ny, nz, np_cap, 7, 2
+        self.nx, self.ny, self.nz, self.np, self.ndim, self.nsp, self.bc = nx, ny, nz, np_cap, 7, 2, bc
         self.q = np.ascontiguousarray(q, dtype=np.float64)
         self.r = np.ascontiguousarray(r, dtype=np.float64)
         self.delx, self.delt, self.c, self.gfac = delx, delt, c, gfac
@@ -135,8 +155,17 @@ class World3:
     def field_fdtd_i(self, stage=0):
         self.L.orc3_field_fdtd_i(self.h, stage)
 
-    def bc_particle_x(self):
-        self.L.orc3_bc_particle_x(self.h)
+    def set_xrange(self, nxs, nxe):
+        self.L.orc3_set_xrange(self.h, nxs, nxe)
+
+    def bc_particle_x(self, kind=None):
+        if (0 if self.bc == 0 else 1) if kind is None else kind:
+            self.L.orc3_bc_particle_x_reflect(self.h)
+        else:
+            self.L.orc3_bc_particle_x(self.h)
+
+    def bc_injection(self, u0):
+        self.L.orc3_bc_injection(self.h, u0)
 
     def bc_particle_yz(self):
         self.L.orc3_bc_particle_yz(self.h)
@@ -144,8 +173,8 @@ class World3:
     def sort_bucket(self):
         self.L.orc3_sort_bucket(self.h)
 
-    def step(self):
-        self.L.orc3_step(self.h)
+    def step(self, order=0, u0=0.0):
+        self.L.orc3_step_order(self.h, order, u0)
 
     def error(self):
         return self.L.orc3_error(self.h)
@@ -163,4 +192,109 @@ class World3:
     def gauss(self, which=0):
         e = (C.c_double * 2)()
         self.L.orc3_gauss(self.h, which, e)
+        return e[0], e[1]
+
+
+class World2:
+    """In-process emulation of an nproc-rank (1-D y slabs) MPI run of the 2-D reference loop.
+    bc: 0 periodic (Weibel), 1 reconnection walls, 2 shock walls; order (of step()): 0 Weibel, 1 reconnection, 2 shock."""
+
+    def __init__(self, nx, ny, np_cap, nproc=1, delx=1.0, delt=1.0, c=1.0, gfac=0.501, q=(1.0, -1.0), r=(1.0, 1.0),
+                 bc=0, fast=False):
+        self.L = lib(fast)
+        self.nx, self.ny, self.np, self.ndim, self.nsp, self.bc = nx, ny, np_cap, 6, 2, bc
+        self.q = np.ascontiguousarray(q, dtype=np.float64)
+        self.r = np.ascontiguousarray(r, dtype=np.float64)
+        self.delx, self.delt, self.c, self.gfac = delx, delt, c, gfac
+        dp = C.POINTER(C.c_double)
+        self.h = C.c_void_p(self.L.orc2_create(nx, ny, np_cap, nproc, delx, delt, c, gfac, self.q.ctypes.data_as(dp),
+                                               self.r.ctypes.data_as(dp), bc))
+        self.nranks = self.L.orc2_nranks(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.orc2_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def geom(self, rank=0):
+        g = (C.c_int * 4)()
+        self.L.orc2_rank_geom(self.h, rank, g)
+        d = dict(zip(("nys", "nye", "nup", "ndown"), list(g)))
+        d["nzs"] = d["nze"] = 0
+        return d
+
+    def _shape(self, rank, which):
+        g = self.geom(rank)
+        nyl = g["nye"] - g["nys"] + 1
+        if which in ("up", "gp"):
+            return (self.nsp, nyl, self.np, self.ndim)
+        if which in ("uf", "df"):
+            return (nyl + 4, self.nx + 4, 6)
+        if which == "uj":
+            return (nyl + 4, self.nx + 4, 3)
+        if which == "gkl":
+            return (nyl, self.nx, 3)
+        if which == "np2":
+            return (self.nsp, nyl)
+        if which == "cumcnt":
+            return (self.nsp, nyl, self.nx + 1)
+        raise KeyError(which)
+
+    def arr(self, which, rank=0):
+        shape = self._shape(rank, which)
+        if which in ("np2", "cumcnt"):
+            p = self.L.orc2_iptr(self.h, rank, 0 if which == "np2" else 1)
+        else:
+            p = self.L.orc2_dptr(self.h, rank, ("up", "gp", "uf", "df", "uj", "gkl").index(which))
+        return np.ctypeslib.as_array(p, shape=shape)
+
+    def load_weibel(self, n0, v_thi=0.1, v_the=0.1, t_ani=5.0, b0=0.0, seed=20240601):
+        self.L.orc2_load_weibel(self.h, n0, v_thi, v_the, t_ani, b0, seed)
+
+    def set_xrange(self, nxs, nxe):
+        self.L.orc2_set_xrange(self.h, nxs, nxe)
+
+    def particle_solv(self):
+        self.L.orc2_particle_solv(self.h)
+
+    def field_fdtd_i(self, stage=0):
+        self.L.orc2_field_fdtd_i(self.h, stage)
+
+    def bc_particle_x(self, kind=None):
+        self.L.orc2_bc_particle_x(self.h, (0 if self.bc == 0 else 1) if kind is None else kind)
+
+    def bc_injection(self, u0):
+        self.L.orc2_bc_injection(self.h, u0)
+
+    def bc_particle_y(self):
+        self.L.orc2_bc_particle_y(self.h)
+
+    def sort_bucket(self):
+        self.L.orc2_sort_bucket(self.h)
+
+    def step(self, order=0, u0=0.0):
+        self.L.orc2_step(self.h, order, u0)
+
+    def error(self):
+        return self.L.orc2_error(self.h)
+
+    def cg_iterations(self):
+        it = (C.c_int * 3)()
+        self.L.orc2_cg_iterations(self.h, it)
+        return list(it)
+
+    def energy(self):
+        e = (C.c_double * 4)()
+        self.L.orc2_energy(self.h, e)
+        return np.array(list(e))
+
+    def gauss(self, which=0):
+        e = (C.c_double * 2)()
+        self.L.orc2_gauss(self.h, which, e)
         return e[0], e[1]

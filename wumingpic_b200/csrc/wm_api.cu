@@ -408,7 +408,8 @@ int wm_bc_particle_x(wm_ctx* c, int nxs, int nxe) {
   if (!c) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
   if (!c->gp_valid) { wm_set_error("bc__particle_x acts on the pushed particles (call particle__solv first)"); return WM_ERR_STATE; }
-  return wm_k_bc_x(c, nxs, nxe, c->g.bc, 0.0);
+  // boundary_shock__particle_x is the same reflecting-wall rule as boundary_reconnection__particle_x
+  return wm_k_bc_x(c, nxs, nxe, c->g.bc == WM_BC_PERIODIC ? WM_BC_PERIODIC : WM_BC_RECONNECTION, 0.0);
 }
 
 int wm_bc_injection(wm_ctx* c, int nxs, int nxe, double u0) {

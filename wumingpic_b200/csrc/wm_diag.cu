@@ -163,8 +163,9 @@ __global__ void k_rho(Geo g, Ptcl A, long long n, long long n_sp0, double* __res
   }
 }
 
+// walls (bc != periodic): only the cells nxs+1 .. nxe-2 that no wall rule touches are checked
 __global__ void k_gauss(Geo g, const double* __restrict__ uf, const double* __restrict__ rho,
-                        unsigned long long* __restrict__ out) {
+                        unsigned long long* __restrict__ out, int i_lo, int i_hi) {
   const long long n = (long long)g.nx * g.nyl * g.nzl;
   const long long sY = (long long)g.bx * 6, sZ = (long long)g.bx * g.by * 6;
   double res = 0, mx = 0;
@@ -172,6 +173,7 @@ __global__ void k_gauss(Geo g, const double* __restrict__ uf, const double* __re
     int i = g.nxgs + (int)(e % g.nx);
     long long r = e / g.nx;
     int j = g.nys + (int)(r % g.nyl), k = g.dim == 3 ? g.nzs + (int)(r / g.nyl) : 0;
+    if (i < i_lo || i > i_hi) continue;
     const size_t o = g.box(i, j, k);
     const double* f = uf + o * 6;
     double div = (f[3 + 6] - f[3]) + (f[4 + sY] - f[4]);
@@ -232,10 +234,13 @@ int wm_k_gauss(wm_ctx* ctx, double* out_host) {
     k_rho<<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->A, ctx->ntot, ctx->n_sp0, rho);
     WM_LAUNCH_CHECK(ctx);
   }
-  WM_TRY(wm_k_scalar_fold(ctx, rho, g.nxgs, g.nxge));
+  const bool per = g.bc == WM_BC_PERIODIC;
+  const int gx0 = per ? g.nxgs : ctx->last_nxs, gx1 = per ? g.nxge : ctx->last_nxe;
+  WM_TRY(wm_k_scalar_fold(ctx, rho, gx0, gx1));
   unsigned long long* acc = (unsigned long long*)(ctx->red + 4096 + 24);
   WM_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(unsigned long long), ctx->stream));
-  k_gauss<<<grid_for((long long)g.nx * g.nyl * g.nzl), TPB, 0, ctx->stream>>>(g, ctx->uf, rho, acc);
+  k_gauss<<<grid_for((long long)g.nx * g.nyl * g.nzl), TPB, 0, ctx->stream>>>(g, ctx->uf, rho, acc, per ? g.nxgs : gx0 + 1,
+                                                                             per ? g.nxge : gx1 - 2);
   WM_LAUNCH_CHECK(ctx);
   WM_CUDA(cudaMemcpyAsync(out_host, acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   WM_CUDA(cudaStreamSynchronize(ctx->stream));

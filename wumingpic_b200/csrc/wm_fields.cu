@@ -135,6 +135,48 @@ __global__ void k_x_copy(double* __restrict__ arr, Geo g, int nxs, int nxe, int 
   }
 }
 
+// conducting-wall x rule of boundary_{reconnection,shock}__dfield over all j,k incl. ghosts
+// ({2d,3d}/proj/reconnection/boundary_reconnection.f90:350-359 / :672-682, {2d,3d}/proj/shock/boundary_shock.f90:396-405 / :674-686)
+__global__ void k_x_wall_dfield(double* __restrict__ df, Geo g, int nxs, int nxe, int j0, int j1, int k0, int k1) {
+  const int nj = j1 - j0 + 1, nk = k1 - k0 + 1;
+  const int n = nj * nk;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int j = j0 + e % nj, k = k0 + e / nj;
+    double* row = df + g.box(g.nxgs - 2, j, k) * 6;
+    auto D = [&](int c, int i) -> double& { return row[(size_t)(i - (g.nxgs - 2)) * 6 + (c - 1)]; };
+    D(1, nxs - 1) = -D(1, nxs);
+    for (int c = 2; c <= 4; ++c) D(c, nxs - 1) = D(c, nxs + 1);
+    for (int c = 5; c <= 6; ++c) D(c, nxs - 1) = -D(c, nxs);
+    if (g.bc == WM_BC_RECONNECTION) {
+      D(1, nxe) = -D(1, nxe - 1);
+      for (int c = 2; c <= 4; ++c) D(c, nxe + 1) = D(c, nxe - 1);
+      for (int c = 5; c <= 6; ++c) D(c, nxe) = -D(c, nxe - 1);
+    } else {
+      for (int c = 1; c <= 6; ++c) D(c, nxe + 1) = 0.0;
+    }
+  }
+}
+
+// x rule of boundary_{reconnection,shock}__phi for component l (1: odd about the wall face, 2,3: even about the wall cell)
+// ({2d,3d}/proj/reconnection/boundary_reconnection.f90:557-577 / :1094-1116, {2d,3d}/proj/shock/boundary_shock.f90:603-623 / :1086-1108)
+__global__ void k_x_wall_phi(double* __restrict__ a, Geo g, int nxs, int nxe, int l, int j0, int j1, int k0, int k1) {
+  const int nj = j1 - j0 + 1, nk = k1 - k0 + 1;
+  const int n = nj * nk;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int j = j0 + e % nj, k = k0 + e / nj;
+    double* row = a + g.box(g.nxgs - 2, j, k);
+    auto X = [&](int i) -> double& { return row[i - (g.nxgs - 2)]; };
+    const bool rec = g.bc == WM_BC_RECONNECTION;
+    if (l == 1) {
+      X(nxs - 1) = -X(nxs);
+      X(nxe + 1) = rec ? -X(nxe - 2) : 0.0;
+    } else {
+      X(nxs - 1) = X(nxs + 1);
+      X(nxe + 1) = rec ? X(nxe - 1) : 0.0;
+    }
+  }
+}
+
 // one-layer periodic x fold of a scalar box array: a(nxe) += a(nxs-1); a(nxs) += a(nxe+1)
 __global__ void k_x_fold1(double* __restrict__ arr, Geo g, int nxs, int nxe, int j0, int j1, int k0, int k1) {
   const int nj = j1 - j0 + 1, nk = k1 - k0 + 1;
@@ -560,7 +602,7 @@ int grid_for(long long n) {
 }
 
 // boundary_*__phi: one ghost layer of a scalar box array (boundary_periodic.f90:981-1099)
-int bc_phi(wm_ctx* ctx, double* a, int nxs, int nxe, int /*l*/) {
+int bc_phi(wm_ctx* ctx, double* a, int nxs, int nxe, int l) {
   const Geo& g = ctx->g;
   const int k0 = g.dim == 3 ? g.nzs : 0, k1 = g.dim == 3 ? g.nze : 0;
   // y: row nys -> jdown's nye+1 ; row nye -> jup's nys-1   (i interior, k interior)
@@ -574,7 +616,10 @@ int bc_phi(wm_ctx* ctx, double* a, int nxs, int nxe, int /*l*/) {
   // x periodic, one layer, over the ghost-extended transverse ranges
   const int kk0 = g.dim == 3 ? g.nzs - 1 : 0, kk1 = g.dim == 3 ? g.nze + 1 : 0;
   const int n = (g.nye - g.nys + 3) * (kk1 - kk0 + 1);
-  k_x_copy<1><<<wm_blocks(n, TPB), TPB, 0, ctx->stream>>>(a, g, nxs, nxe, 1, g.nys - 1, g.nye + 1, kk0, kk1);
+  if (g.bc == WM_BC_PERIODIC)
+    k_x_copy<1><<<wm_blocks(n, TPB), TPB, 0, ctx->stream>>>(a, g, nxs, nxe, 1, g.nys - 1, g.nye + 1, kk0, kk1);
+  else
+    k_x_wall_phi<<<wm_blocks(n, TPB), TPB, 0, ctx->stream>>>(a, g, nxs, nxe, l, g.nys - 1, g.nye + 1, kk0, kk1);
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
 }
@@ -645,6 +690,11 @@ int wm_k_dfield(wm_ctx* ctx, int nxs, int nxe) {
     const int kk0 = g.dim == 3 ? g.nzs - 2 : 0, kk1 = g.dim == 3 ? g.nze + 2 : 0;
     const int n = g.by * (kk1 - kk0 + 1) * 6;
     k_x_copy<6><<<wm_blocks(n, TPB), TPB, 0, ctx->stream>>>(df, g, nxs, nxe, 2, g.nys - 2, g.nye + 2, kk0, kk1);
+    WM_LAUNCH_CHECK(ctx);
+  } else {
+    const int kk0 = g.dim == 3 ? g.nzs - 2 : 0, kk1 = g.dim == 3 ? g.nze + 2 : 0;
+    const int n = g.by * (kk1 - kk0 + 1);
+    k_x_wall_dfield<<<wm_blocks(n, TPB), TPB, 0, ctx->stream>>>(df, g, nxs, nxe, g.nys - 2, g.nye + 2, kk0, kk1);
     WM_LAUNCH_CHECK(ctx);
   }
   return WM_OK;

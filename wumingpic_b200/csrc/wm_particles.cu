@@ -304,15 +304,48 @@ __global__ void __launch_bounds__(TPB) k_deposit(Geo g, Ptcl A, Ptcl B, const in
 }
 
 // ---------------------------------------------------------------------------------------------
-// K12: x boundary on the pushed set   boundary_periodic.f90:68-101
+// K12: x boundary on the pushed set
+//   periodic     3d/common/boundary_periodic.f90:68-101 (int(x*d_delx), round-to-nearest)
+//                2d/common/boundary_periodic.f90:61-96  (int(x/delx) and the wrap under ieee_down, :74)
+//   reflecting   {2d,3d}/proj/reconnection/boundary_reconnection.f90:61-99 / :69-110, 2d/proj/shock/boundary_shock.f90:62-100
+//   injection    2d/proj/shock/boundary_shock.f90:255-297, 3d/proj/shock/boundary_shock.f90:424-469
 // ---------------------------------------------------------------------------------------------
+template <int D>
 __global__ void k_bc_x_periodic(Geo g, double* __restrict__ x, long long n) {
-  const double len = (g.nxge - g.nxgs + 1) * g.delx;
+  const double len = D == 2 ? __dmul_rd((double)(g.nxge - g.nxgs + 1), g.delx) : (g.nxge - g.nxgs + 1) * g.delx;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
     double xx = x[p];
-    int ipos = (int)(xx * g.d_delx);
-    if (ipos < g.nxgs) x[p] = xx + len;
-    else if (ipos >= g.nxge + 1) x[p] = xx - len;
+    int ipos = D == 2 ? (int)__ddiv_rd(xx, g.delx) : (int)(xx * g.d_delx);
+    if (ipos < g.nxgs) x[p] = D == 2 ? __dadd_rd(xx, len) : xx + len;
+    else if (ipos >= g.nxge + 1) x[p] = D == 2 ? __dadd_rd(xx, -len) : xx - len;
+  }
+}
+
+// kind 1: reflecting walls at (nxs+1) delx and (nxe-1) delx; kind 2: left wall + moving right wall xend (injection)
+template <int D>
+__global__ void k_bc_x_walls(Geo g, Ptcl P, long long n, int nxs, int nxe, int kind, double u0) {
+  constexpr int U = D;
+  const double xend = nxe * g.delx + u0 / sqrt(1.0 + (u0 * u0) / (g.c * g.c)) * g.delt;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    const double xx = P.c[0][p];
+    // the 2-D modules and the 3-D reconnection module divide by delx; the 3-D shock module multiplies by d_delx
+    const int ipos = (D == 3 && kind == 2) ? (int)(xx * g.d_delx) : (int)(xx / g.delx);
+    if (ipos < nxs + 1) {
+      P.c[0][p] = 2.0 * (nxs + 1) * g.delx - xx;
+      P.c[U][p] = -P.c[U][p];
+      P.c[U + 1][p] = -P.c[U + 1][p];
+      P.c[U + 2][p] = -P.c[U + 2][p];
+    } else if (kind == 1 ? ipos >= nxe - 1 : xx > xend) {
+      if (kind == 1) {
+        P.c[0][p] = 2.0 * (nxe - 1) * g.delx - xx;
+        P.c[U][p] = -P.c[U][p];
+      } else {
+        P.c[0][p] = 2.0 * xend - xx;
+        P.c[U][p] = 2.0 * u0 - P.c[U][p];
+      }
+      P.c[U + 1][p] = -P.c[U + 1][p];
+      P.c[U + 2][p] = -P.c[U + 2][p];
+    }
   }
 }
 
@@ -390,14 +423,19 @@ int wm_k_deposit(wm_ctx* ctx, int nxs, int nxe) {
   return WM_OK;
 }
 
-int wm_k_bc_x(wm_ctx* ctx, int /*nxs*/, int /*nxe*/, int kind, double /*u0*/) {
+// kind: WM_BC_PERIODIC wrap, WM_BC_RECONNECTION reflecting walls (also boundary_shock__particle_x), WM_BC_SHOCK injection
+int wm_k_bc_x(wm_ctx* ctx, int nxs, int nxe, int kind, double u0) {
   const Geo& g = ctx->g;
-  if (kind != WM_BC_PERIODIC) {
-    wm_set_error("x boundary kind not implemented yet");
-    return WM_ERR_ARG;
-  }
   if (ctx->ntot == 0) return WM_OK;
-  k_bc_x_periodic<<<grid_for(ctx->ntot), TPB, 0, ctx->stream>>>(g, ctx->B.c[0], ctx->ntot);
+  const int blocks = grid_for(ctx->ntot);
+  if (kind == WM_BC_PERIODIC) {
+    if (g.dim == 3) k_bc_x_periodic<3><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->B.c[0], ctx->ntot);
+    else k_bc_x_periodic<2><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->B.c[0], ctx->ntot);
+  } else {
+    const int k = kind == WM_BC_SHOCK ? 2 : 1;
+    if (g.dim == 3) k_bc_x_walls<3><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->B, ctx->ntot, nxs, nxe, k, u0);
+    else k_bc_x_walls<2><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->B, ctx->ntot, nxs, nxe, k, u0);
+  }
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
 }

@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(TPB) k_classify(Geo g, Ptcl B, Ptcl P, const d
   const int nxr = nxe - nxs + 1;
   const int npl = g.nyl * g.nzl;
   const long long per_sp = (long long)nxr * npl;
-  const double len_y = (g.nyge - g.nygs + 1) * g.delx, len_z = (g.nzge - g.nzgs + 1) * g.delx;
+  const double len_y = D == 2 ? __dmul_rd((double)(g.nyge - g.nygs + 1), g.delx) : (g.nyge - g.nygs + 1) * g.delx;
+  const double len_z = (g.nzge - g.nzgs + 1) * g.delx;
   for (long long w = warp; w < per_sp * 2; w += nwarps) {
     const int isp = (int)(w / per_sp);
     const long long wi = w % per_sp;
@@ -77,8 +78,8 @@ __global__ void __launch_bounds__(TPB) k_classify(Geo g, Ptcl B, Ptcl P, const d
         int ix = (int)v[0];                          // sort.f90:65: no d_delx
         if (ix == nxe + 1) ix = nxe;                 // a periodic wrap that rounded onto the upper edge stays in the last cell
         int di = ix - i;
-        if (di > 1) di -= g.nx; else if (di < -1) di += g.nx;
-        const int jpos = (int)(v[1] * g.d_delx);
+        if (g.bc == WM_BC_PERIODIC) { if (di > 1) di -= g.nx; else if (di < -1) di += g.nx; }
+        const int jpos = D == 2 ? (int)__ddiv_rd(v[1], g.delx) : (int)(v[1] * g.d_delx);   // 2-D: int(y/delx) under ieee_down
         int dj = jpos - j, dk = 0;
         if (jpos <= g.nygs - 1) v[1] = D == 2 ? __dadd_rd(v[1], len_y) : v[1] + len_y;
         else if (jpos >= g.nyge + 1) v[1] = D == 2 ? __dadd_rd(v[1], -len_y) : v[1] - len_y;
