@@ -143,6 +143,11 @@ int wm_create(const wm_params* prm, wm_ctx** out) {
   g.delx = p.delx; g.delt = p.delt; g.c = p.c; g.gfac = p.gfac;
   g.d_delx = 1.0 / p.delx; g.d_delt = 1.0 / p.delt;
   for (int s = 0; s < 2; ++s) { g.q[s] = p.q[s]; g.r[s] = p.r[s]; }
+  for (int s = 0; s < 2; ++s) {
+    g.fac1[s] = p.q[s] / p.r[s] * 5e-1 * p.delt;
+    g.fac2[s] = p.q[s] * p.delt / p.r[s];
+    g.qdxdt[s] = p.q[s] * p.delx * g.d_delt;
+  }
   // field__init: 3d/common/field.f90:57-63, 2d/common/field.f90:53-59
   g.f1 = p.c * p.delt / p.delx;
   g.f2 = p.gfac * g.f1 * g.f1;

@@ -15,6 +15,12 @@
 //       phase B  one OUTPUT STRIP per thread: (cell, component, transverse index) owns 4x5 current values
 //                in REGISTERS and walks the records of its cell: acc[r][kp] += c[r] * (A*S0[kp] + B*DS[kp]).
 //     No atomics and no shuffles on the per-particle path; each strip ends with <= 20 RED.F64 to global J.
+//     Records are written two-ended inside a batch: particles that stay in their cell (inc = 0 on every axis, the
+//     majority) from slot 0 up, cell-crossers from slot 15 down.  A stayer has S0 = DS = 0 on the two outer stencil
+//     points of every axis and c0 = 0, c3 = O(eps), so phase B runs a lean 2x3 loop over the stayer slots (15 fp64
+//     instructions per particle and strip instead of 31) and the full 4x5 loop only over the crossers.
+//   * the next batch's particle loads are issued before the current batch is processed (register prefetch), so the
+//     global-load latency hides behind ~1.5 k instructions of phase A/B work instead of stalling 4 warps per scheduler.
 //   * a CTA owns 16 consecutive x cells of one (j,k) pencil: their particles are one contiguous run of the
 //     cell-sorted SoA (coalesced 128-byte loads per half-warp) and share an 18x3x3 field tile.
 //   * the kernel also counts, per source cell, how many particles go to each of the 27 neighbour cells.
@@ -82,20 +88,13 @@ __device__ __forceinline__ void shape3(double dh, double& sm, double& s0, double
   sp = 5e-1 * (5e-1 + dh) * (5e-1 + dh);
 }
 
-// S0 (about the loop cell) and DS = S1 - S0 (S1 about int(x_new)) on the 5-point stencil, field.f90:255-325
-__device__ __forceinline__ int s0ds(double xo, double xn, int cell, double d_delx, double s0[5], double ds[5],
-                                    int* flags) {
+// S0 (about the loop cell) and DS = S1 - S0 (S1 about int(x_new) = cell + inc) on the 5-point stencil, field.f90:255-325
+__device__ __forceinline__ void s0ds(double xo, double xn, int cell, int inc, double d_delx, double s0[5], double ds[5]) {
   double dh = xo * d_delx - 5e-1 - cell;
   s0[0] = 0.0;
   shape3(dh, s0[1], s0[2], s0[3]);
   s0[4] = 0.0;
-  int i2 = (int)(xn * d_delx);
-  dh = xn * d_delx - 5e-1 - i2;
-  int inc = i2 - cell;
-  if (inc < -1 || inc > 1) {
-    atomicOr(flags, 2);
-    inc = inc < 0 ? -1 : 1;
-  }
+  dh = xn * d_delx - 5e-1 - (cell + inc);
   double a, b, c;
   shape3(dh, a, b, c);
   ds[0] = inc == -1 ? a : 0.0;
@@ -105,7 +104,6 @@ __device__ __forceinline__ int s0ds(double xo, double xn, int cell, double d_del
   ds[4] = inc == 1 ? c : 0.0;
 #pragma unroll
   for (int m = 0; m < 5; ++m) ds[m] = ds[m] - s0[m];
-  return inc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -167,8 +165,8 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
 #pragma unroll
   for (int e = 0; e < 20; ++e) acc[e] = 0.0;
 
-  // record field indices: 0..5 = c prefix sums (x01 x23 y01 y23 z01 z23), 6+5a+m = (S0,DS)[m] of axis a
-  const int f_c = 2 * comp;
+  // record field indices: 2a = (c1,c2), 2a+1 = (c0,c3) prefix sums of axis a; 6+5a+m = (S0,DS)[m] of axis a
+  const int f_c = 2 * comp;                       // (c1,c2) of the running axis; f_c + 1 = (c0,c3)
   const int ax1 = comp == 0 ? 1 : 0;              // first transverse axis (A,B): y for Jx, x for Jy and Jz
   const int ax2 = comp == 2 ? 1 : 2;              // second transverse axis: z for Jx and Jy, y for Jz
   const double fac = 1.0 / 3.0;
@@ -181,19 +179,34 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
   mbar_wait(&S.bar, 0);
 
   int ns0 = 0, nl0 = 0, ns1 = 0, nl1 = 0;   // stayers / leavers of this thread's cell written so far, per species
+  // register prefetch of the next batch's particle (index -1: none)
+  double nx_ = 0, ny_ = 0, nz_ = 0, nux = 0, nuy = 0, nuz = 0, nid = 0;
+  int np_ = -1, nisp = 0;
+  auto fetch = [&](int batch) {
+    const int idx = batch * SLOTS + sa;
+    np_ = -1; nisp = 0;
+    if (idx < n0a) { np_ = S.beg[0][ca] + idx; }
+    else if (idx < n0a + n1a) { np_ = S.beg[1][ca] + (idx - n0a); nisp = 1; }
+    if (np_ >= 0) {
+      nx_ = A.c[0][np_]; ny_ = A.c[1][np_]; nz_ = A.c[2][np_];
+      nux = A.c[3][np_]; nuy = A.c[4][np_]; nuz = A.c[5][np_];
+      nid = id_in[np_];
+    }
+  };
+  fetch(0);
   for (int batch = 0; batch < nbatch; ++batch) {
+    int nst = 0, ncr = 0;   // stayer / crosser records of this half-warp's cell in this batch
     // ------------------------------ phase A ------------------------------
     {
-      const int idx = batch * SLOTS + sa;
-      int p = -1, isp = 0;
-      if (idx < n0a) { p = S.beg[0][ca] + idx; }
-      else if (idx < n0a + n1a) { p = S.beg[1][ca] + (idx - n0a); isp = 1; }
-      double xn = 0, yn = 0, zn = 0, ux = 0, uy = 0, uz = 0, idv = 0;
+      const int p = np_, isp = nisp;
+      const double x = nx_, y = ny_, z = nz_;
+      double ux = nux, uy = nuy, uz = nuz;
+      const double idv = nid;
+      if (batch + 1 < nbatch) fetch(batch + 1);
+      double xn = 0, yn = 0, zn = 0;
       int o = 13;
+      int inc0 = 0, inc1 = 0, inc2 = 0;
       if (p >= 0) {
-        const double x = A.c[0][p], y = A.c[1][p], z = A.c[2][p];
-        ux = A.c[3][p]; uy = A.c[4][p]; uz = A.c[5][p];
-        idv = id_in[p];
         double sx[3], sy[3], sz[3];
         shape3(x * g.d_delx - 5e-1 - ia, sx[0], sx[1], sx[2]);
         shape3(y * g.d_delx - 5e-1 - j, sy[0], sy[1], sy[2]);
@@ -219,9 +232,9 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
           for (int c = 0; c < 6; ++c) f[c] = kk == 0 ? pl[c] * sz[0] : f[c] + pl[c] * sz[kk];
         }
         // Buneman-Boris  particle.f90:186-217
-        const double fac1 = g.q[isp] / g.r[isp] * 5e-1 * g.delt;
+        const double fac1 = g.fac1[isp];   // per-species constants computed once on the host (wm_create)
         const double txxx = fac1 * fac1;
-        const double fac2 = g.q[isp] * g.delt / g.r[isp];
+        const double fac2 = g.fac2[isp];
         {
           const double bpx = f[0], bpy = f[1], bpz = f[2], epx = f[3], epy = f[4], epz = f[5];
           double uvm1 = ux + fac1 * epx, uvm2 = uy + fac1 * epy, uvm3 = uz + fac1 * epz;
@@ -246,26 +259,47 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
           yn = y + uy * g.delt * gam;
           zn = z + uz * g.delt * gam;
         }
+        // cell increments (field.f90:280-283): the destination offset of the sort and the stayer / crosser class
+        inc0 = (int)(xn * g.d_delx) - ia;
+        inc1 = (int)(yn * g.d_delx) - j;
+        inc2 = (int)(zn * g.d_delx) - k;
+        if (inc0 < -1 || inc0 > 1 || inc1 < -1 || inc1 > 1 || inc2 < -1 || inc2 > 1) {
+          atomicOr(flags, 2);
+          inc0 = max(-1, min(1, inc0)); inc1 = max(-1, min(1, inc1)); inc2 = max(-1, min(1, inc2));
+        }
+        o = (inc0 + 1) + 3 * (inc1 + 1) + 9 * (inc2 + 1);
+        atomicAdd(&S.cnt27[isp][o][ca], 1);
+      }
+      // The 16 lanes of a half-warp share the cell; ranks come from ballots.  Stayers take record slots 0.. and the
+      // front of the cell's run in the pushed set, leavers record slots 15.. downwards and the back of the run (what
+      // wm_sort.cu's gather expects).
+      const unsigned lane = t & 31u;
+      const unsigned half = 0xffffu << (lane & 16u);
+      const unsigned lower = half & ((1u << lane) - 1u);
+      const bool v0 = p >= 0 && isp == 0, v1 = p >= 0 && isp == 1, st = o == 13;
+      const unsigned bs0 = __ballot_sync(0xffffffffu, v0 && st) & half, bl0 = __ballot_sync(0xffffffffu, v0 && !st) & half;
+      const unsigned bs1 = __ballot_sync(0xffffffffu, v1 && st) & half, bl1 = __ballot_sync(0xffffffffu, v1 && !st) & half;
+      nst = __popc(bs0 | bs1);
+      ncr = __popc(bl0 | bl1);
+      if (p >= 0) {
         // Esirkepov 1-D factors -> record
-        const double qdxdt = g.q[isp] * g.delx * g.d_delt;
-        const int slot = ca * CSTR + sa;
-        int inc[3];
-        {
-          const double xo[3] = {x, y, z}, xnw[3] = {xn, yn, zn};
-          const int cell[3] = {ia, j, k};
+        const double qdxdt = g.qdxdt[isp];
+        const int slot = ca * CSTR + (st ? __popc((bs0 | bs1) & lower) : SLOTS - 1 - __popc((bl0 | bl1) & lower));
+        const double xo[3] = {x, y, z}, xnw[3] = {xn, yn, zn};
+        const int cell[3] = {ia, j, k};
+        const int inc[3] = {inc0, inc1, inc2};
 #pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            double s0[5], ds[5];
-            inc[a] = s0ds(xo[a], xnw[a], cell[a], g.d_delx, s0, ds, flags);
-            const double c0 = -ds[0] * qdxdt;
-            const double c1 = c0 - ds[1] * qdxdt;
-            const double c2 = c1 - ds[2] * qdxdt;
-            const double c3 = c2 - ds[3] * qdxdt;
-            S.rec[(2 * a) * FSTR + slot] = make_double2(c0, c1);
-            S.rec[(2 * a + 1) * FSTR + slot] = make_double2(c2, c3);
+        for (int a = 0; a < 3; ++a) {
+          double s0[5], ds[5];
+          s0ds(xo[a], xnw[a], cell[a], inc[a], g.d_delx, s0, ds);
+          const double c0 = -ds[0] * qdxdt;
+          const double c1 = c0 - ds[1] * qdxdt;
+          const double c2 = c1 - ds[2] * qdxdt;
+          const double c3 = c2 - ds[3] * qdxdt;
+          S.rec[(2 * a) * FSTR + slot] = make_double2(c1, c2);
+          S.rec[(2 * a + 1) * FSTR + slot] = make_double2(c0, c3);
 #pragma unroll
-            for (int m = 0; m < 5; ++m) S.rec[(6 + 5 * a + m) * FSTR + slot] = make_double2(s0[m], ds[m]);
-          }
+          for (int m = 0; m < 5; ++m) S.rec[(6 + 5 * a + m) * FSTR + slot] = make_double2(s0[m], ds[m]);
         }
         // boundaries: periodic x (boundary_periodic.f90:86-92) and periodic y,z wrap of the coordinate (:161-171).
         // The destination cell is fixed by the pre-wrap integer cell, as in the reference.
@@ -280,38 +314,39 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
           if (kpos <= g.nzgs - 1) zn = zn + len_z;
           else if (kpos >= g.nzge + 1) zn = zn - len_z;
         }
-        o = (inc[0] + 1) + 3 * (inc[1] + 1) + 9 * (inc[2] + 1);
-        atomicAdd(&S.cnt27[isp][o][ca], 1);
+        int pw;
+        if (isp == 0) pw = st ? S.beg[0][ca] + ns0 + __popc(bs0 & lower) : S.beg[0][ca + 1] - 1 - (nl0 + __popc(bl0 & lower));
+        else          pw = st ? S.beg[1][ca] + ns1 + __popc(bs1 & lower) : S.beg[1][ca + 1] - 1 - (nl1 + __popc(bl1 & lower));
+        B.c[0][pw] = xn; B.c[1][pw] = yn; B.c[2][pw] = zn;
+        B.c[3][pw] = ux; B.c[4][pw] = uy; B.c[5][pw] = uz;
+        id_out[pw] = idv;
+        if (!st) dst_off[pw] = (unsigned char)o;
       }
-      // two-ended write of the pushed set inside the source cell: stayers packed at the front, leavers at the back
-      // (what wm_sort.cu's gather expects).  The 16 lanes of a half-warp share the cell; ranks come from ballots.
-      {
-        const unsigned lane = t & 31u;
-        const unsigned half = 0xffffu << (lane & 16u);
-        const unsigned lower = half & ((1u << lane) - 1u);
-        const bool v0 = p >= 0 && isp == 0, v1 = p >= 0 && isp == 1, st = o == 13;
-        const unsigned bs0 = __ballot_sync(0xffffffffu, v0 && st) & half, bl0 = __ballot_sync(0xffffffffu, v0 && !st) & half;
-        const unsigned bs1 = __ballot_sync(0xffffffffu, v1 && st) & half, bl1 = __ballot_sync(0xffffffffu, v1 && !st) & half;
-        if (p >= 0) {
-          int pw;
-          if (isp == 0) pw = st ? S.beg[0][ca] + ns0 + __popc(bs0 & lower) : S.beg[0][ca + 1] - 1 - (nl0 + __popc(bl0 & lower));
-          else          pw = st ? S.beg[1][ca] + ns1 + __popc(bs1 & lower) : S.beg[1][ca + 1] - 1 - (nl1 + __popc(bl1 & lower));
-          B.c[0][pw] = xn; B.c[1][pw] = yn; B.c[2][pw] = zn;
-          B.c[3][pw] = ux; B.c[4][pw] = uy; B.c[5][pw] = uz;
-          id_out[pw] = idv;
-          if (!st) dst_off[pw] = (unsigned char)o;
-        }
-        ns0 += __popc(bs0); nl0 += __popc(bl0); ns1 += __popc(bs1); nl1 += __popc(bl1);
-      }
+      ns0 += __popc(bs0); nl0 += __popc(bl0); ns1 += __popc(bs1); nl1 += __popc(bl1);
     }
     __syncwarp();
     // ------------------------------ phase B ------------------------------
     if (b_active) {
-      const int nv = min(SLOTS, ncb - batch * SLOTS);
-      for (int s = 0; s < nv; ++s) {
+      // stayers: S0 = DS = 0 at m = 0, 4 on every axis, c0 = 0 and c3 = -(sum of DS) q = O(eps) q (dropped: it is the
+      // round-off residue of a term that is exactly zero, field.f90:341-349)
+      for (int s = 0; s < nst; ++s) {
         const int slot = cb * CSTR + s;
-        const double2 c01 = S.rec[f_c * FSTR + slot];
-        const double2 c23 = S.rec[(f_c + 1) * FSTR + slot];
+        const double2 c12 = S.rec[f_c * FSTR + slot];
+        const double2 p1 = S.rec[(6 + 5 * ax1 + mb) * FSTR + slot];
+        const double Av = p1.x + 5e-1 * p1.y;
+        const double Bv = 5e-1 * p1.x + fac * p1.y;
+#pragma unroll
+        for (int kp = 1; kp < 4; ++kp) {
+          const double2 p2 = S.rec[(6 + 5 * ax2 + kp) * FSTR + slot];
+          const double D = Av * p2.x + Bv * p2.y;
+          acc[1 * 5 + kp] += c12.x * D;
+          acc[2 * 5 + kp] += c12.y * D;
+        }
+      }
+      for (int s = SLOTS - ncr; s < SLOTS; ++s) {
+        const int slot = cb * CSTR + s;
+        const double2 c12 = S.rec[f_c * FSTR + slot];
+        const double2 c03 = S.rec[(f_c + 1) * FSTR + slot];
         const double2 p1 = S.rec[(6 + 5 * ax1 + mb) * FSTR + slot];
         const double Av = p1.x + 5e-1 * p1.y;
         const double Bv = 5e-1 * p1.x + fac * p1.y;
@@ -319,10 +354,10 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
         for (int kp = 0; kp < 5; ++kp) {
           const double2 p2 = S.rec[(6 + 5 * ax2 + kp) * FSTR + slot];
           const double D = (kp == 0 || kp == 4) ? Bv * p2.y : Av * p2.x + Bv * p2.y;
-          acc[0 * 5 + kp] += c01.x * D;
-          acc[1 * 5 + kp] += c01.y * D;
-          acc[2 * 5 + kp] += c23.x * D;
-          acc[3 * 5 + kp] += c23.y * D;
+          acc[0 * 5 + kp] += c03.x * D;
+          acc[1 * 5 + kp] += c12.x * D;
+          acc[2 * 5 + kp] += c12.y * D;
+          acc[3 * 5 + kp] += c03.y * D;
         }
       }
     }

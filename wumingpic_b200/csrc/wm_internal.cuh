@@ -28,6 +28,8 @@ struct Geo {
   double delx, delt, c, gfac, d_delx, d_delt;
   double q[2], r[2];
   double f1, f2, f3, f4, f5;
+  // per-species constants: fac1 = q/r*0.5*delt, fac2 = q*delt/r (particle.f90:101-103), qdxdt = q*delx*d_delt (field.f90:297)
+  double fac1[2], fac2[2], qdxdt[2];
 
   __host__ __device__ inline size_t box(int i, int j, int k) const {
     return ((size_t)(dim == 3 ? (k - (nzs - 2)) : 0) * by + (j - (nys - 2))) * bx + (i - (nxgs - 2));

@@ -142,9 +142,17 @@ __global__ void k_add_incoming(Geo g, const int* __restrict__ inc, int* __restri
 // k_gather: the data movement of the sort, destination-centric (see the file header).
 // (A source-centric scatter writes 10-20 partial 32-byte sectors per cell and array, and every partial-sector
 //  write miss costs a DRAM sector fill: measured 2.1x read / 1.5x write amplification, profiles/r01_sort.md.)
+// Three phases per CTA, so that a CTA waits for global memory three times instead of twice per source zone
+// (profiles/r01_gather_v2.md: the per-zone dependent chain dst_off -> ballot -> payload load was 60 % of the stalls):
+//   1  the offset bytes of all <= 90 leaver zones around the run -> shared memory (independent coalesced loads)
+//   2  index arithmetic only: src[pos] = source index of the particle that lands on position pos of the run
+//      (stayers: a block per cell; arrivals: ballot-ranked out of the zone bytes, cursors in registers)
+//   3  A[base + pos] = B[src[pos]] for the 6 coordinate arrays and the ID: full-sector coalesced stores,
+//      all loads of a thread independent
 // ---------------------------------------------------------------------------------------------
 constexpr int GD = 8;       // destination cells per CTA
-constexpr int CAP = 768;    // tile capacity in particles; the (rare) overflow of a dense run goes straight to global
+constexpr int CAP = 1024;   // run capacity of the index tile; the (rare) overflow of a dense run is copied directly
+constexpr int ZCAP = 6144;  // capacity of the zone-byte buffer; zones that do not fit are read from global memory
 constexpr int MAXSLOT = (GD + 2) * 9;
 
 struct Slot { int beg, end, obase, pos[3]; };   // leaver zone of one source cell; run position per di, or -1
@@ -182,13 +190,14 @@ __global__ void __launch_bounds__(TPB) k_gather(Geo g, Ptcl B, Ptcl A, const dou
                                                 const int* __restrict__ cs_new, const int* __restrict__ cnt,
                                                 const unsigned char* __restrict__ dst_off, int nxs, int nxe, int ngx) {
   constexpr int NC = D == 3 ? 6 : 5;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* tile = reinterpret_cast<double*>(smem_raw);                 // [NC+1][CAP], laid out like the output run
-  int* s_new = reinterpret_cast<int*>(tile + (NC + 1) * CAP);         // [GD+1] new cell starts of the run
-  int* s_P = s_new + GD + 1;                                          // [GD][28] group sizes -> exclusive prefix per cell
-  int* s_stay = s_P + GD * 28;                                        // [GD][2] source start of the stayers, count
-  int* s_list = s_stay + GD * 2;                                      // [MAXSLOT+1] live slots, count
-  Slot* s_slot = reinterpret_cast<Slot*>(s_list + MAXSLOT + 1);       // [MAXSLOT]
+  __shared__ int s_src[CAP];                 // source index per position of the output run
+  __shared__ unsigned char s_zone[ZCAP];     // offset bytes of the live leaver zones, back to back
+  __shared__ int s_new[GD + 1];              // new cell starts of the run
+  __shared__ int s_P[GD * 28];               // group sizes -> exclusive prefix per destination cell
+  __shared__ int s_stay[GD * 2];             // source start of the stayers, count
+  __shared__ int s_list[MAXSLOT + 1];        // live slots, count
+  __shared__ int s_zoff[MAXSLOT];            // start of a live slot's bytes in s_zone, or -1 (read from global memory)
+  __shared__ Slot s_slot[MAXSLOT];
   const int t = threadIdx.x, lane = t & 31, wib = t >> 5;
   // ---- which destination run: local rows in strip order, ghost rows last; x groups fastest ----
   const int gx = blockIdx.x % ngx;
@@ -270,30 +279,51 @@ __global__ void __launch_bounds__(TPB) k_gather(Geo g, Ptcl B, Ptcl A, const dou
     s_slot[t] = sl;
   }
   __syncthreads();
-  // compact list of the slots that have something to scan (one warp, ballot compaction)
+  // compact list of the slots that have something to scan, and where their bytes go (one warp, ballot compaction)
   if (wib == 0) {
-    int n = 0;
+    int n = 0, zo = 0;
     for (int q0 = 0; q0 < nslot; q0 += 32) {
       const int q = q0 + lane;
-      const bool live = q < nslot && s_slot[q].beg < s_slot[q].end;
+      const int len = q < nslot ? s_slot[q].end - s_slot[q].beg : 0;
+      const bool live = len > 0;
       const unsigned m = __ballot_sync(0xffffffffu, live);
-      if (live) s_list[n + __popc(m & ((1u << lane) - 1u))] = q;
+      // exclusive prefix of the (16-byte padded) zone lengths over the lanes
+      const int plen = live ? (len + 15) & ~15 : 0;
+      int incl = plen;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (live) {
+        const int idx = n + __popc(m & ((1u << lane) - 1u));
+        const int start = zo + incl - plen;
+        s_list[idx] = q;
+        s_zoff[idx] = start + plen <= ZCAP ? start : -1;
+      }
       n += __popc(m);
+      zo += __shfl_sync(0xffffffffu, incl, 31);
     }
     if (lane == 0) s_list[MAXSLOT] = n;
   }
   __syncthreads();
   const int nlist = s_list[MAXSLOT];
-  // ---- stayers: block copies ----
+  // ---- phase 1: zone bytes -> shared memory ----
+  for (int q = wib; q < nlist; q += TPB / 32) {
+    const int zo = s_zoff[q];
+    if (zo < 0) continue;
+    const Slot& sl = s_slot[s_list[q]];
+    const int beg = sl.beg, len = sl.end - beg;
+    for (int e = lane; e < len; e += 32) s_zone[zo + e] = dst_off[beg + e];
+  }
+  // ---- phase 2a: stayers (index arithmetic only; no shared-memory dependence on phase 1) ----
   for (int d = wib; d < ncg; d += TPB / 32) {
     const int sb = s_stay[2 * d], n = s_stay[2 * d + 1];
     const int dp = (s_new[d] - base) + s_P[d * 28 + 13];
     for (int e = lane; e < n; e += 32) {
       const int pos = dp + e;
       if (pos < CAP) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) tile[c * CAP + pos] = B.c[c][sb + e];
-        tile[NC * CAP + pos] = id_in[sb + e];
+        s_src[pos] = sb + e;
       } else {
 #pragma unroll
         for (int c = 0; c < NC; ++c) A.c[c][base + pos] = B.c[c][sb + e];
@@ -301,15 +331,16 @@ __global__ void __launch_bounds__(TPB) k_gather(Geo g, Ptcl B, Ptcl A, const dou
       }
     }
   }
-  // ---- arrivals: ballot-ranked pick out of the leaver zones (cursors live in registers, warp-uniform) ----
+  __syncthreads();
+  // ---- phase 2b: arrivals: ballot-ranked pick out of the leaver zones (cursors live in registers, warp-uniform) ----
   for (int q = wib; q < nlist; q += TPB / 32) {
     const Slot& sl = s_slot[s_list[q]];
-    const int end = sl.end, obase = sl.obase;
+    const int beg = sl.beg, end = sl.end, obase = sl.obase, zo = s_zoff[q];
     int c0 = sl.pos[0], c1 = sl.pos[1], c2 = sl.pos[2];
-    for (int p0 = sl.beg; p0 < end; p0 += 32) {
+    for (int p0 = beg; p0 < end; p0 += 32) {
       const int p = p0 + lane;
       int r = -1;
-      if (p < end) r = (int)dst_off[p] - obase;
+      if (p < end) r = (int)(zo >= 0 ? s_zone[zo + (p - beg)] : dst_off[p]) - obase;
       const unsigned m0 = __ballot_sync(0xffffffffu, r == 0 && c0 >= 0);
       const unsigned m1 = __ballot_sync(0xffffffffu, r == 1 && c1 >= 0);
       const unsigned m2 = __ballot_sync(0xffffffffu, r == 2 && c2 >= 0);
@@ -321,9 +352,7 @@ __global__ void __launch_bounds__(TPB) k_gather(Geo g, Ptcl B, Ptcl A, const dou
       c0 += __popc(m0); c1 += __popc(m1); c2 += __popc(m2);
       if (pos >= 0) {
         if (pos < CAP) {
-#pragma unroll
-          for (int c = 0; c < NC; ++c) tile[c * CAP + pos] = B.c[c][p];
-          tile[NC * CAP + pos] = id_in[p];
+          s_src[pos] = p;
         } else {
 #pragma unroll
           for (int c = 0; c < NC; ++c) A.c[c][base + pos] = B.c[c][p];
@@ -333,11 +362,17 @@ __global__ void __launch_bounds__(TPB) k_gather(Geo g, Ptcl B, Ptcl A, const dou
     }
   }
   __syncthreads();
+  // ---- phase 3: the data movement ----
   const int nw = min(ntile, CAP);
   for (int e = t; e < nw; e += TPB) {
+    const int p = s_src[e];
+    double v[NC + 1];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) A.c[c][base + e] = tile[c * CAP + e];
-    id_out[base + e] = tile[NC * CAP + e];
+    for (int c = 0; c < NC; ++c) v[c] = B.c[c][p];
+    v[NC] = id_in[p];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) A.c[c][base + e] = v[c];
+    id_out[base + e] = v[NC];
   }
 }
 
@@ -516,21 +551,12 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
   {
     const int ngx = (nxe - nxs + 1 + GD - 1) / GD;
     const int blocks = g.nrows * ngx;
-    const size_t nint = (GD + 1) + GD * 28 + GD * 2 + MAXSLOT + 1;
-    const size_t smem3 = (size_t)7 * CAP * sizeof(double) + nint * sizeof(int) + MAXSLOT * sizeof(Slot);
-    const size_t smem2 = (size_t)6 * CAP * sizeof(double) + nint * sizeof(int) + MAXSLOT * sizeof(Slot);
-    static bool attr_set = false;
-    if (!attr_set) {
-      WM_CUDA(cudaFuncSetAttribute(k_gather<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-      WM_CUDA(cudaFuncSetAttribute(k_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      attr_set = true;
-    }
     if (g.dim == 3)
-      k_gather<3><<<blocks, TPB, smem3, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs, ctx->cs_new,
-                                              ctx->cnt27, ctx->dst_off, nxs, nxe, ngx);
+      k_gather<3><<<blocks, TPB, 0, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs, ctx->cs_new,
+                                          ctx->cnt27, ctx->dst_off, nxs, nxe, ngx);
     else
-      k_gather<2><<<blocks, TPB, smem2, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs, ctx->cs_new,
-                                              ctx->cnt27, ctx->dst_off, nxs, nxe, ngx);
+      k_gather<2><<<blocks, TPB, 0, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs, ctx->cs_new,
+                                          ctx->cnt27, ctx->dst_off, nxs, nxe, ngx);
     WM_LAUNCH_CHECK(ctx);
   }
   if (g.multi) {
