@@ -7,6 +7,8 @@
 !     3d/common/field.f90              (field__init, field__fdtd_i)
 !     3d/common/sort.f90               (sort__init, sort__bucket)
 !     3d/common/boundary_periodic.f90  (boundary_periodic__init, __particle_x, __particle_yz, __dfield, __curre, __phi)
+!     3d/proj/reconnection/boundary_reconnection.f90  (boundary_reconnection__init, __particle_x, __particle_yz, ...)
+!     3d/proj/shock/boundary_shock.f90                (boundary_shock__init, __injection, __particle_yz, ...)
 ! so that `use wuming3d` / `use boundary_periodic, bc__init => boundary_periodic__init, ...` in
 ! 3d/proj/weibel/app.f90:1-58 keep compiling.  Link these objects INSTEAD of the four reference files
 ! (INTEGRATION.md shows the two-line Makefile change); everything else of libwuming3d_common.a (mpi_set, paraio,
@@ -412,3 +414,127 @@ contains
   end subroutine boundary_periodic__phi
 
 end module boundary_periodic
+
+!-----------------------------------------------------------------------------------------------------------
+! Wall set-ups.  Same pattern as boundary_periodic: __init registers the boundary kind (so that wm_field_fdtd_i applies
+! the conducting-wall rules of __dfield / __phi and skips the x fold of __curre), the particle procedures forward to the
+! C ABI, the field-side procedures only exist so that the driver's procedure arguments resolve.
+!-----------------------------------------------------------------------------------------------------------
+module boundary_reconnection         ! replaces 3d/proj/reconnection/boundary_reconnection.f90
+  use iso_c_binding
+  use wuming_b200_c
+  implicit none
+  private
+  public :: boundary_reconnection__init
+  public :: boundary_reconnection__dfield, boundary_reconnection__particle_x, boundary_reconnection__particle_yz
+  public :: boundary_reconnection__curre, boundary_reconnection__phi
+  integer, save :: ndim, np, nsp, nxgs, nxge, nygs, nyge, nzgs, nzge, nys, nye, nzs, nze
+contains
+
+  subroutine boundary_reconnection__init(ndim_in,np_in,nsp_in,nxgs_in,nxge_in,nygs_in,nyge_in,nzgs_in, &
+       & nzge_in,nys_in,nye_in,nzs_in,nze_in,jup_in,jdown_in,kup_in,kdown_in,mnpi_in,mnpr_in, &
+       & ncomw_in,nerr_in,nstat_in,delx_in,delt_in,c_in)                       ! boundary_reconnection.f90:26-66
+    integer, intent(in) :: ndim_in, np_in, nsp_in
+    integer, intent(in) :: nxgs_in, nxge_in, nygs_in, nyge_in, nzgs_in, nzge_in, nys_in, nye_in, nzs_in, nze_in
+    integer, intent(in) :: jup_in, jdown_in, kup_in, kdown_in, mnpi_in, mnpr_in, ncomw_in, nerr_in, nstat_in(:)
+    real(8), intent(in) :: delx_in, delt_in, c_in
+    ndim = ndim_in; np = np_in; nsp = nsp_in
+    nxgs = nxgs_in; nxge = nxge_in; nygs = nygs_in; nyge = nyge_in; nzgs = nzgs_in; nzge = nzge_in
+    nys = nys_in; nye = nye_in; nzs = nzs_in; nze = nze_in
+    prm%bc_kind = WM_BC_RECONNECTION
+    call wm_shim_set_geom(ndim,np,nsp,nxgs,nxge,nygs,nyge,nzgs,nzge,nys,nye,nzs,nze,delx_in,delt_in,c_in)
+  end subroutine boundary_reconnection__init
+
+  subroutine boundary_reconnection__particle_x(up,np2,nxs,nxe)                 ! boundary_reconnection.f90:69-110
+    integer, intent(in)    :: nxs, nxe
+    real(8), intent(inout) :: up(ndim,np,nys:nye,nzs:nze,nsp)
+    integer, intent(in)    :: np2(nys:nye,nzs:nze,nsp)
+    integer(c_int) :: ierr
+    ierr = wm_bc_particle_x(ctx, int(nxs,c_int), int(nxe,c_int))              ! reflecting walls at nxs+1, nxe-1
+    call wm_check(ierr, 'bc__particle_x')
+  end subroutine boundary_reconnection__particle_x
+
+  subroutine boundary_reconnection__particle_yz(up,np2)                        ! boundary_reconnection.f90:112-464
+    real(8), intent(inout) :: up(ndim,np,nys:nye,nzs:nze,nsp)
+    integer, intent(inout) :: np2(nys:nye,nzs:nze,nsp)
+    integer(c_int) :: ierr
+    ierr = wm_bc_particle_yz(ctx)
+    call wm_check(ierr, 'bc__particle_yz')
+  end subroutine boundary_reconnection__particle_yz
+
+  subroutine boundary_reconnection__dfield(df,nxs,nxe,nys_in,nye_in,nzs_in,nze_in,nxgs_in,nxge_in)
+    integer, intent(in)    :: nxs, nxe, nys_in, nye_in, nzs_in, nze_in, nxgs_in, nxge_in
+    real(8), intent(inout) :: df(6,nxgs_in-2:nxge_in+2,nys_in-2:nye_in+2,nzs_in-2:nze_in+2)
+  end subroutine boundary_reconnection__dfield
+  subroutine boundary_reconnection__curre(uj,nxs,nxe,nys_in,nye_in,nzs_in,nze_in,nxgs_in,nxge_in)
+    integer, intent(in)    :: nxs, nxe, nys_in, nye_in, nzs_in, nze_in, nxgs_in, nxge_in
+    real(8), intent(inout) :: uj(3,nxgs_in-2:nxge_in+2,nys_in-2:nye_in+2,nzs_in-2:nze_in+2)
+  end subroutine boundary_reconnection__curre
+  subroutine boundary_reconnection__phi(phi,nxs,nxe,nys_in,nye_in,nzs_in,nze_in,l)
+    integer, intent(in)    :: nxs, nxe, nys_in, nye_in, nzs_in, nze_in, l
+    real(8), intent(inout) :: phi(nxs-1:nxe+1,nys_in-1:nye_in+1,nzs_in-1:nze_in+1)
+  end subroutine boundary_reconnection__phi
+
+end module boundary_reconnection
+
+!-----------------------------------------------------------------------------------------------------------
+module boundary_shock                ! replaces 3d/proj/shock/boundary_shock.f90
+  use iso_c_binding
+  use wuming_b200_c
+  implicit none
+  private
+  public :: boundary_shock__init
+  public :: boundary_shock__dfield, boundary_shock__particle_yz, boundary_shock__injection
+  public :: boundary_shock__curre, boundary_shock__phi
+  integer, save :: ndim, np, nsp, nxgs, nxge, nygs, nyge, nzgs, nzge, nys, nye, nzs, nze
+contains
+
+  subroutine boundary_shock__init(ndim_in,np_in,nsp_in,nxgs_in,nxge_in,nygs_in,nyge_in,nzgs_in,nzge_in, &
+       & nys_in,nye_in,nzs_in,nze_in,jup_in,jdown_in,kup_in,kdown_in,mnpi_in,mnpr_in, &
+       & ncomw_in,nerr_in,nstat_in,delx_in,delt_in,c_in)                       ! boundary_shock.f90:25-67
+    integer, intent(in) :: ndim_in, np_in, nsp_in
+    integer, intent(in) :: nxgs_in, nxge_in, nygs_in, nyge_in, nzgs_in, nzge_in, nys_in, nye_in, nzs_in, nze_in
+    integer, intent(in) :: jup_in, jdown_in, kup_in, kdown_in, mnpi_in, mnpr_in, ncomw_in, nerr_in, nstat_in(:)
+    real(8), intent(in) :: delx_in, delt_in, c_in
+    ndim = ndim_in; np = np_in; nsp = nsp_in
+    nxgs = nxgs_in; nxge = nxge_in; nygs = nygs_in; nyge = nyge_in; nzgs = nzgs_in; nzge = nzge_in
+    nys = nys_in; nye = nye_in; nzs = nzs_in; nze = nze_in
+    prm%bc_kind = WM_BC_SHOCK
+    call wm_shim_set_geom(ndim,np,nsp,nxgs,nxge,nygs,nyge,nzgs,nzge,nys,nye,nzs,nze,delx_in,delt_in,c_in)
+  end subroutine boundary_shock__init
+
+  ! The shock driver mutates up, np2, cumcnt(nxe), uf(:,nxe-1:nxe) and nxe on the host after every sort (inject /
+  ! relocate, 3d/proj/shock/app.f90): in WM_SHIM_RESIDENT mode it brackets those calls with wm_shim_sync_to_host() and
+  ! wm_shim_host_modified(); the default WM_SHIM_SYNC_EVERY_CALL mode needs no change.
+  subroutine boundary_shock__injection(up,np2,nxs,nxe,u0)                      ! boundary_shock.f90:424-469
+    integer, intent(in)    :: nxs, nxe
+    real(8), intent(inout) :: up(ndim,np,nys:nye,nzs:nze,nsp)
+    integer, intent(in)    :: np2(nys:nye,nzs:nze,nsp)
+    real(8), intent(in)    :: u0
+    integer(c_int) :: ierr
+    ierr = wm_bc_injection(ctx, int(nxs,c_int), int(nxe,c_int), real(u0,c_double))
+    call wm_check(ierr, 'bc__injection')
+  end subroutine boundary_shock__injection
+
+  subroutine boundary_shock__particle_yz(up,np2)                               ! boundary_shock.f90:70-421
+    real(8), intent(inout) :: up(ndim,np,nys:nye,nzs:nze,nsp)
+    integer, intent(inout) :: np2(nys:nye,nzs:nze,nsp)
+    integer(c_int) :: ierr
+    ierr = wm_bc_particle_yz(ctx)
+    call wm_check(ierr, 'bc__particle_yz')
+  end subroutine boundary_shock__particle_yz
+
+  subroutine boundary_shock__dfield(df,nxs,nxe,nys_in,nye_in,nzs_in,nze_in,nxgs_in,nxge_in)
+    integer, intent(in)    :: nxs, nxe, nys_in, nye_in, nzs_in, nze_in, nxgs_in, nxge_in
+    real(8), intent(inout) :: df(6,nxgs_in-2:nxge_in+2,nys_in-2:nye_in+2,nzs_in-2:nze_in+2)
+  end subroutine boundary_shock__dfield
+  subroutine boundary_shock__curre(uj,nxs,nxe,nys_in,nye_in,nzs_in,nze_in,nxgs_in,nxge_in)
+    integer, intent(in)    :: nxs, nxe, nys_in, nye_in, nzs_in, nze_in, nxgs_in, nxge_in
+    real(8), intent(inout) :: uj(3,nxgs_in-2:nxge_in+2,nys_in-2:nye_in+2,nzs_in-2:nze_in+2)
+  end subroutine boundary_shock__curre
+  subroutine boundary_shock__phi(phi,nxs,nxe,nys_in,nye_in,nzs_in,nze_in,l)
+    integer, intent(in)    :: nxs, nxe, nys_in, nye_in, nzs_in, nze_in, l
+    real(8), intent(inout) :: phi(nxs-1:nxe+1,nys_in-1:nye_in+1,nzs_in-1:nze_in+1)
+  end subroutine boundary_shock__phi
+
+end module boundary_shock

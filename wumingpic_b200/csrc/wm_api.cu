@@ -219,7 +219,7 @@ int wm_destroy(wm_ctx* c) {
   double* d[] = {c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->pcg2, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
                  c->hbuf[2], c->stage};
   for (double* p : d) if (p) cudaFree(p);
-  int* ii[] = {c->cs, c->cs_new, c->np2, c->poff, c->flags, c->cnt27, c->inc, c->inc_off, c->totals};
+  int* ii[] = {c->cs, c->cs_new, c->np2, c->poff, c->flags, c->cnt27, c->inc, c->inc_off, c->totals, c->inv, c->goff};
   if (c->dst_off) cudaFree(c->dst_off);
   for (int* p : ii) if (p) cudaFree(p);
   if (c->scan_tmp) cudaFree(c->scan_tmp);

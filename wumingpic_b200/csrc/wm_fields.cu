@@ -444,7 +444,7 @@ __global__ void k_cg_store(double* __restrict__ df, const double* __restrict__ p
 }
 
 // ---------------------------------------------------------------------------------------------
-// cgm as ONE persistent cooperative kernel (single rank, periodic): all three components, all
+// cgm as ONE persistent cooperative kernel (single rank; periodic or wall boundaries): all three components, all
 // iterations, no host round trip.  Control flow is field.f90:437-558 verbatim, including
 // the reference's stop rule quirks; the periodic ghost fill of boundary_periodic__phi becomes index
 // wrapping.  Dot products: per-block partials in a fixed order, then EVERY block folds all partials in the
@@ -500,12 +500,27 @@ __global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const
   const int ite_max = 100;
   const bool d3 = g.dim == 3;
   int red_idx = 0;
-  // neighbours with periodic wrap inside [nxs,nxe] x [nys,nye] x [nzs,nze]
+  // neighbours: periodic wrap inside [nys,nye] x [nzs,nze]; in x periodic wrap, or the wall rule of boundary_*__phi as an
+  // (index, coefficient) pair: l = 1 (odd about the wall face): phi(nxs-1) = -phi(nxs), phi(nxe+1) = -phi(nxe-2) [reconnection]
+  // or 0 [shock]; l = 2,3 (even about the wall cell): phi(nxs-1) = phi(nxs+1), phi(nxe+1) = phi(nxe-1) or 0
+  const bool per = g.bc == WM_BC_PERIODIC, rec = g.bc == WM_BC_RECONNECTION;
 #define WM_NBR(e)                                                                     \
   int i, j, k;                                                                        \
   cell_of32(g, e, nxs, nxr, i, j, k);                                                 \
   const long long o = (long long)g.box(i, j, k);                                      \
-  const long long xm = i == nxs ? o + (nxr - 1) : o - 1, xp = i == nxe ? o - (nxr - 1) : o + 1;              \
+  long long xm = o - 1, xp = o + 1;                                                   \
+  double cxm = 1.0, cxp = 1.0;                                                        \
+  if (i == nxs) {                                                                     \
+    if (per) xm = o + (nxr - 1);                                                      \
+    else if (l == 0) { xm = o; cxm = -1.0; }                                          \
+    else xm = o + 1;                                                                  \
+  }                                                                                   \
+  if (i == nxe) {                                                                     \
+    if (per) xp = o - (nxr - 1);                                                      \
+    else if (!rec) { xp = o; cxp = 0.0; }                                             \
+    else if (l == 0) { xp = o - 2; cxp = -1.0; }                                      \
+    else xp = o - 1;                                                                  \
+  }                                                                                   \
   const long long ym = j == g.nys ? o + (g.nyl - 1) * sy : o - sy, yp = j == g.nye ? o - (g.nyl - 1) * sy : o + sy; \
   const long long zm = !d3 ? o : (k == g.nzs ? o + (g.nzl - 1) * sz : o - sz);                                \
   const long long zp = !d3 ? o : (k == g.nze ? o - (g.nzl - 1) * sz : o + sz);
@@ -530,8 +545,8 @@ __global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const
     for (int e = tid; e < n; e += nth) {
       WM_NBR(e)
       double rr;
-      if (d3) rr = b[o] + phi[zm] + phi[ym] + phi[xm] - g.f4 * phi[o] + phi[xp] + phi[yp] + phi[zp];
-      else rr = b[o] + phi[ym] + phi[xm] - g.f4 * phi[o] + phi[xp] + phi[yp];
+      if (d3) rr = b[o] + phi[zm] + phi[ym] + cxm * phi[xm] - g.f4 * phi[o] + cxp * phi[xp] + phi[yp] + phi[zp];
+      else rr = b[o] + phi[ym] + cxm * phi[xm] - g.f4 * phi[o] + cxp * phi[xp] + phi[yp];
       r[o] = rr;
       pold[o] = rr;
       s = s + rr * rr;
@@ -550,8 +565,8 @@ __global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const
 #define WM_P(x) fma(bv, pold[x], r[x])
           const double pc = WM_P(o);
           double a;
-          if (d3) a = -WM_P(zm) - WM_P(ym) - WM_P(xm) + g.f4 * pc - WM_P(xp) - WM_P(yp) - WM_P(zp);
-          else a = -WM_P(ym) - WM_P(xm) + g.f4 * pc - WM_P(xp) - WM_P(yp);
+          if (d3) a = -WM_P(zm) - WM_P(ym) - cxm * WM_P(xm) + g.f4 * pc - cxp * WM_P(xp) - WM_P(yp) - WM_P(zp);
+          else a = -WM_P(ym) - cxm * WM_P(xm) + g.f4 * pc - cxp * WM_P(xp) - WM_P(yp);
 #undef WM_P
           pnew[o] = pc;
           ap[o] = a;
@@ -722,8 +737,8 @@ int wm_k_cgm(wm_ctx* ctx, int nxs, int nxe) {
   const Geo& g = ctx->g;
   const long long n = (long long)(nxe - nxs + 1) * g.nyl * g.nzl;
   static const bool no_coop = getenv("WM_CG_HOSTLOOP") != nullptr;
-  if (ctx->nranks == 1 && g.bc == WM_BC_PERIODIC && !no_coop && n < (1LL << 30)) {
-    // single rank, periodic: the whole solve is one cooperative launch
+  if (ctx->nranks == 1 && !no_coop && n < (1LL << 30)) {
+    // single rank (periodic or walls): the whole solve is one cooperative launch
     static int per_sm = 0;
     if (per_sm == 0) WM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cgm_coop, TPB, 0));
     int nsm = 0;

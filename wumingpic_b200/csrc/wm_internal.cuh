@@ -68,6 +68,8 @@ struct wm_ctx {
   int* flags = nullptr;    // sticky device error flags
   int* cnt27 = nullptr;    // per (offset, species, source cell) counts -> offsets (wm_sort.cu)
   unsigned char* dst_off = nullptr;  // destination offset (0..26) of every pushed particle
+  int* inv = nullptr;      // the sort's permutation: inv[new position] = old position (wm_sort.cu)
+  int* goff = nullptr;     // per (destination cell, offset): absolute start of that source group
   int* inc = nullptr;      // multi-rank: arrivals per edge-plane cell announced by the neighbours [side][isp][t][0..nx]
   int* inc_off = nullptr;  // exclusive scan of inc (+ total)
   int* totals = nullptr;   // device copy of the six per-step totals (k_totals)

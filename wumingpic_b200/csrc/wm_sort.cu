@@ -13,11 +13,18 @@
 //               line per (cell, species), and add each group's size to the histogram of its destination cell
 //               (integer RED; this is the histogram sort.f90:62-69 builds with a per-pencil loop);
 //   scan        exclusive sum over all cells = the new cumcnt (sort.f90:71-74), as absolute offsets;
-//   k_gather    per DESTINATION run of 8 cells (one CTA): prefix over the <= 27 source groups of each of its cells,
-//               block copy of the stayers, ballot-ranked pick of the arrivals out of the leaver zones of the <= 90
-//               source cells around it, staged in shared memory and written with full sectors.  No atomics on the
-//               data path; the order inside every cell is deterministic:
+//   k_goff      per DESTINATION cell: exclusive prefix over its <= 27 source groups (one warp, shuffle scan) -> the
+//               absolute position where every (source cell, offset) group starts;
+//   k_perm      per SOURCE cell (one warp): the permutation.  inv[new position] = old position for the stayers (a block)
+//               and for every leaver (rank inside its group = number of earlier leavers of the zone with the same
+//               offset byte, from match.any).  Only the offset bytes are read: 1 byte per leaver;
+//   k_apply     A[pos] = B[inv[pos]] for the 6 coordinate arrays and the ID, destination-ordered: coalesced
+//               full-sector stores, all loads of a thread independent, ~25 instructions per particle.
+//               No atomics on the data path; the order inside every cell is deterministic:
 //               [local sources by offset, each in zone order][arrivals from the low neighbour][from the high one].
+//   (r01 history: a source-centric scatter cost 2.1x read / 1.5x write amplification from partial sectors; a
+//    destination-centric gather that re-scanned every leaver zone from its 9 neighbouring rows was instruction bound at
+//    36 warp-instructions per particle -- profiles/r01_s3_gather.md.)
 // Multi-GPU (slabs along the last axis: z in 3-D, y in 2-D; the reference's rank grid with nproc_j = 1): cells one
 // layer outside the slab are extra destination rows ("ghost rows") of the same sort, placed behind the local
 // particles.  Their per-cell counts travel first (the reference's count message, boundary_periodic.f90:192,243), are
@@ -139,23 +146,9 @@ __global__ void k_add_incoming(Geo g, const int* __restrict__ inc, int* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_gather: the data movement of the sort, destination-centric (see the file header).
-// (A source-centric scatter writes 10-20 partial 32-byte sectors per cell and array, and every partial-sector
-//  write miss costs a DRAM sector fill: measured 2.1x read / 1.5x write amplification, profiles/r01_sort.md.)
-// Three phases per CTA, so that a CTA waits for global memory three times instead of twice per source zone
-// (profiles/r01_gather_v2.md: the per-zone dependent chain dst_off -> ballot -> payload load was 60 % of the stalls):
-//   1  the offset bytes of all <= 90 leaver zones around the run -> shared memory (independent coalesced loads)
-//   2  index arithmetic only: src[pos] = source index of the particle that lands on position pos of the run
-//      (stayers: a block per cell; arrivals: ballot-ranked out of the zone bytes, cursors in registers)
-//   3  A[base + pos] = B[src[pos]] for the 6 coordinate arrays and the ID: full-sector coalesced stores,
-//      all loads of a thread independent
+// The data movement of the sort: permutation (k_goff, k_perm), then one pass that applies it (k_apply).
 // ---------------------------------------------------------------------------------------------
-constexpr int GD = 8;       // destination cells per CTA
-constexpr int CAP = 1024;   // run capacity of the index tile; the (rare) overflow of a dense run is copied directly
-constexpr int ZCAP = 6144;  // capacity of the zone-byte buffer; zones that do not fit are read from global memory
-constexpr int MAXSLOT = (GD + 2) * 9;
-
-struct Slot { int beg, end, obase, pos[3]; };   // leaver zone of one source cell; run position per di, or -1
+constexpr int GD = 8;       // destination cells per CTA of k_apply
 
 // source cell (si,sj,sk) of destination (i, virtual j, virtual k) and offset o; need_dl: required slab-axis offset of
 // a ghost row's sources, 2 = any (local rows)
@@ -184,26 +177,10 @@ __device__ __forceinline__ bool src_of(const Geo& g, int i, int j, int k, int ne
   return true;
 }
 
-template <int D>
-__global__ void __launch_bounds__(TPB) k_gather(Geo g, Ptcl B, Ptcl A, const double* __restrict__ id_in,
-                                                double* __restrict__ id_out, const int* __restrict__ cs,
-                                                const int* __restrict__ cs_new, const int* __restrict__ cnt,
-                                                const unsigned char* __restrict__ dst_off, int nxs, int nxe, int ngx) {
-  constexpr int NC = D == 3 ? 6 : 5;
-  __shared__ int s_src[CAP];                 // source index per position of the output run
-  __shared__ unsigned char s_zone[ZCAP];     // offset bytes of the live leaver zones, back to back
-  __shared__ int s_new[GD + 1];              // new cell starts of the run
-  __shared__ int s_P[GD * 28];               // group sizes -> exclusive prefix per destination cell
-  __shared__ int s_stay[GD * 2];             // source start of the stayers, count
-  __shared__ int s_list[MAXSLOT + 1];        // live slots, count
-  __shared__ int s_zoff[MAXSLOT];            // start of a live slot's bytes in s_zone, or -1 (read from global memory)
-  __shared__ Slot s_slot[MAXSLOT];
-  const int t = threadIdx.x, lane = t & 31, wib = t >> 5;
-  // ---- which destination run: local rows in strip order, ghost rows last; x groups fastest ----
-  const int gx = blockIdx.x % ngx;
-  const int wrow = blockIdx.x / ngx;
+// destination row (local rows in strip order, ghost rows last) -> (isp, virtual j, virtual k, row id, need_dl)
+__device__ __forceinline__ void dest_row(const Geo& g, int wrow, int& isp, int& j, int& k, int& row, int& need_dl) {
   const int npl = g.nyl * g.nzl;
-  int isp, j, k, row, need_dl = 2;
+  need_dl = 2;
   if (wrow < g.npen) {
     isp = wrow / npl;
     wm_strip_pencil(g, wrow % npl, j, k);
@@ -215,164 +192,127 @@ __global__ void __launch_bounds__(TPB) k_gather(Geo g, Ptcl B, Ptcl A, const dou
     isp = (r / g.ngrow) % g.nsp;
     const int tt = r % g.ngrow;
     need_dl = side == 0 ? -1 : 1;
-    if (D == 3) { j = g.nys + tt; k = side == 0 ? g.nzs - 1 : g.nze + 1; }
+    if (g.dim == 3) { j = g.nys + tt; k = side == 0 ? g.nzs - 1 : g.nze + 1; }
     else { j = side == 0 ? g.nys - 1 : g.nye + 1; k = 0; }
   }
+}
+
+// goff[(row*nx + i-nxgs)*32 + o] = absolute start of the group (source cell of offset o) inside destination cell (row, i).
+// One block per destination row and chunk of XCH x-cells; everything that depends only on (row, o) is hoisted out of
+// the loop over the cells (the integer divisions of the row decode cost more than the scan itself).
+constexpr int XCH = 64;
+__global__ void __launch_bounds__(TPB) k_goff(Geo g, const int* __restrict__ cs_new, const int* __restrict__ cnt,
+                                              int* __restrict__ goff, int nxs, int nxe, int nch) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int isp, j, k, row, need_dl;
+  dest_row(g, blockIdx.x / nch, isp, j, k, row, need_dl);
+  const int i_lo = nxs + (blockIdx.x % nch) * XCH, i_hi = min(nxe, i_lo + XCH - 1);
+  // lane o: the source row of offset o (cell index of its x = nxgs), or -1
+  const int di = lane % 3 - 1;
+  long long srow = -1;
+  {
+    int si, sj, sk;
+    if (lane < 27 && src_of(g, nxs + (di > 0 ? 1 : 0), j, k, need_dl, lane, nxs - 1, nxe + 1, si, sj, sk))
+      srow = (long long)wm_cell_index(g, g.nxgs, sj, sk);
+  }
+  const int* crow = cs_new + (size_t)row * (g.nx + 1) - g.nxgs;
+  int* grow = goff + ((size_t)row * g.nx - g.nxgs) * WM_CNT_LINE + lane;
+  for (int i = i_lo + wib; i <= i_hi; i += TPB / 32) {
+    int c = 0;
+    if (srow >= 0) {
+      int si = i - di;
+      if (g.bc == WM_BC_PERIODIC) si = wm_unwrap(si, g.nxgs, g.nxge, g.nx);
+      if (si >= nxs && si <= nxe) c = cnt[((size_t)(srow + (si - g.nxgs)) * 2 + isp) * WM_CNT_LINE + lane];
+    }
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    grow[(size_t)i * WM_CNT_LINE] = crow[i] + incl - c;
+  }
+}
+
+// inv[new position] = old position, source-centric: one warp per (cell, species); one block per source row and chunk of
+// XCH x-cells, the destination rows of the 27 offsets hoisted out of the loop over the cells
+__global__ void __launch_bounds__(TPB) k_perm(Geo g, const int* __restrict__ cs, const int* __restrict__ cnt,
+                                              const int* __restrict__ goff, const unsigned char* __restrict__ dst_off,
+                                              int* __restrict__ inv, int* flags, int nxs, int nxe, int nch) {
+  __shared__ int s_run[TPB / 32][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int npl = g.nyl * g.nzl;
+  const int wrow = blockIdx.x / nch;
+  const int isp = wrow / npl;
+  int j, k;
+  wm_strip_pencil(g, wrow % npl, j, k);
+  const int i_lo = nxs + (blockIdx.x % nch) * XCH, i_hi = min(nxe, i_lo + XCH - 1);
+  // lane o: destination row of offset o (x handled per cell), or -1 if that offset leaves the domain in y / z
+  const int di = lane % 3 - 1;
+  int drow = -1;
+  {
+    int ti;
+    if (lane < 27 && wm_dest_of(g, nxs + (di < 0 ? 1 : 0), j, k, lane, isp, nxs - 1, nxe + 1, drow, ti)) {} else drow = -1;
+  }
+  const int* row = cs + (size_t)g.pen(j, k, isp) * (g.nx + 1) - g.nxgs;
+  const size_t cell0 = wm_cell_index(g, g.nxgs, j, k);
+  for (int i = i_lo + wib; i <= i_hi; i += TPB / 32) {
+    const int beg = row[i], end = row[i + 1];
+    if (beg == end) continue;
+    // lane o: where the group of offset o starts in its destination cell
+    const int c = lane < 27 ? cnt[((cell0 + (i - g.nxgs)) * 2 + isp) * WM_CNT_LINE + lane] : 0;
+    int mygoff = -1;
+    if (c > 0) {
+      int ti = i + di;
+      if (g.bc == WM_BC_PERIODIC) ti = wm_unwrap(ti, g.nxgs, g.nxge, g.nx);
+      if (drow >= 0 && ti >= nxs && ti <= nxe) mygoff = goff[((size_t)drow * g.nx + (ti - g.nxgs)) * WM_CNT_LINE + lane];
+      else atomicOr(flags, 2);
+    }
+    const int nstay = __shfl_sync(0xffffffffu, c, 13);
+    const int g13 = __shfl_sync(0xffffffffu, mygoff, 13);
+    for (int e = lane; e < nstay; e += 32) inv[g13 + e] = beg + e;
+    if (beg + nstay == end) continue;
+    s_run[wib][lane] = 0;
+    __syncwarp();
+    for (int p0 = beg + nstay; p0 < end; p0 += 32) {
+      const int p = p0 + lane;
+      const bool act = p < end;
+      const int o = act ? (int)dst_off[p] : 31;                 // 31: idle lanes form their own group
+      const unsigned m = __match_any_sync(0xffffffffu, o);
+      const int rank = s_run[wib][o] + __popc(m & ((1u << lane) - 1u));
+      const int gbase = __shfl_sync(0xffffffffu, mygoff, o & 31);
+      __syncwarp();
+      if (act && (m & ((1u << lane) - 1u)) == 0) s_run[wib][o] += __popc(m);   // group leader
+      if (act && gbase >= 0) inv[gbase + rank] = p;
+      __syncwarp();
+    }
+  }
+}
+
+// A[pos] = B[inv[pos]]: one CTA per run of GD destination cells, rows in strip order (sources of a run live within a few
+// MB of it in the same traversal, so partially used source sectors are still in L2 when their other users arrive)
+template <int D>
+__global__ void __launch_bounds__(TPB) k_apply(Geo g, Ptcl B, Ptcl A, const double* __restrict__ id_in,
+                                               double* __restrict__ id_out, const int* __restrict__ cs_new,
+                                               const int* __restrict__ inv, int nxs, int nxe, int ngx, int multi) {
+  constexpr int NC = D == 3 ? 6 : 5;
+  const int gx = blockIdx.x % ngx;
+  int isp, j, k, row, need_dl;
+  dest_row(g, blockIdx.x / ngx, isp, j, k, row, need_dl);
   const int ia = nxs + gx * GD;
   const int ncg = min(GD, nxe - ia + 1);
-  if (t <= GD) s_new[t] = cs_new[(size_t)row * (g.nx + 1) + (ia - g.nxgs) + min(t, ncg)];
-  // ---- group sizes of every destination cell of the run ----
-  if (t < GD * 27) {
-    const int d = t / 27, o = t % 27;
-    int c = 0, si, sj, sk;
-    if (d < ncg && src_of(g, ia + d, j, k, need_dl, o, nxs, nxe, si, sj, sk))
-      c = cnt[(wm_cell_index(g, si, sj, sk) * 2 + isp) * WM_CNT_LINE + o];
-    s_P[d * 28 + o] = c;
-  }
-  __syncthreads();
-  const int base = s_new[0];
-  const int ntile = s_new[ncg] - base;
-  if (ntile == 0) return;
-  if (t < ncg) {
-    int run = 0;
-    for (int o = 0; o < 27; ++o) {
-      const int c = s_P[t * 28 + o];
-      s_P[t * 28 + o] = run;
-      run += c;
-      if (o == 13) s_stay[2 * t + 1] = need_dl == 2 ? c : 0;
-    }
-    s_stay[2 * t] = need_dl == 2 ? cs[(size_t)row * (g.nx + 1) + (ia + t - g.nxgs)] : 0;
-  }
-  __syncthreads();
-  // ---- source slots: unwrapped x in [ia-1, ia+ncg], pencil offsets (sj,sk); only the leaver zone is scanned ----
-  const int nsx = ncg + 2;
-  const int nslot = nsx * (D == 3 ? 9 : 3);
-  if (t < nslot) {
-    const int sx = ia - 1 + t % nsx;
-    const int sjk = t / nsx;
-    const int sj = sjk % 3 - 1, sk = D == 3 ? sjk / 3 - 1 : 0;
-    Slot sl;
-    sl.beg = sl.end = 0;
-    sl.obase = 3 * (1 - sj) + 9 * (1 - sk);                             // offsets with dj = -sj, dk = -sk: obase + (di+1)
-    // the slot's particles need offset (di, -sj, -sk) with sx + di inside the run; the source must be reachable
-    int si, pj, pk;
-    const int o_mid = sl.obase + 1;                                     // di = 0 representative for the pencil part of src_of
-    bool ok = src_of(g, sx, j, k, need_dl, o_mid, nxs - 1, nxe + 1, si, pj, pk);   // x handled below (sx is unwrapped)
-    si = sx;
-    if (g.bc == WM_BC_PERIODIC) si = wm_unwrap(si, g.nxgs, g.nxge, g.nx);
-    if (si < nxs || si > nxe) ok = false;
-    bool any = false;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int d = sx + (r - 1) - ia;
-      int v = -1;
-      if (ok && d >= 0 && d < ncg && !(sl.obase + r == 13)) v = (s_new[d] - base) + s_P[d * 28 + sl.obase + r];
-      sl.pos[r] = v;
-      any = any || v >= 0;
-    }
-    if (ok && any) {
-      const size_t sc = wm_cell_index(g, si, pj, pk);
-      const int* crow = cs + (size_t)g.pen(pj, pk, isp) * (g.nx + 1) + (si - g.nxgs);
-      sl.beg = crow[0] + cnt[(sc * 2 + isp) * WM_CNT_LINE + 13];
-      sl.end = crow[1];
-    }
-    s_slot[t] = sl;
-  }
-  __syncthreads();
-  // compact list of the slots that have something to scan, and where their bytes go (one warp, ballot compaction)
-  if (wib == 0) {
-    int n = 0, zo = 0;
-    for (int q0 = 0; q0 < nslot; q0 += 32) {
-      const int q = q0 + lane;
-      const int len = q < nslot ? s_slot[q].end - s_slot[q].beg : 0;
-      const bool live = len > 0;
-      const unsigned m = __ballot_sync(0xffffffffu, live);
-      // exclusive prefix of the (16-byte padded) zone lengths over the lanes
-      const int plen = live ? (len + 15) & ~15 : 0;
-      int incl = plen;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      if (live) {
-        const int idx = n + __popc(m & ((1u << lane) - 1u));
-        const int start = zo + incl - plen;
-        s_list[idx] = q;
-        s_zoff[idx] = start + plen <= ZCAP ? start : -1;
-      }
-      n += __popc(m);
-      zo += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) s_list[MAXSLOT] = n;
-  }
-  __syncthreads();
-  const int nlist = s_list[MAXSLOT];
-  // ---- phase 1: zone bytes -> shared memory ----
-  for (int q = wib; q < nlist; q += TPB / 32) {
-    const int zo = s_zoff[q];
-    if (zo < 0) continue;
-    const Slot& sl = s_slot[s_list[q]];
-    const int beg = sl.beg, len = sl.end - beg;
-    for (int e = lane; e < len; e += 32) s_zone[zo + e] = dst_off[beg + e];
-  }
-  // ---- phase 2a: stayers (index arithmetic only; no shared-memory dependence on phase 1) ----
-  for (int d = wib; d < ncg; d += TPB / 32) {
-    const int sb = s_stay[2 * d], n = s_stay[2 * d + 1];
-    const int dp = (s_new[d] - base) + s_P[d * 28 + 13];
-    for (int e = lane; e < n; e += 32) {
-      const int pos = dp + e;
-      if (pos < CAP) {
-        s_src[pos] = sb + e;
-      } else {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) A.c[c][base + pos] = B.c[c][sb + e];
-        id_out[base + pos] = id_in[sb + e];
-      }
-    }
-  }
-  __syncthreads();
-  // ---- phase 2b: arrivals: ballot-ranked pick out of the leaver zones (cursors live in registers, warp-uniform) ----
-  for (int q = wib; q < nlist; q += TPB / 32) {
-    const Slot& sl = s_slot[s_list[q]];
-    const int beg = sl.beg, end = sl.end, obase = sl.obase, zo = s_zoff[q];
-    int c0 = sl.pos[0], c1 = sl.pos[1], c2 = sl.pos[2];
-    for (int p0 = beg; p0 < end; p0 += 32) {
-      const int p = p0 + lane;
-      int r = -1;
-      if (p < end) r = (int)(zo >= 0 ? s_zone[zo + (p - beg)] : dst_off[p]) - obase;
-      const unsigned m0 = __ballot_sync(0xffffffffu, r == 0 && c0 >= 0);
-      const unsigned m1 = __ballot_sync(0xffffffffu, r == 1 && c1 >= 0);
-      const unsigned m2 = __ballot_sync(0xffffffffu, r == 2 && c2 >= 0);
-      const unsigned lower = (1u << lane) - 1u;
-      int pos = -1;
-      if (r == 0 && c0 >= 0) pos = c0 + __popc(m0 & lower);
-      else if (r == 1 && c1 >= 0) pos = c1 + __popc(m1 & lower);
-      else if (r == 2 && c2 >= 0) pos = c2 + __popc(m2 & lower);
-      c0 += __popc(m0); c1 += __popc(m1); c2 += __popc(m2);
-      if (pos >= 0) {
-        if (pos < CAP) {
-          s_src[pos] = p;
-        } else {
-#pragma unroll
-          for (int c = 0; c < NC; ++c) A.c[c][base + pos] = B.c[c][p];
-          id_out[base + pos] = id_in[p];
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // ---- phase 3: the data movement ----
-  const int nw = min(ntile, CAP);
-  for (int e = t; e < nw; e += TPB) {
-    const int p = s_src[e];
+  const int* crow = cs_new + (size_t)row * (g.nx + 1) + (ia - g.nxgs);
+  const int base = crow[0], end = crow[ncg];
+  for (int pos = base + threadIdx.x; pos < end; pos += TPB) {
+    const int p = inv[pos];
+    if (multi && p < 0) continue;            // a slot reserved for an arrival from a neighbour rank (k_insert fills it)
     double v[NC + 1];
 #pragma unroll
     for (int c = 0; c < NC; ++c) v[c] = B.c[c][p];
     v[NC] = id_in[p];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) A.c[c][base + e] = v[c];
-    id_out[base + e] = v[NC];
+    for (int c = 0; c < NC; ++c) A.c[c][pos] = v[c];
+    id_out[pos] = v[NC];
   }
 }
 
@@ -459,10 +399,16 @@ int ensure_sort_buffers(wm_ctx* ctx) {
   }
   if (ctx->dst_off_cap < ctx->cap) {
     if (ctx->dst_off) cudaFree(ctx->dst_off);
+    if (ctx->inv) cudaFree(ctx->inv);
     ctx->dst_off = nullptr;
+    ctx->inv = nullptr;
     WM_CUDA(cudaMalloc(&ctx->dst_off, ctx->cap));
+    WM_CUDA(cudaMalloc(&ctx->inv, ctx->cap * sizeof(int)));
+    WM_CUDA(cudaMemsetAsync(ctx->inv, 0, ctx->cap * sizeof(int), ctx->stream));   // stale entries must stay valid indices
     ctx->dst_off_cap = ctx->cap;
   }
+  const size_t ngoff = ((size_t)g.npen + 2 * g.nsp * g.ngrow) * g.nx * WM_CNT_LINE;
+  if (!ctx->goff) WM_CUDA(cudaMalloc(&ctx->goff, ngoff * sizeof(int)));
   return WM_OK;
 }
 
@@ -549,14 +495,21 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
   }
   const int old_cid = 1 - ctx->cid;   // the producers moved the IDs along with the particles into the spare array
   {
-    const int ngx = (nxe - nxs + 1 + GD - 1) / GD;
+    const int nxr = nxe - nxs + 1;
+    const int nch = (nxr + XCH - 1) / XCH;
+    k_goff<<<g.nrows * nch, TPB, 0, st>>>(g, ctx->cs_new, ctx->cnt27, ctx->goff, nxs, nxe, nch);
+    WM_LAUNCH_CHECK(ctx);
+    if (g.multi) WM_CUDA(cudaMemsetAsync(ctx->inv, 0xff, ctx->cap * sizeof(int), st));   // arrival slots stay -1
+    k_perm<<<g.npen * nch, TPB, 0, st>>>(g, ctx->cs, ctx->cnt27, ctx->goff, ctx->dst_off, ctx->inv, ctx->flags, nxs, nxe, nch);
+    WM_LAUNCH_CHECK(ctx);
+    const int ngx = (nxr + GD - 1) / GD;
     const int blocks = g.nrows * ngx;
     if (g.dim == 3)
-      k_gather<3><<<blocks, TPB, 0, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs, ctx->cs_new,
-                                          ctx->cnt27, ctx->dst_off, nxs, nxe, ngx);
+      k_apply<3><<<blocks, TPB, 0, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs_new, ctx->inv, nxs,
+                                         nxe, ngx, g.multi);
     else
-      k_gather<2><<<blocks, TPB, 0, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs, ctx->cs_new,
-                                          ctx->cnt27, ctx->dst_off, nxs, nxe, ngx);
+      k_apply<2><<<blocks, TPB, 0, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs_new, ctx->inv, nxs,
+                                         nxe, ngx, g.multi);
     WM_LAUNCH_CHECK(ctx);
   }
   if (g.multi) {
