@@ -123,10 +123,14 @@ def test_boundary_migration_sort_exact(dim, bc, order, u0):
     b.close()
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "per-procedure"])
 @pytest.mark.parametrize("dim,bc,order,u0", VARIANTS, ids=IDS)
-def test_multistep(dim, bc, order, u0):
+def test_multistep(dim, bc, order, u0, fused):
+    """Whole steps through wm_step: the fused push+deposit kernels (k_fused3 / k_fused2, all three time loops) and the
+    per-procedure kernels (set_fused(False): what a driver calling the five entry points one by one runs)."""
     w = make(dim, bc, order, u0, steps=0)
     b = backend_for(w)
+    b.set_fused(fused)
     upload_from_world(b, w)
     ntot = int(w.arr("np2").sum())
     np.testing.assert_allclose(b.energy(), w.energy(), rtol=1e-12)

@@ -448,7 +448,7 @@ int wm_sort_bucket(wm_ctx* c, int nxs, int nxe) {
 int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
   if (!c || !range_ok(c, nxs, nxe)) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
-  const bool fused = c->use_fused && c->g.dim == 3 && c->g.bc == WM_BC_PERIODIC && order == WM_ORDER_WEIBEL;
+  const bool fused = c->use_fused && wm_fused_supported(c, order);
   for (int it = 0; it < nsteps; ++it) {
     if (c->timing) WM_CUDA(cudaEventRecord(c->ev[0], c->stream));
     if (fused) {

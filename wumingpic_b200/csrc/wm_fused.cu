@@ -108,13 +108,16 @@ __device__ __forceinline__ void s0ds(double xo, double xn, int cell, int inc, do
 
 // ---------------------------------------------------------------------------------------------
 // fused push + boundary + deposit + destination counting (3-D)
-//   ORDER 0 (Weibel/beam): deposit sees the un-wrapped new position, the periodic x wrap follows
+//   ORDER 0 (Weibel/beam): deposit sees the un-wrapped new position, the periodic x wrap follows (3d/proj/weibel/app.f90:100-108)
+//   ORDER 1 (reconnection): reflecting walls act on the pushed particle BEFORE the deposit (3d/proj/reconnection/app.f90:103-108,
+//            boundary_reconnection.f90:69-110); ORDER 2 (shock): boundary_shock__injection likewise (boundary_shock.f90:424-469)
 // ---------------------------------------------------------------------------------------------
 template <int ORDER, int G>
 __global__ void __launch_bounds__(16 * G, 32 / G)
 k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __restrict__ id_out,
          const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj, int* __restrict__ cnt,
-         int* __restrict__ hist, unsigned char* __restrict__ dst_off, int* flags, int nxs, int nxe, int ngx) {
+         int* __restrict__ hist, unsigned char* __restrict__ dst_off, int* flags, int nxs, int nxe, int ngx, double u0,
+         double xend) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = Smem<G>;
   constexpr int TPB = 16 * G, FSTR = SM::FSTR, TILE_ROW = SM::TILE_ROW;
@@ -259,6 +262,18 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
           yn = y + uy * g.delt * gam;
           zn = z + uz * g.delt * gam;
         }
+        if (ORDER != 0) {
+          // x walls on the pushed particle, before the deposit sees it
+          const int ipos = ORDER == 2 ? (int)(xn * g.d_delx) : (int)(xn / g.delx);
+          if (ipos < nxs + 1) {
+            xn = 2.0 * (nxs + 1) * g.delx - xn;
+            ux = -ux; uy = -uy; uz = -uz;
+          } else if (ORDER == 1 ? ipos >= nxe - 1 : xn > xend) {
+            if (ORDER == 1) { xn = 2.0 * (nxe - 1) * g.delx - xn; ux = -ux; }
+            else { xn = 2.0 * xend - xn; ux = 2.0 * u0 - ux; }
+            uy = -uy; uz = -uz;
+          }
+        }
         // cell increments (field.f90:280-283): the destination offset of the sort and the stayer / crosser class
         inc0 = (int)(xn * g.d_delx) - ia;
         inc1 = (int)(yn * g.d_delx) - j;
@@ -304,9 +319,11 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
         // boundaries: periodic x (boundary_periodic.f90:86-92) and periodic y,z wrap of the coordinate (:161-171).
         // The destination cell is fixed by the pre-wrap integer cell, as in the reference.
         {
-          int ipos = (int)(xn * g.d_delx);
-          if (ipos < g.nxgs) xn = xn + len_x;
-          else if (ipos >= g.nxge + 1) xn = xn - len_x;
+          if (ORDER == 0) {
+            int ipos = (int)(xn * g.d_delx);
+            if (ipos < g.nxgs) xn = xn + len_x;
+            else if (ipos >= g.nxge + 1) xn = xn - len_x;
+          }
           int jpos = (int)(yn * g.d_delx);
           if (jpos <= g.nygs - 1) yn = yn + len_y;
           else if (jpos >= g.nyge + 1) yn = yn - len_y;
@@ -403,32 +420,334 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused push + boundary + deposit + destination counting (2-D)
+//   particle__solv 2d/common/particle.f90:85-171, ele_cur 2d/common/field.f90:209-314 (Jx, Jy: 2-D Esirkepov prefix sums;
+//   Jz = q vz (S0x S0y + 1/2 DSx S0y + 1/2 S0x DSy + 1/3 DSx DSy) with vz of the pushed particle, :262-264, 288-294),
+//   boundary_periodic__particle_x / __particle_y (2d/common/boundary_periodic.f90:61-96, 99-248: int(x/delx) and the
+//   wraps run under ieee_down -> __ddiv_rd / __dadd_rd), walls as in the 3-D kernel (2d/proj/reconnection/
+//   boundary_reconnection.f90:61-99, 2d/proj/shock/boundary_shock.f90:255-297).
+// Same structure as k_fused3: a CTA owns G x-cells of one row j, 16 lanes per cell; record fields (double2):
+//   0 (cx1,cx2) 1 (cx0,cx3) 2 (cy1,cy2) 3 (cy0,cy3) 4+m (S0x,DSx)[m] 9+m (S0y,DSy)[m] 14 (q vz, -)
+// phase-B lanes: (Jx, jp) own Jx(i-1..i+2, j+jp-2); (Jy, ip) own Jy(i+ip-2, j-1..j+2); (Jz, ip) own Jz(i+ip-2, j-2..j+2).
+// ---------------------------------------------------------------------------------------------
+constexpr int NF2 = 15;
+
 template <int G>
-int launch_fused(wm_ctx* ctx, int nxs, int nxe) {
+struct __align__(16) Smem2 {
+  static constexpr int FSTR = G * CSTR + 1;
+  static constexpr int TILE_X = G + 2;
+  static constexpr int TILE_ROW = TILE_X * 6;
+  double tile[3 * TILE_ROW];
+  double2 rec[NF2 * FSTR];
+  int beg[2][G + 1];
+  int cnt27[2][27][G];
+  unsigned long long bar;
+};
+
+template <int ORDER, int G>
+__global__ void __launch_bounds__(16 * G, 32 / G)
+k_fused2(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __restrict__ id_out,
+         const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj, int* __restrict__ cnt,
+         int* __restrict__ hist, unsigned char* __restrict__ dst_off, int* flags, int nxs, int nxe, int ngx, double u0,
+         double xend) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using SM = Smem2<G>;
+  constexpr int TPB = 16 * G, FSTR = SM::FSTR, TILE_ROW = SM::TILE_ROW;
+  SM& S = *reinterpret_cast<SM*>(smem_raw);
+  const int t = threadIdx.x;
+  const int gx = blockIdx.x % ngx;
+  int j, k;
+  wm_strip_pencil(g, blockIdx.x / ngx, j, k);
+  const int i0 = nxs + gx * G;
+  const int ncg = min(G, nxe - i0 + 1);
+
+  if (t == 0) mbar_init(&S.bar, 1);
+  if (t < 2 * (G + 1)) {
+    const int isp = t / (G + 1), ii = t % (G + 1);
+    const int* row = cs + (size_t)g.pen(j, 0, isp) * (g.nx + 1) + (i0 - g.nxgs);
+    S.beg[isp][ii] = row[min(ii, ncg)];
+  }
+  for (int e = t; e < 2 * 27 * G; e += TPB) (&S.cnt27[0][0][0])[e] = 0;
+  __syncthreads();
+  if (t == 0) {
+    const uint32_t row_bytes = (uint32_t)(ncg + 2) * 48u;
+    mbar_expect_tx(&S.bar, 3u * row_bytes);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) tma_bulk_g2s(&S.tile[r * TILE_ROW], tmpf + g.box(i0 - 1, j + r - 1, 0) * 6, row_bytes, &S.bar);
+  }
+  const int ca = t >> 4, sa = t & 15;
+  const int cb = t >> 4, hb = t & 15;
+  const int comp = hb / 5, mb = hb % 5;
+  const bool b_active = hb < 15 && cb < ncg;
+  const int n0a = ca < ncg ? S.beg[0][ca + 1] - S.beg[0][ca] : 0;
+  const int n1a = ca < ncg ? S.beg[1][ca + 1] - S.beg[1][ca] : 0;
+  const int ncb = cb < ncg ? (S.beg[0][cb + 1] - S.beg[0][cb]) + (S.beg[1][cb + 1] - S.beg[1][cb]) : 0;
+  const int nbatch = (max(ncb, __shfl_xor_sync(0xffffffffu, ncb, 16)) + SLOTS - 1) / SLOTS;
+
+  double acc[5];
+#pragma unroll
+  for (int e = 0; e < 5; ++e) acc[e] = 0.0;
+  const double fac = 1.0 / 3.0;
+  const double inv_c2 = 1.0 / (g.c * g.c);
+  const int ia = i0 + ca;
+  const double len_x = __dmul_rd((double)(g.nxge - g.nxgs + 1), g.delx);
+  const double len_y = __dmul_rd((double)(g.nyge - g.nygs + 1), g.delx);
+
+  mbar_wait(&S.bar, 0);
+
+  int ns0 = 0, nl0 = 0, ns1 = 0, nl1 = 0;
+  for (int batch = 0; batch < nbatch; ++batch) {
+    // ------------------------------ phase A ------------------------------
+    {
+      const int idx = batch * SLOTS + sa;
+      int p = -1, isp = 0;
+      if (idx < n0a) { p = S.beg[0][ca] + idx; }
+      else if (idx < n0a + n1a) { p = S.beg[1][ca] + (idx - n0a); isp = 1; }
+      double xn = 0, yn = 0, ux = 0, uy = 0, uz = 0, idv = 0;
+      int o = 13;
+      if (p >= 0) {
+        const double x = A.c[0][p], y = A.c[1][p];
+        ux = A.c[2][p]; uy = A.c[3][p]; uz = A.c[4][p];
+        idv = id_in[p];
+        double sx[3], sy[3];
+        shape3(x * g.d_delx - 0.5 - ia, sx[0], sx[1], sx[2]);
+        shape3(y * g.d_delx - 0.5 - j, sy[0], sy[1], sy[2]);
+        double f[6];
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+          const double2* tr = reinterpret_cast<const double2*>(&S.tile[jj * TILE_ROW + ca * 6]);
+          double v[18];
+#pragma unroll
+          for (int e = 0; e < 9; ++e) { double2 d = tr[e]; v[2 * e] = d.x; v[2 * e + 1] = d.y; }
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            double row = +v[c] * sx[0] + v[6 + c] * sx[1] + v[12 + c] * sx[2];
+            f[c] = jj == 0 ? row * sy[0] : f[c] + row * sy[jj];
+          }
+        }
+        const double fac1 = g.fac1[isp];
+        const double txxx = fac1 * fac1;
+        const double fac2 = g.fac2[isp];
+        {
+          const double bpx = f[0], bpy = f[1], bpz = f[2], epx = f[3], epy = f[4], epz = f[5];
+          double uvm1 = ux + fac1 * epx, uvm2 = uy + fac1 * epy, uvm3 = uz + fac1 * epz;
+          const double qg = g.c * g.c + uvm1 * uvm1 + uvm2 * uvm2 + uvm3 * uvm3;
+          double igam = rsqrt(qg);
+          double gam = qg * igam;
+          double fac1r = fac1 * igam;
+          double fac2r = fac2 / (gam + txxx * (bpx * bpx + bpy * bpy + bpz * bpz) * igam);
+          double uvm4 = uvm1 + fac1r * (+uvm2 * bpz - uvm3 * bpy);
+          double uvm5 = uvm2 + fac1r * (+uvm3 * bpx - uvm1 * bpz);
+          double uvm6 = uvm3 + fac1r * (+uvm1 * bpy - uvm2 * bpx);
+          uvm1 = uvm1 + fac2r * (+uvm5 * bpz - uvm6 * bpy);
+          uvm2 = uvm2 + fac2r * (+uvm6 * bpx - uvm4 * bpz);
+          uvm3 = uvm3 + fac2r * (+uvm4 * bpy - uvm5 * bpx);
+          ux = uvm1 + fac1 * epx;
+          uy = uvm2 + fac1 * epy;
+          uz = uvm3 + fac1 * epz;
+          gam = rsqrt(1.0 + (+ux * ux + uy * uy + uz * uz) * inv_c2);
+          xn = x + ux * g.delt * gam;
+          yn = y + uy * g.delt * gam;
+        }
+        if (ORDER != 0) {
+          const int ipos = (int)(xn / g.delx);
+          if (ipos < nxs + 1) {
+            xn = 2.0 * (nxs + 1) * g.delx - xn;
+            ux = -ux; uy = -uy; uz = -uz;
+          } else if (ORDER == 1 ? ipos >= nxe - 1 : xn > xend) {
+            if (ORDER == 1) { xn = 2.0 * (nxe - 1) * g.delx - xn; ux = -ux; }
+            else { xn = 2.0 * xend - xn; ux = 2.0 * u0 - ux; }
+            uy = -uy; uz = -uz;
+          }
+        }
+        // deposit increments (field.f90:227-246: int(gp*d_delx)); the re-binning cell of y is int(y/delx) under ieee_down
+        int inc0 = (int)(xn * g.d_delx) - ia;
+        int inc1 = (int)(yn * g.d_delx) - j;
+        const int jpos = (int)__ddiv_rd(yn, g.delx);
+        int dj = jpos - j;
+        if (inc0 < -1 || inc0 > 1 || inc1 < -1 || inc1 > 1 || dj < -1 || dj > 1) {
+          atomicOr(flags, 2);
+          inc0 = max(-1, min(1, inc0)); inc1 = max(-1, min(1, inc1)); dj = max(-1, min(1, dj));
+        }
+        const double qdxdt = g.qdxdt[isp];
+        const int slot = ca * CSTR + sa;
+        {
+          double s0[5], ds[5];
+          s0ds(x, xn, ia, inc0, g.d_delx, s0, ds);
+          const double c0 = -ds[0] * qdxdt, c1 = c0 - ds[1] * qdxdt, c2 = c1 - ds[2] * qdxdt, c3 = c2 - ds[3] * qdxdt;
+          S.rec[0 * FSTR + slot] = make_double2(c1, c2);
+          S.rec[1 * FSTR + slot] = make_double2(c0, c3);
+#pragma unroll
+          for (int m = 0; m < 5; ++m) S.rec[(4 + m) * FSTR + slot] = make_double2(s0[m], ds[m]);
+          s0ds(y, yn, j, inc1, g.d_delx, s0, ds);
+          const double e0 = -ds[0] * qdxdt, e1 = e0 - ds[1] * qdxdt, e2 = e1 - ds[2] * qdxdt, e3 = e2 - ds[3] * qdxdt;
+          S.rec[2 * FSTR + slot] = make_double2(e1, e2);
+          S.rec[3 * FSTR + slot] = make_double2(e0, e3);
+#pragma unroll
+          for (int m = 0; m < 5; ++m) S.rec[(9 + m) * FSTR + slot] = make_double2(s0[m], ds[m]);
+          // gvz = uz / sqrt(1 + u^2/c^2) of the pushed (and wall-reflected) particle, field.f90:262-264
+          const double gvz = uz * rsqrt(1.0 + (+ux * ux + uy * uy + uz * uz) * inv_c2);
+          S.rec[14 * FSTR + slot] = make_double2(g.q[isp] * gvz, 0.0);
+        }
+        // boundaries: periodic x wrap (Weibel order) and periodic y wrap, both under round-down as in the reference
+        if (ORDER == 0) {
+          const int ipos = (int)__ddiv_rd(xn, g.delx);
+          if (ipos < g.nxgs) xn = __dadd_rd(xn, len_x);
+          else if (ipos >= g.nxge + 1) xn = __dadd_rd(xn, -len_x);
+        }
+        if (jpos <= g.nygs - 1) yn = __dadd_rd(yn, len_y);
+        else if (jpos >= g.nyge + 1) yn = __dadd_rd(yn, -len_y);
+        o = (inc0 + 1) + 3 * (dj + 1) + 9;
+        atomicAdd(&S.cnt27[isp][o][ca], 1);
+      }
+      {
+        const unsigned lane = t & 31u;
+        const unsigned half = 0xffffu << (lane & 16u);
+        const unsigned lower = half & ((1u << lane) - 1u);
+        const bool v0 = p >= 0 && isp == 0, v1 = p >= 0 && isp == 1, st = o == 13;
+        const unsigned bs0 = __ballot_sync(0xffffffffu, v0 && st) & half, bl0 = __ballot_sync(0xffffffffu, v0 && !st) & half;
+        const unsigned bs1 = __ballot_sync(0xffffffffu, v1 && st) & half, bl1 = __ballot_sync(0xffffffffu, v1 && !st) & half;
+        if (p >= 0) {
+          int pw;
+          if (isp == 0) pw = st ? S.beg[0][ca] + ns0 + __popc(bs0 & lower) : S.beg[0][ca + 1] - 1 - (nl0 + __popc(bl0 & lower));
+          else          pw = st ? S.beg[1][ca] + ns1 + __popc(bs1 & lower) : S.beg[1][ca + 1] - 1 - (nl1 + __popc(bl1 & lower));
+          B.c[0][pw] = xn; B.c[1][pw] = yn;
+          B.c[2][pw] = ux; B.c[3][pw] = uy; B.c[4][pw] = uz;
+          id_out[pw] = idv;
+          if (!st) dst_off[pw] = (unsigned char)o;
+        }
+        ns0 += __popc(bs0); nl0 += __popc(bl0); ns1 += __popc(bs1); nl1 += __popc(bl1);
+      }
+    }
+    __syncwarp();
+    // ------------------------------ phase B ------------------------------
+    if (b_active) {
+      const int nv = min(SLOTS, ncb - batch * SLOTS);
+      if (comp < 2) {
+        // Jx (comp 0): acc[r] += cx[r] (S0y + DSy/2)[jp] ; Jy (comp 1): acc[r] += cy[r] (S0x + DSx/2)[ip]
+        const int f_c = 2 * comp, f_a = comp == 0 ? 9 + mb : 4 + mb;
+        for (int s = 0; s < nv; ++s) {
+          const int slot = cb * CSTR + s;
+          const double2 c12 = S.rec[f_c * FSTR + slot];
+          const double2 c03 = S.rec[(f_c + 1) * FSTR + slot];
+          const double2 p1 = S.rec[f_a * FSTR + slot];
+          const double Av = p1.x + 0.5 * p1.y;
+          acc[0] += c03.x * Av;
+          acc[1] += c12.x * Av;
+          acc[2] += c12.y * Av;
+          acc[3] += c03.y * Av;
+        }
+      } else {
+        // Jz: acc[jp] += q vz (S0x[ip] (S0y + DSy/2)[jp] + DSx[ip] (S0y/2 + DSy/3)[jp])
+        for (int s = 0; s < nv; ++s) {
+          const int slot = cb * CSTR + s;
+          const double2 px = S.rec[(4 + mb) * FSTR + slot];
+          const double qg = S.rec[14 * FSTR + slot].x;
+          const double qs = qg * px.x, qd = qg * px.y;
+#pragma unroll
+          for (int jp = 0; jp < 5; ++jp) {
+            const double2 py = S.rec[(9 + jp) * FSTR + slot];
+            acc[jp] += qs * (py.x + 0.5 * py.y) + qd * (0.5 * py.x + fac * py.y);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  if (b_active) {
+    const int ib = i0 + cb;
+    const long long sY = (long long)g.bx * 3;
+    double* J0 = uj + g.box(ib, j, 0) * 3 + comp;
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      const double v = acc[e];
+      if (v != 0.0 && (comp == 2 || e < 4)) {
+        long long off;
+        if (comp == 0) off = (e - 1) * 3 + (mb - 2) * sY;        // Jx(i+r-1, j+jp-2)
+        else if (comp == 1) off = (mb - 2) * 3 + (e - 1) * sY;   // Jy(i+ip-2, j+r-1)
+        else off = (mb - 2) * 3 + (e - 2) * sY;                  // Jz(i+ip-2, j+jp-2)
+        atomicAdd(J0 + off, v);
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const size_t cell0 = wm_cell_index(g, i0, j, 0);
+    for (int e = t; e < G * 2 * WM_CNT_LINE; e += TPB) {
+      const int o = e % WM_CNT_LINE, isp = (e / WM_CNT_LINE) % 2, c = e / (2 * WM_CNT_LINE);
+      if (c < ncg) cnt[cell0 * 2 * WM_CNT_LINE + e] = o < 27 ? S.cnt27[isp][o][c] : 0;
+    }
+    for (int e = t; e < 2 * 27 * G; e += TPB) {
+      const int c = e % G, o = (e / G) % 27, isp = e / (G * 27);
+      const int n = c < ncg ? S.cnt27[isp][o][c] : 0;
+      if (n > 0) {
+        int drow, ti;
+        if (wm_dest_of(g, i0 + c, j, 0, o, isp, nxs, nxe, drow, ti)) atomicAdd(hist + (size_t)drow * (g.nx + 1) + (ti - g.nxgs), n);
+        else atomicOr(flags, 2);
+      }
+    }
+  }
+}
+
+template <int ORDER, int G>
+int launch_fused2(wm_ctx* ctx, int nxs, int nxe, double u0) {
   const Geo& g = ctx->g;
   static bool attr_set = false;
   if (!attr_set) {
-    WM_CUDA(cudaFuncSetAttribute(k_fused3<0, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<G>)));
+    WM_CUDA(cudaFuncSetAttribute(k_fused2<ORDER, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem2<G>)));
+    attr_set = true;
+  }
+  const int ngx = (nxe - nxs + 1 + G - 1) / G;
+  const int blocks = ngx * g.nyl;
+  const double xend = nxe * g.delx + u0 / sqrt(1 + (u0 * u0) / (g.c * g.c)) * g.delt;   // 2d/proj/shock/boundary_shock.f90:271
+  k_fused2<ORDER, G><<<blocks, 16 * G, sizeof(Smem2<G>), ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
+                                                                       ctx->cs, ctx->tmpf, ctx->uj, ctx->cnt27, ctx->cs_new,
+                                                                       ctx->dst_off, ctx->flags, nxs, nxe, ngx, u0, xend);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+template <int ORDER, int G>
+int launch_fused(wm_ctx* ctx, int nxs, int nxe, double u0) {
+  const Geo& g = ctx->g;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WM_CUDA(cudaFuncSetAttribute(k_fused3<ORDER, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<G>)));
     attr_set = true;
   }
   const int ngx = (nxe - nxs + 1 + G - 1) / G;
   const int blocks = ngx * g.nyl * g.nzl;
-  k_fused3<0, G><<<blocks, 16 * G, sizeof(Smem<G>), ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
-                                                                  ctx->cs, ctx->tmpf, ctx->uj, ctx->cnt27, ctx->cs_new,
-                                                                  ctx->dst_off, ctx->flags, nxs, nxe, ngx);
+  const double xend = nxe * g.delx + u0 / sqrt(1.0 + (u0 * u0) / (g.c * g.c)) * g.delt;   // boundary_shock.f90:438
+  k_fused3<ORDER, G><<<blocks, 16 * G, sizeof(Smem<G>), ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
+                                                                      ctx->cs, ctx->tmpf, ctx->uj, ctx->cnt27, ctx->cs_new,
+                                                                      ctx->dst_off, ctx->flags, nxs, nxe, ngx, u0, xend);
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
 }
 
 }  // namespace
 
-int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double /*u0*/) {
+// which (order, boundary kind) pairs the fused kernel covers: the three time loops of the reference with their own boundary module
+bool wm_fused_supported(const wm_ctx* ctx, int order) {
   const Geo& g = ctx->g;
-  if (g.dim != 3 || order != WM_ORDER_WEIBEL || g.bc != WM_BC_PERIODIC) {
-    wm_set_error("fused path: only 3-D periodic (Weibel order) so far");
+  return (order == WM_ORDER_WEIBEL && g.bc == WM_BC_PERIODIC) || (order == WM_ORDER_RECONNECTION && g.bc == WM_BC_RECONNECTION) ||
+         (order == WM_ORDER_SHOCK && g.bc == WM_BC_SHOCK);
+}
+
+int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double u0) {
+  if (!wm_fused_supported(ctx, order)) {
+    wm_set_error("fused path: the time loop (order) must be used with its own boundary module (bc_kind)");
     return WM_ERR_ARG;
   }
   WM_TRY(wm_sort_prepare(ctx));
-  static const int cells_per_cta = [] { const char* e = getenv("WM_FUSED_G"); return e ? atoi(e) : 8; }();
-  return cells_per_cta == 16 ? launch_fused<16>(ctx, nxs, nxe) : launch_fused<8>(ctx, nxs, nxe);
+  if (ctx->g.dim == 2) {
+    if (order == WM_ORDER_RECONNECTION) return launch_fused2<1, 8>(ctx, nxs, nxe, 0.0);
+    if (order == WM_ORDER_SHOCK) return launch_fused2<2, 8>(ctx, nxs, nxe, u0);
+    return launch_fused2<0, 8>(ctx, nxs, nxe, 0.0);
+  }
+  if (order == WM_ORDER_RECONNECTION) return launch_fused<1, 8>(ctx, nxs, nxe, 0.0);
+  if (order == WM_ORDER_SHOCK) return launch_fused<2, 8>(ctx, nxs, nxe, u0);
+  return launch_fused<0, 8>(ctx, nxs, nxe, 0.0);
 }

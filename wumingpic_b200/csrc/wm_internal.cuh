@@ -139,6 +139,7 @@ int wm_k_tmpf(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_push(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_deposit(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double u0);
+bool wm_fused_supported(const wm_ctx* ctx, int order);
 int wm_k_bc_x(wm_ctx* ctx, int nxs, int nxe, int kind, double u0);
 // sort / migration (wm_sort.cu)
 int wm_sort_prepare(wm_ctx* ctx);
