@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-nz", type=int, default=4, help="z cells of the bounded CPU sample")
     ap.add_argument("--unfused", action="store_true", help="time the per-procedure kernels instead of the fused step")
+    ap.add_argument("--dim", type=int, default=3, choices=[2, 3],
+                    help="3 (default): the C2 3-D Weibel workload of the metric; 2: a 2-D Weibel sheet nx x (ny per GPU) for the "
+                         "2-D code path (not a bench line of BASELINE.json; ndim = 6 -> 192 B per particle-step)")
     return ap.parse_args()
 
 
@@ -162,11 +165,17 @@ def main():
 
     nx, ny, n0 = args.nx, args.ny, args.ppc
     nz_glob = args.nz * world                           # weak scaling: z-slabs, per-GPU work fixed
-    lay = wm.SlabLayout(2, ny + 1, 2, nz_glob + 1, 1, world, rank)
     q, r, _ = wm.weibel_constants(n0)
     np_cap = int(n0 * nx * 1.25)
-    b = wm.Backend(3, np_cap, 2, nx + 1, 2, ny + 1, 2, nz_glob + 1, nys=lay.nys, nye=lay.nye, nzs=lay.nzs, nze=lay.nze,
-                   q=q, r=r, nproc_j=1, nproc_k=world, rank_j=0, rank_k=rank, device=local_rank)
+    if args.dim == 3:
+        lay = wm.SlabLayout(2, ny + 1, 2, nz_glob + 1, 1, world, rank)
+        b = wm.Backend(3, np_cap, 2, nx + 1, 2, ny + 1, 2, nz_glob + 1, nys=lay.nys, nye=lay.nye, nzs=lay.nzs, nze=lay.nze,
+                       q=q, r=r, nproc_j=1, nproc_k=world, rank_j=0, rank_k=rank, device=local_rank)
+    else:
+        ny_glob = ny * world                            # 2-D: y-slabs
+        lay = wm.SlabLayout(2, ny_glob + 1, 0, 0, world, 1, rank)
+        b = wm.Backend(2, np_cap, 2, nx + 1, 2, ny_glob + 1, nys=lay.nys, nye=lay.nye, q=q, r=r, nproc_j=world, nproc_k=1,
+                       rank_j=rank, rank_k=0, device=local_rank)
     if world > 1:
         box = [b.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
@@ -177,8 +186,9 @@ def main():
     npart = npart_rank * world
     stream = torch.cuda.ExternalStream(b.stream(), device=torch.device("cuda", local_rank))
     order = wm.backend.WM_ORDER_WEIBEL
-    step = (lambda n: b.step_unfused(2, nx + 1, n)) if args.unfused and hasattr(b, "step_unfused") else \
-           (lambda n: b.step(2, nx + 1, n, order))
+    if args.unfused:
+        b.set_fused(False)      # wm_step then sequences the per-procedure kernels, like a driver calling the five entry points
+    step = lambda n: b.step(2, nx + 1, n, order)  # noqa: E731
 
     def barrier():
         torch.cuda.synchronize()
@@ -214,25 +224,34 @@ def main():
 
     # ---- roofline of the dominant kernel (push+deposit), timed live with CUDA events on the library stream ----
     peak, peak_src = measured_peak()
+    bytes_push = BYTES_PER_UPDATE_PUSH if args.dim == 3 else 96      # 2 * ndim * 8 B
+    bytes_step = BYTES_PER_UPDATE_STEP if args.dim == 3 else 192     # 4 * ndim * 8 B
     k_ms = (st["ms_push"] + st["ms_deposit"]) / max(1, st["timed_steps"])
-    achieved = npart_rank * BYTES_PER_UPDATE_PUSH / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    achieved = npart_rank * bytes_push / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("push_deposit_dram_bytes_per_launch")
+            tj = json.load(f)
+            # measured DRAM bytes per particle of the kernel (ncu, one capture at C2) x the particles this launch processes
+            traffic = tj["push_deposit_dram_bytes_per_particle"] * npart_rank if args.dim == 3 else None
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "push+deposit", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": npart_rank * BYTES_PER_UPDATE_PUSH,
+                "algorithmic_bytes_per_launch": npart_rank * bytes_push,
+                "co_limiters": "ncu (profiles/r01_s3_fused_v2.md): fp64 pipe 48 % active, LSU data-pipe wavefronts 74 %, issue slots "
+                               "53 %, DRAM 18 % -- the kernel is fp64/shared-memory/issue bound, not HBM bound; measured DFMA peak "
+                               "1.71e13/s (profiles/r01_fp64_peak.json)",
                 "kernel_ms": k_ms,
-                "step": {"bytes_per_update": BYTES_PER_UPDATE_STEP,
-                         "achieved": npart_rank * BYTES_PER_UPDATE_STEP / (ms_per_step * 1e-3) / 1e9,
-                         "frac": npart_rank * BYTES_PER_UPDATE_STEP / (ms_per_step * 1e-3) / 1e9 / peak},
+                "step": {"bytes_per_update": bytes_step,
+                         "achieved": npart_rank * bytes_step / (ms_per_step * 1e-3) / 1e9,
+                         "frac": npart_rank * bytes_step / (ms_per_step * 1e-3) / 1e9 / peak},
                 "phases_ms": {k: st[k] / max(1, st["timed_steps"]) for k in ("ms_push", "ms_deposit", "ms_field", "ms_sort")}}
 
     # ---- end to end through the host-buffer C ABI call: pinned host state in, one step, host state out ----
     e2e = None
+    if not args.no_e2e and args.dim == 2:
+        args.no_e2e = True   # the end-to-end leg is defined on the 3-D workload of the metric
     if not args.no_e2e:
         try:
             shp = b.shapes()
@@ -265,7 +284,7 @@ def main():
                    "error": f"{type(ex).__name__}: {ex}"}
 
     cb = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and args.dim == 3:
         try:
             cb = cpu_baseline(args)
             cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -276,9 +295,11 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"3-D Weibel {nx}x{ny}x{args.nz} cells/GPU, {n0} ppc x 2 species "
-                                       f"({npart_rank} particles/GPU), periodic, cfl=1, gfac=0.501",
-                           "parallelism": f"z-slabs x{world}",
+                "config": {"workload": (f"3-D Weibel {nx}x{ny}x{args.nz} cells/GPU, {n0} ppc x 2 species "
+                                        f"({npart_rank} particles/GPU), periodic, cfl=1, gfac=0.501") if args.dim == 3 else
+                                       (f"2-D Weibel {nx}x{ny} cells/GPU, {n0} ppc x 2 species ({npart_rank} particles/GPU), "
+                                        "periodic (NOT the metric's workload: 2-D code path check)"),
+                           "parallelism": f"{'z' if args.dim == 3 else 'y'}-slabs x{world}",
                            "l2": "inputs (particle arrays, >= 30 GB) far exceed the 126 MB L2; no flush needed",
                            "particles": npart, "path": "per-procedure kernels" if args.unfused else "wm_step"},
                 "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -58,7 +58,8 @@ ABI_SYMBOLS = [
 
 
 def library_path():
-    return os.path.join(_HERE, "lib", "libwuming_b200.so")
+    # WM_B200_LIB: an alternative build of the same library (kernel-tuning experiments); never a different backend
+    return os.environ.get("WM_B200_LIB") or os.path.join(_HERE, "lib", "libwuming_b200.so")
 
 
 def load_library():

@@ -112,8 +112,11 @@ __device__ __forceinline__ void s0ds(double xo, double xn, int cell, int inc, do
 //   ORDER 1 (reconnection): reflecting walls act on the pushed particle BEFORE the deposit (3d/proj/reconnection/app.f90:103-108,
 //            boundary_reconnection.f90:69-110); ORDER 2 (shock): boundary_shock__injection likewise (boundary_shock.f90:424-469)
 // ---------------------------------------------------------------------------------------------
+#ifndef WM_FUSED_MINB
+#define WM_FUSED_MINB 3   // 3 x 128-thread CTAs per SM: 168 registers, no spills (4 CTAs at 128 registers: 3 % slower)
+#endif
 template <int ORDER, int G>
-__global__ void __launch_bounds__(16 * G, 32 / G)
+__global__ void __launch_bounds__(16 * G, WM_FUSED_MINB)
 k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __restrict__ id_out,
          const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj, int* __restrict__ cnt,
          int* __restrict__ hist, unsigned char* __restrict__ dst_off, int* flags, int nxs, int nxe, int ngx, double u0,
@@ -345,38 +348,46 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
     // ------------------------------ phase B ------------------------------
     if (b_active) {
       // stayers: S0 = DS = 0 at m = 0, 4 on every axis, c0 = 0 and c3 = -(sum of DS) q = O(eps) q (dropped: it is the
-      // round-off residue of a term that is exactly zero, field.f90:341-349)
-      for (int s = 0; s < nst; ++s) {
-        const int slot = cb * CSTR + s;
-        const double2 c12 = S.rec[f_c * FSTR + slot];
-        const double2 p1 = S.rec[(6 + 5 * ax1 + mb) * FSTR + slot];
+      // round-off residue of a term that is exactly zero, field.f90:341-349).  Two slots per trip: their load -> D ->
+      // accumulate chains are independent, which halves the fixed-latency stalls of the 4 warps per scheduler.
+      const double2* rc = S.rec + f_c * FSTR + cb * CSTR;
+      const double2* r1 = S.rec + (6 + 5 * ax1 + mb) * FSTR + cb * CSTR;
+      const double2* r2 = S.rec + (6 + 5 * ax2) * FSTR + cb * CSTR;
+      auto stay = [&](int s) {
+        const double2 c12 = rc[s];
+        const double2 p1 = r1[s];
         const double Av = p1.x + 5e-1 * p1.y;
         const double Bv = 5e-1 * p1.x + fac * p1.y;
 #pragma unroll
         for (int kp = 1; kp < 4; ++kp) {
-          const double2 p2 = S.rec[(6 + 5 * ax2 + kp) * FSTR + slot];
+          const double2 p2 = r2[kp * FSTR + s];
           const double D = Av * p2.x + Bv * p2.y;
           acc[1 * 5 + kp] += c12.x * D;
           acc[2 * 5 + kp] += c12.y * D;
         }
-      }
-      for (int s = SLOTS - ncr; s < SLOTS; ++s) {
-        const int slot = cb * CSTR + s;
-        const double2 c12 = S.rec[f_c * FSTR + slot];
-        const double2 c03 = S.rec[(f_c + 1) * FSTR + slot];
-        const double2 p1 = S.rec[(6 + 5 * ax1 + mb) * FSTR + slot];
+      };
+      auto cross = [&](int s) {
+        const double2 c12 = rc[s];
+        const double2 c03 = rc[FSTR + s];
+        const double2 p1 = r1[s];
         const double Av = p1.x + 5e-1 * p1.y;
         const double Bv = 5e-1 * p1.x + fac * p1.y;
 #pragma unroll
         for (int kp = 0; kp < 5; ++kp) {
-          const double2 p2 = S.rec[(6 + 5 * ax2 + kp) * FSTR + slot];
+          const double2 p2 = r2[kp * FSTR + s];
           const double D = (kp == 0 || kp == 4) ? Bv * p2.y : Av * p2.x + Bv * p2.y;
           acc[0 * 5 + kp] += c03.x * D;
           acc[1 * 5 + kp] += c12.x * D;
           acc[2 * 5 + kp] += c12.y * D;
           acc[3 * 5 + kp] += c03.y * D;
         }
-      }
+      };
+      int s = 0;
+      for (; s + 1 < nst; s += 2) { stay(s); stay(s + 1); }
+      if (s < nst) stay(s);
+      s = SLOTS - ncr;
+      for (; s + 1 < SLOTS; s += 2) { cross(s); cross(s + 1); }
+      if (s < SLOTS) cross(s);
     }
     __syncwarp();
   }
