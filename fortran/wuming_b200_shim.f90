@@ -538,3 +538,57 @@ contains
   end subroutine boundary_shock__phi
 
 end module boundary_shock
+
+!-----------------------------------------------------------------------------------------------------------
+! Moments (SURVEY.md 8f #1).  The drivers' output block is
+!     call mom_calc__accl(gp,up,uf,cumcnt,nxs,nxe); call mom_calc__nvt(mom,gp,np2); call bc__mom(mom); call io__mom(mom,uf,it)
+! (3d/proj/weibel/app.f90:121-125).  wm_mom_calc does accl + nvt + the ghost fold of bc__mom on the device-resident
+! particles, so __accl is a no-op, __nvt fills mom with the folded result, and the boundary_*__mom shims are no-ops.
+!-----------------------------------------------------------------------------------------------------------
+module mom_calc                      ! replaces 3d/common/mom_calc.f90
+  use iso_c_binding
+  use wuming_b200_c
+  implicit none
+  private
+  public :: mom_calc__init, mom_calc__accl, mom_calc__nvt
+  integer, save :: ndim, np, nsp, nxgs, nxge, nygs, nyge, nzgs, nzge, nys, nye, nzs, nze
+  integer, save :: last_nxs, last_nxe
+  interface
+    function wm_mom_calc(c, nxs, nxe, mom) bind(c, name='wm_mom_calc') result(ierr)
+      import; type(c_ptr), value :: c; integer(c_int), value :: nxs, nxe; type(c_ptr), value :: mom; integer(c_int) :: ierr
+    end function
+  end interface
+contains
+
+  subroutine mom_calc__init(ndim_in,np_in,nsp_in,nxgs_in,nxge_in,nygs_in,nyge_in,nzgs_in,nzge_in,nys_in,nye_in,nzs_in,nze_in, &
+                            delx_in,delt_in,c_in,q_in,r_in)                    ! mom_calc.f90:16-47
+    integer, intent(in) :: ndim_in, np_in, nsp_in
+    integer, intent(in) :: nxgs_in, nxge_in, nygs_in, nyge_in, nzgs_in, nzge_in, nys_in, nye_in, nzs_in, nze_in
+    real(8), intent(in) :: delx_in, delt_in, c_in, q_in(nsp_in), r_in(nsp_in)
+    ndim = ndim_in; np = np_in; nsp = nsp_in
+    nxgs = nxgs_in; nxge = nxge_in; nygs = nygs_in; nyge = nyge_in; nzgs = nzgs_in; nzge = nzge_in
+    nys = nys_in; nye = nye_in; nzs = nzs_in; nze = nze_in
+    last_nxs = nxgs; last_nxe = nxge
+  end subroutine mom_calc__init
+
+  subroutine mom_calc__accl(gp,up,uf,cumcnt,nxs,nxe)                           ! mom_calc.f90:49-216
+    integer, intent(in)  :: nxs, nxe
+    integer, intent(in)  :: cumcnt(nxgs:nxge+1,nys:nye,nzs:nze,nsp)
+    real(8), intent(in)  :: up(ndim,np,nys:nye,nzs:nze,nsp)
+    real(8), intent(in)  :: uf(6,nxgs-2:nxge+2,nys-2:nye+2,nzs-2:nze+2)
+    real(8), intent(out) :: gp(ndim,np,nys:nye,nzs:nze,nsp)
+    last_nxs = nxs; last_nxe = nxe           ! the re-centred momenta never leave the device (wm_mom_calc)
+  end subroutine mom_calc__accl
+
+  subroutine mom_calc__nvt(mom,up,np2)                                         ! mom_calc.f90:219-332 (+ the fold of bc__mom)
+    integer, intent(in)    :: np2(nys:nye,nzs:nze,nsp)
+    real(8), intent(in)    :: up(ndim,np,nys:nye,nzs:nze,nsp)
+    real(8), intent(inout), target :: mom(7,nxgs-1:nxge+1,nys-1:nye+1,nzs-1:nze+1,1:nsp)
+    integer(c_int) :: ierr
+    ierr = wm_mom_calc(ctx, int(last_nxs,c_int), int(last_nxe,c_int), c_loc(mom))
+    call wm_check(ierr, 'mom_calc__nvt')
+  end subroutine mom_calc__nvt
+
+end module mom_calc
+! boundary_periodic__mom / boundary_reconnection__mom / boundary_shock__mom: add to the three boundary modules above
+!   subroutine boundary_*__mom(mom); real(8), intent(inout) :: mom(...); end subroutine   (no-op: already folded)

@@ -135,6 +135,11 @@ int wm_h_step(wm_ctx* ctx, double* up, double* uf, int* np2, int* cumcnt, int nx
 /* Weibel load of 3d/proj/weibel/app.f90:311-338,391-504 (2d/proj/weibel/app.f90:404-432) generated on
  * the device with the Philox stream the oracle uses (positions bit-identical, Maxwellian to libm ulp). */
 int wm_load_weibel(wm_ctx* ctx, int n0, double v_thi, double v_the, double t_ani, double b0, unsigned long long seed);
+/* mom_calc__accl + mom_calc__nvt (3d/common/mom_calc.f90:49-216, 219-332 [2d :49-163, 166-252]) + boundary_*__mom
+ * (3d/common/boundary_periodic.f90:1102-1235 [2d :571-636]) on the sorted device-resident particles: the moment block of
+ * the drivers (3d/proj/weibel/app.f90:121-124) without downloading a single particle.
+ * mom(7, nxgs-1:nxge+1, nys-1:nye+1, [nzs-1:nze+1,] nsp): N, Vx, Vy, Vz, Txx, Tyy, Tzz sums at (i+1/2, j+1/2, k+1/2). */
+int wm_mom_calc(wm_ctx* ctx, int nxs, int nxe, double* mom);
 /* out[0..nsp-1] kinetic energy per species, out[nsp] E^2/8pi, out[nsp+1] B^2/8pi  (energy_history, app.f90:509-577) */
 int wm_energy(wm_ctx* ctx, double* out);
 /* out[0] = max|div E - 4 pi rho| , out[1] = max|4 pi rho| over this rank's interior cells */

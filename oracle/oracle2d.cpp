@@ -18,6 +18,7 @@
 //                                  :254-361 (dfield), :364-502 (curre), :505-579 (phi)
 //   boundary_shock__*              2d/proj/shock/boundary_shock.f90:62-100 (particle_x), :255-297 (injection),
 //                                  :300-407 (dfield), :410-548 (curre), :551-625 (phi)
+//   mom_calc__accl / __nvt          2d/common/mom_calc.f90:49-163, 166-252 ; boundary_*__mom 2d/common/boundary_periodic.f90:571-636
 //   mpi_set (rank table, slabs)    2d/common/mpi_set.f90:21-51
 //   time loops                     2d/proj/weibel/app.f90:99-107, 2d/proj/reconnection/app.f90:99-106,
 //                                  2d/proj/shock/app.f90:112-118
@@ -83,8 +84,11 @@ struct Rank2 {
   int rank = 0;
   int nys = 0, nye = 0, nyl = 0;
   int nup = 0, ndown = 0;
-  std::vector<double> up, gp, uf, df, gkl, uj;
+  std::vector<double> up, gp, uf, df, gkl, uj, mom;
   std::vector<int> np2, cumcnt;
+  inline size_t im(int l, int i, int j, int isp) const {  // mom(7,nxgs-1:nxge+1,nys-1:nye+1,nsp)
+    return ((((size_t)(isp - 1) * (nyl + 2) + (j - (nys - 1))) * (w->nx() + 2) + (i - (w->nxgs - 1)))) * 7 + (l - 1);
+  }
   inline size_t ip(int d, int ii, int j, int isp) const {  // up/gp(ndim,np,nys:nye,nsp)
     return (((size_t)(isp - 1) * nyl + (j - nys)) * w->np + (size_t)(ii - 1)) * w->ndim + (d - 1);
   }
@@ -126,9 +130,10 @@ void sendrecv(World2& w, Dir d, Pack pack, Unpack unpack) {
 // ---------------------------------------------------------------------------
 // particle__solv -- 2d/common/particle.f90:48-179
 // ---------------------------------------------------------------------------
-void particle_solv(World2& w, Rank2& R, std::vector<double>& gp, const std::vector<double>& up) {
+// accl = true: mom_calc__accl (2d/common/mom_calc.f90:49-163): same gather and rotation with delt/2 (:34), no move
+void particle_solv(World2& w, Rank2& R, std::vector<double>& gp, const std::vector<double>& up, bool accl = false) {
   const int nxs = w.nxs, nxe = w.nxe, nys = R.nys, nye = R.nye;
-  const double d_delx = w.d_delx, delt = w.delt, c = w.c;
+  const double d_delx = w.d_delx, delt = accl ? w.delt * 0.5 : w.delt, c = w.c;
   const int tx = nxe - nxs + 3, ty = nye - nys + 3;
   std::vector<double> tmp((size_t)6 * tx * ty);
   auto T = [&](int cc, int i, int j) -> double& {
@@ -189,13 +194,14 @@ void particle_solv(World2& w, Rank2& R, std::vector<double>& gp, const std::vect
           g[2] = uvm1 + fac1 * epx;
           g[3] = uvm2 + fac1 * epy;
           g[4] = uvm3 + fac1 * epz;
+          if (accl) { g[0] = u[0]; g[1] = u[1]; continue; }
           gam = 1.0 / std::sqrt(1.0 + (+g[2] * g[2] + g[3] * g[3] + g[4] * g[4]) / (c * c));
           g[0] = u[0] + g[2] * delt * gam;
           g[1] = u[1] + g[3] * delt * gam;
         }
       }
   // particle.f90:173-177 -- ID carry over the whole padded array
-  if (w.ndim == 6) {
+  if (w.ndim == 6 && !accl) {
     const size_t n = up.size() / 6;
 #pragma omp parallel for
     for (size_t t = 0; t < n; ++t) gp[t * 6 + 5] = up[t * 6 + 5];
@@ -803,6 +809,75 @@ void sort_bucket(World2& w, Rank2& R, std::vector<double>& dst, const std::vecto
   }
 }
 
+// ---------------------------------------------------------------------------
+// mom_calc__nvt -- 2d/common/mom_calc.f90:166-252 (ih = int(x*d_delx - 0.5), dx = x*d_delx - 0.5 - ih)
+// ---------------------------------------------------------------------------
+void mom_nvt(World2& w, Rank2& R, const std::vector<double>& up) {
+  std::fill(R.mom.begin(), R.mom.end(), 0.0);
+  for (int isp = 1; isp <= w.nsp; ++isp)
+    for (int j = R.nys; j <= R.nye; ++j) {
+      const int n = R.np2[R.in2(j, isp)];
+      for (int ii = 1; ii <= n; ++ii) {
+        const double* u = &up[R.ip(1, ii, j, isp)];
+        const int ih = (int)(u[0] * w.d_delx - 0.5);
+        const int jh = (int)(u[1] * w.d_delx - 0.5);
+        const double dx = u[0] * w.d_delx - 0.5 - ih, dxm = 1.0 - dx;
+        const double dy = u[1] * w.d_delx - 0.5 - jh, dym = 1.0 - dy;
+        const double gam = 1.0 / std::sqrt(1.0 + (+u[2] * u[2] + u[3] * u[3] + u[4] * u[4]) / (w.c * w.c));
+        const double wx[2] = {dxm, dx}, wy[2] = {dym, dy};
+        const double val[7] = {1.0, u[2] * gam, u[3] * gam, u[4] * gam, u[2] * u[2] * gam, u[3] * u[3] * gam, u[4] * u[4] * gam};
+        for (int l = 1; l <= 7; ++l)
+          for (int b = 0; b < 2; ++b)
+            for (int a = 0; a < 2; ++a) {
+              double& m = R.mom[R.im(l, ih + a, jh + b, isp)];
+              m = l == 1 ? m + wx[a] * wy[b] : m + val[l - 1] * wx[a] * wy[b];
+            }
+      }
+    }
+}
+
+// boundary_periodic__mom -- 2d/common/boundary_periodic.f90:571-636; walls fold x onto the same side
+// (2d/proj/reconnection/boundary_reconnection.f90:582-647, 2d/proj/shock/boundary_shock.f90:628-693)
+void bc_mom(World2& w) {
+  for (Rank2& R : w.ranks)
+    for (int isp = 1; isp <= w.nsp; ++isp)
+      for (int j = R.nys - 1; j <= R.nye + 1; ++j)
+        for (int l = 1; l <= 7; ++l) {
+          if (w.bc == 0) {
+            R.mom[R.im(l, w.nxgs, j, isp)] += R.mom[R.im(l, w.nxge + 1, j, isp)];
+            R.mom[R.im(l, w.nxge, j, isp)] += R.mom[R.im(l, w.nxgs - 1, j, isp)];
+          } else {
+            R.mom[R.im(l, w.nxgs, j, isp)] += R.mom[R.im(l, w.nxgs - 1, j, isp)];
+            R.mom[R.im(l, w.nxge, j, isp)] += R.mom[R.im(l, w.nxge + 1, j, isp)];
+          }
+        }
+  for (int isp = 1; isp <= w.nsp; ++isp) {
+    sendrecv<double>(w, TO_DOWN,
+        [&](Rank2& R, std::vector<double>& b) {
+          for (int i = w.nxgs - 1; i <= w.nxge + 1; ++i) for (int l = 1; l <= 7; ++l) b.push_back(R.mom[R.im(l, i, R.nys - 1, isp)]);
+        },
+        [&](Rank2& R, const std::vector<double>& b) {
+          size_t t = 0;
+          for (int i = w.nxgs - 1; i <= w.nxge + 1; ++i) for (int l = 1; l <= 7; ++l) R.mom[R.im(l, i, R.nye, isp)] += b[t++];
+        });
+    sendrecv<double>(w, TO_UP,
+        [&](Rank2& R, std::vector<double>& b) {
+          for (int i = w.nxgs - 1; i <= w.nxge + 1; ++i) for (int l = 1; l <= 7; ++l) b.push_back(R.mom[R.im(l, i, R.nye + 1, isp)]);
+        },
+        [&](Rank2& R, const std::vector<double>& b) {
+          size_t t = 0;
+          for (int i = w.nxgs - 1; i <= w.nxge + 1; ++i) for (int l = 1; l <= 7; ++l) R.mom[R.im(l, i, R.nys, isp)] += b[t++];
+        });
+  }
+}
+
+// the moment block of the drivers (2d/proj/weibel/app.f90:116-119): accl (gp <- up), nvt (mom <- gp), bc__mom
+void mom_calc(World2& w) {
+  for (Rank2& R : w.ranks) particle_solv(w, R, R.gp, R.up, true);
+  for (Rank2& R : w.ranks) mom_nvt(w, R, R.gp);
+  bc_mom(w);
+}
+
 // one time step; order: 0 Weibel (2d/proj/weibel/app.f90:99-107), 1 reconnection (2d/proj/reconnection/app.f90:99-106),
 // 2 shock without the driver's inject/relocate (2d/proj/shock/app.f90:112-118)
 void step(World2& w, int order, double u0) {
@@ -853,6 +928,7 @@ void* orc2_create(int nx, int ny, int np, int nproc, double delx, double delt, d
     R.up.assign(npart, 0.0); R.gp.assign(npart, 0.0);
     R.uf.assign(6 * nbox, 0.0); R.df.assign(6 * nbox, 0.0); R.uj.assign(3 * nbox, 0.0);
     R.gkl.assign((size_t)3 * nx * R.nyl, 0.0);
+    R.mom.assign((size_t)7 * (nx + 2) * (R.nyl + 2) * w->nsp, 0.0);
     R.np2.assign((size_t)R.nyl * w->nsp, 0);
     R.cumcnt.assign((size_t)(nx + 1) * R.nyl * w->nsp, 0);
   }
@@ -880,6 +956,7 @@ double* orc2_dptr(void* h, int rank, int which) {
     case 3: return R.df.data();
     case 4: return R.uj.data();
     case 5: return R.gkl.data();
+    case 6: return R.mom.data();
   }
   return nullptr;
 }
@@ -901,6 +978,7 @@ void orc2_bc_particle_x(void* h, int kind) {
 void orc2_bc_injection(void* h, double u0) { World2& w = *(World2*)h; for (Rank2& R : w.ranks) bc_injection(w, R, R.gp, u0); }
 void orc2_bc_particle_y(void* h) { bc_particle_y(*(World2*)h, 0); }
 void orc2_sort_bucket(void* h) { World2& w = *(World2*)h; for (Rank2& R : w.ranks) sort_bucket(w, R, R.up, R.gp); }
+void orc2_mom_calc(void* h) { mom_calc(*(World2*)h); }
 void orc2_step(void* h, int order, double u0) { step(*(World2*)h, order, u0); }
 
 // Deterministic Weibel load -- 2d/proj/weibel/app.f90:311-328 (np2, cumcnt), :389-432 (uf, positions,

@@ -18,6 +18,7 @@
 //   boundary_reconnection__*       3d/proj/reconnection/boundary_reconnection.f90:69-110 (particle_x), :672-682 (dfield x rule),
 //                                  :689-978 (curre: no x treatment), :1094-1116 (phi x rule)
 //   boundary_shock__*              3d/proj/shock/boundary_shock.f90:424-469 (injection), :674-686 (dfield), :1086-1108 (phi)
+//   mom_calc__accl / __nvt         3d/common/mom_calc.f90:49-216, 219-332 ; boundary_*__mom 3d/common/boundary_periodic.f90:1102-1235
 //   mpi_set (rank table, slabs)   3d/common/mpi_set.f90:21-97
 //   time loop                     3d/proj/weibel/app.f90:100-108
 //   Weibel initial load           3d/proj/weibel/app.f90:298-338, 391-504
@@ -64,8 +65,11 @@ struct Rank3 {
   int rank = 0, rj = 0, rk = 0;
   int nys = 0, nye = 0, nzs = 0, nze = 0, nyl = 0, nzl = 0;
   int jup = 0, jdown = 0, kup = 0, kdown = 0;
-  std::vector<double> up, gp, uf, df, gkl, uj;
+  std::vector<double> up, gp, uf, df, gkl, uj, mom;
   std::vector<int> np2, cumcnt;
+  inline size_t im(int l, int i, int j, int k, int isp) const {  // mom(7,nxgs-1:nxge+1,nys-1:nye+1,nzs-1:nze+1,nsp)
+    return (((((size_t)(isp - 1) * (nzl + 2) + (k - (nzs - 1))) * (nyl + 2) + (j - (nys - 1))) * (w->nx() + 2) + (i - (w->nxgs - 1)))) * 7 + (l - 1);
+  }
 
   // ---- Fortran-indexed accessors ------------------------------------------
   inline size_t ip(int d, int ii, int j, int k, int isp) const {  // up/gp(ndim,np,nys:nye,nzs:nze,nsp)
@@ -118,9 +122,11 @@ void sendrecv(World3& w, Dir d, Pack pack, Unpack unpack) {
 // ---------------------------------------------------------------------------
 // particle__solv -- 3d/common/particle.f90:52-233
 // ---------------------------------------------------------------------------
-void particle_solv(World3& w, Rank3& R, std::vector<double>& gp, const std::vector<double>& up) {
+// accl = true: mom_calc__accl (3d/common/mom_calc.f90:49-216) -- the same gather and Boris rotation with delt/2
+// (mom_calc__init :36), no move: gp(1:3) = up(1:3), gp(4:6) = re-centred momenta; gp(7) is not written.
+void particle_solv(World3& w, Rank3& R, std::vector<double>& gp, const std::vector<double>& up, bool accl = false) {
   const int nxs = w.nxs, nxe = w.nxe, nys = R.nys, nye = R.nye, nzs = R.nzs, nze = R.nze;
-  const double d_delx = w.d_delx, delt = w.delt, c = w.c;
+  const double d_delx = w.d_delx, delt = accl ? w.delt * 5e-1 : w.delt, c = w.c;
   const int tx = nxe - nxs + 3, ty = nye - nys + 3, tz = nze - nzs + 3;
   std::vector<double> tmpf((size_t)6 * tx * ty * tz);
   auto T = [&](int cc, int i, int j, int k) -> double& {
@@ -205,6 +211,7 @@ void particle_solv(World3& w, Rank3& R, std::vector<double>& gp, const std::vect
             g[3] = uvm1 + fac1 * epx;
             g[4] = uvm2 + fac1 * epy;
             g[5] = uvm3 + fac1 * epz;
+            if (accl) { g[0] = u[0]; g[1] = u[1]; g[2] = u[2]; continue; }
 
             gam = 1.0 / std::sqrt(1.0 + (+g[3] * g[3] + g[4] * g[4] + g[5] * g[5]) / (c * c));
             g[0] = u[0] + g[3] * delt * gam;
@@ -214,7 +221,7 @@ void particle_solv(World3& w, Rank3& R, std::vector<double>& gp, const std::vect
         }
 
   // particle.f90:227-231 -- ID carry over the whole padded array
-  if (w.ndim == 7) {
+  if (w.ndim == 7 && !accl) {
     const size_t n = up.size() / 7;
 #pragma omp parallel for
     for (size_t t = 0; t < n; ++t) gp[t * 7 + 6] = up[t * 7 + 6];
@@ -1078,6 +1085,100 @@ void sort_bucket(World3& w, Rank3& R, std::vector<double>& dst, const std::vecto
   }
 }
 
+// ---------------------------------------------------------------------------
+// mom_calc__nvt -- 3d/common/mom_calc.f90:219-332 (serial CIC deposit of N, V, T at (i+1/2, j+1/2, k+1/2))
+// NB the reference forms dx = x - 0.5 - ih without d_delx (:246-251); reproduced.
+// ---------------------------------------------------------------------------
+void mom_nvt(World3& w, Rank3& R, const std::vector<double>& up) {
+  std::fill(R.mom.begin(), R.mom.end(), 0.0);
+  for (int isp = 1; isp <= w.nsp; ++isp)
+    for (int k = R.nzs; k <= R.nze; ++k)
+      for (int j = R.nys; j <= R.nye; ++j) {
+        const int n = R.np2[R.in2(j, k, isp)];
+        for (int ii = 1; ii <= n; ++ii) {
+          const double* u = &up[R.ip(1, ii, j, k, isp)];
+          const int ih = (int)std::floor(u[0] * w.d_delx - 5e-1);
+          const int jh = (int)std::floor(u[1] * w.d_delx - 5e-1);
+          const int kh = (int)std::floor(u[2] * w.d_delx - 5e-1);
+          const double dx = u[0] - 5e-1 - ih, dxm = 1.0 - dx;
+          const double dy = u[1] - 5e-1 - jh, dym = 1.0 - dy;
+          const double dz = u[2] - 5e-1 - kh, dzm = 1.0 - dz;
+          const double gam = 1.0 / std::sqrt(1.0 + (+u[3] * u[3] + u[4] * u[4] + u[5] * u[5]) / (w.c * w.c));
+          const double wx[2] = {dxm, dx}, wy[2] = {dym, dy}, wz[2] = {dzm, dz};
+          // per moment the eight nodes in the reference's order (x fastest, then y, then z), weights as wx*wy*wz
+          const double val[7] = {1.0, u[3] * gam, u[4] * gam, u[5] * gam, u[3] * u[3] * gam, u[4] * u[4] * gam, u[5] * u[5] * gam};
+          for (int l = 1; l <= 7; ++l)
+            for (int c = 0; c < 2; ++c)
+              for (int b = 0; b < 2; ++b)
+                for (int a = 0; a < 2; ++a) {
+                  double& m = R.mom[R.im(l, ih + a, jh + b, kh + c, isp)];
+                  m = l == 1 ? m + wx[a] * wy[b] * wz[c] : m + val[l - 1] * wx[a] * wy[b] * wz[c];
+                }
+        }
+      }
+}
+
+// boundary_periodic__mom -- 3d/common/boundary_periodic.f90:1102-1235; walls (x fold onto the same side):
+// 3d/proj/reconnection/boundary_reconnection.f90:1122-1258, 3d/proj/shock/boundary_shock.f90:1112-1249
+void bc_mom(World3& w) {
+  for (Rank3& R : w.ranks)
+    for (int isp = 1; isp <= w.nsp; ++isp)
+      for (int k = R.nzs - 1; k <= R.nze + 1; ++k)
+        for (int j = R.nys - 1; j <= R.nye + 1; ++j)
+          for (int l = 1; l <= 7; ++l) {
+            if (w.bc == 0) {
+              R.mom[R.im(l, w.nxgs, j, k, isp)] += R.mom[R.im(l, w.nxge + 1, j, k, isp)];
+              R.mom[R.im(l, w.nxge, j, k, isp)] += R.mom[R.im(l, w.nxgs - 1, j, k, isp)];
+            } else {
+              R.mom[R.im(l, w.nxgs, j, k, isp)] += R.mom[R.im(l, w.nxgs - 1, j, k, isp)];
+              R.mom[R.im(l, w.nxge, j, k, isp)] += R.mom[R.im(l, w.nxge + 1, j, k, isp)];
+            }
+          }
+  for (int isp = 1; isp <= w.nsp; ++isp) {
+    auto xfer = [&](Dir d, bool along_j, int src_off, bool src_top, int dst_off, bool dst_top) {
+      sendrecv<double>(w, d,
+          [&](Rank3& R, std::vector<double>& b) {
+            if (along_j) {
+              const int js = (src_top ? R.nye : R.nys) + src_off;
+              for (int k = R.nzs - 1; k <= R.nze + 1; ++k)
+                for (int i = w.nxgs - 1; i <= w.nxge + 1; ++i)
+                  for (int l = 1; l <= 7; ++l) b.push_back(R.mom[R.im(l, i, js, k, isp)]);
+            } else {
+              const int ks = (src_top ? R.nze : R.nzs) + src_off;
+              for (int j = R.nys; j <= R.nye; ++j)
+                for (int i = w.nxgs - 1; i <= w.nxge + 1; ++i)
+                  for (int l = 1; l <= 7; ++l) b.push_back(R.mom[R.im(l, i, j, ks, isp)]);
+            }
+          },
+          [&](Rank3& R, const std::vector<double>& b) {
+            size_t t = 0;
+            if (along_j) {
+              const int jd = (dst_top ? R.nye : R.nys) + dst_off;
+              for (int k = R.nzs - 1; k <= R.nze + 1; ++k)
+                for (int i = w.nxgs - 1; i <= w.nxge + 1; ++i)
+                  for (int l = 1; l <= 7; ++l) R.mom[R.im(l, i, jd, k, isp)] += b[t++];
+            } else {
+              const int kd = (dst_top ? R.nze : R.nzs) + dst_off;
+              for (int j = R.nys; j <= R.nye; ++j)
+                for (int i = w.nxgs - 1; i <= w.nxge + 1; ++i)
+                  for (int l = 1; l <= 7; ++l) R.mom[R.im(l, i, j, kd, isp)] += b[t++];
+            }
+          });
+    };
+    xfer(TO_JDOWN, true, -1, false, 0, true);    // row nys-1 -> jdown, added into its nye
+    xfer(TO_JUP, true, +1, true, 0, false);      // row nye+1 -> jup, added into its nys
+    xfer(TO_KDOWN, false, -1, false, 0, true);   // plane nzs-1 -> kdown, added into its nze (j interior)
+    xfer(TO_KUP, false, +1, true, 0, false);     // plane nze+1 -> kup, added into its nzs
+  }
+}
+
+// the moment block of the drivers (3d/proj/weibel/app.f90:121-124): accl (gp <- up), nvt (mom <- gp), bc__mom
+void mom_calc(World3& w) {
+  for (Rank3& R : w.ranks) particle_solv(w, R, R.gp, R.up, true);
+  for (Rank3& R : w.ranks) mom_nvt(w, R, R.gp);
+  bc_mom(w);
+}
+
 // one time step; order 0: Weibel/beam (3d/proj/weibel/app.f90:100-108), 1: reconnection (3d/proj/reconnection/app.f90:103-108),
 // 2: shock without the driver's inject/relocate (3d/proj/shock/app.f90, same call order as 2d/proj/shock/app.f90:112-118)
 void step(World3& w, int order = 0, double u0 = 0.0) {
@@ -1133,6 +1234,7 @@ void* orc3_create(int nx, int ny, int nz, int np, int nproc_j, int nproc_k, doub
       R.up.assign(npart, 0.0); R.gp.assign(npart, 0.0);
       R.uf.assign(6 * nbox, 0.0); R.df.assign(6 * nbox, 0.0); R.uj.assign(3 * nbox, 0.0);
       R.gkl.assign((size_t)3 * nx * R.nyl * R.nzl, 0.0);
+      R.mom.assign((size_t)7 * (nx + 2) * (R.nyl + 2) * (R.nzl + 2) * w->nsp, 0.0);
       R.np2.assign((size_t)R.nyl * R.nzl * w->nsp, 0);
       R.cumcnt.assign((size_t)(nx + 1) * R.nyl * R.nzl * w->nsp, 0);
     }
@@ -1162,6 +1264,7 @@ double* orc3_dptr(void* h, int rank, int which) {
     case 3: return R.df.data();
     case 4: return R.uj.data();
     case 5: return R.gkl.data();
+    case 6: return R.mom.data();
   }
   return nullptr;
 }
@@ -1179,6 +1282,7 @@ void orc3_field_fdtd_i(void* h, int stage) { field_fdtd_i(*(World3*)h, stage); }
 void orc3_bc_particle_x(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) bc_particle_x(w, R, R.gp); }
 void orc3_bc_particle_yz(void* h) { bc_particle_yz(*(World3*)h, 0); }
 void orc3_sort_bucket(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) sort_bucket(w, R, R.up, R.gp); }
+void orc3_mom_calc(void* h) { mom_calc(*(World3*)h); }
 void orc3_step(void* h) { step(*(World3*)h); }
 void orc3_step_order(void* h, int order, double u0) { step(*(World3*)h, order, u0); }
 void orc3_bc_particle_x_reflect(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) bc_particle_x_reflect(w, R, R.gp); }

@@ -46,6 +46,8 @@ def lib(fast=False):
                      "clear_error"):
             getattr(L, "orc3_" + name).argtypes = [C.c_void_p]
         L.orc3_field_fdtd_i.argtypes = [C.c_void_p, C.c_int]
+        L.orc3_mom_calc.argtypes = [C.c_void_p]
+        L.orc2_mom_calc.argtypes = [C.c_void_p]
         L.orc3_step_order.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.orc3_bc_particle_x_reflect.argtypes = [C.c_void_p]
         L.orc3_bc_injection.argtypes = [C.c_void_p, C.c_double]
@@ -132,6 +134,8 @@ class World3:
             return (nzl + 4, nyl + 4, self.nx + 4, 3)
         if which == "gkl":
             return (nzl, nyl, self.nx, 3)
+        if which == "mom":
+            return (self.nsp, nzl + 2, nyl + 2, self.nx + 2, 7)
         if which == "np2":
             return (self.nsp, nzl, nyl)
         if which == "cumcnt":
@@ -143,7 +147,7 @@ class World3:
         if which in ("np2", "cumcnt"):
             p = self.L.orc3_iptr(self.h, rank, 0 if which == "np2" else 1)
         else:
-            p = self.L.orc3_dptr(self.h, rank, ("up", "gp", "uf", "df", "uj", "gkl").index(which))
+            p = self.L.orc3_dptr(self.h, rank, ("up", "gp", "uf", "df", "uj", "gkl", "mom").index(which))
         return np.ctypeslib.as_array(p, shape=shape)
 
     def load_weibel(self, n0, v_thi=0.1, v_the=0.1, t_ani=5.0, b0=0.0, seed=20240601):
@@ -172,6 +176,10 @@ class World3:
 
     def sort_bucket(self):
         self.L.orc3_sort_bucket(self.h)
+
+    def mom_calc(self):
+        """mom_calc__accl + mom_calc__nvt + bc__mom (3d/proj/weibel/app.f90:121-124); overwrites gp like the reference"""
+        self.L.orc3_mom_calc(self.h)
 
     def step(self, order=0, u0=0.0):
         self.L.orc3_step_order(self.h, order, u0)
@@ -240,6 +248,8 @@ class World2:
             return (nyl + 4, self.nx + 4, 3)
         if which == "gkl":
             return (nyl, self.nx, 3)
+        if which == "mom":
+            return (self.nsp, nyl + 2, self.nx + 2, 7)
         if which == "np2":
             return (self.nsp, nyl)
         if which == "cumcnt":
@@ -251,7 +261,7 @@ class World2:
         if which in ("np2", "cumcnt"):
             p = self.L.orc2_iptr(self.h, rank, 0 if which == "np2" else 1)
         else:
-            p = self.L.orc2_dptr(self.h, rank, ("up", "gp", "uf", "df", "uj", "gkl").index(which))
+            p = self.L.orc2_dptr(self.h, rank, ("up", "gp", "uf", "df", "uj", "gkl", "mom").index(which))
         return np.ctypeslib.as_array(p, shape=shape)
 
     def load_weibel(self, n0, v_thi=0.1, v_the=0.1, t_ani=5.0, b0=0.0, seed=20240601):
@@ -277,6 +287,9 @@ class World2:
 
     def sort_bucket(self):
         self.L.orc2_sort_bucket(self.h)
+
+    def mom_calc(self):
+        self.L.orc2_mom_calc(self.h)
 
     def step(self, order=0, u0=0.0):
         self.L.orc2_step(self.h, order, u0)

@@ -185,3 +185,25 @@ def test_2d_host_buffer_step_and_weibel_loader():
     assert rel_err(uf, w.arr("uf")) < 1e-10
     b.close()
     assert wm.backend.WM_BC_SHOCK == 2
+
+
+@pytest.mark.parametrize("dim,bc,order,u0", [(3, 0, 0, 0.0)] + VARIANTS, ids=["3d-periodic"] + IDS)
+def test_moments(dim, bc, order, u0):
+    """wm_mom_calc = mom_calc__accl + mom_calc__nvt + bc__mom against the oracle: sums over <= 8 x ppc
+    contributions per node in a different order -> 1e-12 relative to the max-norm of each moment."""
+    w = make(dim, bc, order, u0, steps=3)
+    b = backend_for(w)
+    upload_from_world(b, w)
+    got = b.mom_calc(2, NX + 1)
+    w.mom_calc()
+    ref = w.arr("mom")
+    inner = (slice(None),) + (slice(1, -1),) * dim     # after bc__mom only the interior nodes are meaningful
+    for l in range(7):
+        assert rel_err(got[inner][..., l], ref[inner][..., l]) < 1e-12, l
+    assert abs(got[inner][..., 0].sum() - w.arr("np2").sum()) < 1e-9 * w.arr("np2").sum()
+    # the moment block leaves the particle state untouched
+    up, np2, cc = b.empty("up"), b.empty("np2"), b.empty("cumcnt")
+    b.download(up, np2, cc)
+    m = active_mask(np2, w.np)
+    assert np.array_equal(up[m].view(np.int64), w.arr("up")[m].view(np.int64))
+    b.close()

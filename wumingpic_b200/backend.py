@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     "wm_upload", "wm_download", "wm_download_work", "wm_upload_work", "wm_particle_solv", "wm_field_fdtd_i", "wm_field_stage",
     "wm_bc_particle_x", "wm_bc_injection", "wm_bc_particle_yz", "wm_sort_bucket", "wm_step", "wm_set_fused",
     "wm_h_particle_solv", "wm_h_field_fdtd_i", "wm_h_step", "wm_load_weibel", "wm_energy", "wm_gauss",
-    "wm_get_stats", "wm_sync", "wm_set_timing", "wm_launch_count", "wm_stream",
+    "wm_get_stats", "wm_sync", "wm_set_timing", "wm_launch_count", "wm_stream", "wm_mom_calc",
 ]
 
 
@@ -94,6 +94,7 @@ def load_library():
         L.wm_h_step.argtypes = [vp, dp, dp, ip, ip, C.c_int, C.c_int, C.c_int, C.c_double]
         L.wm_load_weibel.argtypes = [vp, C.c_int] + [C.c_double] * 4 + [C.c_ulonglong]
         L.wm_energy.argtypes = [vp, dp]
+        L.wm_mom_calc.argtypes = [vp, C.c_int, C.c_int, dp]
         L.wm_gauss.argtypes = [vp, dp]
         L.wm_get_stats.argtypes = [vp, C.POINTER(_Stats)]
         L.wm_sync.argtypes = [vp]
@@ -278,6 +279,13 @@ class Backend:
     # -- synthetic load, diagnostics ---------------------------------------------------------------
     def load_weibel(self, n0, v_thi=0.1, v_the=0.1, t_ani=5.0, b0=0.0, seed=20240601):
         self._ck(self.L.wm_load_weibel(self.h, n0, v_thi, v_the, t_ani, b0, seed))
+
+    def mom_calc(self, nxs, nxe):
+        """mom_calc__accl + mom_calc__nvt + bc__mom on the device; returns mom with the reference's shape (C order reversed)"""
+        shp = (self.nsp, self.nzl + 2, self.nyl + 2, self.nx + 2, 7) if self.dim == 3 else (self.nsp, self.nyl + 2, self.nx + 2, 7)
+        out = np.zeros(shp)
+        self._ck(self.L.wm_mom_calc(self.h, nxs, nxe, _dptr(out)))
+        return out
 
     def energy(self):
         out = np.zeros(4)

@@ -216,7 +216,7 @@ int wm_destroy(wm_ctx* c) {
   cudaStreamSynchronize(c->stream);
   wm_comm_destroy(c);
   free_particles(c);
-  double* d[] = {c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->pcg2, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
+  double* d[] = {c->mom, c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->pcg2, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
                  c->hbuf[2], c->stage};
   for (double* p : d) if (p) cudaFree(p);
   int* ii[] = {c->cs, c->cs_new, c->np2, c->poff, c->flags, c->cnt27, c->inc, c->inc_off, c->totals, c->inv, c->goff};
@@ -567,6 +567,34 @@ int wm_load_weibel(wm_ctx* c, int n0, double v_thi, double v_the, double t_ani, 
   WM_TRY(wm_k_load_weibel(c, n0, v_thi, v_the, t_ani, b0, seed));
   c->gp_valid = false;
   return WM_OK;
+}
+
+// mom_calc__accl + mom_calc__nvt + bc__mom of the drivers' output block (3d/proj/weibel/app.f90:121-124), on the sorted
+// device-resident particles; only the (7, nx+2, nyl+2, [nzl+2,] nsp) moment array crosses to the host.
+int wm_mom_calc(wm_ctx* c, int nxs, int nxe, double* mom) {
+  if (!c || !mom || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling mom_calc__init()"); return WM_ERR_ARG; }
+  WM_CUDA(cudaSetDevice(c->device));
+  const Geo& g = c->g;
+  if (c->gp_valid) { wm_set_error("mom_calc acts on the sorted particles (call it after sort__bucket)"); return WM_ERR_STATE; }
+  const size_t nb = g.nbox(), nel = nb * 7 * g.nsp;
+  if (!c->mom) WM_CUDA(cudaMalloc(&c->mom, nel * sizeof(double)));
+  WM_CUDA(cudaMemsetAsync(c->mom, 0, nel * sizeof(double), c->stream));
+  WM_TRY(wm_k_tmpf(c, nxs, nxe));
+  if (c->ntot > 0) WM_TRY(wm_k_mom(c, nxs, nxe));
+  WM_TRY(wm_k_mom_fold(c));
+  std::vector<double> tmp(nel);
+  WM_CUDA(cudaMemcpyAsync(tmp.data(), c->mom, nel * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  WM_CUDA(cudaStreamSynchronize(c->stream));
+  size_t t = 0;
+  const int k0 = g.dim == 3 ? g.nzs - 1 : 0, k1 = g.dim == 3 ? g.nze + 1 : 0;
+  for (int isp = 0; isp < g.nsp; ++isp)
+    for (int k = k0; k <= k1; ++k)
+      for (int j = g.nys - 1; j <= g.nye + 1; ++j)
+        for (int i = g.nxgs - 1; i <= g.nxge + 1; ++i) {
+          const double* s = &tmp[((size_t)isp * nb + g.box(i, j, k)) * 7];
+          for (int l = 0; l < 7; ++l) mom[t++] = s[l];
+        }
+  return check_flags(c);
 }
 
 int wm_energy(wm_ctx* c, double* out) {

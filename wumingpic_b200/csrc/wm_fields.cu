@@ -816,6 +816,47 @@ int wm_k_cgm(wm_ctx* ctx, int nxs, int nxe) {
   return WM_OK;
 }
 
+// boundary_*__mom: fold the one-cell ghost layer of the moment boxes into the owning cells, x first, then y, then z
+// (3d/common/boundary_periodic.f90:1102-1235 [2d :571-636]; walls fold x onto the same side:
+//  3d/proj/reconnection/boundary_reconnection.f90:1122-1258, 2d :582-647)
+namespace {
+__global__ void k_x_fold_mom(double* __restrict__ arr, Geo g, int j0, int j1, int k0, int k1) {
+  const int nj = j1 - j0 + 1, nk = k1 - k0 + 1;
+  const int n = nj * nk * 7;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int c = e % 7, j = j0 + (e / 7) % nj, k = k0 + (e / 7) / nj;
+    double* row = arr + g.box(g.nxgs - 2, j, k) * 7 + c;
+    auto X = [&](int i) -> double& { return row[(size_t)(i - (g.nxgs - 2)) * 7]; };
+    if (g.bc == WM_BC_PERIODIC) {
+      X(g.nxgs) = X(g.nxgs) + X(g.nxge + 1);
+      X(g.nxge) = X(g.nxge) + X(g.nxgs - 1);
+    } else {
+      X(g.nxgs) = X(g.nxgs) + X(g.nxgs - 1);
+      X(g.nxge) = X(g.nxge) + X(g.nxge + 1);
+    }
+  }
+}
+
+}  // namespace
+
+int wm_k_mom_fold(wm_ctx* ctx) {
+  const Geo& g = ctx->g;
+  const int k0 = g.dim == 3 ? g.nzs - 1 : 0, k1 = g.dim == 3 ? g.nze + 1 : 0;
+  for (int isp = 0; isp < g.nsp; ++isp) {
+    double* a = ctx->mom + (size_t)isp * g.nbox() * 7;
+    const int n = (g.nyl + 2) * (k1 - k0 + 1) * 7;
+    k_x_fold_mom<<<wm_blocks(n, TPB), TPB, 0, ctx->stream>>>(a, g, g.nys - 1, g.nye + 1, k0, k1);
+    WM_LAUNCH_CHECK(ctx);
+    WM_TRY((exchange<7, true>(ctx, a, 1, true, g.nys - 1, g.nye, 1, g.nxgs - 1, g.nxge + 1, k0, k1)));
+    WM_TRY((exchange<7, true>(ctx, a, 1, false, g.nye + 1, g.nys, 1, g.nxgs - 1, g.nxge + 1, k0, k1)));
+    if (g.dim == 3) {
+      WM_TRY((exchange<7, true>(ctx, a, 2, true, g.nzs - 1, g.nze, 1, g.nxgs - 1, g.nxge + 1, g.nys, g.nye)));
+      WM_TRY((exchange<7, true>(ctx, a, 2, false, g.nze + 1, g.nzs, 1, g.nxgs - 1, g.nxge + 1, g.nys, g.nye)));
+    }
+  }
+  return WM_OK;
+}
+
 // Diagnostic helper (Gauss check): fold the one-cell ghost layer of a scalar box array into the
 // owning cells -- the 1-layer analogue of boundary_periodic__curre's add phase (y, then z, then x).
 int wm_k_scalar_fold(wm_ctx* ctx, double* a, int nxs, int nxe) {

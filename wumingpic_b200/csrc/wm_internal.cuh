@@ -79,6 +79,7 @@ struct wm_ctx {
   size_t scan_tmp_bytes = 0;
   // fields
   double *uf = nullptr, *df = nullptr, *uj = nullptr, *gkl = nullptr, *tmpf = nullptr;
+  double* mom = nullptr;   // moments N,V,T: nsp boxes of 7 components (allocated on first wm_mom_calc)
   // cg work arrays: phi, p (one ghost layer: (nx+2)(nyl+2)(nzl+2)), r, b, ap (interior)
   double *pcg2 = nullptr;  // second search-direction buffer of the cooperative cgm
   double *phi = nullptr, *pcg = nullptr, *rcg = nullptr, *bcg = nullptr, *apcg = nullptr;
@@ -138,6 +139,8 @@ static inline int wm_blocks(long long n, int threads) { return (int)((n + thread
 int wm_k_tmpf(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_push(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_deposit(wm_ctx* ctx, int nxs, int nxe);
+int wm_k_mom(wm_ctx* ctx, int nxs, int nxe);
+int wm_k_mom_fold(wm_ctx* ctx);
 int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double u0);
 bool wm_fused_supported(const wm_ctx* ctx, int order);
 int wm_k_bc_x(wm_ctx* ctx, int nxs, int nxe, int kind, double u0);

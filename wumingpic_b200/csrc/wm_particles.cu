@@ -304,6 +304,80 @@ __global__ void __launch_bounds__(TPB) k_deposit(Geo g, Ptcl A, Ptcl B, const in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Moments: mom_calc__accl + mom_calc__nvt in one pass, no particle ever leaves the device.
+//   mom_calc__accl  3d/common/mom_calc.f90:49-216 [2d :49-163]  the gather + Boris rotation of particle__solv with
+//                   delt/2 (mom_calc__init :36) and no move: momenta re-centred to the time level of the positions
+//   mom_calc__nvt   3d/common/mom_calc.f90:219-332 [2d :166-252] CIC deposit of N, V, T at (i+1/2, j+1/2, k+1/2);
+//                   3-D: ih = floor(x*d_delx - 1/2), dx = x - 1/2 - ih (no d_delx, :246-251); 2-D: ih = int(x*d_delx - 1/2),
+//                   dx = x*d_delx - 1/2 - ih
+// mom lives on the box layout (two ghost layers, 7 components fastest), one box per species.  Output-cadence code:
+// one RED.F64 per (moment, node).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(TPB) k_mom(Geo g, Ptcl A, const int* __restrict__ cs, const double* __restrict__ tmpf,
+                                             double* __restrict__ mom, int nxs, int nxe) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nxr = nxe - nxs + 1;
+  const long long ncell = (long long)nxr * g.nyl * g.nzl;
+  constexpr int U = D;
+  const double delth = g.delt * 5e-1;
+  const long long sY = (long long)g.bx * 7, sZ = (long long)g.bx * g.by * 7;
+  for (long long cidx = warp; cidx < ncell; cidx += nwarps) {
+    int i, j, k;
+    active_cell(g, cidx, nxs, nxr, i, j, k);
+    const double* T = tmpf + g.box(i, j, k) * 6;
+    for (int isp = 0; isp < g.nsp; ++isp) {
+      const int* row = cs + (size_t)g.pen(j, k, isp) * (g.nx + 1) + (i - g.nxgs);
+      const int beg = row[0], end = row[1];
+      const double fac1 = g.q[isp] / g.r[isp] * 5e-1 * delth;
+      const double txxx = fac1 * fac1;
+      const double fac2 = g.q[isp] * delth / g.r[isp];
+      double* M = mom + (size_t)isp * g.nbox() * 7;
+      for (int p = beg + lane; p < end; p += 32) {
+        const double x = A.c[0][p], y = A.c[1][p];
+        const double z = D == 3 ? A.c[2][p] : 0.0;
+        double ux = A.c[U][p], uy = A.c[U + 1][p], uz = A.c[U + 2][p];
+        double sx[3], sy[3], sz[3] = {0, 1, 0};
+        shape3(x * g.d_delx - 5e-1 - i, sx[0], sx[1], sx[2]);
+        shape3(y * g.d_delx - 5e-1 - j, sy[0], sy[1], sy[2]);
+        if (D == 3) shape3(z * g.d_delx - 5e-1 - k, sz[0], sz[1], sz[2]);
+        double f[6];
+        gather<D>(T, g, sx, sy, sz, f);
+        double gam;
+        boris(f, fac1, fac2, txxx, g.c, delth, ux, uy, uz, gam);
+        int ih, jh, kh = 0;
+        double wx[2], wy[2], wz[2] = {1.0, 0.0};
+        if (D == 3) {
+          ih = (int)floor(x * g.d_delx - 5e-1); jh = (int)floor(y * g.d_delx - 5e-1); kh = (int)floor(z * g.d_delx - 5e-1);
+          wx[1] = x - 5e-1 - ih; wy[1] = y - 5e-1 - jh; wz[1] = z - 5e-1 - kh;
+          wz[0] = 1.0 - wz[1];
+        } else {
+          ih = (int)(x * g.d_delx - 0.5); jh = (int)(y * g.d_delx - 0.5);
+          wx[1] = x * g.d_delx - 0.5 - ih; wy[1] = y * g.d_delx - 0.5 - jh;
+        }
+        wx[0] = 1.0 - wx[1]; wy[0] = 1.0 - wy[1];
+        const double val[7] = {1.0, ux * gam, uy * gam, uz * gam, ux * ux * gam, uy * uy * gam, uz * uz * gam};
+        double* base = M + g.box(ih, jh, D == 3 ? kh : 0) * 7;
+#pragma unroll
+        for (int c = 0; c < (D == 3 ? 2 : 1); ++c)
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              double* node = base + c * sZ + b * sY + a * 7;
+              const double w3 = D == 3 ? wx[a] * wy[b] * wz[c] : wx[a] * wy[b];
+              atomicAdd(node, w3);
+#pragma unroll
+              for (int l = 1; l < 7; ++l) atomicAdd(node + l, D == 3 ? val[l] * wx[a] * wy[b] * wz[c] : val[l] * wx[a] * wy[b]);
+            }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K12: x boundary on the pushed set
 //   periodic     3d/common/boundary_periodic.f90:68-101 (int(x*d_delx), round-to-nearest)
 //                2d/common/boundary_periodic.f90:61-96  (int(x/delx) and the wrap under ieee_down, :74)
@@ -407,6 +481,16 @@ int wm_k_push(wm_ctx* ctx, int nxs, int nxe) {
     k_push<3><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->tmpf, nxs, nxe);
   else
     k_push<2><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->tmpf, nxs, nxe);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+int wm_k_mom(wm_ctx* ctx, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const long long ncell = (long long)(nxe - nxs + 1) * g.nyl * g.nzl;
+  const int blocks = (int)std::min<long long>((ncell * 32 + TPB - 1) / TPB, 148LL * 8);
+  if (g.dim == 3) k_mom<3><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->cs, ctx->tmpf, ctx->mom, nxs, nxe);
+  else k_mom<2><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->cs, ctx->tmpf, ctx->mom, nxs, nxe);
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
 }
