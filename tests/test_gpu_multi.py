@@ -27,3 +27,17 @@ def test_slab_parity(nranks, fused):
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" ok: ") == nranks
+
+
+@pytest.mark.parametrize("dim,bc", [(2, 0), (2, 1), (3, 1), (3, 2)], ids=["2d-periodic", "2d-reconnection", "3d-reconnection", "3d-shock"])
+def test_slab_parity_variants(dim, bc):
+    """y-slabs in 2-D and the wall set-ups across slabs (BASELINE.json configs 3-5), 2 ranks, fused step."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(29560 + 3 * dim + bc),
+           os.path.join(ROOT, "tests", "multigpu_check.py"), "--fused", "1", "--dim", str(dim), "--bc", str(bc),
+           "--nx", "18", "--ny", "12", "--nz", "8"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok: ") == 2
