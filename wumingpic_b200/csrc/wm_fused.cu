@@ -396,19 +396,18 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
   if (b_active) {
     const int ib = i0 + cb;
     const long long sY = (long long)g.bx * 3, sZ = (long long)g.bx * g.by * 3;
-    double* J0 = uj + g.box(ib, j, k) * 3 + comp;
+    // strides of the strip's three indices (running r, first transverse mb, second transverse kp) per component:
+    //   Jx(i+r-1, j+mb-2, k+kp-2)   Jy(i+mb-2, j+r-1, k+kp-2)   Jz(i+mb-2, j+kp-2, k+r-1)
+    const long long s_r = comp == 0 ? 3 : (comp == 1 ? sY : sZ);
+    const long long s_m = comp == 0 ? sY : 3;
+    const long long s_k = comp == 2 ? sY : sZ;
+    double* J0 = uj + g.box(ib, j, k) * 3 + comp - s_r + (mb - 2) * s_m - 2 * s_k;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int kp = 0; kp < 5; ++kp) {
         const double v = acc[r * 5 + kp];
-        if (v != 0.0) {
-          long long off;
-          if (comp == 0) off = (r - 1) * 3 + (mb - 2) * sY + (kp - 2) * sZ;        // Jx(i+r-1, j+jp-2, k+kp-2)
-          else if (comp == 1) off = (mb - 2) * 3 + (r - 1) * sY + (kp - 2) * sZ;   // Jy(i+ip-2, j+r-1, k+kp-2)
-          else off = (mb - 2) * 3 + (kp - 2) * sY + (r - 1) * sZ;                  // Jz(i+ip-2, j+jp-2, k+r-1)
-          atomicAdd(J0 + off, v);
-        }
+        if (v != 0.0) atomicAdd(J0 + r * s_r + kp * s_k, v);
       }
   }
   // ---- re-binning information for the sort: one count line per (cell, species), group sizes -> histogram ----
