@@ -140,11 +140,33 @@ def run_reference(args):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else written to fd 1 meanwhile (NCCL's version banner,
+    library chatter) was redirected to stderr by quiet_stdout()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -305,7 +327,7 @@ def main():
                 "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "checks": {"gauss_residual": res, "max_4pi_rho": rho, "cg_iterations": st["cg_iterations"],
                            "error_flags": st["error_flags"]}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     b.close()
     if world > 1:
         dist.destroy_process_group()
