@@ -610,6 +610,203 @@ __global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const
 #undef WM_NBR
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-rank cgm (slabs along the last axis): the host sequences the iterations (NCCL cannot be called from a kernel),
+// but every iteration is 5 kernels + ONE send/recv group + 2 all-reduces instead of 14 kernels + 2 groups + 2 all-reduces:
+//   * the slab-axis halo of p travels as one pack kernel, one NCCL group (both directions), one unpack kernel;
+//   * the x rule (periodic wrap or wall) and the wrap of the non-decomposed transverse axis are index arithmetic inside
+//     the stencil kernels, exactly as in k_cgm_coop;
+//   * the block partials are folded by the last block to finish (fixed order -> deterministic), no separate fold launch.
+// ---------------------------------------------------------------------------------------------
+__device__ inline void block_sum2_fold(double a, double b, double* part, double* S, int o0, int o1, unsigned* counter) {
+  __shared__ double sa[TPB], sb[TPB];
+  __shared__ bool last;
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, o);
+    b += __shfl_down_sync(0xffffffffu, b, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sa[w] = a; sb[w] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0, tb = 0;
+    for (int t = 0; t < TPB / 32; ++t) { ta += sa[t]; tb += sb[t]; }
+    part[2 * blockIdx.x] = ta;
+    part[2 * blockIdx.x + 1] = tb;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double x = 0, y = 0;
+  for (int t = threadIdx.x; t < (int)gridDim.x; t += TPB) { x += __ldcg(part + 2 * t); y += __ldcg(part + 2 * t + 1); }
+  sa[threadIdx.x] = x; sb[threadIdx.x] = y;
+  __syncthreads();
+  for (int s = TPB / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { S[o0] = sa[0]; if (o1 >= 0) S[o1] = sb[0]; *counter = 0; }
+}
+
+// neighbour indices of interior cell (i,j,k) for the slab-decomposed solve: slab axis (z in 3-D, y in 2-D) reads the ghost
+// planes, the other transverse axis wraps periodically, x wraps or follows the wall rule of component l (0-based)
+struct Nbr { long long xm, xp, ym, yp, zm, zp; double cxm, cxp; };
+__device__ __forceinline__ Nbr slab_nbr(const Geo& g, long long o, int i, int j, int nxs, int nxe, int l) {
+  const long long sy = g.bx, sz = (long long)g.bx * g.by;
+  const int nxr = nxe - nxs + 1;
+  Nbr n;
+  n.xm = o - 1; n.xp = o + 1; n.cxm = 1.0; n.cxp = 1.0;
+  const bool per = g.bc == WM_BC_PERIODIC, rec = g.bc == WM_BC_RECONNECTION;
+  if (i == nxs) {
+    if (per) n.xm = o + (nxr - 1);
+    else if (l == 0) { n.xm = o; n.cxm = -1.0; }
+    else n.xm = o + 1;
+  }
+  if (i == nxe) {
+    if (per) n.xp = o - (nxr - 1);
+    else if (!rec) { n.xp = o; n.cxp = 0.0; }
+    else if (l == 0) { n.xp = o - 2; n.cxp = -1.0; }
+    else n.xp = o - 1;
+  }
+  if (g.dim == 3) {
+    n.ym = j == g.nys ? o + (g.nyl - 1) * sy : o - sy;
+    n.yp = j == g.nye ? o - (g.nyl - 1) * sy : o + sy;
+    n.zm = o - sz; n.zp = o + sz;
+  } else {
+    n.ym = o - sy; n.yp = o + sy; n.zm = o; n.zp = o;
+  }
+  return n;
+}
+
+__global__ void k_cgw_init(const double* __restrict__ df, const double* __restrict__ gkl, double* __restrict__ phi,
+                           double* __restrict__ b, double* __restrict__ part, double* S, unsigned* counter, Geo g, int nxs,
+                           int nxe, int l) {
+  const int nxr = nxe - nxs + 1;
+  const long long n = (long long)nxr * g.nyl * g.nzl;
+  double s = 0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    cell_of(g, e, nxs, nxr, i, j, k);
+    const size_t o = g.box(i, j, k);
+    phi[o] = df[o * 6 + l];
+    const double bb = g.f5 * gkl[o * 3 + l];
+    b[o] = bb;
+    s = s + bb * bb;
+  }
+  block_sum2_fold(s, 0.0, part, S, 3, -1, counter);
+}
+
+__global__ void k_cgw_r0(const double* __restrict__ phi, const double* __restrict__ b, double* __restrict__ r,
+                         double* __restrict__ p, double* __restrict__ part, double* S, unsigned* counter, Geo g, int nxs,
+                         int nxe, int l) {
+  const int nxr = nxe - nxs + 1;
+  const long long n = (long long)nxr * g.nyl * g.nzl;
+  double s = 0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    cell_of(g, e, nxs, nxr, i, j, k);
+    const long long o = (long long)g.box(i, j, k);
+    const Nbr nb = slab_nbr(g, o, i, j, nxs, nxe, l);
+    double rr;
+    if (g.dim == 3)
+      rr = b[o] + phi[nb.zm] + phi[nb.ym] + nb.cxm * phi[nb.xm] - g.f4 * phi[o] + nb.cxp * phi[nb.xp] + phi[nb.yp] + phi[nb.zp];
+    else
+      rr = b[o] + phi[nb.ym] + nb.cxm * phi[nb.xm] - g.f4 * phi[o] + nb.cxp * phi[nb.xp] + phi[nb.yp];
+    r[o] = rr;
+    p[o] = rr;
+    s = s + rr * rr;
+  }
+  block_sum2_fold(s, 0.0, part, S, 0, -1, counter);
+}
+
+__global__ void k_cgw_ap(const double* __restrict__ p, const double* __restrict__ r, double* __restrict__ ap,
+                         double* __restrict__ part, double* S, unsigned* counter, Geo g, int nxs, int nxe, int l) {
+  const int nxr = nxe - nxs + 1;
+  const long long n = (long long)nxr * g.nyl * g.nzl;
+  double s1 = 0, s2 = 0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    cell_of(g, e, nxs, nxr, i, j, k);
+    const long long o = (long long)g.box(i, j, k);
+    const Nbr nb = slab_nbr(g, o, i, j, nxs, nxe, l);
+    double a;
+    if (g.dim == 3)
+      a = -p[nb.zm] - p[nb.ym] - nb.cxm * p[nb.xm] + g.f4 * p[o] - nb.cxp * p[nb.xp] - p[nb.yp] - p[nb.zp];
+    else
+      a = -p[nb.ym] - nb.cxm * p[nb.xm] + g.f4 * p[o] - nb.cxp * p[nb.xp] - p[nb.yp];
+    ap[o] = a;
+    s1 = s1 + r[o] * r[o];
+    s2 = s2 + p[o] * a;
+  }
+  block_sum2_fold(s1, s2, part, S, 0, 1, counter);
+}
+
+__global__ void k_cgw_update(double* __restrict__ phi, double* __restrict__ r, const double* __restrict__ p,
+                             const double* __restrict__ ap, double* S, double* __restrict__ part, unsigned* counter, Geo g,
+                             int nxs, int nxe) {
+  const int nxr = nxe - nxs + 1;
+  const long long n = (long long)nxr * g.nyl * g.nzl;
+  const double av = S[0] / S[1];
+  double s = 0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    cell_of(g, e, nxs, nxr, i, j, k);
+    const size_t o = g.box(i, j, k);
+    phi[o] = phi[o] + av * p[o];
+    const double rn = r[o] - av * ap[o];
+    r[o] = rn;
+    s = s + rn * rn;
+  }
+  block_sum2_fold(s, 0.0, part, S, 2, -1, counter);
+}
+
+// both faces of the slab axis of a scalar box array: buf = [lo face | hi face], each (transverse interior) x (nxs..nxe)
+__global__ void k_halo_pack2(const double* __restrict__ a, double* __restrict__ buf, Geo g, int nxs, int nxe) {
+  const int nxr = nxe - nxs + 1;
+  const int ntr = g.dim == 3 ? g.nyl : 1;
+  const int n1 = nxr * ntr;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 2 * n1; e += gridDim.x * blockDim.x) {
+    const int face = e / n1, r = e % n1;
+    const int i = nxs + r % nxr, t = r / nxr;
+    const size_t o = g.dim == 3 ? g.box(i, g.nys + t, face == 0 ? g.nzs : g.nze) : g.box(i, face == 0 ? g.nys : g.nye, 0);
+    buf[e] = a[o];
+  }
+}
+// buf = [from the up neighbour (its lo face) -> my hi ghost | from the down neighbour (its hi face) -> my lo ghost]
+__global__ void k_halo_unpack2(double* __restrict__ a, const double* __restrict__ buf, Geo g, int nxs, int nxe) {
+  const int nxr = nxe - nxs + 1;
+  const int ntr = g.dim == 3 ? g.nyl : 1;
+  const int n1 = nxr * ntr;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 2 * n1; e += gridDim.x * blockDim.x) {
+    const int face = e / n1, r = e % n1;
+    const int i = nxs + r % nxr, t = r / nxr;
+    const size_t o = g.dim == 3 ? g.box(i, g.nys + t, face == 0 ? g.nze + 1 : g.nzs - 1) : g.box(i, face == 0 ? g.nye + 1 : g.nys - 1, 0);
+    a[o] = buf[e];
+  }
+}
+
+int halo_slab(wm_ctx* ctx, double* a, int nxs, int nxe) {
+  const Geo& g = ctx->g;
+  const int ax = g.dim == 3 ? 1 : 0;
+  const size_t n1 = (size_t)(nxe - nxs + 1) * (g.dim == 3 ? g.nyl : 1);
+  if (2 * n1 > ctx->hbuf_elems) { wm_set_error("halo buffer too small"); return WM_ERR_ARG; }
+  double *snd = ctx->hbuf[0], *rcv = ctx->hbuf[2];
+  const int blocks = wm_blocks((long long)2 * n1, TPB);
+  k_halo_pack2<<<blocks, TPB, 0, ctx->stream>>>(a, snd, g, nxs, nxe);
+  WM_LAUNCH_CHECK(ctx);
+  WM_TRY(wm_comm_group_begin(ctx));
+  WM_TRY(wm_comm_send(ctx, ctx->rank_down[ax], snd, n1 * sizeof(double)));
+  WM_TRY(wm_comm_recv(ctx, ctx->rank_up[ax], rcv, n1 * sizeof(double)));
+  WM_TRY(wm_comm_send(ctx, ctx->rank_up[ax], snd + n1, n1 * sizeof(double)));
+  WM_TRY(wm_comm_recv(ctx, ctx->rank_down[ax], rcv + n1, n1 * sizeof(double)));
+  WM_TRY(wm_comm_group_end(ctx));
+  k_halo_unpack2<<<blocks, TPB, 0, ctx->stream>>>(a, rcv, g, nxs, nxe);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
 int grid_for(long long n) {
   long long b = (n + TPB - 1) / TPB;
   const long long cap = 148LL * 8;  // persistent-style grid: 8 CTAs of 256 threads per SM
@@ -764,6 +961,53 @@ int wm_k_cgm(wm_ctx* ctx, int nxs, int nxe) {
   const int ite_max = 100;
   const double err = 1e-6;
   cudaStream_t st = ctx->stream;
+  static const bool generic = getenv("WM_CG_GENERIC") != nullptr;
+  if (ctx->nranks > 1 && !generic) {
+    // slab-decomposed solve: see the comment above block_sum2_fold
+    unsigned* counter = reinterpret_cast<unsigned*>(ctx->totals + 12);
+    for (int l = 0; l < 3; ++l) {
+      int ite = 0;
+      k_cgw_init<<<nb, TPB, 0, st>>>(ctx->df, ctx->gkl, ctx->phi, ctx->bcg, part, S, counter, g, nxs, nxe, l);
+      WM_LAUNCH_CHECK(ctx);
+      WM_TRY(wm_comm_allreduce_sum(ctx, S + 3, 1));
+      WM_TRY(halo_slab(ctx, ctx->phi, nxs, nxe));
+      k_cgw_r0<<<nb, TPB, 0, st>>>(ctx->phi, ctx->bcg, ctx->rcg, ctx->pcg, part, S, counter, g, nxs, nxe, l);
+      WM_LAUNCH_CHECK(ctx);
+      WM_TRY(wm_comm_allreduce_sum(ctx, S, 1));
+      WM_CUDA(cudaMemcpyAsync(h, S, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      WM_CUDA(cudaStreamSynchronize(st));
+      double sum_g = h[3];
+      const double eps = sqrt(sum_g) * err;
+      double sumr_g = h[0];
+      if (sqrt(sumr_g) > eps) {
+        while (sum_g > eps) {
+          ite = ite + 1;
+          WM_TRY(halo_slab(ctx, ctx->pcg, nxs, nxe));
+          k_cgw_ap<<<nb, TPB, 0, st>>>(ctx->pcg, ctx->rcg, ctx->apcg, part, S, counter, g, nxs, nxe, l);
+          WM_LAUNCH_CHECK(ctx);
+          WM_TRY(wm_comm_allreduce_sum(ctx, S, 2));
+          WM_CUDA(cudaMemcpyAsync(h, S, sizeof(double), cudaMemcpyDeviceToHost, st));
+          k_cgw_update<<<nb, TPB, 0, st>>>(ctx->phi, ctx->rcg, ctx->pcg, ctx->apcg, S, part, counter, g, nxs, nxe);
+          WM_LAUNCH_CHECK(ctx);
+          if (ite >= ite_max) {
+            WM_CUDA(cudaStreamSynchronize(st));
+            wm_set_error("********** stop at cgm after ite_max **********");
+            return WM_ERR_CG_ITEMAX;
+          }
+          WM_TRY(wm_comm_allreduce_sum(ctx, S + 2, 1));
+          k_cg_p<<<nb, TPB, 0, st>>>(ctx->pcg, ctx->rcg, S, g, nxs, nxe);
+          WM_LAUNCH_CHECK(ctx);
+          WM_CUDA(cudaStreamSynchronize(st));
+          sumr_g = h[0];
+          sum_g = sqrt(sumr_g);
+        }
+      }
+      k_cg_store<<<nb, TPB, 0, st>>>(ctx->df, ctx->phi, g, nxs, nxe, l);
+      WM_LAUNCH_CHECK(ctx);
+      ctx->cg_ite[l] = ite;
+    }
+    return WM_OK;
+  }
   for (int l = 0; l < 3; ++l) {
     int ite = 0;
     k_cg_init<<<nb, TPB, 0, st>>>(ctx->df, ctx->gkl, ctx->phi, ctx->bcg, part, g, nxs, nxe, l);
