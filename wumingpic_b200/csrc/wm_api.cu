@@ -69,6 +69,10 @@ int check_flags(wm_ctx* c) {
     wm_set_error("********** stop at cgm after ite_max **********");
     return WM_ERR_CG_ITEMAX;
   }
+  if (f & 8) {
+    wm_set_error("peer-memory cgm: a neighbour rank never arrived at a reduction (rank died or diverged)");
+    return WM_ERR_CUDA;
+  }
   if (f & 2) {
     wm_set_error("a particle left the one-cell neighbourhood of its cell (|inc| > 1 or outside the slab)");
     return WM_ERR_PARTICLE_LOST;
@@ -214,7 +218,7 @@ int wm_destroy(wm_ctx* c) {
   if (!c) return WM_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  wm_comm_destroy(c);
+  wm_comm_destroy(c);   // also releases the peer arena (and nulls the CG arrays that lived in it)
   free_particles(c);
   double* d[] = {c->mom, c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->pcg2, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
                  c->hbuf[2], c->stage};

@@ -8,7 +8,9 @@
 #include "wm_internal.cuh"
 
 #include <dlfcn.h>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace {
 
@@ -26,6 +28,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -45,6 +48,7 @@ NcclApi& api() {
   LOAD(Send, "ncclSend");
   LOAD(Recv, "ncclRecv");
   LOAD(AllReduce, "ncclAllReduce");
+  LOAD(AllGather, "ncclAllGather");
   LOAD(GroupStart, "ncclGroupStart");
   LOAD(GroupEnd, "ncclGroupEnd");
   LOAD(GetErrorString, "ncclGetErrorString");
@@ -61,6 +65,145 @@ NcclApi& api() {
       return WM_ERR_CUDA;                                                                      \
     }                                                                                          \
   } while (0)
+
+
+// ---------------------------------------------------------------------------------------------
+// Peer-memory set-up of the multi-GPU cgm (PeerCG, wm_internal.cuh).  The four CG operand arrays that neighbours write into
+// (phi, p, p2, r), the reduction mailbox and the reduction counter move into ONE allocation per rank, whose CUDA IPC handle
+// (+ the offset inside the driver's underlying block: small allocations are sub-allocated) is all-gathered over NCCL; every
+// rank then maps all peers' arenas.  A magic-number handshake through the mapped pointers verifies the mapping, and the ranks
+// agree collectively (all-reduce) before k_cgm_coop<true> is used; otherwise the NCCL-sequenced solve stays in place.
+// ---------------------------------------------------------------------------------------------
+struct PeerBlob {
+  cudaIpcMemHandle_t handle;    // 64 bytes
+  unsigned long long offset;    // arena - base of the underlying allocation
+  int nl;                       // slab thickness (nzl in 3-D, nyl in 2-D)
+  int rank;
+};
+
+size_t round256(size_t b) { return (b + 255) / 256 * 256; }
+
+int peer_setup(wm_ctx* ctx) {
+  static const bool off = getenv("WM_CG_NCCL") != nullptr;   // measurement switch: keep the NCCL-sequenced solve
+  NcclApi& a = api();
+  const int R = ctx->nranks;
+  ctx->peer_ok = false;
+  if (off || R > WM_MAX_PEERS || !a.AllGather) return WM_OK;
+  const Geo& g = ctx->g;
+  const size_t arr = round256(g.nbox() * sizeof(double));
+  const size_t mail_bytes = round256((size_t)2 * R * sizeof(WmMail));
+  const size_t total = 4 * arr + mail_bytes + 256;
+  unsigned char* arena = nullptr;
+  WM_CUDA(cudaMalloc(&arena, total));
+  WM_CUDA(cudaMemsetAsync(arena, 0, total, ctx->stream));
+  // the operand arrays move into the arena
+  double** old[4] = {&ctx->phi, &ctx->pcg, &ctx->pcg2, &ctx->rcg};
+  for (int q = 0; q < 4; ++q) {
+    if (*old[q]) cudaFree(*old[q]);
+    *old[q] = reinterpret_cast<double*>(arena + q * arr);
+  }
+  ctx->peer_arena = arena;
+  WmMail* my_mail = reinterpret_cast<WmMail*>(arena + 4 * arr);
+  unsigned long long* my_seq = reinterpret_cast<unsigned long long*>(arena + 4 * arr + mail_bytes);
+
+  // base of the underlying allocation (driver API, resolved at run time like NCCL)
+  PeerBlob mine;
+  std::memset(&mine, 0, sizeof(mine));
+  bool ok = true;
+  {
+    typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+    void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    GetRange get = cu ? (GetRange)dlsym(cu, "cuMemGetAddressRange_v2") : nullptr;
+    unsigned long long base = 0;
+    size_t sz = 0;
+    if (!get || get(&base, &sz, (unsigned long long)(uintptr_t)arena) != 0) ok = false;
+    else mine.offset = (unsigned long long)(uintptr_t)arena - base;
+  }
+  if (ok && cudaIpcGetMemHandle(&mine.handle, arena) != cudaSuccess) { ok = false; cudaGetLastError(); }
+  mine.nl = g.dim == 3 ? g.nzl : g.nyl;
+  mine.rank = ok ? ctx->rank : -1;
+
+  // all-gather the blobs
+  unsigned char* dev = nullptr;
+  WM_CUDA(cudaMalloc(&dev, sizeof(PeerBlob) * (R + 1)));
+  WM_CUDA(cudaMemcpyAsync(dev, &mine, sizeof(PeerBlob), cudaMemcpyHostToDevice, ctx->stream));
+  WM_NCCL(a.AllGather(dev, dev + sizeof(PeerBlob), sizeof(PeerBlob), ncclInt8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  std::vector<PeerBlob> all(R);
+  WM_CUDA(cudaMemcpyAsync(all.data(), dev + sizeof(PeerBlob), sizeof(PeerBlob) * R, cudaMemcpyDeviceToHost, ctx->stream));
+  WM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int r = 0; r < R; ++r) if (all[r].rank != r) ok = false;
+
+  // map every peer's arena
+  unsigned char* arenas[WM_MAX_PEERS] = {};
+  if (ok) {
+    for (int r = 0; r < R && ok; ++r) {
+      if (r == ctx->rank) { arenas[r] = arena; continue; }
+      void* base = nullptr;
+      if (cudaIpcOpenMemHandle(&base, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+        break;
+      }
+      ctx->peer_opened[r] = base;
+      arenas[r] = static_cast<unsigned char*>(base) + all[r].offset;
+    }
+  }
+  // handshake: every rank writes a magic number behind its counter and reads everybody else's through the mapping
+  const unsigned long long magic = 0x574d5045455200ull;   // "WMPEER"
+  unsigned long long mine_magic = magic + (unsigned long long)ctx->rank;
+  WM_CUDA(cudaMemcpyAsync(my_seq + 1, &mine_magic, sizeof(mine_magic), cudaMemcpyHostToDevice, ctx->stream));
+  double* flag = reinterpret_cast<double*>(dev);   // reuse: 1.0 = ok on this rank
+  double one = 1.0;
+  WM_CUDA(cudaMemcpyAsync(flag, &one, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  WM_NCCL(a.AllReduce(flag, flag, 1, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));   // barrier: magic written everywhere
+  WM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ok) {
+    for (int r = 0; r < R && ok; ++r) {
+      const size_t seq_off = 4 * round256((size_t)g.nbox() * sizeof(double)) + mail_bytes;
+      // a neighbour's arena differs in size when the slabs are uneven: its counter sits behind ITS four arrays
+      size_t nbox_r = g.nbox();
+      if (g.dim == 3) nbox_r = (size_t)g.bx * g.by * (all[r].nl + 4); else nbox_r = (size_t)g.bx * (all[r].nl + 4);
+      const size_t off_r = 4 * round256(nbox_r * sizeof(double)) + mail_bytes;
+      (void)seq_off;
+      unsigned long long got = 0;
+      if (cudaMemcpy(&got, arenas[r] + off_r + 8, sizeof(got), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); ok = false; }
+      else if (got != magic + (unsigned long long)r) ok = false;
+    }
+  }
+  double okv = ok ? 0.0 : 1.0;   // number of ranks that failed
+  WM_CUDA(cudaMemcpyAsync(flag, &okv, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  WM_NCCL(a.AllReduce(flag, flag, 1, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  WM_CUDA(cudaMemcpyAsync(&okv, flag, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  WM_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dev);
+  if (okv != 0.0) {
+    fprintf(stderr, "[wuming_b200] rank %d: peer-memory cgm unavailable (CUDA IPC mapping failed on %d rank(s)); using the NCCL-sequenced solve\n",
+            ctx->rank, (int)okv);
+    return WM_OK;
+  }
+  // tables
+  const int ax = g.dim == 3 ? 1 : 0;
+  const int lo = ctx->rank_down[ax], hi = ctx->rank_up[ax];
+  const long long ss = g.dim == 3 ? (long long)g.bx * g.by : (long long)g.bx;   // box stride of the slab axis
+  PeerCG& pc = ctx->peer;
+  auto arr_of = [&](int r) {
+    const size_t nbox_r = g.dim == 3 ? (size_t)g.bx * g.by * (all[r].nl + 4) : (size_t)g.bx * (all[r].nl + 4);
+    return round256(nbox_r * sizeof(double));
+  };
+  for (int q = 0; q < 4; ++q) {
+    pc.lo[q] = reinterpret_cast<double*>(arenas[lo] + q * arr_of(lo));
+    pc.hi[q] = reinterpret_cast<double*>(arenas[hi] + q * arr_of(hi));
+  }
+  pc.shift_lo = (long long)all[lo].nl * ss;
+  pc.shift_hi = -(long long)mine.nl * ss;
+  for (int r = 0; r < R; ++r) pc.mail[r] = reinterpret_cast<WmMail*>(arenas[r] + 4 * arr_of(r));
+  pc.seq = my_seq;
+  pc.nranks = R;
+  pc.rank = ctx->rank;
+  (void)my_mail;
+  ctx->peer_ok = true;
+  return WM_OK;
+}
 
 }  // namespace
 
@@ -105,10 +248,19 @@ extern "C" int wm_comm_init(wm_ctx* ctx, int nranks, int rank, const char* id_by
   WM_CUDA(cudaSetDevice(ctx->device));
   WM_NCCL(a.CommInitRank(&comm, nranks, id, rank));
   ctx->nccl_comm = comm;
+  WM_TRY(peer_setup(ctx));
   return wm_enable_slab_migration(ctx);
 }
 
 int wm_comm_destroy(wm_ctx* ctx) {
+  for (int r = 0; r < WM_MAX_PEERS; ++r)
+    if (ctx->peer_opened[r]) { cudaIpcCloseMemHandle(ctx->peer_opened[r]); ctx->peer_opened[r] = nullptr; }
+  if (ctx->peer_arena) {
+    cudaFree(ctx->peer_arena);
+    ctx->peer_arena = nullptr;
+    ctx->phi = ctx->pcg = ctx->pcg2 = ctx->rcg = nullptr;   // they lived in the arena
+    ctx->peer_ok = false;
+  }
   if (ctx->nccl_comm && api().CommDestroy) api().CommDestroy((ncclComm_t)ctx->nccl_comm);
   ctx->nccl_comm = nullptr;
   return WM_OK;

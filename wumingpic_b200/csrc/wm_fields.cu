@@ -479,6 +479,68 @@ __device__ __forceinline__ void grid_sum2(cg::grid_group& grid, double a, double
   tb = block_fold(y, sh);
 }
 
+// ---- multi-GPU form of grid_sum2 (PeerCG, wm_internal.cuh): the all-reduce of the reference's MPI_ALLREDUCE over NVLink peer
+// memory, inside the kernel.  After the local grid sync, block 0 folds the block partials and one thread per destination
+// rank stores (a, b) and then -- behind a system fence -- the sequence number into that rank's mailbox slot [parity][my rank];
+// thread 0 of every block then polls the LOCAL mailbox until all ranks' slots carry this sequence number and sums them in rank
+// order, so every block of every rank gets bit-identical totals and takes the same branches.  The same fence + flag also
+// publishes the ghost-plane stores a rank made into its neighbours' operand arrays before the reduction (threads that stored to
+// a peer run __threadfence_system() before the grid sync), and the system fence after the poll orders the ghost reads behind it.
+// Two parities suffice: a rank cannot start reduction n+2 before every rank has finished reading reduction n.
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_sum2(cg::grid_group& grid, const PeerCG& pc, unsigned long long& seq, double a, double b,
+                                          double* part, int& red_idx, double* sh, double* sh2, int* flags, double& ta, double& tb) {
+  a = block_fold(a, sh);
+  b = block_fold(b, sh);
+  double* buf = part + (size_t)(red_idx & 1) * 2 * gridDim.x;
+  red_idx++;
+  if (threadIdx.x == 0) { buf[2 * blockIdx.x] = a; buf[2 * blockIdx.x + 1] = b; }
+  grid.sync();
+  seq++;
+  const int par = (int)(seq & 1ull);
+  if (blockIdx.x == 0) {
+    double x = 0, y = 0;
+    for (int q = threadIdx.x; q < (int)gridDim.x; q += TPB) { x += __ldcg(buf + 2 * q); y += __ldcg(buf + 2 * q + 1); }
+    x = block_fold(x, sh);
+    y = block_fold(y, sh);
+    if ((int)threadIdx.x < pc.nranks) {
+      WmMail* m = pc.mail[threadIdx.x] + (par * pc.nranks + pc.rank);
+      st_volatile_u64(reinterpret_cast<unsigned long long*>(&m->a), (unsigned long long)__double_as_longlong(x));
+      st_volatile_u64(reinterpret_cast<unsigned long long*>(&m->b), (unsigned long long)__double_as_longlong(y));
+      __threadfence_system();
+      st_volatile_u64(&m->seq, seq);
+    }
+  }
+  if (threadIdx.x == 0) {
+    const WmMail* mine = pc.mail[pc.rank] + par * pc.nranks;
+    double x = 0, y = 0;
+    bool dead = (*(volatile int*)flags & 8) != 0;
+    for (int s = 0; s < pc.nranks; ++s) {
+      long long spins = 0;
+      while (!dead && ld_volatile_u64(&mine[s].seq) != seq) {
+        if (++spins > (1ll << 27)) { dead = true; atomicOr(flags, 8); }   // a peer never arrived: sticky error, no hang
+      }
+    }
+    __threadfence_system();
+    for (int s = 0; s < pc.nranks; ++s) {
+      x += __longlong_as_double((long long)ld_volatile_u64(reinterpret_cast<const unsigned long long*>(&mine[s].a)));
+      y += __longlong_as_double((long long)ld_volatile_u64(reinterpret_cast<const unsigned long long*>(&mine[s].b)));
+    }
+    sh2[0] = x; sh2[1] = y;
+  }
+  __syncthreads();
+  ta = sh2[0];
+  tb = sh2[1];
+  __syncthreads();
+}
+
 __device__ __forceinline__ void cell_of32(const Geo& g, int e, int nxs, int nxr, int& i, int& j, int& k) {
   i = nxs + e % nxr;
   const int r = e / nxr;
@@ -486,12 +548,37 @@ __device__ __forceinline__ void cell_of32(const Geo& g, int e, int nxs, int nxr,
   k = g.nzs + r / g.nyl;
 }
 
+// PEER = true: the slab-decomposed solve of a multi-GPU run as the same single launch per GPU.  The slab-axis neighbours
+// (z in 3-D, y in 2-D) are the ghost planes of the local arrays, which the NEIGHBOUR RANKS fill: every sweep that writes phi, p
+// or r also stores its two edge planes into the neighbours' ghost planes over NVLink, and the dot products are peer_sum2.
+template <bool PEER>
 __global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const double* __restrict__ gkl,
-                                                  double* __restrict__ phi, double* p0, double* p1, double* __restrict__ r,
+                                                  double* phi, double* p0, double* p1, double* r,
                                                   double* __restrict__ b, double* __restrict__ ap, double* __restrict__ part,
-                                                  int* __restrict__ ite_out, int* flags, Geo g, int nxs, int nxe) {
+                                                  int* __restrict__ ite_out, int* flags, Geo g, int nxs, int nxe, PeerCG pc) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sh[TPB / 32];
+  __shared__ double sh2[2];
+  unsigned long long seq = 0;
+  if (PEER) seq = *pc.seq;    // reductions done by earlier solves (identical on every rank)
+  // edge-plane pushes: my first plane along the slab axis goes to the lower neighbour's upper ghost plane, my last one to the
+  // upper neighbour's lower ghost plane (index shifts pc.shift_lo / pc.shift_hi inside the same box layout)
+  bool pushed = false;
+#define WM_PUSH(which, o, jj, kk, val)                                                          \
+  if (PEER) {                                                                                   \
+    const int sl = d3 ? (kk) : (jj);                                                            \
+    if (sl == (d3 ? g.nzs : g.nys)) { pc.lo[which][(long long)(o) + pc.shift_lo] = (val); pushed = true; } \
+    if (sl == (d3 ? g.nze : g.nye)) { pc.hi[which][(long long)(o) + pc.shift_hi] = (val); pushed = true; } \
+  }
+#define WM_SUM2(a_, b_, ta_, tb_)                                                               \
+  do {                                                                                          \
+    if (PEER) {                                                                                 \
+      if (pushed) { __threadfence_system(); pushed = false; }                                   \
+      peer_sum2(grid, pc, seq, a_, b_, part, red_idx, sh, sh2, flags, ta_, tb_);                \
+    } else {                                                                                    \
+      grid_sum2(grid, a_, b_, part, red_idx, sh, ta_, tb_);                                     \
+    }                                                                                           \
+  } while (0)
   const int nxr = nxe - nxs + 1;
   const int n = nxr * g.nyl * g.nzl;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -521,38 +608,47 @@ __global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const
     else if (l == 0) { xp = o - 2; cxp = -1.0; }                                      \
     else xp = o - 1;                                                                  \
   }                                                                                   \
-  const long long ym = j == g.nys ? o + (g.nyl - 1) * sy : o - sy, yp = j == g.nye ? o - (g.nyl - 1) * sy : o + sy; \
-  const long long zm = !d3 ? o : (k == g.nzs ? o + (g.nzl - 1) * sz : o - sz);                                \
-  const long long zp = !d3 ? o : (k == g.nze ? o - (g.nzl - 1) * sz : o + sz);
+  const bool ywrap = !(PEER && !d3), zwrap = !PEER;   /* the slab axis reads the ghost planes the neighbours fill */ \
+  const long long ym = (ywrap && j == g.nys) ? o + (g.nyl - 1) * sy : o - sy;                                  \
+  const long long yp = (ywrap && j == g.nye) ? o - (g.nyl - 1) * sy : o + sy;                                  \
+  const long long zm = !d3 ? o : ((zwrap && k == g.nzs) ? o + (g.nzl - 1) * sz : o - sz);                      \
+  const long long zp = !d3 ? o : ((zwrap && k == g.nze) ? o - (g.nzl - 1) * sz : o + sz);
+  // slab-axis neighbours (ghost planes written by other GPUs) are read through L2
+#define WM_LDS(arr, x) (PEER ? __ldcg((arr) + (x)) : (arr)[x])
   for (int l = 0; l < 3; ++l) {
     int ite = 0;
     double s = 0, dummy;
     double* pold = p0;   // the search direction of the previous iteration (complete)
     double* pnew = p1;
+    int wold = 1, wnew = 2;   // the same two buffers in the neighbours' tables (pc.lo / pc.hi)
     for (int e = tid; e < n; e += nth) {
       int i, j, k;
       cell_of32(g, e, nxs, nxr, i, j, k);
       const size_t o = g.box(i, j, k);
-      phi[o] = df[o * 6 + l];
+      const double ph = df[o * 6 + l];
+      phi[o] = ph;
+      WM_PUSH(0, o, j, k, ph)
       const double bb = g.f5 * gkl[o * 3 + l];
       b[o] = bb;
       s = s + bb * bb;
     }
     double sum_g;
-    grid_sum2(grid, s, 0.0, part, red_idx, sh, sum_g, dummy);      // its sync also orders phi before the stencil below
+    WM_SUM2(s, 0.0, sum_g, dummy);      // its sync also orders phi before the stencil below
     const double eps = sqrt(sum_g) * err;
     s = 0;
     for (int e = tid; e < n; e += nth) {
       WM_NBR(e)
       double rr;
-      if (d3) rr = b[o] + phi[zm] + phi[ym] + cxm * phi[xm] - g.f4 * phi[o] + cxp * phi[xp] + phi[yp] + phi[zp];
-      else rr = b[o] + phi[ym] + cxm * phi[xm] - g.f4 * phi[o] + cxp * phi[xp] + phi[yp];
+      if (d3) rr = b[o] + WM_LDS(phi, zm) + WM_LDS(phi, ym) + cxm * phi[xm] - g.f4 * phi[o] + cxp * phi[xp] + WM_LDS(phi, yp) + WM_LDS(phi, zp);
+      else rr = b[o] + WM_LDS(phi, ym) + cxm * phi[xm] - g.f4 * phi[o] + cxp * phi[xp] + WM_LDS(phi, yp);
       r[o] = rr;
       pold[o] = rr;
+      WM_PUSH(3, o, j, k, rr)
+      WM_PUSH(wold, o, j, k, rr)
       s = s + rr * rr;
     }
     double sumr_g;
-    grid_sum2(grid, s, 0.0, part, red_idx, sh, sumr_g, dummy);
+    WM_SUM2(s, 0.0, sumr_g, dummy);
     if (sqrt(sumr_g) > eps) {
       double bv = 0.0;   // first iteration: p = r
       while (sum_g > eps) {
@@ -563,18 +659,21 @@ __global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const
         for (int e = tid; e < n; e += nth) {
           WM_NBR(e)
 #define WM_P(x) fma(bv, pold[x], r[x])
-          const double pc = WM_P(o);
+#define WM_PS(x) fma(bv, WM_LDS(pold, x), WM_LDS(r, x))
+          const double pc_ = WM_P(o);
           double a;
-          if (d3) a = -WM_P(zm) - WM_P(ym) - cxm * WM_P(xm) + g.f4 * pc - cxp * WM_P(xp) - WM_P(yp) - WM_P(zp);
-          else a = -WM_P(ym) - cxm * WM_P(xm) + g.f4 * pc - cxp * WM_P(xp) - WM_P(yp);
+          if (d3) a = -WM_PS(zm) - WM_PS(ym) - cxm * WM_P(xm) + g.f4 * pc_ - cxp * WM_P(xp) - WM_PS(yp) - WM_PS(zp);
+          else a = -WM_PS(ym) - cxm * WM_P(xm) + g.f4 * pc_ - cxp * WM_P(xp) - WM_PS(yp);
 #undef WM_P
-          pnew[o] = pc;
+#undef WM_PS
+          pnew[o] = pc_;
+          WM_PUSH(wnew, o, j, k, pc_)
           ap[o] = a;
           s1 = s1 + r[o] * r[o];
-          s2 = s2 + pc * a;
+          s2 = s2 + pc_ * a;
         }
         double sum2_g;
-        grid_sum2(grid, s1, s2, part, red_idx, sh, sumr_g, sum2_g);
+        WM_SUM2(s1, s2, sumr_g, sum2_g);
         const double av = sumr_g / sum2_g;
         s = 0;
         for (int e = tid; e < n; e += nth) {
@@ -584,6 +683,7 @@ __global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const
           phi[o] = phi[o] + av * pnew[o];
           const double rn = r[o] - av * ap[o];
           r[o] = rn;
+          WM_PUSH(3, o, j, k, rn)
           s = s + rn * rn;
         }
         sum_g = sqrt(sumr_g);
@@ -592,11 +692,13 @@ __global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const
           break;
         }
         double sum1_g;
-        grid_sum2(grid, s, 0.0, part, red_idx, sh, sum1_g, dummy);   // its sync completes r and pnew for the next stencil
+        WM_SUM2(s, 0.0, sum1_g, dummy);   // its sync completes r and pnew for the next stencil
         bv = sum1_g / sumr_g;
         double* tsw = pold; pold = pnew; pnew = tsw;
+        const int wsw = wold; wold = wnew; wnew = wsw;
       }
     }
+    if (PEER && pushed) { __threadfence_system(); pushed = false; }
     grid.sync();   // every block is past the stencil reads of phi / r before df and the next component's phi are written
     for (int e = tid; e < n; e += nth) {
       int i, j, k;
@@ -607,6 +709,10 @@ __global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const
     if (tid == 0) ite_out[l] = ite;
     grid.sync();
   }
+  if (PEER && tid == 0) *pc.seq = seq;
+#undef WM_LDS
+#undef WM_PUSH
+#undef WM_SUM2
 #undef WM_NBR
 }
 
@@ -934,21 +1040,25 @@ int wm_k_cgm(wm_ctx* ctx, int nxs, int nxe) {
   const Geo& g = ctx->g;
   const long long n = (long long)(nxe - nxs + 1) * g.nyl * g.nzl;
   static const bool no_coop = getenv("WM_CG_HOSTLOOP") != nullptr;
-  if (ctx->nranks == 1 && !no_coop && n < (1LL << 30)) {
-    // single rank (periodic or walls): the whole solve is one cooperative launch
-    static int per_sm = 0;
-    if (per_sm == 0) WM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cgm_coop, TPB, 0));
+  const bool peer = ctx->nranks > 1 && ctx->peer_ok;
+  if ((ctx->nranks == 1 || peer) && !no_coop && n < (1LL << 30)) {
+    // the whole solve is one cooperative launch per GPU: single rank (periodic or walls), or slab-decomposed with the halo
+    // planes and the all-reduces exchanged over NVLink peer memory inside the kernel (k_cgm_coop<true>)
+    static int per_sm[2] = {0, 0};
+    void* kern = peer ? (void*)k_cgm_coop<true> : (void*)k_cgm_coop<false>;
+    if (per_sm[peer] == 0) WM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[peer], kern, TPB, 0));
     int nsm = 0;
     WM_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
-    int nb = (int)std::min<long long>((long long)nsm * per_sm, (n + TPB - 1) / TPB);
+    int nb = (int)std::min<long long>((long long)nsm * per_sm[peer], (n + TPB - 1) / TPB);
     nb = std::max(1, std::min(nb, 1024));   // 2 ping-pong partial buffers of 2*nb doubles in ctx->red
     double *df = ctx->df, *gkl = ctx->gkl, *phi = ctx->phi, *p = ctx->pcg, *p2 = ctx->pcg2, *r = ctx->rcg, *b = ctx->bcg, *ap = ctx->apcg;
     double* part = ctx->red;
     int* ite_dev = ctx->totals + 6;
     int* flags = ctx->flags;
     Geo gg = g;
-    void* args[] = {&df, &gkl, &phi, &p, &p2, &r, &b, &ap, &part, &ite_dev, &flags, &gg, &nxs, &nxe};
-    WM_CUDA(cudaLaunchCooperativeKernel((void*)k_cgm_coop, dim3(nb), dim3(TPB), args, 0, ctx->stream));
+    PeerCG pc = ctx->peer;
+    void* args[] = {&df, &gkl, &phi, &p, &p2, &r, &b, &ap, &part, &ite_dev, &flags, &gg, &nxs, &nxe, &pc};
+    WM_CUDA(cudaLaunchCooperativeKernel(kern, dim3(nb), dim3(TPB), args, 0, ctx->stream));
     ctx->launches++;
     ctx->cg_ite_on_device = true;
     return WM_OK;

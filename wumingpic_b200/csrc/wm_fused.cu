@@ -45,7 +45,8 @@ struct __align__(16) Smem {
   static constexpr int FSTR = G * CSTR + 1;   // double2 stride between record fields (== 1 mod 8)
   static constexpr int TILE_X = G + 2;
   static constexpr int TILE_ROW = TILE_X * 6; // doubles per (jj,kk) row of the field tile
-  double tile[9 * TILE_ROW];          // tmpf for cells i0-1..i0+16, j-1..j+1, k-1..k+1
+  double tile[9 * TILE_ROW];          // tmpf for cells i0-1..i0+G, j-1..j+1, k-1..k+1
+  double dtile[9 * TILE_ROW];         // x differences of the tile: dtile[row][x] = tile[row][x+1] - tile[row][x]
   double2 rec[NF * FSTR];             // per-particle deposit factors, field-major
   int beg[2][G + 1];                  // cs row segments of both species
   int cnt27[2][27][G];                // destination-offset counts per (species, offset, cell)
@@ -183,6 +184,13 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
   const double len_z = (g.nzge - g.nzgs + 1) * g.delx;
 
   mbar_wait(&S.bar, 0);
+  // x differences of the field tile, once per CTA (shared by the ~128 particles of every cell): the x sum of the gather
+  // becomes f(i) + sx(+1) d(i) - sx(-1) d(i-1), two DFMA instead of DMUL + two DFMA (sx(-1) + sx(0) + sx(+1) = 1)
+  for (int e = t; e < 9 * (G + 1) * 6; e += TPB) {
+    const int r = e / ((G + 1) * 6), q = e % ((G + 1) * 6);
+    S.dtile[r * TILE_ROW + q] = S.tile[r * TILE_ROW + q + 6] - S.tile[r * TILE_ROW + q];
+  }
+  __syncthreads();
 
   int ns0 = 0, nl0 = 0, ns1 = 0, nl1 = 0;   // stayers / leavers of this thread's cell written so far, per species
   // register prefetch of the next batch's particle (index -1: none)
@@ -217,20 +225,25 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
         shape3(x * g.d_delx - 5e-1 - ia, sx[0], sx[1], sx[2]);
         shape3(y * g.d_delx - 5e-1 - j, sy[0], sy[1], sy[2]);
         shape3(z * g.d_delx - 5e-1 - k, sz[0], sz[1], sz[2]);
-        // gather from the smem tile, reference nesting (x-sum, *shy, *shz)  particle.f90:126-184
+        // gather from the smem tile, reference nesting (x-sum, *shy, *shz)  particle.f90:126-184; the x sum in the
+        // difference form above (same value up to one rounding of 1e-16 |f|)
+        const double nsx0 = -sx[0];
         double f[6];
 #pragma unroll
         for (int kk = 0; kk < 3; ++kk) {
           double pl[6];
 #pragma unroll
           for (int jj = 0; jj < 3; ++jj) {
-            const double2* tr = reinterpret_cast<const double2*>(&S.tile[(kk * 3 + jj) * TILE_ROW + ca * 6]);
-            double v[18];
+            const double2* tc = reinterpret_cast<const double2*>(&S.tile[(kk * 3 + jj) * TILE_ROW + (ca + 1) * 6]);
+            const double2* td = reinterpret_cast<const double2*>(&S.dtile[(kk * 3 + jj) * TILE_ROW + ca * 6]);
+            double v[6], d[12];
 #pragma unroll
-            for (int e = 0; e < 9; ++e) { double2 d = tr[e]; v[2 * e] = d.x; v[2 * e + 1] = d.y; }
+            for (int e = 0; e < 3; ++e) { double2 q2 = tc[e]; v[2 * e] = q2.x; v[2 * e + 1] = q2.y; }
+#pragma unroll
+            for (int e = 0; e < 6; ++e) { double2 q2 = td[e]; d[2 * e] = q2.x; d[2 * e + 1] = q2.y; }
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
-              double row = +v[c] * sx[0] + v[6 + c] * sx[1] + v[12 + c] * sx[2];
+              double row = fma(sx[2], d[6 + c], fma(nsx0, d[c], v[c]));
               pl[c] = jj == 0 ? row * sy[0] : pl[c] + row * sy[jj];
             }
           }
@@ -250,7 +263,8 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
           double igam = rsqrt(qg);
           double gam = qg * igam;
           double fac1r = fac1 * igam;
-          double fac2r = fac2 / (gam + txxx * (bpx * bpx + bpy * bpy + bpz * bpz) * igam);
+          // reciprocal + multiply instead of a division (one more rounding, 1e-16 relative)
+          double fac2r = fac2 * __drcp_rn(gam + txxx * (bpx * bpx + bpy * bpy + bpz * bpz) * igam);
           double uvm4 = uvm1 + fac1r * (+uvm2 * bpz - uvm3 * bpy);
           double uvm5 = uvm2 + fac1r * (+uvm3 * bpx - uvm1 * bpz);
           double uvm6 = uvm3 + fac1r * (+uvm1 * bpy - uvm2 * bpx);
@@ -383,8 +397,10 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
         }
       };
       int s = 0;
-      for (; s + 1 < nst; s += 2) { stay(s); stay(s + 1); }
-      if (s < nst) stay(s);
+      if (mb >= 1 && mb <= 3) {   // a stayer's S0 = DS = 0 at the outer points: the strips mb = 0, 4 receive exactly nothing
+        for (; s + 1 < nst; s += 2) { stay(s); stay(s + 1); }
+        if (s < nst) stay(s);
+      }
       s = SLOTS - ncr;
       for (; s + 1 < SLOTS; s += 2) { cross(s); cross(s + 1); }
       if (s < SLOTS) cross(s);
@@ -411,19 +427,21 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
       }
   }
   // ---- re-binning information for the sort: one count line per (cell, species), group sizes -> histogram ----
-  __syncthreads();   // S.cnt27 was accumulated by all warps
-  {
-    const size_t cell0 = wm_cell_index(g, i0, j, k);
-    for (int e = t; e < G * 2 * WM_CNT_LINE; e += TPB) {
-      const int o = e % WM_CNT_LINE, isp = (e / WM_CNT_LINE) % 2, c = e / (2 * WM_CNT_LINE);
-      if (c < ncg) cnt[cell0 * 2 * WM_CNT_LINE + e] = o < 27 ? S.cnt27[isp][o][c] : 0;
+  // A cell's counts were accumulated by its own half-warp only, so every warp flushes its two cells and leaves: no CTA
+  // barrier at the tail (the slowest warp of a CTA no longer holds the other three).
+  __syncwarp();
+  if (ca < ncg) {
+    const size_t cell = wm_cell_index(g, i0, j, k) + ca;
+    for (int e = sa; e < 2 * WM_CNT_LINE; e += 16) {
+      const int o = e % WM_CNT_LINE, isp = e / WM_CNT_LINE;
+      cnt[cell * 2 * WM_CNT_LINE + e] = o < 27 ? S.cnt27[isp][o][ca] : 0;
     }
-    for (int e = t; e < 2 * 27 * G; e += TPB) {
-      const int c = e % G, o = (e / G) % 27, isp = e / (G * 27);
-      const int n = c < ncg ? S.cnt27[isp][o][c] : 0;
+    for (int e = sa; e < 2 * 27; e += 16) {
+      const int o = e % 27, isp = e / 27;
+      const int n = S.cnt27[isp][o][ca];
       if (n > 0) {
         int drow, ti;
-        if (wm_dest_of(g, i0 + c, j, k, o, isp, nxs, nxe, drow, ti)) atomicAdd(hist + (size_t)drow * (g.nx + 1) + (ti - g.nxgs), n);
+        if (wm_dest_of(g, i0 + ca, j, k, o, isp, nxs, nxe, drow, ti)) atomicAdd(hist + (size_t)drow * (g.nx + 1) + (ti - g.nxgs), n);
         else atomicOr(flags, 2);
       }
     }

@@ -48,6 +48,23 @@ struct Ptcl {
   double* c[6];  // 3-D: x y z ux uy uz ; 2-D: x y ux uy uz (c[5] unused)
 };
 
+// ---------------------------------------------------------------------------------------------
+// Peer-memory tables of the multi-GPU cgm (wm_fields.cu k_cgm_coop<true>, set up by wm_comm.cu): every rank maps its two
+// slab neighbours' CG operand arrays and every rank's reduction mailbox through CUDA IPC, so that the ghost-plane exchange
+// and the two all-reduces of a CG iteration are stores / polls over NVLink inside ONE cooperative kernel per GPU.
+// ---------------------------------------------------------------------------------------------
+constexpr int WM_MAX_PEERS = 16;
+struct WmMail { double a, b; unsigned long long seq, pad; };   // one slot per (parity, source rank)
+struct PeerCG {
+  double* lo[4];        // phi, p0, p1, r of the lower neighbour along the slab axis (peer pointers)
+  double* hi[4];        // ... of the upper neighbour
+  long long shift_lo;   // box-index shift from my first slab plane to the lower neighbour's upper ghost plane
+  long long shift_hi;   // ... from my last slab plane to the upper neighbour's lower ghost plane
+  WmMail* mail[WM_MAX_PEERS];   // mailbox [2][nranks] of every rank (mail[rank] is the local one)
+  unsigned long long* seq;      // local: number of reductions done so far (same on all ranks)
+  int nranks, rank;
+};
+
 struct wm_ctx {
   wm_params prm;
   Geo g;
@@ -98,6 +115,10 @@ struct wm_ctx {
   bool keys_valid = false;   // migration pass done (histogram in cs_new)
   int last_nxs = 0, last_nxe = 0;  // x range of the last particle__solv (bc__particle_y[z] has no range argument)
   // comm
+  PeerCG peer = {};
+  bool peer_ok = false;            // the peer-memory cgm is usable (all ranks agreed)
+  void* peer_arena = nullptr;      // phi | pcg | pcg2 | rcg | mailbox | seq in ONE allocation = one IPC handle per rank
+  void* peer_opened[WM_MAX_PEERS] = {};   // bases returned by cudaIpcOpenMemHandle (to close)
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
   int rank_up[2] = {0, 0}, rank_down[2] = {0, 0};  // [0]: y neighbours, [1]: z neighbours
@@ -171,3 +192,4 @@ int wm_comm_group_begin(wm_ctx* ctx);
 int wm_comm_group_end(wm_ctx* ctx);
 int wm_comm_send(wm_ctx* ctx, int peer, const void* buf, size_t bytes);
 int wm_comm_recv(wm_ctx* ctx, int peer, void* buf, size_t bytes);
+int wm_comm_destroy(wm_ctx* ctx);
