@@ -3,7 +3,7 @@
 ! libwuming_b200.so (include/wuming_b200.h).
 !
 ! It provides modules with the SAME names, public procedures and argument lists as the reference's
-!     3d/common/particle.f90           (particle__init, particle__solv)
+!     3d/common/particle.f90           (particle__init, particle__solv, particle__solv_vay)
 !     3d/common/field.f90              (field__init, field__fdtd_i)
 !     3d/common/sort.f90               (sort__init, sort__bucket)
 !     3d/common/boundary_periodic.f90  (boundary_periodic__init, __particle_x, __particle_yz, __dfield, __curre, __phi)
@@ -85,6 +85,12 @@ module wuming_b200_c
       integer(c_int)     :: ierr
     end function
     function wm_particle_solv(c, nxs, nxe) bind(c, name='wm_particle_solv') result(ierr)
+      import :: c_int, c_ptr
+      type(c_ptr), value    :: c
+      integer(c_int), value :: nxs, nxe
+      integer(c_int)        :: ierr
+    end function
+    function wm_particle_solv_vay(c, nxs, nxe) bind(c, name='wm_particle_solv_vay') result(ierr)
       import :: c_int, c_ptr
       type(c_ptr), value    :: c
       integer(c_int), value :: nxs, nxe
@@ -212,7 +218,7 @@ module particle                      ! replaces 3d/common/particle.f90
   use wuming_b200_c
   implicit none
   private
-  public :: particle__init, particle__solv
+  public :: particle__init, particle__solv, particle__solv_vay
   integer, save :: ndim, np, nsp, nxgs, nxge, nygs, nyge, nzgs, nzge, nys, nye, nzs, nze
   logical, save :: is_init = .false.
 contains
@@ -256,6 +262,32 @@ contains
       call wm_check(ierr, 'wm_download(gp)')
     end if
   end subroutine particle__solv
+
+  subroutine particle__solv_vay(gp,up,uf,cumcnt,nxs,nxe)                            ! particle.f90:236-419
+    integer, intent(in)          :: nxs, nxe
+    integer, intent(in), target  :: cumcnt(nxgs:nxge+1,nys:nye,nzs:nze,nsp)
+    real(8), intent(in), target  :: up(ndim,np,nys:nye,nzs:nze,nsp)
+    real(8), intent(in), target  :: uf(6,nxgs-2:nxge+2,nys-2:nye+2,nzs-2:nze+2)
+    real(8), intent(out), target :: gp(ndim,np,nys:nye,nzs:nze,nsp)
+    integer, target :: np2(nys:nye,nzs:nze,nsp)
+    integer(c_int)  :: ierr
+    if(.not.is_init)then
+      write(6,*)'Initialize first by calling particle__init()'
+      stop
+    endif
+    if (shim_mode == WM_SHIM_SYNC_EVERY_CALL .or. host_dirty) then
+      np2(:,:,:) = cumcnt(nxe+1,:,:,:)          ! the pencil population is the last prefix count (sort.f90:71-74)
+      ierr = wm_upload(ctx, c_loc(up), c_loc(np2), c_loc(cumcnt), c_loc(uf))
+      call wm_check(ierr, 'wm_upload')
+      host_dirty = .false.
+    end if
+    ierr = wm_particle_solv_vay(ctx, int(nxs,c_int), int(nxe,c_int))
+    call wm_check(ierr, 'particle__solv_vay')
+    if (shim_mode == WM_SHIM_SYNC_EVERY_CALL) then
+      ierr = wm_download(ctx, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_loc(gp))
+      call wm_check(ierr, 'wm_download(gp)')
+    end if
+  end subroutine particle__solv_vay
 
 end module particle
 

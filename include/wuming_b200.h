@@ -47,6 +47,9 @@ enum { WM_BC_PERIODIC = 0, WM_BC_RECONNECTION = 1, WM_BC_SHOCK = 2 };
 enum { WM_ORDER_WEIBEL = 0,        /* solv, fdtd_i, particle_x, particle_yz, sort   (3d/proj/weibel/app.f90:100-108) */
        WM_ORDER_RECONNECTION = 1,  /* solv, particle_x, fdtd_i, particle_yz, sort   (3d/proj/reconnection/app.f90:103-108) */
        WM_ORDER_SHOCK = 2 };       /* solv, injection, fdtd_i, particle_yz, sort    (2d/proj/shock/app.f90:112-125) */
+/* the two pushers of the reference's particle module (3d/common/particle.f90:7) */
+enum { WM_PUSHER_BORIS = 0,        /* particle__solv      Buneman-Boris  3d/common/particle.f90:52-233  [2d :48-179]  */
+       WM_PUSHER_VAY = 1 };        /* particle__solv_vay  Vay (2008)     3d/common/particle.f90:236-419 [2d :182-315] */
 
 /* Geometry and constants: the union of the arguments of particle__init (3d/common/particle.f90:18-49),
  * field__init (3d/common/field.f90:22-67), sort__init (3d/common/sort.f90:16-37),
@@ -107,6 +110,7 @@ int wm_upload_work(wm_ctx* ctx, int which, const double* in);
 
 /* -- the hot path on device-resident state, one entry per reference procedure -------------------- */
 int wm_particle_solv(wm_ctx* ctx, int nxs, int nxe);    /* particle__solv       3d/common/particle.f90:52-233 [2d :48-179] */
+int wm_particle_solv_vay(wm_ctx* ctx, int nxs, int nxe); /* particle__solv_vay  3d/common/particle.f90:236-419 [2d :182-315] */
 int wm_field_fdtd_i(wm_ctx* ctx, int nxs, int nxe);     /* field__fdtd_i        3d/common/field.f90:70-208    [2d :66-186]
                                                             incl. ele_cur :211-406, cgm :409-560 and the three boundary
                                                             callbacks (bc__curre, bc__phi, bc__dfield) of ctx's bc_kind  */
@@ -122,10 +126,15 @@ int wm_step(wm_ctx* ctx, int nxs, int nxe, int order, double u0, int nsteps);
 /* 1 (default): wm_step uses the fused push+deposit kernel and the deterministic sort where available;
  * 0: wm_step calls the per-procedure kernels, exactly like a driver calling the five entry points above */
 int wm_set_fused(wm_ctx* ctx, int on);
+/* which pusher wm_step / wm_h_step run (WM_PUSHER_*): a driver that calls particle__solv_vay in its time loop sets
+ * WM_PUSHER_VAY once; wm_particle_solv and wm_particle_solv_vay always run their own pusher */
+int wm_set_pusher(wm_ctx* ctx, int pusher);
 
 /* -- host-buffer forms with the reference's own argument lists (upload, run, download) ---------- */
 int wm_h_particle_solv(wm_ctx* ctx, double* gp, const double* up, const double* uf, const int* cumcnt,
                        const int* np2, int nxs, int nxe);
+int wm_h_particle_solv_vay(wm_ctx* ctx, double* gp, const double* up, const double* uf, const int* cumcnt,
+                           const int* np2, int nxs, int nxe);
 int wm_h_field_fdtd_i(wm_ctx* ctx, double* uf, const double* up, const double* gp, const int* cumcnt,
                       const int* np2, int nxs, int nxe);
 /* one whole step on host state: up, uf, np2, cumcnt in -> out (gp is scratch on the device only) */

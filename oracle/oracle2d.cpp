@@ -76,6 +76,7 @@ struct World2 {
   std::vector<Rank2> ranks;
   int cg_ite[3] = {0, 0, 0};
   int err = 0;  // 1: cgm ite_max, 2: memory over, 3: moved more than one row, 4: x outside [nxs,nxe] at the sort
+  int pusher = 0;  // the pusher step() calls: 0 particle__solv (Buneman-Boris), 1 particle__solv_vay
   int nx() const { return nxge - nxgs + 1; }
 };
 
@@ -131,7 +132,8 @@ void sendrecv(World2& w, Dir d, Pack pack, Unpack unpack) {
 // particle__solv -- 2d/common/particle.f90:48-179
 // ---------------------------------------------------------------------------
 // accl = true: mom_calc__accl (2d/common/mom_calc.f90:49-163): same gather and rotation with delt/2 (:34), no move
-void particle_solv(World2& w, Rank2& R, std::vector<double>& gp, const std::vector<double>& up, bool accl = false) {
+// vay = true: particle__solv_vay (2d/common/particle.f90:182-315): same staging and gather, Vay velocity update (:268-292)
+void particle_solv(World2& w, Rank2& R, std::vector<double>& gp, const std::vector<double>& up, bool accl = false, bool vay = false) {
   const int nxs = w.nxs, nxe = w.nxe, nys = R.nys, nye = R.nye;
   const double d_delx = w.d_delx, delt = accl ? w.delt * 0.5 : w.delt, c = w.c;
   const int tx = nxe - nxs + 3, ty = nye - nys + 3;
@@ -178,6 +180,28 @@ void particle_solv(World2& w, Rank2& R, std::vector<double>& gp, const std::vect
                         + (+T(cc, i - 1, j) * sx[0] + T(cc, i, j) * sx[1] + T(cc, i + 1, j) * sx[2]) * sy[1]
                         + (+T(cc, i - 1, j + 1) * sx[0] + T(cc, i, j + 1) * sx[1] + T(cc, i + 1, j + 1) * sx[2]) * sy[2];
           const double bpx = f[0], bpy = f[1], bpz = f[2], epx = f[3], epy = f[4], epz = f[5];
+          if (vay) {   // particle.f90:268-299
+            double uvm1 = u[2], uvm2 = u[3], uvm3 = u[4];
+            double gam = std::sqrt(c * c + uvm1 * uvm1 + uvm2 * uvm2 + uvm3 * uvm3);
+            const double fac1r = fac1 / gam;
+            const double uvm4 = uvm1 + fac2 * epx + fac1r * (+uvm2 * bpz - uvm3 * bpy);
+            const double uvm5 = uvm2 + fac2 * epy + fac1r * (+uvm3 * bpx - uvm1 * bpz);
+            const double uvm6 = uvm3 + fac2 * epz + fac1r * (+uvm1 * bpy - uvm2 * bpx);
+            const double taux = fac1 * bpx / c, tauy = fac1 * bpy / c, tauz = fac1 * bpz / c;
+            const double tau2 = taux * taux + tauy * tauy + tauz * tauz;
+            const double ua = (uvm4 * taux + uvm5 * tauy + uvm6 * tauz) / c;
+            const double sigma = 1.0 + (uvm4 * uvm4 + uvm5 * uvm5 + uvm6 * uvm6) / (c * c) - tau2;
+            const double gam2 = 0.5 * (sigma + std::sqrt(sigma * sigma + 4.0 * (tau2 + ua * ua)));
+            gam = std::sqrt(gam2);
+            const double s_ = 1.0 / (tau2 + gam2);
+            g[2] = s_ * (gam2 * uvm4 + c * ua * taux + gam * (uvm5 * tauz - uvm6 * tauy));
+            g[3] = s_ * (gam2 * uvm5 + c * ua * tauy + gam * (uvm6 * taux - uvm4 * tauz));
+            g[4] = s_ * (gam2 * uvm6 + c * ua * tauz + gam * (uvm4 * tauy - uvm5 * taux));
+            gam = 1.0 / gam;
+            g[0] = u[0] + g[2] * delt * gam;
+            g[1] = u[1] + g[3] * delt * gam;
+            continue;
+          }
           double uvm1 = u[2] + fac1 * epx;
           double uvm2 = u[3] + fac1 * epy;
           double uvm3 = u[4] + fac1 * epz;
@@ -881,7 +905,7 @@ void mom_calc(World2& w) {
 // one time step; order: 0 Weibel (2d/proj/weibel/app.f90:99-107), 1 reconnection (2d/proj/reconnection/app.f90:99-106),
 // 2 shock without the driver's inject/relocate (2d/proj/shock/app.f90:112-118)
 void step(World2& w, int order, double u0) {
-  for (Rank2& R : w.ranks) particle_solv(w, R, R.gp, R.up);
+  for (Rank2& R : w.ranks) particle_solv(w, R, R.gp, R.up, false, w.pusher == 1);
   if (order == 1) for (Rank2& R : w.ranks) bc_particle_x_reflect(w, R, R.gp);
   if (order == 2) for (Rank2& R : w.ranks) bc_injection(w, R, R.gp, u0);
   field_fdtd_i(w, 0);
@@ -969,6 +993,8 @@ void orc2_set_xrange(void* h, int nxs, int nxe) { ((World2*)h)->nxs = nxs; ((Wor
 void orc2_cg_iterations(void* h, int* out) { for (int l = 0; l < 3; ++l) out[l] = ((World2*)h)->cg_ite[l]; }
 
 void orc2_particle_solv(void* h) { World2& w = *(World2*)h; for (Rank2& R : w.ranks) particle_solv(w, R, R.gp, R.up); }
+void orc2_particle_solv_vay(void* h) { World2& w = *(World2*)h; for (Rank2& R : w.ranks) particle_solv(w, R, R.gp, R.up, false, true); }
+void orc2_set_pusher(void* h, int kind) { ((World2*)h)->pusher = kind; }
 void orc2_field_fdtd_i(void* h, int stage) { field_fdtd_i(*(World2*)h, stage); }
 // kind: 0 periodic wrap, 1 reflecting walls
 void orc2_bc_particle_x(void* h, int kind) {

@@ -57,6 +57,7 @@ struct World3 {
   std::vector<Rank3> ranks;
   int cg_ite[3] = {0, 0, 0};
   int err = 0;  // 1: cgm ite_max, 2: memory over (np2 > np)
+  int pusher = 0;  // the pusher step() calls: 0 particle__solv (Buneman-Boris), 1 particle__solv_vay
   int nx() const { return nxge - nxgs + 1; }
 };
 
@@ -124,7 +125,9 @@ void sendrecv(World3& w, Dir d, Pack pack, Unpack unpack) {
 // ---------------------------------------------------------------------------
 // accl = true: mom_calc__accl (3d/common/mom_calc.f90:49-216) -- the same gather and Boris rotation with delt/2
 // (mom_calc__init :36), no move: gp(1:3) = up(1:3), gp(4:6) = re-centred momenta; gp(7) is not written.
-void particle_solv(World3& w, Rank3& R, std::vector<double>& gp, const std::vector<double>& up, bool accl = false) {
+// vay = true: particle__solv_vay (3d/common/particle.f90:236-419, Vay, PoP 15, 056701 (2008)): the same staging and gather,
+// then the Vay velocity update (:375-400) and the move with the new gamma (:402-406).
+void particle_solv(World3& w, Rank3& R, std::vector<double>& gp, const std::vector<double>& up, bool accl = false, bool vay = false) {
   const int nxs = w.nxs, nxe = w.nxe, nys = R.nys, nye = R.nye, nzs = R.nzs, nze = R.nze;
   const double d_delx = w.d_delx, delt = accl ? w.delt * 5e-1 : w.delt, c = w.c;
   const int tx = nxe - nxs + 3, ty = nye - nys + 3, tz = nze - nzs + 3;
@@ -190,6 +193,30 @@ void particle_solv(World3& w, Rank3& R, std::vector<double>& gp, const std::vect
               f[cc - 1] = acc;
             }
             const double bpx = f[0], bpy = f[1], bpz = f[2], epx = f[3], epy = f[4], epz = f[5];
+
+            if (vay) {   // particle.f90:375-406
+              double uvm1 = u[3], uvm2 = u[4], uvm3 = u[5];
+              double gam = std::sqrt(c * c + uvm1 * uvm1 + uvm2 * uvm2 + uvm3 * uvm3);
+              const double fac1r = fac1 / gam;
+              const double uvm4 = uvm1 + fac2 * epx + fac1r * (+uvm2 * bpz - uvm3 * bpy);
+              const double uvm5 = uvm2 + fac2 * epy + fac1r * (+uvm3 * bpx - uvm1 * bpz);
+              const double uvm6 = uvm3 + fac2 * epz + fac1r * (+uvm1 * bpy - uvm2 * bpx);
+              const double taux = fac1 * bpx / c, tauy = fac1 * bpy / c, tauz = fac1 * bpz / c;
+              const double tau2 = taux * taux + tauy * tauy + tauz * tauz;
+              const double ua = (uvm4 * taux + uvm5 * tauy + uvm6 * tauz) / c;
+              const double sigma = 1.0 + (uvm4 * uvm4 + uvm5 * uvm5 + uvm6 * uvm6) / (c * c) - tau2;
+              const double gam2 = 0.5 * (sigma + std::sqrt(sigma * sigma + 4.0 * (tau2 + ua * ua)));
+              gam = std::sqrt(gam2);
+              const double s_ = 1.0 / (tau2 + gam2);
+              g[3] = s_ * (gam2 * uvm4 + c * ua * taux + gam * (uvm5 * tauz - uvm6 * tauy));
+              g[4] = s_ * (gam2 * uvm5 + c * ua * tauy + gam * (uvm6 * taux - uvm4 * tauz));
+              g[5] = s_ * (gam2 * uvm6 + c * ua * tauz + gam * (uvm4 * tauy - uvm5 * taux));
+              gam = 1.0 / gam;
+              g[0] = u[0] + g[3] * delt * gam;
+              g[1] = u[1] + g[4] * delt * gam;
+              g[2] = u[2] + g[5] * delt * gam;
+              continue;
+            }
 
             double uvm1 = u[3] + fac1 * epx;
             double uvm2 = u[4] + fac1 * epy;
@@ -1182,7 +1209,7 @@ void mom_calc(World3& w) {
 // one time step; order 0: Weibel/beam (3d/proj/weibel/app.f90:100-108), 1: reconnection (3d/proj/reconnection/app.f90:103-108),
 // 2: shock without the driver's inject/relocate (3d/proj/shock/app.f90, same call order as 2d/proj/shock/app.f90:112-118)
 void step(World3& w, int order = 0, double u0 = 0.0) {
-  for (Rank3& R : w.ranks) particle_solv(w, R, R.gp, R.up);
+  for (Rank3& R : w.ranks) particle_solv(w, R, R.gp, R.up, false, w.pusher == 1);
   if (order == 1) for (Rank3& R : w.ranks) bc_particle_x_reflect(w, R, R.gp);
   if (order == 2) for (Rank3& R : w.ranks) bc_injection(w, R, R.gp, u0);
   field_fdtd_i(w, 0);
@@ -1278,6 +1305,8 @@ void orc3_set_xrange(void* h, int nxs, int nxe) { ((World3*)h)->nxs = nxs; ((Wor
 void orc3_cg_iterations(void* h, int* out) { for (int l = 0; l < 3; ++l) out[l] = ((World3*)h)->cg_ite[l]; }
 
 void orc3_particle_solv(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) particle_solv(w, R, R.gp, R.up); }
+void orc3_particle_solv_vay(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) particle_solv(w, R, R.gp, R.up, false, true); }
+void orc3_set_pusher(void* h, int kind) { ((World3*)h)->pusher = kind; }
 void orc3_field_fdtd_i(void* h, int stage) { field_fdtd_i(*(World3*)h, stage); }
 void orc3_bc_particle_x(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) bc_particle_x(w, R, R.gp); }
 void orc3_bc_particle_yz(void* h) { bc_particle_yz(*(World3*)h, 0); }

@@ -42,11 +42,13 @@ def lib(fast=False):
         L.orc3_dptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc3_iptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc3_load_weibel.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 4 + [C.c_uint64]
-        for name in ("destroy", "particle_solv", "bc_particle_x", "bc_particle_yz", "sort_bucket", "step",
+        for name in ("destroy", "particle_solv", "particle_solv_vay", "bc_particle_x", "bc_particle_yz", "sort_bucket", "step",
                      "clear_error"):
             getattr(L, "orc3_" + name).argtypes = [C.c_void_p]
         L.orc3_field_fdtd_i.argtypes = [C.c_void_p, C.c_int]
         L.orc3_mom_calc.argtypes = [C.c_void_p]
+        L.orc3_set_pusher.argtypes = [C.c_void_p, C.c_int]
+        L.orc2_set_pusher.argtypes = [C.c_void_p, C.c_int]
         L.orc2_mom_calc.argtypes = [C.c_void_p]
         L.orc3_step_order.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.orc3_bc_particle_x_reflect.argtypes = [C.c_void_p]
@@ -62,7 +64,7 @@ def lib(fast=False):
         L.orc2_dptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc2_iptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc2_load_weibel.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 4 + [C.c_uint64]
-        for name in ("destroy", "particle_solv", "bc_particle_y", "sort_bucket", "clear_error"):
+        for name in ("destroy", "particle_solv", "particle_solv_vay", "bc_particle_y", "sort_bucket", "clear_error"):
             getattr(L, "orc2_" + name).argtypes = [C.c_void_p]
         L.orc2_bc_particle_x.argtypes = [C.c_void_p, C.c_int]
         L.orc2_bc_injection.argtypes = [C.c_void_p, C.c_double]
@@ -155,6 +157,13 @@ class World3:
 
     def particle_solv(self):
         self.L.orc3_particle_solv(self.h)
+
+    def particle_solv_vay(self):
+        self.L.orc3_particle_solv_vay(self.h)
+
+    def set_pusher(self, kind):
+        """the pusher step() calls: 0 particle__solv (Buneman-Boris), 1 particle__solv_vay"""
+        self.L.orc3_set_pusher(self.h, kind)
 
     def field_fdtd_i(self, stage=0):
         self.L.orc3_field_fdtd_i(self.h, stage)
@@ -272,6 +281,12 @@ class World2:
 
     def particle_solv(self):
         self.L.orc2_particle_solv(self.h)
+
+    def particle_solv_vay(self):
+        self.L.orc2_particle_solv_vay(self.h)
+
+    def set_pusher(self, kind):
+        self.L.orc2_set_pusher(self.h, kind)
 
     def field_fdtd_i(self, stage=0):
         self.L.orc2_field_fdtd_i(self.h, stage)

@@ -54,6 +54,7 @@ ABI_SYMBOLS = [
     "wm_bc_particle_x", "wm_bc_injection", "wm_bc_particle_yz", "wm_sort_bucket", "wm_step", "wm_set_fused",
     "wm_h_particle_solv", "wm_h_field_fdtd_i", "wm_h_step", "wm_load_weibel", "wm_energy", "wm_gauss",
     "wm_get_stats", "wm_sync", "wm_set_timing", "wm_launch_count", "wm_stream", "wm_mom_calc",
+    "wm_particle_solv_vay", "wm_h_particle_solv_vay", "wm_set_pusher",
 ]
 
 
@@ -82,13 +83,15 @@ def load_library():
         L.wm_download.argtypes = [vp, dp, ip, ip, dp, dp]
         L.wm_download_work.argtypes = [vp, C.c_int, dp]
         L.wm_upload_work.argtypes = [vp, C.c_int, dp]
-        for name in ("wm_particle_solv", "wm_field_fdtd_i", "wm_bc_particle_x", "wm_sort_bucket"):
+        for name in ("wm_particle_solv", "wm_particle_solv_vay", "wm_field_fdtd_i", "wm_bc_particle_x", "wm_sort_bucket"):
             getattr(L, name).argtypes = [vp, C.c_int, C.c_int]
         L.wm_field_stage.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         L.wm_bc_injection.argtypes = [vp, C.c_int, C.c_int, C.c_double]
         L.wm_bc_particle_yz.argtypes = [vp]
         L.wm_step.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
         L.wm_set_fused.argtypes = [vp, C.c_int]
+        L.wm_set_pusher.argtypes = [vp, C.c_int]
+        L.wm_h_particle_solv_vay.argtypes = [vp, dp, dp, dp, ip, ip, C.c_int, C.c_int]
         L.wm_h_particle_solv.argtypes = [vp, dp, dp, dp, ip, ip, C.c_int, C.c_int]
         L.wm_h_field_fdtd_i.argtypes = [vp, dp, dp, dp, ip, ip, C.c_int, C.c_int]
         L.wm_h_step.argtypes = [vp, dp, dp, ip, ip, C.c_int, C.c_int, C.c_int, C.c_double]
@@ -239,6 +242,14 @@ class Backend:
     # -- the reference's procedures on resident state ------------------------------------------
     def particle__solv(self, nxs, nxe):
         self._ck(self.L.wm_particle_solv(self.h, nxs, nxe))
+
+    def particle__solv_vay(self, nxs, nxe):
+        """particle__solv_vay (3d/common/particle.f90:236-419): the Vay pusher on resident state."""
+        self._ck(self.L.wm_particle_solv_vay(self.h, nxs, nxe))
+
+    def set_pusher(self, kind):
+        """which pusher step()/h_step() run: WM_PUSHER_BORIS (0, particle__solv) or WM_PUSHER_VAY (1, particle__solv_vay)"""
+        self._ck(self.L.wm_set_pusher(self.h, kind))
 
     def field__fdtd_i(self, nxs, nxe, stage=0):
         if stage:

@@ -372,17 +372,23 @@ int wm_upload_work(wm_ctx* c, int which, const double* in) {
 // ---------------------------------------------------------------------------------------------
 // the hot path, one entry per reference procedure
 // ---------------------------------------------------------------------------------------------
-int wm_particle_solv(wm_ctx* c, int nxs, int nxe) {
+static int particle_solv_with(wm_ctx* c, int nxs, int nxe, int pusher) {
   if (!c || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling particle__init()"); return WM_ERR_ARG; }
   WM_CUDA(cudaSetDevice(c->device));
   WM_TRY(wm_k_tmpf(c, nxs, nxe));
-  WM_TRY(wm_k_push(c, nxs, nxe));
+  const int saved = c->pusher;
+  c->pusher = pusher;
+  const int rc = wm_k_push(c, nxs, nxe);
+  c->pusher = saved;
+  WM_TRY(rc);
   c->gp_valid = true;
   c->keys_valid = false;
   c->last_nxs = nxs;
   c->last_nxe = nxe;
   return WM_OK;
 }
+int wm_particle_solv(wm_ctx* c, int nxs, int nxe) { return particle_solv_with(c, nxs, nxe, WM_PUSHER_BORIS); }
+int wm_particle_solv_vay(wm_ctx* c, int nxs, int nxe) { return particle_solv_with(c, nxs, nxe, WM_PUSHER_VAY); }
 
 int wm_field_stage(wm_ctx* c, int nxs, int nxe, int stage) {
   if (!c || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling field__init()"); return WM_ERR_ARG; }
@@ -468,7 +474,7 @@ int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
       c->gp_valid = false;
       c->keys_valid = false;
     } else {
-      WM_TRY(wm_particle_solv(c, nxs, nxe));
+      WM_TRY(particle_solv_with(c, nxs, nxe, c->pusher));
       if (c->timing) WM_CUDA(cudaEventRecord(c->ev[1], c->stream));
       if (order == WM_ORDER_RECONNECTION) WM_TRY(wm_bc_particle_x(c, nxs, nxe));
       if (order == WM_ORDER_SHOCK) WM_TRY(wm_bc_injection(c, nxs, nxe, u0));
@@ -511,6 +517,12 @@ int wm_set_fused(wm_ctx* c, int on) {
   return WM_OK;
 }
 
+int wm_set_pusher(wm_ctx* c, int pusher) {
+  if (!c || (pusher != WM_PUSHER_BORIS && pusher != WM_PUSHER_VAY)) { wm_set_error("wm_set_pusher: WM_PUSHER_BORIS or WM_PUSHER_VAY"); return WM_ERR_ARG; }
+  c->pusher = pusher;
+  return WM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-buffer forms
 // ---------------------------------------------------------------------------------------------
@@ -518,6 +530,13 @@ int wm_h_particle_solv(wm_ctx* c, double* gp, const double* up, const double* uf
                        int nxs, int nxe) {
   WM_TRY(wm_upload(c, up, np2, cumcnt, uf));
   WM_TRY(wm_particle_solv(c, nxs, nxe));
+  return wm_download(c, nullptr, nullptr, nullptr, nullptr, gp);
+}
+
+int wm_h_particle_solv_vay(wm_ctx* c, double* gp, const double* up, const double* uf, const int* cumcnt, const int* np2,
+                           int nxs, int nxe) {
+  WM_TRY(wm_upload(c, up, np2, cumcnt, uf));
+  WM_TRY(wm_particle_solv_vay(c, nxs, nxe));
   return wm_download(c, nullptr, nullptr, nullptr, nullptr, gp);
 }
 

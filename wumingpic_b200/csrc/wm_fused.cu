@@ -28,6 +28,7 @@
 //     per-cell prefix over the 27 sources and ranks from the (stable) order inside the source cell, which
 //     makes the scatter atomic-free and the particle order -- hence every later sum -- deterministic.
 #include "wm_cells.cuh"
+#include "wm_push.cuh"
 
 #include <cstdlib>
 
@@ -116,7 +117,7 @@ __device__ __forceinline__ void s0ds(double xo, double xn, int cell, int inc, do
 #ifndef WM_FUSED_MINB
 #define WM_FUSED_MINB 3   // 3 x 128-thread CTAs per SM: 168 registers, no spills (4 CTAs at 128 registers: 3 % slower)
 #endif
-template <int ORDER, int G>
+template <int ORDER, int G, bool VAY>
 __global__ void __launch_bounds__(16 * G, WM_FUSED_MINB)
 k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __restrict__ id_out,
          const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj, int* __restrict__ cnt,
@@ -254,7 +255,14 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
         const double fac1 = g.fac1[isp];   // per-species constants computed once on the host (wm_create)
         const double txxx = fac1 * fac1;
         const double fac2 = g.fac2[isp];
-        {
+        if (VAY) {
+          // particle__solv_vay  particle.f90:369-406
+          double igam;
+          wm_vay_update(f, fac1, fac2, g.c, ux, uy, uz, igam);
+          xn = x + ux * g.delt * igam;
+          yn = y + uy * g.delt * igam;
+          zn = z + uz * g.delt * igam;
+        } else {
           const double bpx = f[0], bpy = f[1], bpz = f[2], epx = f[3], epy = f[4], epz = f[5];
           double uvm1 = ux + fac1 * epx, uvm2 = uy + fac1 * epy, uvm3 = uz + fac1 * epz;
           // gam = sqrt(q), igam = 1/gam through one rsqrt (two roundings instead of a correctly rounded sqrt and a
@@ -473,7 +481,7 @@ struct __align__(16) Smem2 {
   unsigned long long bar;
 };
 
-template <int ORDER, int G>
+template <int ORDER, int G, bool VAY>
 __global__ void __launch_bounds__(16 * G, 32 / G)
 k_fused2(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __restrict__ id_out,
          const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj, int* __restrict__ cnt,
@@ -557,7 +565,13 @@ k_fused2(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
         const double fac1 = g.fac1[isp];
         const double txxx = fac1 * fac1;
         const double fac2 = g.fac2[isp];
-        {
+        if (VAY) {
+          // particle__solv_vay  2d/common/particle.f90:264-299
+          double igam;
+          wm_vay_update(f, fac1, fac2, g.c, ux, uy, uz, igam);
+          xn = x + ux * g.delt * igam;
+          yn = y + uy * g.delt * igam;
+        } else {
           const double bpx = f[0], bpy = f[1], bpz = f[2], epx = f[3], epy = f[4], epz = f[5];
           double uvm1 = ux + fac1 * epx, uvm2 = uy + fac1 * epy, uvm3 = uz + fac1 * epz;
           const double qg = g.c * g.c + uvm1 * uvm1 + uvm2 * uvm2 + uvm3 * uvm3;
@@ -719,36 +733,36 @@ k_fused2(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
   }
 }
 
-template <int ORDER, int G>
+template <int ORDER, int G, bool VAY>
 int launch_fused2(wm_ctx* ctx, int nxs, int nxe, double u0) {
   const Geo& g = ctx->g;
   static bool attr_set = false;
   if (!attr_set) {
-    WM_CUDA(cudaFuncSetAttribute(k_fused2<ORDER, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem2<G>)));
+    WM_CUDA(cudaFuncSetAttribute(k_fused2<ORDER, G, VAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem2<G>)));
     attr_set = true;
   }
   const int ngx = (nxe - nxs + 1 + G - 1) / G;
   const int blocks = ngx * g.nyl;
   const double xend = nxe * g.delx + u0 / sqrt(1 + (u0 * u0) / (g.c * g.c)) * g.delt;   // 2d/proj/shock/boundary_shock.f90:271
-  k_fused2<ORDER, G><<<blocks, 16 * G, sizeof(Smem2<G>), ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
+  k_fused2<ORDER, G, VAY><<<blocks, 16 * G, sizeof(Smem2<G>), ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
                                                                        ctx->cs, ctx->tmpf, ctx->uj, ctx->cnt27, ctx->cs_new,
                                                                        ctx->dst_off, ctx->flags, nxs, nxe, ngx, u0, xend);
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
 }
 
-template <int ORDER, int G>
+template <int ORDER, int G, bool VAY>
 int launch_fused(wm_ctx* ctx, int nxs, int nxe, double u0) {
   const Geo& g = ctx->g;
   static bool attr_set = false;
   if (!attr_set) {
-    WM_CUDA(cudaFuncSetAttribute(k_fused3<ORDER, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<G>)));
+    WM_CUDA(cudaFuncSetAttribute(k_fused3<ORDER, G, VAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<G>)));
     attr_set = true;
   }
   const int ngx = (nxe - nxs + 1 + G - 1) / G;
   const int blocks = ngx * g.nyl * g.nzl;
   const double xend = nxe * g.delx + u0 / sqrt(1.0 + (u0 * u0) / (g.c * g.c)) * g.delt;   // boundary_shock.f90:438
-  k_fused3<ORDER, G><<<blocks, 16 * G, sizeof(Smem<G>), ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
+  k_fused3<ORDER, G, VAY><<<blocks, 16 * G, sizeof(Smem<G>), ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
                                                                       ctx->cs, ctx->tmpf, ctx->uj, ctx->cnt27, ctx->cs_new,
                                                                       ctx->dst_off, ctx->flags, nxs, nxe, ngx, u0, xend);
   WM_LAUNCH_CHECK(ctx);
@@ -770,12 +784,15 @@ int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double u0)
     return WM_ERR_ARG;
   }
   WM_TRY(wm_sort_prepare(ctx));
+  const bool vay = ctx->pusher == WM_PUSHER_VAY;
+#define WM_DISPATCH(fn, ord, uu) (vay ? fn<ord, 8, true>(ctx, nxs, nxe, uu) : fn<ord, 8, false>(ctx, nxs, nxe, uu))
   if (ctx->g.dim == 2) {
-    if (order == WM_ORDER_RECONNECTION) return launch_fused2<1, 8>(ctx, nxs, nxe, 0.0);
-    if (order == WM_ORDER_SHOCK) return launch_fused2<2, 8>(ctx, nxs, nxe, u0);
-    return launch_fused2<0, 8>(ctx, nxs, nxe, 0.0);
+    if (order == WM_ORDER_RECONNECTION) return WM_DISPATCH(launch_fused2, 1, 0.0);
+    if (order == WM_ORDER_SHOCK) return WM_DISPATCH(launch_fused2, 2, u0);
+    return WM_DISPATCH(launch_fused2, 0, 0.0);
   }
-  if (order == WM_ORDER_RECONNECTION) return launch_fused<1, 8>(ctx, nxs, nxe, 0.0);
-  if (order == WM_ORDER_SHOCK) return launch_fused<2, 8>(ctx, nxs, nxe, u0);
-  return launch_fused<0, 8>(ctx, nxs, nxe, 0.0);
+  if (order == WM_ORDER_RECONNECTION) return WM_DISPATCH(launch_fused, 1, 0.0);
+  if (order == WM_ORDER_SHOCK) return WM_DISPATCH(launch_fused, 2, u0);
+  return WM_DISPATCH(launch_fused, 0, 0.0);
+#undef WM_DISPATCH
 }

@@ -92,6 +92,7 @@ struct wm_ctx {
   int* totals = nullptr;   // device copy of the six per-step totals (k_totals)
   size_t dst_off_cap = 0;
   int use_fused = 1;
+  int pusher = 0;      // WM_PUSHER_BORIS (particle__solv) or WM_PUSHER_VAY (particle__solv_vay)
   void* scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
   // fields

@@ -12,6 +12,7 @@
 // Each warp owns one cell at a time and its lanes walk that cell's particles, so every global
 // load/store is a contiguous 256-byte run and all lanes share the same 27-cell field stencil.
 #include "wm_internal.cuh"
+#include "wm_push.cuh"
 
 namespace {
 
@@ -126,7 +127,7 @@ __device__ __forceinline__ void boris(const double f[6], double fac1, double fac
 // ---------------------------------------------------------------------------------------------
 // K2: push.  One warp per cell, lanes over that cell's particles.
 // ---------------------------------------------------------------------------------------------
-template <int D>
+template <int D, bool VAY>
 __global__ void __launch_bounds__(TPB) k_push(Geo g, Ptcl A, Ptcl B, const int* __restrict__ cs,
                                               const double* __restrict__ tmpf, int nxs, int nxe) {
   const int lane = threadIdx.x & 31;
@@ -156,7 +157,8 @@ __global__ void __launch_bounds__(TPB) k_push(Geo g, Ptcl A, Ptcl B, const int* 
         double f[6];
         gather<D>(T, g, sx, sy, sz, f);
         double gam;
-        boris(f, fac1, fac2, txxx, g.c, g.delt, ux, uy, uz, gam);
+        if (VAY) wm_vay_update(f, fac1, fac2, g.c, ux, uy, uz, gam);   // particle__solv_vay
+        else boris(f, fac1, fac2, txxx, g.c, g.delt, ux, uy, uz, gam);
         B.c[U][p] = ux;
         B.c[U + 1][p] = uy;
         B.c[U + 2][p] = uz;
@@ -477,10 +479,14 @@ int wm_k_push(wm_ctx* ctx, int nxs, int nxe) {
   const Geo& g = ctx->g;
   const long long ncell = (long long)(nxe - nxs + 1) * g.nyl * g.nzl;
   const int blocks = (int)std::min<long long>((ncell * 32 + TPB - 1) / TPB, 148LL * 8);
-  if (g.dim == 3)
-    k_push<3><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->tmpf, nxs, nxe);
-  else
-    k_push<2><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->tmpf, nxs, nxe);
+  const bool vay = ctx->pusher == WM_PUSHER_VAY;
+  if (g.dim == 3) {
+    if (vay) k_push<3, true><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->tmpf, nxs, nxe);
+    else k_push<3, false><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->tmpf, nxs, nxe);
+  } else {
+    if (vay) k_push<2, true><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->tmpf, nxs, nxe);
+    else k_push<2, false><<<blocks, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->cs, ctx->tmpf, nxs, nxe);
+  }
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
 }
