@@ -39,7 +39,10 @@ namespace {
 // phase-B math than two 256-thread CTAs); G = 16 halves the field-tile halo overhead.
 constexpr int SLOTS = 16;     // particles per cell and batch
 constexpr int NF = 21;        // double2 fields per particle record
-constexpr int CSTR = 17;      // slot stride between cells (bank spreading)
+#ifndef WM_CSTR
+#define WM_CSTR 17
+#endif
+constexpr int CSTR = WM_CSTR;      // slot stride between cells (17: bank spreading between the two cells of a warp)
 
 template <int G>
 struct __align__(16) Smem {
