@@ -44,6 +44,12 @@ module wuming_b200_c
     real(c_double) :: q(2), r(2)
   end type wm_params
 
+  type, bind(c) :: wm_shock_params      ! include/wuming_b200.h: struct wm_shock_params (2d/proj/shock/app.f90 constants)
+    integer(c_int)       :: n0
+    real(c_double)       :: v0, v_thi, v_the, b0, theta_bn, phi_bn, l_damp_ini
+    integer(c_long_long) :: seed
+  end type wm_shock_params
+
   type(c_ptr), save :: ctx = c_null_ptr
   type(wm_params), save :: prm
   integer, save :: shim_mode = WM_SHIM_SYNC_EVERY_CALL
@@ -624,3 +630,66 @@ contains
 end module mom_calc
 ! boundary_periodic__mom / boundary_reconnection__mom / boundary_shock__mom: add to the three boundary modules above
 !   subroutine boundary_*__mom(mom); real(8), intent(inout) :: mom(...); end subroutine   (no-op: already folded)
+
+!-----------------------------------------------------------------------------------------------------------
+! The shock driver's particle source on the device (include/wuming_b200.h: wm_shock_inject / wm_shock_relocate).
+! inject() and relocate() live in the DRIVER (2d/proj/shock/app.f90:615-852, 3d/proj/shock/app.f90:644-906), not in a
+! library module, so this one is an edit of app.f90 rather than a module swap: the driver keeps its integer bookkeeping
+! (nlinj_grid: app.f90:711-743, get_global_cumsum / ncinj_grid: :769-781) and replaces the two particle loops, the np2 /
+! cumcnt updates and the uf columns (:786-849, :637-689) by one call each:
+!
+!     id_first(j,isp) = ncinj_grid(j) + nptotal(isp)                    ! 3-D: id_first(j,k,isp)
+!     call shock_source__inject(nxe, nlinj_grid, id_first, it)
+!     ...
+!     nxe = nxe + 1
+!     id_first(j,isp) = (j-nygs)*n0 + nptotal(isp)                      ! 3-D: ((nyge-nygs+1)*(k-nzgs)+(j-nygs))*n0 + nptotal(isp)
+!     call shock_source__relocate(nxe, id_first, it)
+!
+! np2 / cumcnt / up / uf then change on the device only; the host copies are refreshed at the driver's output cadence by
+! wm_shim_sync_to_host, exactly like the rest of the resident state.
+!-----------------------------------------------------------------------------------------------------------
+module shock_source
+  use iso_c_binding
+  use wuming_b200_c
+  implicit none
+  private
+  public :: shock_source__init, shock_source__inject, shock_source__relocate
+  type(wm_shock_params), save :: sprm
+  interface
+    function wm_shock_inject(c, p, nxe, nlinj, id_first, epoch) bind(c, name='wm_shock_inject') result(ierr)
+      import; type(c_ptr), value :: c; type(wm_shock_params), intent(in) :: p; integer(c_int), value :: nxe
+      type(c_ptr), value :: nlinj, id_first; integer(c_long_long), value :: epoch; integer(c_int) :: ierr
+    end function
+    function wm_shock_relocate(c, p, nxe_new, id_first, epoch) bind(c, name='wm_shock_relocate') result(ierr)
+      import; type(c_ptr), value :: c; type(wm_shock_params), intent(in) :: p; integer(c_int), value :: nxe_new
+      type(c_ptr), value :: id_first; integer(c_long_long), value :: epoch; integer(c_int) :: ierr
+    end function
+  end interface
+contains
+
+  subroutine shock_source__init(n0, v0, v_thi, v_the, b0, theta_bn, phi_bn, l_damp_ini, seed)
+    integer, intent(in)    :: n0
+    real(8), intent(in)    :: v0, v_thi, v_the, b0, theta_bn, phi_bn, l_damp_ini
+    integer(8), intent(in) :: seed
+    sprm%n0 = n0; sprm%v0 = v0; sprm%v_thi = v_thi; sprm%v_the = v_the; sprm%b0 = b0
+    sprm%theta_bn = theta_bn; sprm%phi_bn = phi_bn; sprm%l_damp_ini = l_damp_ini; sprm%seed = seed
+  end subroutine shock_source__init
+
+  subroutine shock_source__inject(nxe, nlinj_grid, id_first, it)          ! app.f90:786-849
+    integer, intent(in)            :: nxe, it
+    integer, intent(in), target    :: nlinj_grid(*)                         ! (nys:nye[,nzs:nze])
+    integer(8), intent(in), target :: id_first(*)                           ! (nys:nye[,nzs:nze],nsp)
+    integer(c_int) :: ierr
+    ierr = wm_shock_inject(ctx, sprm, int(nxe,c_int), c_loc(nlinj_grid), c_loc(id_first), int(it,c_long_long))
+    call wm_check(ierr, 'inject')
+  end subroutine shock_source__inject
+
+  subroutine shock_source__relocate(nxe_new, id_first, it)                 ! app.f90:637-689
+    integer, intent(in)            :: nxe_new, it
+    integer(8), intent(in), target :: id_first(*)
+    integer(c_int) :: ierr
+    ierr = wm_shock_relocate(ctx, sprm, int(nxe_new,c_int), c_loc(id_first), int(it,c_long_long))
+    call wm_check(ierr, 'relocate')
+  end subroutine shock_source__relocate
+
+end module shock_source

@@ -140,6 +140,26 @@ int wm_h_field_fdtd_i(wm_ctx* ctx, double* uf, const double* up, const double* g
 /* one whole step on host state: up, uf, np2, cumcnt in -> out (gp is scratch on the device only) */
 int wm_h_step(wm_ctx* ctx, double* up, double* uf, int* np2, int* cumcnt, int nxs, int nxe, int order, double u0);
 
+/* -- the particle source of the shock set-up on the device --------------------- */
+/* Constants of 2d/proj/shock/app.f90's inject() / relocate() / vprofile() (:615-692, 697-852, 883-893; 3d/proj/shock/app.f90
+ * :644-728, 733-906, 939-949): n0 particles per cell, upstream flow v0 (< 0), thermal spreads, upstream field, damping length;
+ * `seed` keys the Philox streams that replace Fortran's random_number. */
+typedef struct wm_shock_params {
+  int n0;
+  double v0, v_thi, v_the, b0, theta_bn, phi_bn, l_damp_ini;
+  unsigned long long seed;
+} wm_shock_params;
+/* inject(): nlinj[row] new particles per species behind every local pencil, row = (j - nys) + nyl * (k - nzs), placed at
+ * x = nxe*delx + (ii - 1/2)/nlinj*|v0|*delt + (v0 + ux)*delt with a drifting Maxwellian (app.f90:786-841); np2 += nlinj,
+ * cumcnt(nxe) += nlinj, and the upstream field columns nxe-1, nxe are reset (:840-849).  The integer bookkeeping of
+ * :711-781 stays with the caller: nlinj = nlinj_grid, id_first[isp*nrows + row] = ncinj_grid(row) + nptotal(isp), so that
+ * particle ii of the row gets ID -(ii + id_first).  `epoch` = the driver's step counter `it`.  Call after sort__bucket. */
+int wm_shock_inject(wm_ctx* ctx, const wm_shock_params* prm, int nxe, const int* nlinj, const long long* id_first,
+                    long long epoch);
+/* relocate() after the caller's nxe = nxe + 1: n0 particles per row and species fill the new cell nxe_new - 1
+ * (app.f90:637-676), cumcnt(nxe_new) = cumcnt(nxe_new - 1) + n0; id_first[isp*nrows + row] = global_row * n0 + nptotal(isp) */
+int wm_shock_relocate(wm_ctx* ctx, const wm_shock_params* prm, int nxe_new, const long long* id_first, long long epoch);
+
 /* -- synthetic load and diagnostics on the device ----------------------------------------------- */
 /* Weibel load of 3d/proj/weibel/app.f90:311-338,391-504 (2d/proj/weibel/app.f90:404-432) generated on
  * the device with the Philox stream the oracle uses (positions bit-identical, Maxwellian to libm ulp). */

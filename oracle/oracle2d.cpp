@@ -902,6 +902,112 @@ void mom_calc(World2& w) {
   bc_mom(w);
 }
 
+
+// the upstream field columns both inject() and relocate() reset (2d/proj/shock/app.f90:680-689, 840-849)
+void shock_boundary_field(World2& w, Rank2& R, const orc::ShockPrm& sp, int nxe) {
+  const double by = sp.b0 * std::sin(sp.theta_bn) * std::cos(sp.phi_bn), bz = sp.b0 * std::sin(sp.theta_bn) * std::sin(sp.phi_bn);
+  for (int j = R.nys - 2; j <= R.nye + 2; ++j) {
+    R.uf[R.i6(2, nxe - 1, j)] = by;
+    R.uf[R.i6(3, nxe - 1, j)] = bz;
+    R.uf[R.i6(5, nxe - 1, j)] = +sp.v0 * R.uf[R.i6(3, nxe - 1, j)] / w.c;
+    R.uf[R.i6(6, nxe - 1, j)] = -sp.v0 * R.uf[R.i6(2, nxe - 1, j)] / w.c;
+    R.uf[R.i6(2, nxe, j)] = by;
+    R.uf[R.i6(3, nxe, j)] = bz;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// inject -- 2d/proj/shock/app.f90:697-852, with the integer bookkeeping of :711-774 (how many particles each row
+// receives: nlinj_grid) supplied by the caller per GLOBAL row, so that the result does not depend on the rank count.
+// nptotal (:769-770) = global population per species before the call, ncinj_grid (:778-781) = exclusive prefix of the
+// row counts in rank order (= global row order for y slabs).
+// ---------------------------------------------------------------------------
+void shock_inject(World2& w, const orc::ShockPrm& sp, const int* nlinj_rows, uint32_t epoch) {
+  const int nxe = w.nxe;
+  const double delx = w.delx, delt = w.delt, c = w.c;
+  long long nptotal[2] = {0, 0};
+  for (Rank2& R : w.ranks)
+    for (int isp = 1; isp <= 2; ++isp)
+      for (int j = R.nys; j <= R.nye; ++j) nptotal[isp - 1] += R.np2[R.in2(j, isp)];
+  const double x0 = std::fabs(sp.v0) * delt;
+  for (Rank2& R : w.ranks) {
+    for (int j = R.nys; j <= R.nye; ++j) {
+      const uint32_t row = (uint32_t)(j - w.nygs);
+      const int n = nlinj_rows[row];
+      long long ncinj = 0;
+      for (uint32_t rr = 0; rr < row; ++rr) ncinj += nlinj_rows[rr];
+      for (int isp = 1; isp <= 2; ++isp) {
+        const int base = R.np2[R.in2(j, isp)];
+        if (base + n > w.np) { w.err = 2; return; }
+        for (int ii = 1; ii <= n; ++ii) {
+          double* u = &R.up[R.ip(1, base + ii, j, isp)];
+          double ur0, ur1;
+          orc::Philox::uniform2(sp.seed, row, (uint32_t)ii, 0u, ur0, ur1, epoch);
+          u[0] = nxe * delx + (ii - 0.5) / n * x0;      // :790
+          u[1] = (j + ur0) * delx;                      // :791
+          double v[3];
+          orc::shock_velocity(sp, row, (uint32_t)ii, isp, 0u, epoch, c, v);
+          u[2] = v[0]; u[3] = v[1]; u[4] = v[2];
+          u[0] = u[0] + (sp.v0 + u[2]) * delt;          // :817-818 injection (non-relativistic approximation)
+          const double v1 = orc::vprofile(sp, u[0], w.nxgs, delx);
+          const double gam1 = 1 / std::sqrt(1 - (v1 / c) * (v1 / c));
+          const double gamp = std::sqrt(1 + (u[2] * u[2] + u[3] * u[3] + u[4] * u[4]) / (c * c));
+          u[2] = gam1 * (u[2] + v1 * gamp);             // :836
+          const int64_t pid = (int64_t)ii + ncinj + nptotal[isp - 1];   // :839
+          const int64_t neg = -pid;
+          std::memcpy(&u[5], &neg, 8);
+        }
+      }
+      for (int isp = 1; isp <= 2; ++isp) {             // :846-851
+        R.np2[R.in2(j, isp)] += n;
+        R.cumcnt[R.ic(nxe, j, isp)] += n;
+      }
+    }
+    shock_boundary_field(w, R, sp, nxe);
+  }
+}
+
+// relocate -- 2d/proj/shock/app.f90:615-692: the box grows by one cell filled with n0 particles per row and species
+void shock_relocate(World2& w, const orc::ShockPrm& sp, uint32_t epoch) {
+  if (w.nxe == w.nxge) return;
+  w.nxe = w.nxe + 1;
+  const int nxe = w.nxe, n0 = sp.n0;
+  const double delx = w.delx, c = w.c;
+  long long nptotal[2] = {0, 0};
+  for (Rank2& R : w.ranks)
+    for (int isp = 1; isp <= 2; ++isp)
+      for (int j = R.nys; j <= R.nye; ++j) nptotal[isp - 1] += R.np2[R.in2(j, isp)];
+  for (Rank2& R : w.ranks) {
+    for (int j = R.nys; j <= R.nye; ++j) {
+      const uint32_t row = (uint32_t)(j - w.nygs);
+      for (int isp = 1; isp <= 2; ++isp) {
+        const int base = R.np2[R.in2(j, isp)];
+        if (base + n0 > w.np) { w.err = 2; return; }
+        for (int ii = 1; ii <= n0; ++ii) {
+          double* u = &R.up[R.ip(1, base + ii, j, isp)];
+          double ur0, ur1;
+          orc::Philox::uniform2(sp.seed, row, (uint32_t)ii, 16u, ur0, ur1, epoch);
+          u[0] = (nxe - 1) * delx + (ii - 0.5) / n0 * delx;   // :641
+          u[1] = (j + ur0) * delx;
+          double v[3];
+          orc::shock_velocity(sp, row, (uint32_t)ii, isp, 16u, epoch, c, v);
+          u[2] = v[0]; u[3] = v[1]; u[4] = v[2];
+          const double v1 = orc::vprofile(sp, u[0], w.nxgs, delx);
+          const double gam1 = 1 / std::sqrt(1 - (v1 / c) * (v1 / c));
+          const double gamp = std::sqrt(1 + (u[2] * u[2] + u[3] * u[3] + u[4] * u[4]) / (c * c));
+          u[2] = gam1 * (u[2] + v1 * gamp);
+          const int64_t pid = (int64_t)ii + (int64_t)row * n0 + nptotal[isp - 1];   // :670
+          const int64_t neg = -pid;
+          std::memcpy(&u[5], &neg, 8);
+        }
+        R.np2[R.in2(j, isp)] += n0;                                                 // :673-674
+        R.cumcnt[R.ic(nxe, j, isp)] = R.cumcnt[R.ic(nxe - 1, j, isp)] + n0;
+      }
+    }
+    shock_boundary_field(w, R, sp, nxe);
+  }
+}
+
 // one time step; order: 0 Weibel (2d/proj/weibel/app.f90:99-107), 1 reconnection (2d/proj/reconnection/app.f90:99-106),
 // 2 shock without the driver's inject/relocate (2d/proj/shock/app.f90:112-118)
 void step(World2& w, int order, double u0) {
@@ -995,6 +1101,9 @@ void orc2_cg_iterations(void* h, int* out) { for (int l = 0; l < 3; ++l) out[l] 
 void orc2_particle_solv(void* h) { World2& w = *(World2*)h; for (Rank2& R : w.ranks) particle_solv(w, R, R.gp, R.up); }
 void orc2_particle_solv_vay(void* h) { World2& w = *(World2*)h; for (Rank2& R : w.ranks) particle_solv(w, R, R.gp, R.up, false, true); }
 void orc2_set_pusher(void* h, int kind) { ((World2*)h)->pusher = kind; }
+void orc2_shock_inject(void* h, const orc::ShockPrm* sp, const int* nlinj_rows, unsigned epoch) { shock_inject(*(World2*)h, *sp, nlinj_rows, epoch); }
+void orc2_shock_relocate(void* h, const orc::ShockPrm* sp, unsigned epoch) { shock_relocate(*(World2*)h, *sp, epoch); }
+int orc2_nxe(void* h) { return ((World2*)h)->nxe; }
 void orc2_field_fdtd_i(void* h, int stage) { field_fdtd_i(*(World2*)h, stage); }
 // kind: 0 periodic wrap, 1 reflecting walls
 void orc2_bc_particle_x(void* h, int kind) {

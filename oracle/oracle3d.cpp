@@ -1206,6 +1206,117 @@ void mom_calc(World3& w) {
   bc_mom(w);
 }
 
+
+// the upstream field columns both inject() and relocate() reset (3d/proj/shock/app.f90:715-726, 893-904)
+void shock_boundary_field(World3& w, Rank3& R, const orc::ShockPrm& sp, int nxe) {
+  const double by = sp.b0 * std::sin(sp.theta_bn) * std::cos(sp.phi_bn), bz = sp.b0 * std::sin(sp.theta_bn) * std::sin(sp.phi_bn);
+  for (int k = R.nzs - 2; k <= R.nze + 2; ++k)
+    for (int j = R.nys - 2; j <= R.nye + 2; ++j) {
+      R.uf[R.i6(2, nxe - 1, j, k)] = by;
+      R.uf[R.i6(3, nxe - 1, j, k)] = bz;
+      R.uf[R.i6(5, nxe - 1, j, k)] = +sp.v0 * R.uf[R.i6(3, nxe - 1, j, k)] / w.c;
+      R.uf[R.i6(6, nxe - 1, j, k)] = -sp.v0 * R.uf[R.i6(2, nxe - 1, j, k)] / w.c;
+      R.uf[R.i6(2, nxe, j, k)] = by;
+      R.uf[R.i6(3, nxe, j, k)] = bz;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// inject -- 3d/proj/shock/app.f90:733-906; the row counts nlinj_grid (:747-790) come from the caller per GLOBAL row
+// r = (k - nzgs) ny + (j - nygs), which is also the order of ncinj_grid (:799-812) for z slabs (nproc_j = 1).
+// ---------------------------------------------------------------------------
+void shock_inject(World3& w, const orc::ShockPrm& sp, const int* nlinj_rows, uint32_t epoch) {
+  const int nxe = w.nxe, ny = w.nyge - w.nygs + 1;
+  const double delx = w.delx, delt = w.delt, c = w.c;
+  long long nptotal[2] = {0, 0};
+  for (Rank3& R : w.ranks)
+    for (int isp = 1; isp <= 2; ++isp)
+      for (int k = R.nzs; k <= R.nze; ++k)
+        for (int j = R.nys; j <= R.nye; ++j) nptotal[isp - 1] += R.np2[R.in2(j, k, isp)];
+  const double x0 = std::fabs(sp.v0) * delt;
+  for (Rank3& R : w.ranks) {
+    for (int k = R.nzs; k <= R.nze; ++k)
+      for (int j = R.nys; j <= R.nye; ++j) {
+        const uint32_t row = (uint32_t)((k - w.nzgs) * ny + (j - w.nygs));
+        const int n = nlinj_rows[row];
+        long long ncinj = 0;
+        for (uint32_t rr = 0; rr < row; ++rr) ncinj += nlinj_rows[rr];
+        for (int isp = 1; isp <= 2; ++isp) {
+          const int base = R.np2[R.in2(j, k, isp)];
+          if (base + n > w.np) { w.err = 2; return; }
+          for (int ii = 1; ii <= n; ++ii) {
+            double* u = &R.up[R.ip(1, base + ii, j, k, isp)];
+            double ur0, ur1;
+            orc::Philox::uniform2(sp.seed, row, (uint32_t)ii, 0u, ur0, ur1, epoch);
+            u[0] = nxe * delx + (ii - 5e-1) / n * x0;     // :822
+            u[1] = (j + ur0) * delx;                      // :823
+            u[2] = (k + ur1) * delx;                      // :824
+            double v[3];
+            orc::shock_velocity(sp, row, (uint32_t)ii, isp, 0u, epoch, c, v);
+            u[3] = v[0]; u[4] = v[1]; u[5] = v[2];
+            u[0] = u[0] + (sp.v0 + u[3]) * delt;          // :853-854
+            const double v1 = orc::vprofile(sp, u[0], w.nxgs, delx);
+            const double gam1 = 1e0 / std::sqrt(1e0 - (v1 / c) * (v1 / c));
+            const double gamp = std::sqrt(1e0 + (u[3] * u[3] + u[4] * u[4] + u[5] * u[5]) / (c * c));
+            u[3] = gam1 * (u[3] + v1 * gamp);             // :873
+            const int64_t pid = (int64_t)ii + ncinj + nptotal[isp - 1];   // :876
+            const int64_t neg = -pid;
+            std::memcpy(&u[6], &neg, 8);
+          }
+        }
+        for (int isp = 1; isp <= 2; ++isp) {              // :884-887
+          R.np2[R.in2(j, k, isp)] += n;
+          R.cumcnt[R.ic(nxe, j, k, isp)] += n;
+        }
+      }
+    shock_boundary_field(w, R, sp, nxe);
+  }
+}
+
+// relocate -- 3d/proj/shock/app.f90:644-728
+void shock_relocate(World3& w, const orc::ShockPrm& sp, uint32_t epoch) {
+  if (w.nxe == w.nxge) return;
+  w.nxe = w.nxe + 1;
+  const int nxe = w.nxe, n0 = sp.n0, ny = w.nyge - w.nygs + 1;
+  const double delx = w.delx, c = w.c;
+  long long nptotal[2] = {0, 0};
+  for (Rank3& R : w.ranks)
+    for (int isp = 1; isp <= 2; ++isp)
+      for (int k = R.nzs; k <= R.nze; ++k)
+        for (int j = R.nys; j <= R.nye; ++j) nptotal[isp - 1] += R.np2[R.in2(j, k, isp)];
+  for (Rank3& R : w.ranks) {
+    for (int k = R.nzs; k <= R.nze; ++k)
+      for (int j = R.nys; j <= R.nye; ++j) {
+        const uint32_t row = (uint32_t)((k - w.nzgs) * ny + (j - w.nygs));
+        for (int isp = 1; isp <= 2; ++isp) {
+          const int base = R.np2[R.in2(j, k, isp)];
+          if (base + n0 > w.np) { w.err = 2; return; }
+          for (int ii = 1; ii <= n0; ++ii) {
+            double* u = &R.up[R.ip(1, base + ii, j, k, isp)];
+            double ur0, ur1;
+            orc::Philox::uniform2(sp.seed, row, (uint32_t)ii, 16u, ur0, ur1, epoch);
+            u[0] = (nxe - 1) * delx + (ii - 5e-1) / n0 * delx;   // :670
+            u[1] = (j + ur0) * delx;
+            u[2] = (k + ur1) * delx;
+            double v[3];
+            orc::shock_velocity(sp, row, (uint32_t)ii, isp, 16u, epoch, c, v);
+            u[3] = v[0]; u[4] = v[1]; u[5] = v[2];
+            const double v1 = orc::vprofile(sp, u[0], w.nxgs, delx);
+            const double gam1 = 1e0 / std::sqrt(1e0 - (v1 / c) * (v1 / c));
+            const double gamp = std::sqrt(1e0 + (u[3] * u[3] + u[4] * u[4] + u[5] * u[5]) / (c * c));
+            u[3] = gam1 * (u[3] + v1 * gamp);
+            const int64_t pid = (int64_t)ii + (int64_t)row * n0 + nptotal[isp - 1];   // :704
+            const int64_t neg = -pid;
+            std::memcpy(&u[6], &neg, 8);
+          }
+          R.np2[R.in2(j, k, isp)] += n0;                                             // :707-708
+          R.cumcnt[R.ic(nxe, j, k, isp)] = R.cumcnt[R.ic(nxe - 1, j, k, isp)] + n0;
+        }
+      }
+    shock_boundary_field(w, R, sp, nxe);
+  }
+}
+
 // one time step; order 0: Weibel/beam (3d/proj/weibel/app.f90:100-108), 1: reconnection (3d/proj/reconnection/app.f90:103-108),
 // 2: shock without the driver's inject/relocate (3d/proj/shock/app.f90, same call order as 2d/proj/shock/app.f90:112-118)
 void step(World3& w, int order = 0, double u0 = 0.0) {
@@ -1307,6 +1418,9 @@ void orc3_cg_iterations(void* h, int* out) { for (int l = 0; l < 3; ++l) out[l] 
 void orc3_particle_solv(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) particle_solv(w, R, R.gp, R.up); }
 void orc3_particle_solv_vay(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) particle_solv(w, R, R.gp, R.up, false, true); }
 void orc3_set_pusher(void* h, int kind) { ((World3*)h)->pusher = kind; }
+void orc3_shock_inject(void* h, const orc::ShockPrm* sp, const int* nlinj_rows, unsigned epoch) { shock_inject(*(World3*)h, *sp, nlinj_rows, epoch); }
+void orc3_shock_relocate(void* h, const orc::ShockPrm* sp, unsigned epoch) { shock_relocate(*(World3*)h, *sp, epoch); }
+int orc3_nxe(void* h) { return ((World3*)h)->nxe; }
 void orc3_field_fdtd_i(void* h, int stage) { field_fdtd_i(*(World3*)h, stage); }
 void orc3_bc_particle_x(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) bc_particle_x(w, R, R.gp); }
 void orc3_bc_particle_yz(void* h) { bc_particle_yz(*(World3*)h, 0); }

@@ -49,10 +49,11 @@ struct Philox {
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
   }
-  // two uniforms in [0,1) with 53 random bits each
+  // two uniforms in [0,1) with 53 random bits each; `epoch` (the time-step counter of the shock injection) is the fourth
+  // counter word, 0 for the initial loaders
   static inline void uniform2(uint64_t seed, uint32_t stream, uint32_t idx, uint32_t purpose,
-                              double& u0, double& u1) {
-    uint32_t ctr[4] = {idx, purpose, stream, 0u};
+                              double& u0, double& u1, uint32_t epoch = 0u) {
+    uint32_t ctr[4] = {idx, purpose, stream, epoch};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t o[4];
     run(ctr, key, o);
@@ -70,6 +71,34 @@ static inline void box_muller(double x1, double x2, double& n_sin, double& n_cos
   double rr = std::sqrt(-2.0 * std::log(1.0 - x1) + 1.0e-30);
   n_sin = rr * std::sin(2.0 * pi * x2);
   n_cos = rr * std::cos(2.0 * pi * x2);
+}
+
+// Parameters of the shock driver's inject() / relocate() (2d/proj/shock/app.f90:615-852, 3d :644-906) and its velocity
+// profile vprofile (2d :883-893, 3d :939-949).
+struct ShockPrm {
+  int n0;
+  double v0, v_thi, v_the, b0, theta_bn, phi_bn, l_damp_ini;
+  uint64_t seed;
+};
+static inline double vprofile(const ShockPrm& s, double x, int nxgs, double delx) {
+  const double x0 = s.l_damp_ini + nxgs * delx;
+  const double xs = s.l_damp_ini * 0.1;
+  return 0.5 * s.v0 * (1 + std::tanh((x - x0) / xs));
+}
+// Maxwellian in the fluid rest frame + Lorentz transform to the lab frame (2d/proj/shock/app.f90:811-826).  The reference
+// draws from Fortran's random_number (not reproducible, utils/wuming_utils.f90:48-53); here the three normal deviates of
+// particle (stream = global row, idx = ii, species isp) at step `epoch` are Box-Muller pairs of Philox uniforms with
+// purpose base + 2 isp - 1 (-> ux, uy) and base + 2 isp (-> uz), the same convention as the Weibel loader.
+static inline void shock_velocity(const ShockPrm& s, uint32_t row, uint32_t ii, int isp, uint32_t base, uint32_t epoch, double c,
+                                  double u[3]) {
+  const double sd = isp == 1 ? s.v_thi : s.v_the;
+  double a0, a1, b0, b1, ns, nc, ms, mc;
+  Philox::uniform2(s.seed, row, ii, base + (uint32_t)(2 * isp - 1), a0, a1, epoch);
+  Philox::uniform2(s.seed, row, ii, base + (uint32_t)(2 * isp), b0, b1, epoch);
+  box_muller(a0, a1, ns, nc);
+  box_muller(b0, b1, ms, mc);
+  u[0] = sd * ns; u[1] = sd * nc; u[2] = sd * ms;
+  (void)mc; (void)c;
 }
 
 // start/end of a 1-D block decomposition (3d/common/mpi_set.f90:81-94, para_range)

@@ -11,6 +11,12 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+class ShockPrm(C.Structure):
+    """orc::ShockPrm (oracle_common.h) = wm_shock_params (include/wuming_b200.h), field for field"""
+    _fields_ = [("n0", C.c_int), ("v0", C.c_double), ("v_thi", C.c_double), ("v_the", C.c_double), ("b0", C.c_double),
+                ("theta_bn", C.c_double), ("phi_bn", C.c_double), ("l_damp_ini", C.c_double), ("seed", C.c_uint64)]
+
+
 _LIBS = {}
 
 
@@ -47,6 +53,10 @@ def lib(fast=False):
             getattr(L, "orc3_" + name).argtypes = [C.c_void_p]
         L.orc3_field_fdtd_i.argtypes = [C.c_void_p, C.c_int]
         L.orc3_mom_calc.argtypes = [C.c_void_p]
+        for d in (2, 3):
+            getattr(L, f"orc{d}_shock_inject").argtypes = [C.c_void_p, C.POINTER(ShockPrm), ip, C.c_uint]
+            getattr(L, f"orc{d}_shock_relocate").argtypes = [C.c_void_p, C.POINTER(ShockPrm), C.c_uint]
+            getattr(L, f"orc{d}_nxe").argtypes = [C.c_void_p]
         L.orc3_set_pusher.argtypes = [C.c_void_p, C.c_int]
         L.orc2_set_pusher.argtypes = [C.c_void_p, C.c_int]
         L.orc2_mom_calc.argtypes = [C.c_void_p]
@@ -164,6 +174,18 @@ class World3:
     def set_pusher(self, kind):
         """the pusher step() calls: 0 particle__solv (Buneman-Boris), 1 particle__solv_vay"""
         self.L.orc3_set_pusher(self.h, kind)
+
+    def shock_inject(self, prm, nlinj_rows, epoch):
+        """inject() of 3d/proj/shock/app.f90:733-906; nlinj_rows per GLOBAL row (k - nzgs) ny + (j - nygs)"""
+        a = np.ascontiguousarray(nlinj_rows, dtype=np.int32)
+        self.L.orc3_shock_inject(self.h, C.byref(prm), a.ctypes.data_as(C.POINTER(C.c_int)), epoch)
+
+    def shock_relocate(self, prm, epoch):
+        self.L.orc3_shock_relocate(self.h, C.byref(prm), epoch)
+
+    @property
+    def nxe_now(self):
+        return self.L.orc3_nxe(self.h)
 
     def field_fdtd_i(self, stage=0):
         self.L.orc3_field_fdtd_i(self.h, stage)
@@ -287,6 +309,18 @@ class World2:
 
     def set_pusher(self, kind):
         self.L.orc2_set_pusher(self.h, kind)
+
+    def shock_inject(self, prm, nlinj_rows, epoch):
+        """inject() of 2d/proj/shock/app.f90:697-852; nlinj_rows per GLOBAL row j - nygs"""
+        a = np.ascontiguousarray(nlinj_rows, dtype=np.int32)
+        self.L.orc2_shock_inject(self.h, C.byref(prm), a.ctypes.data_as(C.POINTER(C.c_int)), epoch)
+
+    def shock_relocate(self, prm, epoch):
+        self.L.orc2_shock_relocate(self.h, C.byref(prm), epoch)
+
+    @property
+    def nxe_now(self):
+        return self.L.orc2_nxe(self.h)
 
     def field_fdtd_i(self, stage=0):
         self.L.orc2_field_fdtd_i(self.h, stage)

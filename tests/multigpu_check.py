@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--n0", type=int, default=8)
     ap.add_argument("--dim", type=int, default=3, help="3: z-slabs; 2: y-slabs (2d/common/mpi_set.f90:36-47)")
     ap.add_argument("--bc", type=int, default=0, help="0 periodic (Weibel loop), 1 reconnection walls, 2 shock walls")
+    ap.add_argument("--source", type=int, default=0, help="1 (with --bc 2): the shock driver's inject()/relocate() run on the device "
+                                                            "after every step (wm_shock_inject / wm_shock_relocate), box grows from nx-6")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -37,6 +39,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     order, u0 = args.bc, (0.3 if args.bc == 2 else 0.0)     # each boundary module with its own time loop
+    if args.source:
+        return shock_source_check(args, rank, world, local)
     if args.dim == 3:
         w = make_world3(args.nx, args.ny, args.nz, args.n0, steps=2, nproc_k=world, bc=args.bc, order=order, u0=u0)
         b = backend_for(w, rank=rank, device=local, nproc_k=world)
@@ -83,6 +87,59 @@ def main():
     assert rel_err(got[inner], ref[inner]) < 1e-9, "moments differ"
     print(f"rank {rank}/{world} ok: dim={args.dim} bc={args.bc} fused={args.fused} np2/cumcnt/IDs exact, max|dx| {worst:.2e}, uf rel {worst_uf:.2e}",
           flush=True)
+    b.close()
+    dist.destroy_process_group()
+
+
+def shock_source_check(args, rank, world, local):
+    """the shock time loop with the particle source on the device, across slabs"""
+    import torch
+    import torch.distributed as dist
+    import wumingpic_b200 as wm
+    from tests.shock_util import (U0, id_first_inject, id_first_relocate, local_rows, make_shock_world, monotone, row_counts,
+                                  shock_prm)
+    from tests.util import backend_for, canonical_cells, rel_err, upload_from_world
+    n0, nxe = args.n0, args.nx - 5
+    w = make_shock_world(args.dim, args.nx, args.ny, args.nz, n0, nxe, nproc=world)
+    prm = shock_prm(n0)
+    prm_c = wm.ShockParams(n0=prm.n0, v0=prm.v0, v_thi=prm.v_thi, v_the=prm.v_the, b0=prm.b0, theta_bn=prm.theta_bn,
+                           phi_bn=prm.phi_bn, l_damp_ini=prm.l_damp_ini, seed=prm.seed)
+    b = backend_for(w, rank=rank, device=local, nproc_k=world) if args.dim == 3 else backend_for(w, rank=rank, device=local)
+    box = [b.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    b.comm_init(world, rank, box[0])
+    b.set_fused(bool(args.fused))
+    upload_from_world(b, w, rank)
+    rows = local_rows(w, rank, args.dim)
+    nrows_global = args.ny * (args.nz if args.dim == 3 else 1)
+    worst = 0.0
+    for it in range(1, args.steps + 1):
+        w.step(2, U0)
+        b.step(2, nxe, 1, 2, U0)
+        assert w.error() == 0
+        counts = row_counts(nrows_global, it, n0)
+        nptotal = sum(w.arr("np2", r).reshape(2, -1).sum(axis=1) for r in range(world))
+        w.shock_inject(prm, counts, it)
+        b.shock_inject(prm_c, nxe, counts[rows], id_first_inject(rows, counts, nptotal), it)
+        if it % 2 == 0:
+            nptotal = sum(w.arr("np2", r).reshape(2, -1).sum(axis=1) for r in range(world))
+            w.shock_relocate(prm, it)
+            nxe += 1
+            b.shock_relocate(prm_c, nxe, id_first_relocate(rows, n0, nptotal), it)
+        up, np2, cc, uf = b.empty("up"), b.empty("np2"), b.empty("cumcnt"), b.empty("uf")
+        b.download(up, np2, cc, uf)
+        assert np.array_equal(np2, w.arr("np2", rank)), f"rank {rank}: np2 differs at step {it}"
+        cc_ref = monotone(w.arr("cumcnt", rank))
+        assert np.array_equal(cc[..., :nxe], cc_ref[..., :nxe]), f"rank {rank}: cumcnt differs at step {it}"
+        assert rel_err(uf, w.arr("uf", rank)) < 1e-8
+        for (cg, rg), (cr, rr) in zip(canonical_cells(up, np2, cc), canonical_cells(w.arr("up", rank), w.arr("np2", rank), cc_ref)):
+            assert np.array_equal(cg, cr)
+            assert np.array_equal(rg[:, -1].view(np.int64), rr[:, -1].view(np.int64)), f"rank {rank}: particle ID sets differ"
+            if len(rg):
+                worst = max(worst, np.abs(rg[:, :-1] - rr[:, :-1]).max())
+    assert worst < 1e-9, worst
+    assert b.stats()["error_flags"] == 0
+    print(f"rank {rank}/{world} ok: dim={args.dim} shock source on the device, np2/cumcnt/IDs exact, max|dx| {worst:.2e}", flush=True)
     b.close()
     dist.destroy_process_group()
 

@@ -41,3 +41,17 @@ def test_slab_parity_variants(dim, bc):
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" ok: ") == 2
+
+
+@pytest.mark.parametrize("dim", [3, 2])
+def test_slab_shock_source(dim):
+    """the shock loop with inject()/relocate() on the device across two slabs (SURVEY.md 8f #3)"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(29590 + dim),
+           os.path.join(ROOT, "tests", "multigpu_check.py"), "--fused", "1", "--dim", str(dim), "--bc", "2", "--source", "1",
+           "--nx", "22", "--ny", "12", "--nz", "8", "--n0", "6"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok: ") == 2

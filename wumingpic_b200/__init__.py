@@ -6,7 +6,8 @@ module interface for that path (``particle__solv``, ``field__fdtd_i``, ``bc__par
 ``bc__particle_yz``, ``sort__bucket`` ...) over ctypes.  There is no CPU fallback: importing the
 backend without the built library, or creating a context without a CUDA device, fails loudly.
 """
-from .backend import Backend, WmError, load_library, para_range, weibel_constants  # noqa: F401
+from .backend import Backend, ShockParams, WmError, load_library, para_range, weibel_constants  # noqa: F401
+from .shock import inject_counts  # noqa: F401
 from .mpi_set import SlabLayout  # noqa: F401
 
-__all__ = ["Backend", "WmError", "load_library", "para_range", "weibel_constants", "SlabLayout"]
+__all__ = ["Backend", "ShockParams", "inject_counts", "WmError", "load_library", "para_range", "weibel_constants", "SlabLayout"]

@@ -54,8 +54,14 @@ ABI_SYMBOLS = [
     "wm_bc_particle_x", "wm_bc_injection", "wm_bc_particle_yz", "wm_sort_bucket", "wm_step", "wm_set_fused",
     "wm_h_particle_solv", "wm_h_field_fdtd_i", "wm_h_step", "wm_load_weibel", "wm_energy", "wm_gauss",
     "wm_get_stats", "wm_sync", "wm_set_timing", "wm_launch_count", "wm_stream", "wm_mom_calc",
-    "wm_particle_solv_vay", "wm_h_particle_solv_vay", "wm_set_pusher",
+    "wm_particle_solv_vay", "wm_h_particle_solv_vay", "wm_set_pusher", "wm_shock_inject", "wm_shock_relocate",
 ]
+
+
+class ShockParams(C.Structure):
+    """wm_shock_params of include/wuming_b200.h: constants of 2d/proj/shock/app.f90's inject() / relocate() / vprofile()"""
+    _fields_ = [("n0", C.c_int), ("v0", C.c_double), ("v_thi", C.c_double), ("v_the", C.c_double), ("b0", C.c_double),
+                ("theta_bn", C.c_double), ("phi_bn", C.c_double), ("l_damp_ini", C.c_double), ("seed", C.c_ulonglong)]
 
 
 def library_path():
@@ -91,6 +97,9 @@ def load_library():
         L.wm_step.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
         L.wm_set_fused.argtypes = [vp, C.c_int]
         L.wm_set_pusher.argtypes = [vp, C.c_int]
+        lp = C.POINTER(C.c_longlong)
+        L.wm_shock_inject.argtypes = [vp, C.POINTER(ShockParams), C.c_int, ip, lp, C.c_longlong]
+        L.wm_shock_relocate.argtypes = [vp, C.POINTER(ShockParams), C.c_int, lp, C.c_longlong]
         L.wm_h_particle_solv_vay.argtypes = [vp, dp, dp, dp, ip, ip, C.c_int, C.c_int]
         L.wm_h_particle_solv.argtypes = [vp, dp, dp, dp, ip, ip, C.c_int, C.c_int]
         L.wm_h_field_fdtd_i.argtypes = [vp, dp, dp, dp, ip, ip, C.c_int, C.c_int]
@@ -297,6 +306,23 @@ class Backend:
         out = np.zeros(shp)
         self._ck(self.L.wm_mom_calc(self.h, nxs, nxe, _dptr(out)))
         return out
+
+    # -- the shock driver's particle source on the device (2d/proj/shock/app.f90:615-852) --------
+    def shock_inject(self, prm, nxe, nlinj, id_first, epoch):
+        """inject(): nlinj[row] particles per species behind every local pencil (row = (j - nys) + nyl (k - nzs));
+        id_first[isp, row] = ncinj_grid(row) + nptotal(isp)"""
+        nlinj = np.ascontiguousarray(nlinj, dtype=np.int32).ravel()
+        id_first = np.ascontiguousarray(id_first, dtype=np.int64).ravel()
+        assert nlinj.size == self.nyl * self.nzl and id_first.size == self.nsp * self.nyl * self.nzl
+        self._ck(self.L.wm_shock_inject(self.h, C.byref(prm), nxe, nlinj.ctypes.data_as(C.POINTER(C.c_int)),
+                                        id_first.ctypes.data_as(C.POINTER(C.c_longlong)), epoch))
+
+    def shock_relocate(self, prm, nxe_new, id_first, epoch):
+        """relocate() after nxe = nxe + 1: n0 particles per row and species in the new cell; id_first[isp, row] =
+        global_row * n0 + nptotal(isp)"""
+        id_first = np.ascontiguousarray(id_first, dtype=np.int64).ravel()
+        assert id_first.size == self.nsp * self.nyl * self.nzl
+        self._ck(self.L.wm_shock_relocate(self.h, C.byref(prm), nxe_new, id_first.ctypes.data_as(C.POINTER(C.c_longlong)), epoch))
 
     def energy(self):
         out = np.zeros(4)

@@ -171,6 +171,7 @@ int wm_sort_prepare(wm_ctx* ctx);
 int wm_k_classify(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_sort(wm_ctx* ctx, int nxs, int nxe);
 int wm_enable_slab_migration(wm_ctx* ctx);
+int wm_k_refresh_np2(wm_ctx* ctx);
 int wm_k_energy(wm_ctx* ctx, double* out_host);
 int wm_k_gauss(wm_ctx* ctx, double* out_host);
 int wm_k_load_weibel(wm_ctx* ctx, int n0, double v_thi, double v_the, double t_ani, double b0, unsigned long long seed);

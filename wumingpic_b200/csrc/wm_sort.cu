@@ -553,3 +553,12 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
 }
+
+// np2 / poff from the cell index (after the index was edited outside the sort: wm_shock.cu)
+int wm_k_refresh_np2(wm_ctx* ctx) {
+  const Geo& g = ctx->g;
+  k_np2_poff<<<wm_blocks(g.npen + 1, TPB), TPB, 0, ctx->stream>>>(g, ctx->cs, ctx->np2, ctx->poff, ctx->flags,
+                                                                    g.multi ? -1LL : ctx->ntot);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
