@@ -12,6 +12,8 @@
 #include <vector>
 
 int wm_comm_destroy(wm_ctx* ctx);
+static double g_stage_ms[9] = {0};   // WM_FIELD_TIMING (see field_stages)
+static long g_stage_calls = 0;
 
 namespace {
 thread_local std::string g_err;
@@ -218,6 +220,13 @@ int wm_destroy(wm_ctx* c) {
   if (!c) return WM_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (g_stage_calls > 0) {
+    fprintf(stderr, "[wuming_b200] rank %d field__fdtd_i stages over %ld calls (ms/call): ele_cur %.3f curre %.3f gkl %.3f cgm %.3f dfield %.3f dE %.3f dfield %.3f update %.3f\n",
+            c->rank, g_stage_calls, g_stage_ms[1] / g_stage_calls, g_stage_ms[2] / g_stage_calls, g_stage_ms[3] / g_stage_calls,
+            g_stage_ms[4] / g_stage_calls, g_stage_ms[5] / g_stage_calls, g_stage_ms[6] / g_stage_calls, g_stage_ms[7] / g_stage_calls,
+            g_stage_ms[8] / g_stage_calls);
+    g_stage_calls = 0;
+  }
   wm_comm_destroy(c);   // also releases the peer arena (and nulls the CG arrays that lived in it)
   free_particles(c);
   double* d[] = {c->mom, c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->pcg2, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
@@ -414,10 +423,26 @@ int wm_field_stage(wm_ctx* c, int nxs, int nxe, int stage) {
   return WM_ERR_ARG;
 }
 
-int wm_field_fdtd_i(wm_ctx* c, int nxs, int nxe) {
-  for (int s = 1; s <= 8; ++s) WM_TRY(wm_field_stage(c, nxs, nxe, s));
+// stages first..8 of field__fdtd_i; WM_FIELD_TIMING=1 (measurement aid) accumulates per-stage device times, printed by wm_destroy
+static int field_stages(wm_ctx* c, int nxs, int nxe, int first) {
+  static const bool timing = getenv("WM_FIELD_TIMING") != nullptr;
+  if (!timing) {
+    for (int s = first; s <= 8; ++s) WM_TRY(wm_field_stage(c, nxs, nxe, s));
+    return WM_OK;
+  }
+  static cudaEvent_t ev[9] = {};
+  if (!ev[0]) for (auto& e : ev) cudaEventCreate(&e);
+  cudaEventRecord(ev[first - 1], c->stream);
+  for (int s = first; s <= 8; ++s) {
+    WM_TRY(wm_field_stage(c, nxs, nxe, s));
+    cudaEventRecord(ev[s], c->stream);
+  }
+  cudaEventSynchronize(ev[8]);
+  for (int s = first; s <= 8; ++s) { float ms = 0; cudaEventElapsedTime(&ms, ev[s - 1], ev[s]); g_stage_ms[s] += ms; }
+  g_stage_calls++;
   return WM_OK;
 }
+int wm_field_fdtd_i(wm_ctx* c, int nxs, int nxe) { return field_stages(c, nxs, nxe, 1); }
 
 int wm_bc_particle_x(wm_ctx* c, int nxs, int nxe) {
   if (!c) return WM_ERR_ARG;
@@ -468,7 +493,7 @@ int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
       WM_TRY(wm_k_push_deposit_fused(c, nxs, nxe, order, u0));
       c->gp_valid = true;
       if (c->timing) { WM_CUDA(cudaEventRecord(c->ev[1], c->stream)); WM_CUDA(cudaEventRecord(c->ev[2], c->stream)); }
-      for (int s = 2; s <= 8; ++s) WM_TRY(wm_field_stage(c, nxs, nxe, s));
+      WM_TRY(field_stages(c, nxs, nxe, 2));
       if (c->timing) WM_CUDA(cudaEventRecord(c->ev[3], c->stream));
       WM_TRY(wm_k_sort(c, nxs, nxe));
       c->gp_valid = false;
@@ -480,7 +505,7 @@ int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
       if (order == WM_ORDER_SHOCK) WM_TRY(wm_bc_injection(c, nxs, nxe, u0));
       WM_TRY(wm_field_stage(c, nxs, nxe, 1));
       if (c->timing) WM_CUDA(cudaEventRecord(c->ev[2], c->stream));
-      for (int s = 2; s <= 8; ++s) WM_TRY(wm_field_stage(c, nxs, nxe, s));
+      WM_TRY(field_stages(c, nxs, nxe, 2));
       if (c->timing) WM_CUDA(cudaEventRecord(c->ev[3], c->stream));
       if (order == WM_ORDER_WEIBEL) WM_TRY(wm_bc_particle_x(c, nxs, nxe));
       WM_TRY(wm_bc_particle_yz(c));

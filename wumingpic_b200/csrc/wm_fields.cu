@@ -484,8 +484,8 @@ __device__ __forceinline__ void grid_sum2(cg::grid_group& grid, double a, double
 // rank stores (a, b) and then -- behind a system fence -- the sequence number into that rank's mailbox slot [parity][my rank];
 // thread 0 of every block then polls the LOCAL mailbox until all ranks' slots carry this sequence number and sums them in rank
 // order, so every block of every rank gets bit-identical totals and takes the same branches.  The same fence + flag also
-// publishes the ghost-plane stores a rank made into its neighbours' operand arrays before the reduction (threads that stored to
-// a peer run __threadfence_system() before the grid sync), and the system fence after the poll orders the ghost reads behind it.
+// publishes the ghost-plane stores a rank made into its neighbours' operand arrays before the reduction (thread 0 of every block
+// runs __threadfence_system() behind a CTA barrier, before the grid sync), and the system fence after the poll orders the ghost reads behind it.
 // Two parities suffice: a rank cannot start reduction n+2 before every rank has finished reading reduction n.
 __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -497,11 +497,14 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 }
 __device__ __forceinline__ void peer_sum2(cg::grid_group& grid, const PeerCG& pc, unsigned long long& seq, double a, double b,
                                           double* part, int& red_idx, double* sh, double* sh2, int* flags, double& ta, double& tb) {
-  a = block_fold(a, sh);
+  a = block_fold(a, sh);   // contains CTA barriers: every ghost-plane store of this block precedes thread 0's fence below
   b = block_fold(b, sh);
   double* buf = part + (size_t)(red_idx & 1) * 2 * gridDim.x;
   red_idx++;
-  if (threadIdx.x == 0) { buf[2 * blockIdx.x] = a; buf[2 * blockIdx.x + 1] = b; }
+  if (threadIdx.x == 0) {
+    buf[2 * blockIdx.x] = a; buf[2 * blockIdx.x + 1] = b;
+    __threadfence_system();   // one system fence per block (cumulative over the block's peer stores), not one per storing thread
+  }
   grid.sync();
   seq++;
   const int par = (int)(seq & 1ull);
@@ -563,17 +566,15 @@ __global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const
   if (PEER) seq = *pc.seq;    // reductions done by earlier solves (identical on every rank)
   // edge-plane pushes: my first plane along the slab axis goes to the lower neighbour's upper ghost plane, my last one to the
   // upper neighbour's lower ghost plane (index shifts pc.shift_lo / pc.shift_hi inside the same box layout)
-  bool pushed = false;
 #define WM_PUSH(which, o, jj, kk, val)                                                          \
   if (PEER) {                                                                                   \
     const int sl = d3 ? (kk) : (jj);                                                            \
-    if (sl == (d3 ? g.nzs : g.nys)) { pc.lo[which][(long long)(o) + pc.shift_lo] = (val); pushed = true; } \
-    if (sl == (d3 ? g.nze : g.nye)) { pc.hi[which][(long long)(o) + pc.shift_hi] = (val); pushed = true; } \
+    if (sl == (d3 ? g.nzs : g.nys)) pc.lo[which][(long long)(o) + pc.shift_lo] = (val);                   \
+    if (sl == (d3 ? g.nze : g.nye)) pc.hi[which][(long long)(o) + pc.shift_hi] = (val);                   \
   }
 #define WM_SUM2(a_, b_, ta_, tb_)                                                               \
   do {                                                                                          \
     if (PEER) {                                                                                 \
-      if (pushed) { __threadfence_system(); pushed = false; }                                   \
       peer_sum2(grid, pc, seq, a_, b_, part, red_idx, sh, sh2, flags, ta_, tb_);                \
     } else {                                                                                    \
       grid_sum2(grid, a_, b_, part, red_idx, sh, ta_, tb_);                                     \
@@ -698,7 +699,7 @@ __global__ void __launch_bounds__(TPB) k_cgm_coop(double* __restrict__ df, const
         const int wsw = wold; wold = wnew; wnew = wsw;
       }
     }
-    if (PEER && pushed) { __threadfence_system(); pushed = false; }
+    if (PEER) { __syncthreads(); if (threadIdx.x == 0) __threadfence_system(); }
     grid.sync();   // every block is past the stencil reads of phi / r before df and the next component's phi are written
     for (int e = tid; e < n; e += nth) {
       int i, j, k;

@@ -316,6 +316,30 @@ __global__ void __launch_bounds__(TPB) k_apply(Geo g, Ptcl B, Ptcl A, const doub
   }
 }
 
+// inv = -1 on the slots k_insert will fill (the tail of every edge-plane cell that receives arrivals): k_apply skips them.
+// Same slot arithmetic as k_insert; replaces a memset of the whole permutation array (cap x 4 B per step).
+__global__ void k_mark_arrivals(Geo g, const int* __restrict__ inc, const int* __restrict__ cs_new, int* __restrict__ inv) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+  const int per_side = g.nsp * g.ngrow * (g.nx + 1);
+  const bool same_plane = g.dim == 3 ? g.nzs == g.nze : g.nys == g.nye;
+  for (int e = warp; e < 2 * per_side; e += nwarps) {
+    const int n = inc[e];
+    if (n == 0) continue;
+    const int side = e / per_side, r = e % per_side;
+    const int ii = r % (g.nx + 1), t = (r / (g.nx + 1)) % g.ngrow, isp = r / ((g.nx + 1) * g.ngrow);
+    if (ii == g.nx) continue;
+    int j, k;
+    if (g.dim == 3) { j = g.nys + t; k = side == 0 ? g.nzs : g.nze; }
+    else { j = side == 0 ? g.nys : g.nye; k = 0; }
+    const int cell_end = cs_new[(size_t)g.pen(j, k, isp) * (g.nx + 1) + ii + 1];
+    int dst = cell_end - n;
+    if (side == 0 && same_plane) dst -= inc[per_side + r];
+    for (int q = lane; q < n; q += 32) inv[dst + q] = -1;
+  }
+}
+
 // arrivals: recv (in B / the spare ID array) holds [from the low neighbour | from the high neighbour], each sorted by
 // destination cell with the counts `inc` and exclusive offsets `inc_off`.  One warp per arriving cell group.
 template <int D>
@@ -499,7 +523,10 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
     const int nch = (nxr + XCH - 1) / XCH;
     k_goff<<<g.nrows * nch, TPB, 0, st>>>(g, ctx->cs_new, ctx->cnt27, ctx->goff, nxs, nxe, nch);
     WM_LAUNCH_CHECK(ctx);
-    if (g.multi) WM_CUDA(cudaMemsetAsync(ctx->inv, 0xff, ctx->cap * sizeof(int), st));   // arrival slots stay -1
+    if (g.multi) {   // arrival slots are -1 for k_apply
+      k_mark_arrivals<<<std::min(wm_blocks((long long)2 * per_side * 32, TPB), 148 * 8), TPB, 0, st>>>(g, ctx->inc, ctx->cs_new, ctx->inv);
+      WM_LAUNCH_CHECK(ctx);
+    }
     k_perm<<<g.npen * nch, TPB, 0, st>>>(g, ctx->cs, ctx->cnt27, ctx->goff, ctx->dst_off, ctx->inv, ctx->flags, nxs, nxe, nch);
     WM_LAUNCH_CHECK(ctx);
     const int ngx = (nxr + GD - 1) / GD;
