@@ -55,3 +55,16 @@ def test_slab_shock_source(dim):
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" ok: ") == 2
+
+
+def test_slab_parity_uneven_slabs():
+    """nz = 9 over two ranks (slabs of 5 and 4 planes, para_range's remainder rule, 3d/common/mpi_set.f90:81-94): the peer-memory
+    cgm addresses a neighbour arena of a different size and shifts its ghost-plane stores by the NEIGHBOUR's slab thickness"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29587",
+           os.path.join(ROOT, "tests", "multigpu_check.py"), "--fused", "1", "--nz", "9"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok: ") == 2
