@@ -251,6 +251,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     step(args.steps)
+    b.settle()      # the last sort's permutation is applied inside the timed region (wm_step leaves it pending for the next step)
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()

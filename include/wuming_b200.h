@@ -126,6 +126,10 @@ int wm_step(wm_ctx* ctx, int nxs, int nxe, int order, double u0, int nsteps);
 /* 1 (default): wm_step uses the fused push+deposit kernel and the deterministic sort where available;
  * 0: wm_step calls the per-procedure kernels, exactly like a driver calling the five entry points above */
 int wm_set_fused(wm_ctx* ctx, int on);
+/* wm_step leaves the result of its last sort as (pushed set, permutation): the next wm_step's fused kernel reads through the
+ * permutation, which saves one full read + write of the particle store per step.  Every other entry point that reads the sorted
+ * set applies the pending permutation first; wm_settle does so explicitly (asynchronous, on the library stream). */
+int wm_settle(wm_ctx* ctx);
 /* which pusher wm_step / wm_h_step run (WM_PUSHER_*): a driver that calls particle__solv_vay in its time loop sets
  * WM_PUSHER_VAY once; wm_particle_solv and wm_particle_solv_vay always run their own pusher */
 int wm_set_pusher(wm_ctx* ctx, int pusher);

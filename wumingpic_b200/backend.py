@@ -54,7 +54,7 @@ ABI_SYMBOLS = [
     "wm_bc_particle_x", "wm_bc_injection", "wm_bc_particle_yz", "wm_sort_bucket", "wm_step", "wm_set_fused",
     "wm_h_particle_solv", "wm_h_field_fdtd_i", "wm_h_step", "wm_load_weibel", "wm_energy", "wm_gauss",
     "wm_get_stats", "wm_sync", "wm_set_timing", "wm_launch_count", "wm_stream", "wm_mom_calc",
-    "wm_particle_solv_vay", "wm_h_particle_solv_vay", "wm_set_pusher", "wm_shock_inject", "wm_shock_relocate",
+    "wm_particle_solv_vay", "wm_h_particle_solv_vay", "wm_set_pusher", "wm_shock_inject", "wm_shock_relocate", "wm_settle",
 ]
 
 
@@ -97,6 +97,7 @@ def load_library():
         L.wm_step.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
         L.wm_set_fused.argtypes = [vp, C.c_int]
         L.wm_set_pusher.argtypes = [vp, C.c_int]
+        L.wm_settle.argtypes = [vp]
         lp = C.POINTER(C.c_longlong)
         L.wm_shock_inject.argtypes = [vp, C.POINTER(ShockParams), C.c_int, ip, lp, C.c_longlong]
         L.wm_shock_relocate.argtypes = [vp, C.POINTER(ShockParams), C.c_int, lp, C.c_longlong]
@@ -255,6 +256,10 @@ class Backend:
     def particle__solv_vay(self, nxs, nxe):
         """particle__solv_vay (3d/common/particle.f90:236-419): the Vay pusher on resident state."""
         self._ck(self.L.wm_particle_solv_vay(self.h, nxs, nxe))
+
+    def settle(self):
+        """apply the sort permutation wm_step left pending (asynchronous); implied by every call that reads the sorted set"""
+        self._ck(self.L.wm_settle(self.h))
 
     def set_pusher(self, kind):
         """which pusher step()/h_step() run: WM_PUSHER_BORIS (0, particle__solv) or WM_PUSHER_VAY (1, particle__solv_vay)"""

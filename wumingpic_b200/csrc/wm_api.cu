@@ -29,7 +29,15 @@ int free_particles(wm_ctx* c) {
     if (c->id[k]) cudaFree(c->id[k]);
     c->id[k] = nullptr;
   }
+  for (int k = 0; k < 6; ++k) {
+    if (c->R.c[k]) cudaFree(c->R.c[k]);
+    c->R.c[k] = nullptr;
+  }
+  if (c->rid) cudaFree(c->rid);
+  c->rid = nullptr;
+  c->rcap = 0;
   c->cap = 0;
+  c->lazy = false;     // whatever permutation was pending referred to the freed arrays
   return WM_OK;
 }
 
@@ -252,6 +260,7 @@ int wm_upload(wm_ctx* c, const double* up, const int* np2, const int* cumcnt, co
   const Geo& g = c->g;
   if (uf) WM_CUDA(cudaMemcpyAsync(c->uf, uf, g.nbox() * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (up) {
+    c->lazy = false;   // the uploaded state supersedes a pending (lazy) sort permutation
     if (!np2 || !cumcnt) {
       wm_set_error("wm_upload: up needs np2 and cumcnt");
       return WM_ERR_ARG;
@@ -302,6 +311,7 @@ int wm_download(wm_ctx* c, double* up, int* np2, int* cumcnt, double* uf, double
   if (!c) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
   const Geo& g = c->g;
+  WM_TRY(wm_materialize(c));
   WM_TRY(check_flags(c));
   if (uf) WM_CUDA(cudaMemcpyAsync(uf, c->uf, g.nbox() * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   std::vector<int> h_np2(g.npen);
@@ -384,6 +394,7 @@ int wm_upload_work(wm_ctx* c, int which, const double* in) {
 static int particle_solv_with(wm_ctx* c, int nxs, int nxe, int pusher) {
   if (!c || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling particle__init()"); return WM_ERR_ARG; }
   WM_CUDA(cudaSetDevice(c->device));
+  WM_TRY(wm_materialize(c));
   WM_TRY(wm_k_tmpf(c, nxs, nxe));
   const int saved = c->pusher;
   c->pusher = pusher;
@@ -484,6 +495,8 @@ int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
   if (!c || !range_ok(c, nxs, nxe)) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
   const bool fused = c->use_fused && wm_fused_supported(c, order);
+  // a pending lazy sort is consumed by the fused kernel only if it covered the same x range
+  if (c->lazy && (!fused || nxs != c->lazy_nxs || nxe != c->lazy_nxe)) WM_TRY(wm_materialize(c));
   for (int it = 0; it < nsteps; ++it) {
     if (c->timing) WM_CUDA(cudaEventRecord(c->ev[0], c->stream));
     if (fused) {
@@ -495,7 +508,10 @@ int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
       if (c->timing) { WM_CUDA(cudaEventRecord(c->ev[1], c->stream)); WM_CUDA(cudaEventRecord(c->ev[2], c->stream)); }
       WM_TRY(field_stages(c, nxs, nxe, 2));
       if (c->timing) WM_CUDA(cudaEventRecord(c->ev[3], c->stream));
-      WM_TRY(wm_k_sort(c, nxs, nxe));
+      c->allow_lazy = 1;      // the next fused kernel (or wm_materialize) applies the permutation
+      const int rc_sort = wm_k_sort(c, nxs, nxe);
+      c->allow_lazy = 0;
+      WM_TRY(rc_sort);
       c->gp_valid = false;
       c->keys_valid = false;
     } else {
@@ -540,6 +556,12 @@ int wm_set_fused(wm_ctx* c, int on) {
   if (!c) return WM_ERR_ARG;
   c->use_fused = on;
   return WM_OK;
+}
+
+int wm_settle(wm_ctx* c) {
+  if (!c) return WM_ERR_ARG;
+  WM_CUDA(cudaSetDevice(c->device));
+  return wm_materialize(c);
 }
 
 int wm_set_pusher(wm_ctx* c, int pusher) {
@@ -604,6 +626,7 @@ int wm_h_step(wm_ctx* c, double* up, double* uf, int* np2, int* cumcnt, int nxs,
 int wm_load_weibel(wm_ctx* c, int n0, double v_thi, double v_the, double t_ani, double b0, unsigned long long seed) {
   if (!c || n0 <= 0) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
+  c->lazy = false;
   const Geo& g = c->g;
   if ((long long)n0 * g.nx > g.np) {
     wm_set_error("Error: Too large number of particles");  // 3d/proj/weibel/app.f90:315-320
@@ -624,6 +647,7 @@ int wm_mom_calc(wm_ctx* c, int nxs, int nxe, double* mom) {
   WM_CUDA(cudaSetDevice(c->device));
   const Geo& g = c->g;
   if (c->gp_valid) { wm_set_error("mom_calc acts on the sorted particles (call it after sort__bucket)"); return WM_ERR_STATE; }
+  WM_TRY(wm_materialize(c));
   const size_t nb = g.nbox(), nel = nb * 7 * g.nsp;
   if (!c->mom) WM_CUDA(cudaMalloc(&c->mom, nel * sizeof(double)));
   WM_CUDA(cudaMemsetAsync(c->mom, 0, nel * sizeof(double), c->stream));
@@ -648,12 +672,14 @@ int wm_mom_calc(wm_ctx* c, int nxs, int nxe, double* mom) {
 int wm_energy(wm_ctx* c, double* out) {
   if (!c || !out) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
+  WM_TRY(wm_materialize(c));
   return wm_k_energy(c, out);
 }
 
 int wm_gauss(wm_ctx* c, double* out) {
   if (!c || !out) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
+  WM_TRY(wm_materialize(c));
   return wm_k_gauss(c, out);
 }
 

@@ -123,7 +123,7 @@ __device__ __forceinline__ void s0ds(double xo, double xn, int cell, int inc, do
 template <int ORDER, int G, bool VAY>
 __global__ void __launch_bounds__(16 * G, WM_FUSED_MINB)
 k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __restrict__ id_out,
-         const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj, int* __restrict__ cnt,
+         const int* __restrict__ inv, Ptcl R, const double* __restrict__ rid, const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj, int* __restrict__ cnt,
          int* __restrict__ hist, unsigned char* __restrict__ dst_off, int* flags, int nxs, int nxe, int ngx, double u0,
          double xend) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -200,18 +200,34 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
   // register prefetch of the next batch's particle (index -1: none)
   double nx_ = 0, ny_ = 0, nz_ = 0, nux = 0, nuy = 0, nuz = 0, nid = 0;
   int np_ = -1, nisp = 0;
-  auto fetch = [&](int batch) {
+  // two-stage prefetch: the index of batch b+2 (the sorted position, or -- lazy sort -- its image under the pending
+  // permutation) is requested while the particle of batch b+1 is loaded and batch b is processed, so neither load
+  // stalls the warp.  qi: where the next particle sits (>= 0: set A, <= -2: arrival store of a slab run, -1: none)
+  int qi = -1, qisp = 0;
+  auto prep = [&](int batch) {
     const int idx = batch * SLOTS + sa;
-    np_ = -1; nisp = 0;
-    if (idx < n0a) { np_ = S.beg[0][ca] + idx; }
-    else if (idx < n0a + n1a) { np_ = S.beg[1][ca] + (idx - n0a); nisp = 1; }
-    if (np_ >= 0) {
-      nx_ = A.c[0][np_]; ny_ = A.c[1][np_]; nz_ = A.c[2][np_];
-      nux = A.c[3][np_]; nuy = A.c[4][np_]; nuz = A.c[5][np_];
-      nid = id_in[np_];
+    int pos = -1;
+    qi = -1; qisp = 0;
+    if (idx < n0a) { pos = S.beg[0][ca] + idx; }
+    else if (idx < n0a + n1a) { pos = S.beg[1][ca] + (idx - n0a); qisp = 1; }
+    if (pos >= 0) qi = inv ? inv[pos] : pos;
+  };
+  auto fetch = [&]() {
+    np_ = qi == -1 ? -1 : 0; nisp = qisp;
+    if (qi >= 0) {
+      nx_ = A.c[0][qi]; ny_ = A.c[1][qi]; nz_ = A.c[2][qi];
+      nux = A.c[3][qi]; nuy = A.c[4][qi]; nuz = A.c[5][qi];
+      nid = id_in[qi];
+    } else if (qi <= -2) {
+      const int a = -2 - qi;
+      nx_ = R.c[0][a]; ny_ = R.c[1][a]; nz_ = R.c[2][a];
+      nux = R.c[3][a]; nuy = R.c[4][a]; nuz = R.c[5][a];
+      nid = rid[a];
     }
   };
-  fetch(0);
+  prep(0);
+  fetch();
+  prep(1);
   for (int batch = 0; batch < nbatch; ++batch) {
     int nst = 0, ncr = 0;   // stayer / crosser records of this half-warp's cell in this batch
     // ------------------------------ phase A ------------------------------
@@ -220,7 +236,7 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
       const double x = nx_, y = ny_, z = nz_;
       double ux = nux, uy = nuy, uz = nuz;
       const double idv = nid;
-      if (batch + 1 < nbatch) fetch(batch + 1);
+      if (batch + 1 < nbatch) { fetch(); prep(batch + 2); }
       double xn = 0, yn = 0, zn = 0;
       int o = 13;
       int inc0 = 0, inc1 = 0, inc2 = 0;
@@ -487,7 +503,7 @@ struct __align__(16) Smem2 {
 template <int ORDER, int G, bool VAY>
 __global__ void __launch_bounds__(16 * G, 32 / G)
 k_fused2(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __restrict__ id_out,
-         const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj, int* __restrict__ cnt,
+         const int* __restrict__ inv, Ptcl R, const double* __restrict__ rid, const int* __restrict__ cs, const double* __restrict__ tmpf, double* __restrict__ uj, int* __restrict__ cnt,
          int* __restrict__ hist, unsigned char* __restrict__ dst_off, int* flags, int nxs, int nxe, int ngx, double u0,
          double xend) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -546,9 +562,12 @@ k_fused2(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
       double xn = 0, yn = 0, ux = 0, uy = 0, uz = 0, idv = 0;
       int o = 13;
       if (p >= 0) {
-        const double x = A.c[0][p], y = A.c[1][p];
-        ux = A.c[2][p]; uy = A.c[3][p]; uz = A.c[4][p];
-        idv = id_in[p];
+        const int q = inv ? inv[p] : p;          // lazy sort: see k_fused3
+        const bool loc = q >= 0;
+        const int a = loc ? q : -2 - q;
+        const double x = loc ? A.c[0][a] : R.c[0][a], y = loc ? A.c[1][a] : R.c[1][a];
+        ux = loc ? A.c[2][a] : R.c[2][a]; uy = loc ? A.c[3][a] : R.c[3][a]; uz = loc ? A.c[4][a] : R.c[4][a];
+        idv = loc ? id_in[a] : rid[a];
         double sx[3], sy[3];
         shape3(x * g.d_delx - 0.5 - ia, sx[0], sx[1], sx[2]);
         shape3(y * g.d_delx - 0.5 - j, sy[0], sy[1], sy[2]);
@@ -748,7 +767,7 @@ int launch_fused2(wm_ctx* ctx, int nxs, int nxe, double u0) {
   const int blocks = ngx * g.nyl;
   const double xend = nxe * g.delx + u0 / sqrt(1 + (u0 * u0) / (g.c * g.c)) * g.delt;   // 2d/proj/shock/boundary_shock.f90:271
   k_fused2<ORDER, G, VAY><<<blocks, 16 * G, sizeof(Smem2<G>), ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
-                                                                       ctx->cs, ctx->tmpf, ctx->uj, ctx->cnt27, ctx->cs_new,
+                                                                       ctx->lazy ? ctx->inv : nullptr, ctx->R, ctx->rid, ctx->cs, ctx->tmpf, ctx->uj, ctx->cnt27, ctx->cs_new,
                                                                        ctx->dst_off, ctx->flags, nxs, nxe, ngx, u0, xend);
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
@@ -766,7 +785,7 @@ int launch_fused(wm_ctx* ctx, int nxs, int nxe, double u0) {
   const int blocks = ngx * g.nyl * g.nzl;
   const double xend = nxe * g.delx + u0 / sqrt(1.0 + (u0 * u0) / (g.c * g.c)) * g.delt;   // boundary_shock.f90:438
   k_fused3<ORDER, G, VAY><<<blocks, 16 * G, sizeof(Smem<G>), ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid],
-                                                                      ctx->cs, ctx->tmpf, ctx->uj, ctx->cnt27, ctx->cs_new,
+                                                                      ctx->lazy ? ctx->inv : nullptr, ctx->R, ctx->rid, ctx->cs, ctx->tmpf, ctx->uj, ctx->cnt27, ctx->cs_new,
                                                                       ctx->dst_off, ctx->flags, nxs, nxe, ngx, u0, xend);
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;

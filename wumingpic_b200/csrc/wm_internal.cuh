@@ -92,6 +92,15 @@ struct wm_ctx {
   int* totals = nullptr;   // device copy of the six per-step totals (k_totals)
   size_t dst_off_cap = 0;
   int use_fused = 1;
+  // lazy sort (wm_sort.cu): after a sort inside wm_step the permutation is NOT applied; set A then is the pushed set in
+  // source order and the particle at sorted position pos is A[inv[pos]] (or, for arrivals from a neighbour rank,
+  // R[-2 - inv[pos]]).  The next fused kernel reads through inv; every other consumer calls wm_materialize first.
+  bool lazy = false;
+  int allow_lazy = 0;            // set by wm_step around its sort
+  int lazy_nxs = 0, lazy_nxe = 0;
+  Ptcl R = {};                   // arrival store of a slab run (lazy mode): what the neighbours sent, in arrival order
+  double* rid = nullptr;
+  size_t rcap = 0;
   int pusher = 0;      // WM_PUSHER_BORIS (particle__solv) or WM_PUSHER_VAY (particle__solv_vay)
   void* scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
@@ -172,6 +181,7 @@ int wm_k_classify(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_sort(wm_ctx* ctx, int nxs, int nxe);
 int wm_enable_slab_migration(wm_ctx* ctx);
 int wm_k_refresh_np2(wm_ctx* ctx);
+int wm_materialize(wm_ctx* ctx);   // apply a pending (lazy) sort permutation: set A becomes the sorted set again
 int wm_k_energy(wm_ctx* ctx, double* out_host);
 int wm_k_gauss(wm_ctx* ctx, double* out_host);
 int wm_k_load_weibel(wm_ctx* ctx, int n0, double v_thi, double v_the, double t_ani, double b0, unsigned long long seed);

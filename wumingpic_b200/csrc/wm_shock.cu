@@ -205,6 +205,7 @@ int shock_source(wm_ctx* c, const wm_shock_params* sp, int nxe, const int* cnt_r
   if (nxe < g.nxgs + 1 || nxe > g.nxge) { wm_set_error("inject / relocate: nxe outside the box"); return WM_ERR_ARG; }
   if (c->gp_valid) { wm_set_error("inject / relocate act on the sorted particles: call them after sort__bucket"); return WM_ERR_STATE; }
   WM_CUDA(cudaSetDevice(c->device));
+  WM_TRY(wm_materialize(c));   // the shifted copy below moves the cell-sorted set
   cudaStream_t st = c->stream;
   const int nrow = g.nyl * g.nzl;
   long long added_sp = 0;   // per species

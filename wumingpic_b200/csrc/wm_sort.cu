@@ -294,22 +294,30 @@ __global__ void __launch_bounds__(TPB) k_perm(Geo g, const int* __restrict__ cs,
 template <int D>
 __global__ void __launch_bounds__(TPB) k_apply(Geo g, Ptcl B, Ptcl A, const double* __restrict__ id_in,
                                                double* __restrict__ id_out, const int* __restrict__ cs_new,
-                                               const int* __restrict__ inv, int nxs, int nxe, int ngx, int multi) {
+                                               const int* __restrict__ inv, int nxs, int nxe, int ngx, int row0, Ptcl R,
+                                               const double* __restrict__ rid) {
   constexpr int NC = D == 3 ? 6 : 5;
   const int gx = blockIdx.x % ngx;
   int isp, j, k, row, need_dl;
-  dest_row(g, blockIdx.x / ngx, isp, j, k, row, need_dl);
+  dest_row(g, row0 + blockIdx.x / ngx, isp, j, k, row, need_dl);
   const int ia = nxs + gx * GD;
   const int ncg = min(GD, nxe - ia + 1);
   const int* crow = cs_new + (size_t)row * (g.nx + 1) + (ia - g.nxgs);
   const int base = crow[0], end = crow[ncg];
   for (int pos = base + threadIdx.x; pos < end; pos += TPB) {
     const int p = inv[pos];
-    if (multi && p < 0) continue;            // a slot reserved for an arrival from a neighbour rank (k_insert fills it)
+    if (p == -1) continue;                   // a slot reserved for an arrival from a neighbour rank (k_insert fills it)
     double v[NC + 1];
+    if (p >= 0) {
 #pragma unroll
-    for (int c = 0; c < NC; ++c) v[c] = B.c[c][p];
-    v[NC] = id_in[p];
+      for (int c = 0; c < NC; ++c) v[c] = B.c[c][p];
+      v[NC] = id_in[p];
+    } else {                                 // lazy slab run: the arrival sits in the arrival store
+      const int q = -2 - p;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) v[c] = R.c[c][q];
+      v[NC] = rid[q];
+    }
 #pragma unroll
     for (int c = 0; c < NC; ++c) A.c[c][pos] = v[c];
     id_out[pos] = v[NC];
@@ -318,7 +326,9 @@ __global__ void __launch_bounds__(TPB) k_apply(Geo g, Ptcl B, Ptcl A, const doub
 
 // inv = -1 on the slots k_insert will fill (the tail of every edge-plane cell that receives arrivals): k_apply skips them.
 // Same slot arithmetic as k_insert; replaces a memset of the whole permutation array (cap x 4 B per step).
-__global__ void k_mark_arrivals(Geo g, const int* __restrict__ inc, const int* __restrict__ cs_new, int* __restrict__ inv) {
+// inc_off != nullptr (lazy sort): the slot instead points at the arrival itself, inv = -2 - (index in the arrival store).
+__global__ void k_mark_arrivals(Geo g, const int* __restrict__ inc, const int* __restrict__ cs_new, int* __restrict__ inv,
+                                const int* __restrict__ inc_off) {
   const int lane = threadIdx.x & 31;
   const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
@@ -336,7 +346,8 @@ __global__ void k_mark_arrivals(Geo g, const int* __restrict__ inc, const int* _
     const int cell_end = cs_new[(size_t)g.pen(j, k, isp) * (g.nx + 1) + ii + 1];
     int dst = cell_end - n;
     if (side == 0 && same_plane) dst -= inc[per_side + r];
-    for (int q = lane; q < n; q += 32) inv[dst + q] = -1;
+    const int src = inc_off ? inc_off[e] : 0;
+    for (int q = lane; q < n; q += 32) inv[dst + q] = inc_off ? -2 - (src + q) : -1;
   }
 }
 
@@ -518,44 +529,62 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
     }
   }
   const int old_cid = 1 - ctx->cid;   // the producers moved the IDs along with the particles into the spare array
+  static const bool no_lazy = getenv("WM_NO_LAZY_SORT") != nullptr;   // measurement switch
+  const bool lazy = ctx->allow_lazy && !no_lazy;
+  const int nxr = nxe - nxs + 1;
+  const int ngx = (nxr + GD - 1) / GD;
   {
-    const int nxr = nxe - nxs + 1;
     const int nch = (nxr + XCH - 1) / XCH;
     k_goff<<<g.nrows * nch, TPB, 0, st>>>(g, ctx->cs_new, ctx->cnt27, ctx->goff, nxs, nxe, nch);
     WM_LAUNCH_CHECK(ctx);
-    if (g.multi) {   // arrival slots are -1 for k_apply
-      k_mark_arrivals<<<std::min(wm_blocks((long long)2 * per_side * 32, TPB), 148 * 8), TPB, 0, st>>>(g, ctx->inc, ctx->cs_new, ctx->inv);
+    if (g.multi) {   // arrival slots: -1 for k_apply / k_insert, or the index into the arrival store (lazy)
+      k_mark_arrivals<<<std::min(wm_blocks((long long)2 * per_side * 32, TPB), 148 * 8), TPB, 0, st>>>(g, ctx->inc, ctx->cs_new, ctx->inv,
+                                                                                                      lazy ? ctx->inc_off : nullptr);
       WM_LAUNCH_CHECK(ctx);
     }
     k_perm<<<g.npen * nch, TPB, 0, st>>>(g, ctx->cs, ctx->cnt27, ctx->goff, ctx->dst_off, ctx->inv, ctx->flags, nxs, nxe, nch);
     WM_LAUNCH_CHECK(ctx);
-    const int ngx = (nxr + GD - 1) / GD;
-    const int blocks = g.nrows * ngx;
-    if (g.dim == 3)
-      k_apply<3><<<blocks, TPB, 0, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs_new, ctx->inv, nxs,
-                                         nxe, ngx, g.multi);
-    else
-      k_apply<2><<<blocks, TPB, 0, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs_new, ctx->inv, nxs,
-                                         nxe, ngx, g.multi);
-    WM_LAUNCH_CHECK(ctx);
+    // the permutation is applied now -- or, inside wm_step, left to the next fused kernel (which reads through inv); a slab
+    // run still materialises its outgoing ghost rows, behind the local particles of the free set
+    const int row0 = lazy ? g.npen : 0;
+    const int rows = g.nrows - row0;
+    if (rows > 0) {
+      if (g.dim == 3)
+        k_apply<3><<<rows * ngx, TPB, 0, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs_new, ctx->inv, nxs,
+                                               nxe, ngx, row0, ctx->R, ctx->rid);
+      else
+        k_apply<2><<<rows * ngx, TPB, 0, st>>>(g, ctx->B, ctx->A, ctx->id[old_cid], ctx->id[1 - old_cid], ctx->cs_new, ctx->inv, nxs,
+                                               nxe, ngx, row0, ctx->R, ctx->rid);
+      WM_LAUNCH_CHECK(ctx);
+    }
   }
   if (g.multi) {
     // payload: ghost rows of A (behind the local particles) -> neighbours; arrivals land in B / the old ID array,
-    // which are free once the scatter has read them (stream order)
+    // which are free once the scatter has read them (stream order) -- or, lazy, in the arrival store R
     const int ax = g.dim == 3 ? 1 : 0;
     const int ncomp = g.ndim - 1;
     const size_t lo0 = (size_t)tot[0], hi0 = (size_t)tot[0] + tot[2];
+    if (lazy && (size_t)tot[4] + tot[5] > ctx->rcap) {
+      const size_t rcap = ((size_t)tot[4] + tot[5]) * 3 / 2 + 4096;
+      for (int c = 0; c < ncomp; ++c) {
+        if (ctx->R.c[c]) cudaFree(ctx->R.c[c]);
+        WM_CUDA(cudaMalloc(&ctx->R.c[c], rcap * sizeof(double)));
+      }
+      if (ctx->rid) cudaFree(ctx->rid);
+      WM_CUDA(cudaMalloc(&ctx->rid, rcap * sizeof(double)));
+      ctx->rcap = rcap;
+    }
     WM_TRY(wm_comm_group_begin(ctx));
     for (int c = 0; c <= ncomp; ++c) {
       const double* src = c < ncomp ? ctx->A.c[c] : ctx->id[1 - old_cid];
-      double* dst = c < ncomp ? ctx->B.c[c] : ctx->id[old_cid];
+      double* dst = lazy ? (c < ncomp ? ctx->R.c[c] : ctx->rid) : (c < ncomp ? ctx->B.c[c] : ctx->id[old_cid]);
       WM_TRY(wm_comm_send(ctx, ctx->rank_down[ax], src + lo0, (size_t)tot[2] * sizeof(double)));
       WM_TRY(wm_comm_recv(ctx, ctx->rank_up[ax], dst + tot[4], (size_t)tot[5] * sizeof(double)));
       WM_TRY(wm_comm_send(ctx, ctx->rank_up[ax], src + hi0, (size_t)tot[3] * sizeof(double)));
       WM_TRY(wm_comm_recv(ctx, ctx->rank_down[ax], dst, (size_t)tot[4] * sizeof(double)));
     }
     WM_TRY(wm_comm_group_end(ctx));
-    if (tot[4] + tot[5] > 0) {
+    if (!lazy && tot[4] + tot[5] > 0) {
       const int blocks = std::min(wm_blocks((long long)2 * per_side * 32, TPB), 148 * 8);
       if (g.dim == 3)
         k_insert<3><<<blocks, TPB, 0, st>>>(g, ctx->B, ctx->id[old_cid], ctx->A, ctx->id[1 - old_cid], ctx->inc, ctx->inc_off,
@@ -574,7 +603,15 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
     ctx->n_sp0 = tot[1];
   }
   std::swap(ctx->cs, ctx->cs_new);
-  ctx->cid = 1 - old_cid;
+  if (lazy) {
+    std::swap(ctx->A, ctx->B);   // set A = the pushed set (read through inv), set B = free
+    ctx->cid = old_cid;
+    ctx->lazy = true;
+    ctx->lazy_nxs = nxs;
+    ctx->lazy_nxe = nxe;
+  } else {
+    ctx->cid = 1 - old_cid;
+  }
   k_np2_poff<<<wm_blocks(g.npen + 1, TPB), TPB, 0, st>>>(g, ctx->cs, ctx->np2, ctx->poff, ctx->flags,
                                                            g.multi ? -1LL : ctx->ntot);
   WM_LAUNCH_CHECK(ctx);
@@ -587,5 +624,24 @@ int wm_k_refresh_np2(wm_ctx* ctx) {
   k_np2_poff<<<wm_blocks(g.npen + 1, TPB), TPB, 0, ctx->stream>>>(g, ctx->cs, ctx->np2, ctx->poff, ctx->flags,
                                                                     g.multi ? -1LL : ctx->ntot);
   WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+// Apply a pending (lazy) permutation: afterwards set A is the cell-sorted set every other kernel expects.
+int wm_materialize(wm_ctx* ctx) {
+  if (!ctx->lazy) return WM_OK;
+  const Geo& g = ctx->g;
+  const int nxs = ctx->lazy_nxs, nxe = ctx->lazy_nxe;
+  const int ngx = (nxe - nxs + 1 + GD - 1) / GD;
+  if (g.dim == 3)
+    k_apply<3><<<g.npen * ngx, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid], ctx->cs, ctx->inv,
+                                                      nxs, nxe, ngx, 0, ctx->R, ctx->rid);
+  else
+    k_apply<2><<<g.npen * ngx, TPB, 0, ctx->stream>>>(g, ctx->A, ctx->B, ctx->id[ctx->cid], ctx->id[1 - ctx->cid], ctx->cs, ctx->inv,
+                                                      nxs, nxe, ngx, 0, ctx->R, ctx->rid);
+  WM_LAUNCH_CHECK(ctx);
+  std::swap(ctx->A, ctx->B);
+  ctx->cid = 1 - ctx->cid;
+  ctx->lazy = false;
   return WM_OK;
 }
