@@ -103,7 +103,6 @@ int peer_setup(wm_ctx* ctx) {
     *old[q] = reinterpret_cast<double*>(arena + q * arr);
   }
   ctx->peer_arena = arena;
-  WmMail* my_mail = reinterpret_cast<WmMail*>(arena + 4 * arr);
   unsigned long long* my_seq = reinterpret_cast<unsigned long long*>(arena + 4 * arr + mail_bytes);
 
   // base of the underlying allocation (driver API, resolved at run time like NCCL)
@@ -159,12 +158,9 @@ int peer_setup(wm_ctx* ctx) {
   WM_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ok) {
     for (int r = 0; r < R && ok; ++r) {
-      const size_t seq_off = 4 * round256((size_t)g.nbox() * sizeof(double)) + mail_bytes;
       // a neighbour's arena differs in size when the slabs are uneven: its counter sits behind ITS four arrays
-      size_t nbox_r = g.nbox();
-      if (g.dim == 3) nbox_r = (size_t)g.bx * g.by * (all[r].nl + 4); else nbox_r = (size_t)g.bx * (all[r].nl + 4);
+      const size_t nbox_r = g.dim == 3 ? (size_t)g.bx * g.by * (all[r].nl + 4) : (size_t)g.bx * (all[r].nl + 4);
       const size_t off_r = 4 * round256(nbox_r * sizeof(double)) + mail_bytes;
-      (void)seq_off;
       unsigned long long got = 0;
       if (cudaMemcpy(&got, arenas[r] + off_r + 8, sizeof(got), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); ok = false; }
       else if (got != magic + (unsigned long long)r) ok = false;
@@ -200,7 +196,6 @@ int peer_setup(wm_ctx* ctx) {
   pc.seq = my_seq;
   pc.nranks = R;
   pc.rank = ctx->rank;
-  (void)my_mail;
   ctx->peer_ok = true;
   return WM_OK;
 }
