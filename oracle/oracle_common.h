@@ -12,7 +12,9 @@
 // Fortran loop nests (each function cites the file:line it follows) and is
 // additionally checked through the physics invariants the algorithm guarantees
 // (Gauss-law residual at round-off, particle-count / ID-multiset conservation,
-// Boris |u| conservation, N-slab == 1-slab equivalence).
+// Boris |u| conservation, N-slab == 1-slab equivalence) and against a second,
+// independent numpy restatement of push / deposit / field solve
+// (tests/test_oracle_independent.py).
 #pragma once
 #include <cstdint>
 #include <cmath>

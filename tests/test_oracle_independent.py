@@ -1,0 +1,259 @@
+"""A second, independent restatement of the two particle kernels of the reference -- written in numpy straight from the Fortran text,
+sharing no code with oracle/*.cpp -- checked against the C++ oracle.  The reference ships no golden vectors for this path and cannot
+be built here (parity unpinned), so this does not pin the oracle to the reference's OUTPUT; it does rule out
+transcription slips in the oracle, which would have to be made identically twice, in two languages, to go unnoticed.
+
+    push    3d/common/particle.f90:75-91 (tmpf staging), :108-184 (shape factors, 27-point gather), :186-222 (Buneman-Boris, move)
+            3d/common/particle.f90:369-406 (Vay)
+    deposit 3d/common/field.f90:252-396 (S0, shifted S1 through smo_1..3, DS, the three W sums, the transposed flush)
+"""
+import numpy as np
+import pytest
+
+from oracle.pyoracle import World3, weibel_constants
+from tests.util import active_mask, make_world3
+
+
+def _stage_fields(uf):
+    """tmpf(1:6,i,j,k), particle.f90:79-87, on the box of uf (k, j, i, comp); the last plane/row/column of the result is unused"""
+    t = np.zeros_like(uf)
+    f = uf
+    t[:-1, :-1, :, 0] = 2.5e-1 * (+f[:-1, :-1, :, 0] + f[:-1, 1:, :, 0] + f[1:, :-1, :, 0] + f[1:, 1:, :, 0])
+    t[:-1, :, :-1, 1] = 2.5e-1 * (+f[:-1, :, :-1, 1] + f[:-1, :, 1:, 1] + f[1:, :, :-1, 1] + f[1:, :, 1:, 1])
+    t[:, :-1, :-1, 2] = 2.5e-1 * (+f[:, :-1, :-1, 2] + f[:, :-1, 1:, 2] + f[:, 1:, :-1, 2] + f[:, 1:, 1:, 2])
+    t[:, :, :-1, 3] = 5e-1 * (+f[:, :, :-1, 3] + f[:, :, 1:, 3])
+    t[:, :-1, :, 4] = 5e-1 * (+f[:, :-1, :, 4] + f[:, 1:, :, 4])
+    t[:-1, :, :, 5] = 5e-1 * (+f[:-1, :, :, 5] + f[1:, :, :, 5])
+    return t
+
+
+def _shape(dh):
+    return 5e-1 * (5e-1 - dh) * (5e-1 - dh), 7.5e-1 - dh * dh, 5e-1 * (5e-1 + dh) * (5e-1 + dh)
+
+
+def _cells_of(w):
+    """(isp, k, j, ii) -> loop cell i of every active particle, from cumcnt (the push uses the loop cell, never int(x))"""
+    np2, cc = w.arr("np2"), w.arr("cumcnt")
+    m = active_mask(np2, w.np)
+    ii = np.broadcast_to(np.arange(w.np), m.shape)
+    cell = (ii[..., None] >= cc[..., None, :]).sum(axis=-1) - 1      # number of cumcnt entries <= ii, minus one
+    return m, cell + 2                                                 # nxgs = 2
+
+
+def numpy_push(w, vay=False):
+    """gp of every active particle, from up / uf / cumcnt, in the statement order of particle.f90"""
+    up, uf = w.arr("up"), w.arr("uf")
+    tm = _stage_fields(uf)
+    m, ci = _cells_of(w)
+    isp, kk, jj, _ = np.nonzero(m)
+    p = up[m]                                    # (n, 7)
+    i = ci[m]; j = jj + 2; k = kk + 2            # nys = nzs = 2 on a single rank
+    c, delt, d_delx = w.c, w.delt, 1.0 / w.delx
+    q, r = w.q[isp], w.r[isp]
+    fac1 = q / r * 5e-1 * delt
+    txxx = fac1 * fac1
+    fac2 = q * delt / r
+    shx = _shape(p[:, 0] * d_delx - 5e-1 - i)
+    shy = _shape(p[:, 1] * d_delx - 5e-1 - j)
+    shz = _shape(p[:, 2] * d_delx - 5e-1 - k)
+    f = []
+    for comp in range(6):
+        tot = None
+        for dk in (-1, 0, 1):
+            plane = None
+            for dj in (-1, 0, 1):
+                # box index = global index (two ghost layers, origin 2 -> index 2 is the first interior cell)
+                row = (+tm[k + dk, j + dj, i - 1, comp] * shx[0] + tm[k + dk, j + dj, i, comp] * shx[1]
+                       + tm[k + dk, j + dj, i + 1, comp] * shx[2]) * shy[dj + 1]
+                plane = row if plane is None else plane + row
+            term = plane * shz[dk + 1]
+            tot = term if tot is None else tot + term
+        f.append(tot)
+    bpx, bpy, bpz, epx, epy, epz = f
+    g = np.empty_like(p)
+    if not vay:
+        uvm1 = p[:, 3] + fac1 * epx; uvm2 = p[:, 4] + fac1 * epy; uvm3 = p[:, 5] + fac1 * epz
+        gam = np.sqrt(c * c + uvm1 * uvm1 + uvm2 * uvm2 + uvm3 * uvm3)
+        igam = 1e0 / gam
+        fac1r = fac1 * igam
+        fac2r = fac2 / (gam + txxx * (bpx * bpx + bpy * bpy + bpz * bpz) * igam)
+        uvm4 = uvm1 + fac1r * (+uvm2 * bpz - uvm3 * bpy)
+        uvm5 = uvm2 + fac1r * (+uvm3 * bpx - uvm1 * bpz)
+        uvm6 = uvm3 + fac1r * (+uvm1 * bpy - uvm2 * bpx)
+        uvm1 = uvm1 + fac2r * (+uvm5 * bpz - uvm6 * bpy)
+        uvm2 = uvm2 + fac2r * (+uvm6 * bpx - uvm4 * bpz)
+        uvm3 = uvm3 + fac2r * (+uvm4 * bpy - uvm5 * bpx)
+        g[:, 3] = uvm1 + fac1 * epx; g[:, 4] = uvm2 + fac1 * epy; g[:, 5] = uvm3 + fac1 * epz
+        gam = 1e0 / np.sqrt(1e0 + (+g[:, 3] * g[:, 3] + g[:, 4] * g[:, 4] + g[:, 5] * g[:, 5]) / (c * c))
+    else:
+        uvm1, uvm2, uvm3 = p[:, 3], p[:, 4], p[:, 5]
+        gam = np.sqrt(c * c + uvm1 * uvm1 + uvm2 * uvm2 + uvm3 * uvm3)
+        fac1r = fac1 / gam
+        uvm4 = uvm1 + fac2 * epx + fac1r * (+uvm2 * bpz - uvm3 * bpy)
+        uvm5 = uvm2 + fac2 * epy + fac1r * (+uvm3 * bpx - uvm1 * bpz)
+        uvm6 = uvm3 + fac2 * epz + fac1r * (+uvm1 * bpy - uvm2 * bpx)
+        taux, tauy, tauz = fac1 * bpx / c, fac1 * bpy / c, fac1 * bpz / c
+        tau2 = taux * taux + tauy * tauy + tauz * tauz
+        ua = (uvm4 * taux + uvm5 * tauy + uvm6 * tauz) / c
+        sigma = 1.0 + (uvm4 * uvm4 + uvm5 * uvm5 + uvm6 * uvm6) / (c * c) - tau2
+        gam2 = 0.5 * (sigma + np.sqrt(sigma * sigma + 4.0 * (tau2 + ua * ua)))
+        gam = np.sqrt(gam2)
+        txxx = 1.0 / (tau2 + gam2)
+        g[:, 3] = txxx * (gam2 * uvm4 + c * ua * taux + gam * (uvm5 * tauz - uvm6 * tauy))
+        g[:, 4] = txxx * (gam2 * uvm5 + c * ua * tauy + gam * (uvm6 * taux - uvm4 * tauz))
+        g[:, 5] = txxx * (gam2 * uvm6 + c * ua * tauz + gam * (uvm4 * tauy - uvm5 * taux))
+        gam = 1e0 / gam
+    g[:, 0] = p[:, 0] + g[:, 3] * delt * gam
+    g[:, 1] = p[:, 1] + g[:, 4] * delt * gam
+    g[:, 2] = p[:, 2] + g[:, 5] * delt * gam
+    g[:, 6] = p[:, 6]
+    return m, g
+
+
+@pytest.mark.parametrize("vay", [False, True], ids=["buneman-boris", "vay"])
+def test_push_matches_an_independent_numpy_restatement(vay):
+    w = make_world3(10, 6, 5, 4, steps=2)
+    rng = np.random.default_rng(11)
+    uf = w.arr("uf")
+    uf[...] = 5.0 * rng.standard_normal(uf.shape)          # strong fields: every term of the update matters
+    (w.particle_solv_vay if vay else w.particle_solv)()
+    m, g = numpy_push(w, vay)
+    ref = w.arr("gp")[m]
+    assert np.array_equal(ref[:, 6].view(np.int64), g[:, 6].view(np.int64))
+    scale = np.abs(ref[:, :6]).max(axis=0)
+    assert (np.abs(ref[:, :6] - g[:, :6]).max(axis=0) / scale).max() < 5e-15
+    w.close()
+
+
+def numpy_deposit_one(x0, x1, cell, qdxdt):
+    """pjx, pjy, pjz(-2:2,-2:2,-2:2) of ONE particle, field.f90:252-383, returned as uj increments d[(ip,jp,kp)] -> (jx,jy,jz)
+    after the transposed flush of :390-396"""
+    fac = 1e0 / 3e0
+    s0, ds = [], []
+    for a in range(3):
+        dh = x0[a] - 5e-1 - cell[a]
+        s = np.zeros(5)
+        s[1], s[2], s[3] = _shape(dh)
+        i2 = int(x1[a])
+        dh = x1[a] - 5e-1 - i2
+        inc = i2 - cell[a]
+        s1_1, s1_2, s1_3 = _shape(dh)
+        smo_1 = -(inc - abs(inc)) * 5e-1 + 0
+        smo_2 = -abs(inc) + 1
+        smo_3 = (inc + abs(inc)) * 5e-1 + 0
+        d = np.array([s1_1 * smo_1, s1_1 * smo_2 + s1_2 * smo_1, s1_2 * smo_2 + s1_3 * smo_1 + s1_1 * smo_3,
+                      s1_3 * smo_2 + s1_2 * smo_3, s1_3 * smo_3])
+        s0.append(s)
+        ds.append(d - s)
+    (s0x, s0y, s0z), (dsx, dsy, dsz) = s0, ds
+    pjx = np.zeros((5, 5, 5)); pjy = np.zeros((5, 5, 5)); pjz = np.zeros((5, 5, 5))      # index = offset + 2
+    for kp in range(5):
+        for jp in range(5):
+            dstmp = ((s0y[jp] + 5e-1 * dsy[jp]) * s0z[kp] + (5e-1 * s0y[jp] + fac * dsy[jp]) * dsz[kp]) * qdxdt
+            pjtmp = 0.0
+            for r in range(4):
+                pjtmp = pjtmp - dsx[r] * dstmp
+                pjx[r + 1, jp, kp] += pjtmp
+            dstmp = ((s0x[jp] + 5e-1 * dsx[jp]) * s0z[kp] + (5e-1 * s0x[jp] + fac * dsx[jp]) * dsz[kp]) * qdxdt
+            pjtmp = 0.0
+            for r in range(4):
+                pjtmp = pjtmp - dsy[r] * dstmp
+                pjy[r + 1, jp, kp] += pjtmp
+            dstmp = ((s0x[jp] + 5e-1 * dsx[jp]) * s0y[kp] + (5e-1 * s0x[jp] + fac * dsx[jp]) * dsy[kp]) * qdxdt
+            pjtmp = 0.0
+            for r in range(4):
+                pjtmp = pjtmp - dsz[r] * dstmp
+                pjz[r + 1, jp, kp] += pjtmp
+    out = np.zeros((5, 5, 5, 3))                  # [kp, jp, ip, comp]
+    for kp in range(5):
+        for jp in range(5):
+            for ip in range(5):
+                out[kp, jp, ip] = (pjx[ip, jp, kp], pjy[jp, ip, kp], pjz[kp, ip, jp])
+    return out
+
+
+def test_deposit_matches_an_independent_numpy_restatement():
+    rng = np.random.default_rng(5)
+    q, r, _ = weibel_constants(1)
+    for trial in range(12):
+        w = World3(8, 8, 8, 8 * 3, q=q, r=r)
+        up, gp, np2, cc = w.arr("up"), w.arr("gp"), w.arr("np2"), w.arr("cumcnt")
+        np2[...] = 0
+        cc[...] = 0
+        isp = trial % 2
+        np2[isp, 3, 3] = 1
+        cc[isp, 3, 3, 4:] = 1                        # the particle belongs to x-cell 5, pencil (j, k) = (5, 5)
+        x0 = np.array([5.0, 5.0, 5.0]) + rng.random(3)
+        x1 = x0 + rng.uniform(-0.95, 0.95, 3)
+        up[isp, 3, 3, 0, :3] = x0
+        gp[isp, 3, 3, 0, :3] = x1
+        w.field_fdtd_i(1)                            # ele_cur only
+        uj = w.arr("uj")                             # (k, j, i, 3) on the box, index = global index
+        mine = numpy_deposit_one(x0, x1, (5, 5, 5), q[isp] * w.delx / w.delt)
+        got = uj[3:8, 3:8, 3:8]
+        assert np.abs(got - mine).max() <= 4e-16 * max(np.abs(mine).max(), 1e-300), trial
+        outside = uj.copy()
+        outside[3:8, 3:8, 3:8] = 0
+        assert not outside.any()
+        w.close()
+
+
+def test_field_solve_matches_numpy_fft_restatement():
+    """field__fdtd_i on a periodic box, 3d/common/field.f90:126-191 + cgm :409-560, restated with numpy rolls (periodic ghost cells
+    are periodic images) and -- instead of conjugate gradients -- an exact FFT inversion of the same constant-coefficient operator
+    (f4 - sum of the six neighbour shifts) phi = f5 gkl.  Checks the right-hand side, the operator and its coefficients f1..f5
+    (field.f90:57-63), the CG result to its own tolerance (1e-6 of |b|), and the explicit dE update."""
+    w = make_world3(12, 8, 6, 4, steps=3)
+    c, delt, delx, gfac = w.c, w.delt, w.delx, w.gfac
+    f1 = c * delt / delx
+    f2 = gfac * f1 * f1
+    f3 = 4.0 * np.pi * delx / c
+    f5 = (delx / (c * delt * gfac)) ** 2
+    f4 = 6.0 + f5
+    w.particle_solv()
+    w.field_fdtd_i(1)
+    w.field_fdtd_i(2)                                  # ele_cur + bc__curre
+    inner = (slice(2, -2),) * 3
+    uf = w.arr("uf")[inner].copy()                     # (k, j, i, 6) interior, before the update
+    uj = w.arr("uj")[inner].copy()
+    sh = lambda a, dk, dj, di: np.roll(a, (-dk, -dj, -di), axis=(0, 1, 2))      # a(i+di, j+dj, k+dk)  # noqa: E731
+    lap = lambda a: (sh(a, -1, 0, 0) + sh(a, 0, -1, 0) + sh(a, 0, 0, -1) - 6e0 * a + sh(a, 0, 0, 1) + sh(a, 0, 1, 0) + sh(a, 1, 0, 0))  # noqa: E731
+    B = [uf[..., n] for n in range(3)]; E = [uf[..., 3 + n] for n in range(3)]; J = [uj[..., n] for n in range(3)]
+    gkl = [
+        f2 * (lap(B[0]) + f3 * (-sh(J[2], 0, -1, 0) + J[2] + sh(J[1], -1, 0, 0) - J[1])) - f1 * (-sh(E[2], 0, -1, 0) + E[2] + sh(E[1], -1, 0, 0) - E[1]),
+        f2 * (lap(B[1]) + f3 * (-sh(J[0], -1, 0, 0) + J[0] + sh(J[2], 0, 0, -1) - J[2])) - f1 * (-sh(E[0], -1, 0, 0) + E[0] + sh(E[2], 0, 0, -1) - E[2]),
+        f2 * (lap(B[2]) + f3 * (-sh(J[1], 0, 0, -1) + J[1] + sh(J[0], 0, -1, 0) - J[0])) - f1 * (-sh(E[1], 0, 0, -1) + E[1] + sh(E[0], 0, -1, 0) - E[0]),
+    ]
+    w.field_fdtd_i(3)
+    got = w.arr("gkl")
+    for n in range(3):
+        assert np.abs(got[..., n] - gkl[n]).max() <= 1e-13 * np.abs(gkl[n]).max(), n
+    # exact solution of (f4 - shifts) phi = f5 gkl by FFT
+    nz, ny, nx = gkl[0].shape
+    kz, ky, kx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    symbol = f4 - 2 * np.cos(2 * np.pi * kx / nx) - 2 * np.cos(2 * np.pi * ky / ny) - 2 * np.cos(2 * np.pi * kz / nz)
+    w.field_fdtd_i(4)
+    w.field_fdtd_i(5)
+    df = w.arr("df")[inner]
+    dB = []
+    for n in range(3):
+        b = f5 * gkl[n]
+        exact = np.real(np.fft.ifftn(np.fft.fftn(b) / symbol))
+        # the CG stops at |r| <= 1e-6 |b| (field.f90:461-462, 481, 520); the error is bounded by |r| / lambda_min = |r| / f5
+        assert np.linalg.norm(df[..., n] - exact) <= 1e-6 * np.linalg.norm(b) / f5 * 1.5, n
+        assert np.linalg.norm(df[..., n] - exact) > 0       # it IS an iterative result, not the same computation
+        dB.append(df[..., n].copy())
+    w.field_fdtd_i(6)
+    w.field_fdtd_i(7)
+    df = w.arr("df")[inner]
+    dE = [
+        f1 * (gfac * (-dB[2] + sh(dB[2], 0, 1, 0) + dB[1] - sh(dB[1], 1, 0, 0)) + (-B[2] + sh(B[2], 0, 1, 0) + B[1] - sh(B[1], 1, 0, 0))) - 4e0 * np.pi * delt * J[0],
+        f1 * (gfac * (-dB[0] + sh(dB[0], 1, 0, 0) + dB[2] - sh(dB[2], 0, 0, 1)) + (-B[0] + sh(B[0], 1, 0, 0) + B[2] - sh(B[2], 0, 0, 1))) - 4e0 * np.pi * delt * J[1],
+        f1 * (gfac * (-dB[1] + sh(dB[1], 0, 0, 1) + dB[0] - sh(dB[0], 0, 1, 0)) + (-B[1] + sh(B[1], 0, 0, 1) + B[0] - sh(B[0], 0, 1, 0))) - 4e0 * np.pi * delt * J[2],
+    ]
+    for n in range(3):
+        assert np.abs(df[..., 3 + n] - dE[n]).max() <= 1e-13 * max(np.abs(dE[n]).max(), 1e-300), n
+    w.field_fdtd_i(8)
+    new = w.arr("uf")[inner]
+    assert np.abs(new[..., :3] - (uf[..., :3] + np.stack(dB, axis=-1))).max() <= 1e-15
+    w.close()
