@@ -257,3 +257,63 @@ def test_field_solve_matches_numpy_fft_restatement():
     new = w.arr("uf")[inner]
     assert np.abs(new[..., :3] - (uf[..., :3] + np.stack(dB, axis=-1))).max() <= 1e-15
     w.close()
+
+
+def numpy_deposit_one_2d(x0, x1, u1, cell, q, delx, delt, c):
+    """pjx, pjy, pjz(-2:2,-2:2) of ONE particle of the 2-D code, 2d/common/field.f90:225-298 (Jz from the pushed momentum)"""
+    fac = 1.0 / 3.0
+    s0 = np.zeros((5, 2)); ds = np.zeros((5, 2))
+    for a in range(2):
+        dh = x0[a] / delx - 0.5 - cell[a]
+        s0[1, a], s0[2, a], s0[3, a] = _shape(dh)
+        i2 = int(x1[a] / delx)
+        dh = x1[a] / delx - 0.5 - i2
+        inc = i2 - cell[a]
+        s1_1, s1_2, s1_3 = _shape(dh)
+        smo_1 = -(inc - abs(inc)) * 0.5 + 0
+        smo_2 = -abs(inc) + 1
+        smo_3 = (inc + abs(inc)) * 0.5 + 0
+        ds[:, a] = [s1_1 * smo_1, s1_1 * smo_2 + s1_2 * smo_1, s1_2 * smo_2 + s1_3 * smo_1 + s1_1 * smo_3,
+                    s1_3 * smo_2 + s1_2 * smo_3, s1_3 * smo_3]
+    ds = ds - s0
+    gvz = u1[2] / np.sqrt(1. + (+u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]) / (c * c))
+    pjx = np.zeros((5, 5)); pjy = np.zeros((5, 5)); pjz = np.zeros((5, 5))      # [ip+2, jp+2]
+    for jp in range(5):
+        for ip in range(4):
+            pjx[ip + 1, jp] = pjx[ip, jp] - q * delx / delt * ds[ip, 0] * (s0[jp, 1] + 0.5 * ds[jp, 1])
+    for jp in range(4):
+        for ip in range(5):
+            pjy[ip, jp + 1] = pjy[ip, jp] - q * delx / delt * ds[jp, 1] * (s0[ip, 0] + 0.5 * ds[ip, 0])
+    for jp in range(5):
+        for ip in range(5):
+            pjz[ip, jp] = q * gvz * (+s0[ip, 0] * s0[jp, 1] + 0.5 * ds[ip, 0] * s0[jp, 1] + 0.5 * s0[ip, 0] * ds[jp, 1] + fac * ds[ip, 0] * ds[jp, 1])
+    return np.stack([pjx.T, pjy.T, pjz.T], axis=-1)      # [jp, ip, comp]
+
+
+def test_2d_deposit_matches_an_independent_numpy_restatement():
+    from oracle.pyoracle import World2
+    rng = np.random.default_rng(9)
+    q, r, _ = weibel_constants(1)
+    for trial in range(12):
+        w = World2(8, 8, 8 * 3, q=q, r=r)
+        up, gp, np2, cc = w.arr("up"), w.arr("gp"), w.arr("np2"), w.arr("cumcnt")
+        np2[...] = 0
+        cc[...] = 0
+        isp = trial % 2
+        np2[isp, 3] = 1
+        cc[isp, 3, 4:] = 1                           # x-cell 5 of row j = 5
+        x0 = np.array([5.0, 5.0]) + rng.random(2)
+        x1 = x0 + rng.uniform(-0.95, 0.95, 2)
+        u1 = rng.standard_normal(3)
+        up[isp, 3, 0, :2] = x0
+        gp[isp, 3, 0, :2] = x1
+        gp[isp, 3, 0, 2:5] = u1
+        w.field_fdtd_i(1)
+        uj = w.arr("uj")                             # (j, i, 3)
+        mine = numpy_deposit_one_2d(x0, x1, u1, (5, 5), q[isp], w.delx, w.delt, w.c)
+        got = uj[3:8, 3:8]
+        assert np.abs(got - mine).max() <= 4e-16 * max(np.abs(mine).max(), 1e-300), trial
+        outside = uj.copy()
+        outside[3:8, 3:8] = 0
+        assert not outside.any()
+        w.close()
