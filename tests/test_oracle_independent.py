@@ -317,3 +317,52 @@ def test_2d_deposit_matches_an_independent_numpy_restatement():
         outside[3:8, 3:8] = 0
         assert not outside.any()
         w.close()
+
+
+def test_migration_and_sort_match_a_numpy_key_computation():
+    """boundary_periodic__particle_x (3d/common/boundary_periodic.f90:86-92), __particle_yz (:153-171: wrap + destination pencil from
+    the PRE-wrap integer cell) and sort__bucket (3d/common/sort.f90:60-86: key int(x)) restated as one numpy key computation on the
+    pushed set: every particle's (species, k, j, i) destination, its wrapped coordinates and the resulting np2 / cumcnt must equal
+    what the oracle's three procedures produce (records compared as ID-keyed sets: the order inside a cell is not defined)."""
+    w = make_world3(10, 6, 5, 5, steps=2)
+    nx, ny, nz = w.nx, w.ny, w.nz
+    w.particle_solv()
+    w.field_fdtd_i()
+    np2_0 = w.arr("np2").copy()
+    m = active_mask(np2_0, w.np)
+    isp = np.nonzero(m)[0]
+    g = w.arr("gp")[m].copy()
+    w.bc_particle_x(); w.bc_particle_yz(); w.sort_bucket()
+    assert w.error() == 0
+    # --- numpy restatement ---
+    x, y, z = g[:, 0].copy(), g[:, 1].copy(), g[:, 2].copy()
+    ipos = np.trunc(x / w.delx).astype(int)
+    x = np.where(ipos < 2, x + nx * w.delx, np.where(ipos >= nx + 2, x - nx * w.delx, x))
+    jpos = np.trunc(y / w.delx).astype(int); kpos = np.trunc(z / w.delx).astype(int)
+    y = np.where(jpos <= 1, y + ny * w.delx, np.where(jpos >= ny + 2, y - ny * w.delx, y))
+    z = np.where(kpos <= 1, z + nz * w.delx, np.where(kpos >= nz + 2, z - nz * w.delx, z))
+    jd = np.where(jpos <= 1, jpos + ny, np.where(jpos >= ny + 2, jpos - ny, jpos))     # the pencil that receives it (periodic neighbour)
+    kd = np.where(kpos <= 1, kpos + nz, np.where(kpos >= nz + 2, kpos - nz, kpos))
+    icell = np.trunc(x).astype(int)                                                    # sort.f90:65,77: int(x), no d_delx
+    ids = g[:, 6].view(np.int64)
+    expect = {}
+    for n in range(len(ids)):
+        expect[(int(isp[n]), int(ids[n]))] = (int(kd[n]), int(jd[n]), int(icell[n]), x[n], y[n], z[n], g[n, 3], g[n, 4], g[n, 5])
+    up, np2, cc = w.arr("up"), w.arr("np2"), w.arr("cumcnt")
+    assert int(np2.sum()) == len(ids)
+    seen = 0
+    for s in range(2):
+        for k in range(nz):
+            for j in range(ny):
+                n = np2[s, k, j]
+                rec = up[s, k, j, :n]
+                cell = np.searchsorted(cc[s, k, j], np.arange(n), side="right") - 1 + 2
+                for t in range(n):
+                    e = expect[(s, int(rec[t, 6].view(np.int64)))]
+                    assert e[:3] == (k + 2, j + 2, int(cell[t]))
+                    assert np.array_equal(rec[t, :6], np.array(e[3:]))      # wrapped coordinates bit-exact
+                    seen += 1
+                counts = np.bincount(cell - 2, minlength=nx)
+                assert np.array_equal(np.diff(cc[s, k, j]), counts[:nx])
+    assert seen == len(ids)
+    w.close()
