@@ -366,3 +366,82 @@ def test_migration_and_sort_match_a_numpy_key_computation():
                 assert np.array_equal(np.diff(cc[s, k, j]), counts[:nx])
     assert seen == len(ids)
     w.close()
+
+
+@pytest.mark.parametrize("vay", [False, True], ids=["buneman-boris", "vay"])
+def test_2d_push_matches_an_independent_numpy_restatement(vay):
+    """2d/common/particle.f90:70-82 (staging: Ez is NOT averaged in the 2-D code), :97-133 (9-point gather), :135-171 (update)"""
+    from tests.util import make_world2
+    w = make_world2(14, 9, 5, steps=2)
+    rng = np.random.default_rng(13)
+    uf = w.arr("uf")                              # (j, i, 6) on the box
+    uf[...] = 5.0 * rng.standard_normal(uf.shape)
+    (w.particle_solv_vay if vay else w.particle_solv)()
+    f = uf
+    tm = np.zeros_like(uf)
+    tm[:-1, :, 0] = 0.5 * (+f[:-1, :, 0] + f[1:, :, 0])
+    tm[:, :-1, 1] = 0.5 * (+f[:, :-1, 1] + f[:, 1:, 1])
+    tm[:-1, :-1, 2] = 0.25 * (+f[:-1, :-1, 2] + f[:-1, 1:, 2] + f[1:, :-1, 2] + f[1:, 1:, 2])
+    tm[:, :-1, 3] = 0.5 * (+f[:, :-1, 3] + f[:, 1:, 3])
+    tm[:-1, :, 4] = 0.5 * (+f[:-1, :, 4] + f[1:, :, 4])
+    tm[:, :, 5] = f[:, :, 5]
+    np2, cc, up = w.arr("np2"), w.arr("cumcnt"), w.arr("up")
+    m = active_mask(np2, w.np)
+    ii = np.broadcast_to(np.arange(w.np), m.shape)
+    ci = ((ii[..., None] >= cc[..., None, :]).sum(axis=-1) - 1 + 2)[m]
+    isp, jj, _ = np.nonzero(m)
+    p = up[m]
+    i, j = ci, jj + 2
+    c, delt, d_delx = w.c, w.delt, 1.0 / w.delx
+    q, r = w.q[isp], w.r[isp]
+    fac1 = q / r * 0.5 * delt; txxx = fac1 * fac1; fac2 = q * delt / r
+    shx = _shape(p[:, 0] * d_delx - 0.5 - i)
+    shy = _shape(p[:, 1] * d_delx - 0.5 - j)
+    fl = []
+    for comp in range(6):
+        tot = None
+        for dj in (-1, 0, 1):
+            row = (+tm[j + dj, i - 1, comp] * shx[0] + tm[j + dj, i, comp] * shx[1] + tm[j + dj, i + 1, comp] * shx[2]) * shy[dj + 1]
+            tot = row if tot is None else tot + row
+        fl.append(tot)
+    bpx, bpy, bpz, epx, epy, epz = fl
+    g = np.empty_like(p)
+    if not vay:
+        uvm1 = p[:, 2] + fac1 * epx; uvm2 = p[:, 3] + fac1 * epy; uvm3 = p[:, 4] + fac1 * epz
+        gam = np.sqrt(c * c + uvm1 * uvm1 + uvm2 * uvm2 + uvm3 * uvm3)
+        igam = 1. / gam
+        fac1r = fac1 * igam
+        fac2r = fac2 / (gam + txxx * (bpx * bpx + bpy * bpy + bpz * bpz) * igam)
+        uvm4 = uvm1 + fac1r * (+uvm2 * bpz - uvm3 * bpy)
+        uvm5 = uvm2 + fac1r * (+uvm3 * bpx - uvm1 * bpz)
+        uvm6 = uvm3 + fac1r * (+uvm1 * bpy - uvm2 * bpx)
+        uvm1 = uvm1 + fac2r * (+uvm5 * bpz - uvm6 * bpy)
+        uvm2 = uvm2 + fac2r * (+uvm6 * bpx - uvm4 * bpz)
+        uvm3 = uvm3 + fac2r * (+uvm4 * bpy - uvm5 * bpx)
+        g[:, 2] = uvm1 + fac1 * epx; g[:, 3] = uvm2 + fac1 * epy; g[:, 4] = uvm3 + fac1 * epz
+        gam = 1. / np.sqrt(1.0 + (+g[:, 2] * g[:, 2] + g[:, 3] * g[:, 3] + g[:, 4] * g[:, 4]) / (c * c))
+    else:
+        uvm1, uvm2, uvm3 = p[:, 2], p[:, 3], p[:, 4]
+        gam = np.sqrt(c * c + uvm1 * uvm1 + uvm2 * uvm2 + uvm3 * uvm3)
+        fac1r = fac1 / gam
+        uvm4 = uvm1 + fac2 * epx + fac1r * (+uvm2 * bpz - uvm3 * bpy)
+        uvm5 = uvm2 + fac2 * epy + fac1r * (+uvm3 * bpx - uvm1 * bpz)
+        uvm6 = uvm3 + fac2 * epz + fac1r * (+uvm1 * bpy - uvm2 * bpx)
+        taux, tauy, tauz = fac1 * bpx / c, fac1 * bpy / c, fac1 * bpz / c
+        tau2 = taux * taux + tauy * tauy + tauz * tauz
+        ua = (uvm4 * taux + uvm5 * tauy + uvm6 * tauz) / c
+        sigma = 1.0 + (uvm4 * uvm4 + uvm5 * uvm5 + uvm6 * uvm6) / (c * c) - tau2
+        gam2 = 0.5 * (sigma + np.sqrt(sigma * sigma + 4.0 * (tau2 + ua * ua)))
+        gam = np.sqrt(gam2)
+        s_ = 1.0 / (tau2 + gam2)
+        g[:, 2] = s_ * (gam2 * uvm4 + c * ua * taux + gam * (uvm5 * tauz - uvm6 * tauy))
+        g[:, 3] = s_ * (gam2 * uvm5 + c * ua * tauy + gam * (uvm6 * taux - uvm4 * tauz))
+        g[:, 4] = s_ * (gam2 * uvm6 + c * ua * tauz + gam * (uvm4 * tauy - uvm5 * taux))
+        gam = 1.0 / gam
+    g[:, 0] = p[:, 0] + g[:, 2] * delt * gam
+    g[:, 1] = p[:, 1] + g[:, 3] * delt * gam
+    ref = w.arr("gp")[m]
+    scale = np.abs(ref[:, :5]).max(axis=0)
+    assert (np.abs(ref[:, :5] - g[:, :5]).max(axis=0) / scale).max() < 5e-15
+    assert np.array_equal(ref[:, 5].view(np.int64), p[:, 5].view(np.int64))
+    w.close()
