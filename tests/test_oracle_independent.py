@@ -445,3 +445,72 @@ def test_2d_push_matches_an_independent_numpy_restatement(vay):
     assert (np.abs(ref[:, :5] - g[:, :5]).max(axis=0) / scale).max() < 5e-15
     assert np.array_equal(ref[:, 5].view(np.int64), p[:, 5].view(np.int64))
     w.close()
+
+
+@pytest.mark.parametrize("bc", [1, 2], ids=["reconnection", "shock"])
+def test_wall_cg_matches_a_dense_numpy_solve(bc):
+    """cgm of the 2-D wall set-ups (2d/common/field.f90:319-461 with boundary_reconnection__phi, 2d/proj/reconnection/
+    boundary_reconnection.f90:557-577, or boundary_shock__phi, 2d/proj/shock/boundary_shock.f90:603-623) against a dense numpy solve
+    of the same operator: (f4 - neighbours) phi = f5 gkl on cells nxs..nxe, periodic in y, with the wall rule of component l folded
+    into the matrix (l = 1: phi(nxs-1) = -phi(nxs), phi(nxe+1) = -phi(nxe-2) [reconnection] / 0 [shock]; l = 2, 3:
+    phi(nxs-1) = phi(nxs+1), phi(nxe+1) = phi(nxe-1) / 0), then the wall ghost fill of boundary_*__dfield (:350-359 / :396-405)."""
+    from tests.util import make_world2
+    order = bc
+    w = make_world2(14, 8, 6, steps=3, bc=bc, order=order, u0=0.3 if bc == 2 else 0.0)
+    nx, ny = w.nx, w.ny
+    nxs, nxe = 2, nx + 1
+    f5 = (w.delx / (w.c * w.delt * w.gfac)) ** 2
+    f4 = 4.0 + f5
+    w.particle_solv()
+    if bc == 1:
+        w.bc_particle_x()
+    else:
+        w.bc_injection(0.3)
+    for st in (1, 2, 3):
+        w.field_fdtd_i(st)
+    gkl = w.arr("gkl").copy()                      # (j, i, 3) interior
+    w.field_fdtd_i(4)
+    df = w.arr("df").copy()                        # (j, i, 6) on the box
+    nxr = nxe - nxs + 1
+    idx = lambda i, j: (j % ny) * nxr + (i - nxs)  # noqa: E731
+    for l in (1, 2, 3):
+        A = np.zeros((nxr * ny, nxr * ny))
+        for j in range(ny):
+            for i in range(nxs, nxe + 1):
+                row = idx(i, j)
+                A[row, idx(i, j)] += f4
+                A[row, idx(i, j - 1)] -= 1.0
+                A[row, idx(i, j + 1)] -= 1.0
+                # x neighbours with the wall rules
+                if i > nxs:
+                    A[row, idx(i - 1, j)] -= 1.0
+                elif l == 1:
+                    A[row, idx(nxs, j)] -= -1.0
+                else:
+                    A[row, idx(nxs + 1, j)] -= 1.0
+                if i < nxe:
+                    A[row, idx(i + 1, j)] -= 1.0
+                elif bc == 1:
+                    if l == 1:
+                        A[row, idx(nxe - 2, j)] -= -1.0
+                    else:
+                        A[row, idx(nxe - 1, j)] -= 1.0
+                # shock: phi(nxe+1) = 0 -> nothing
+        b = (f5 * gkl[:, :, l - 1]).reshape(-1)
+        exact = np.linalg.solve(A, b).reshape(ny, nxr)
+        got = df[2:-2, 2:-2, l - 1]
+        lam_min = np.linalg.eigvalsh(0.5 * (A + A.T)).min()
+        assert np.linalg.norm(got - exact) <= 1.5e-6 * np.linalg.norm(b) / lam_min, (bc, l)
+    w.field_fdtd_i(5)
+    d5 = w.arr("df")
+    X = lambda i: i                                 # box x index = global index (two ghosts, nxgs = 2)  # noqa: E731
+    assert np.array_equal(d5[:, X(nxs - 1), 0], -d5[:, X(nxs), 0])
+    assert np.array_equal(d5[:, X(nxs - 1), 1:4], d5[:, X(nxs + 1), 1:4])
+    assert np.array_equal(d5[:, X(nxs - 1), 4:6], -d5[:, X(nxs), 4:6])
+    if bc == 1:
+        assert np.array_equal(d5[:, X(nxe), 0], -d5[:, X(nxe - 1), 0])
+        assert np.array_equal(d5[:, X(nxe + 1), 1:4], d5[:, X(nxe - 1), 1:4])
+        assert np.array_equal(d5[:, X(nxe), 4:6], -d5[:, X(nxe - 1), 4:6])
+    else:
+        assert not d5[:, X(nxe + 1), :].any()
+    w.close()
