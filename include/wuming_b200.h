@@ -164,6 +164,13 @@ int wm_shock_inject(wm_ctx* ctx, const wm_shock_params* prm, int nxe, const int*
  * (app.f90:637-676), cumcnt(nxe_new) = cumcnt(nxe_new - 1) + n0; id_first[isp*nrows + row] = global_row * n0 + nptotal(isp) */
 int wm_shock_relocate(wm_ctx* ctx, const wm_shock_params* prm, int nxe_new, const long long* id_first, long long epoch);
 
+/* -- particle output on the device -------------------------------------------- */
+/* get_particle_count of paraio (3d/common/paraio.f90:1007-1085; the packing behind io__ptcl / io__orb, :843-866): mode 0 packs
+ * every active particle, mode 1 the tracers (64-bit ID > 0), species-major in (k, j, cell) order, as consecutive ndim-double
+ * records into the HOST buffer buf (capacity cap_records records); lcount[isp] = records of species isp (the routine's lcount).
+ * buf may be NULL to obtain the counts only.  Only the packed records cross PCIe. */
+int wm_pack_particles(wm_ctx* ctx, int mode, double* buf, long long cap_records, long long* lcount);
+
 /* -- synthetic load and diagnostics on the device ----------------------------------------------- */
 /* Weibel load of 3d/proj/weibel/app.f90:311-338,391-504 (2d/proj/weibel/app.f90:404-432) generated on
  * the device with the Philox stream the oracle uses (positions bit-identical, Maxwellian to libm ulp). */

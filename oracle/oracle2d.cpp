@@ -1100,6 +1100,27 @@ void orc2_cg_iterations(void* h, int* out) { for (int l = 0; l < 3; ++l) out[l] 
 
 void orc2_particle_solv(void* h) { World2& w = *(World2*)h; for (Rank2& R : w.ranks) particle_solv(w, R, R.gp, R.up); }
 void orc2_particle_solv_vay(void* h) { World2& w = *(World2*)h; for (Rank2& R : w.ranks) particle_solv(w, R, R.gp, R.up, false, true); }
+// get_particle_count -- 2d/common/paraio.f90 (the routine of 3d/common/paraio.f90:1007-1085 without k)
+long long orc2_pack_particles(void* h, int rank, int mode, double* buf, long long* lcount) {
+  World2& w = *(World2*)h;
+  Rank2& R = w.ranks[rank];
+  long long ip = 0;
+  for (int isp = 1; isp <= w.nsp; ++isp) {
+    lcount[isp - 1] = 0;
+    for (int j = R.nys; j <= R.nye; ++j)
+      for (int i = 1; i <= R.np2[R.in2(j, isp)]; ++i) {
+        const double* u = &R.up[R.ip(1, i, j, isp)];
+        int64_t pid;
+        std::memcpy(&pid, &u[w.ndim - 1], 8);
+        if (mode == 0 || pid > 0) {
+          lcount[isp - 1] += 1;
+          if (buf) for (int jp = 0; jp < w.ndim; ++jp) buf[ip * w.ndim + jp] = u[jp];
+          ip += 1;
+        }
+      }
+  }
+  return ip;
+}
 void orc2_set_pusher(void* h, int kind) { ((World2*)h)->pusher = kind; }
 void orc2_shock_inject(void* h, const orc::ShockPrm* sp, const int* nlinj_rows, unsigned epoch) { shock_inject(*(World2*)h, *sp, nlinj_rows, epoch); }
 void orc2_shock_relocate(void* h, const orc::ShockPrm* sp, unsigned epoch) { shock_relocate(*(World2*)h, *sp, epoch); }

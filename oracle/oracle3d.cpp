@@ -1417,6 +1417,29 @@ void orc3_cg_iterations(void* h, int* out) { for (int l = 0; l < 3; ++l) out[l] 
 
 void orc3_particle_solv(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) particle_solv(w, R, R.gp, R.up); }
 void orc3_particle_solv_vay(void* h) { World3& w = *(World3*)h; for (Rank3& R : w.ranks) particle_solv(w, R, R.gp, R.up, false, true); }
+// get_particle_count -- 3d/common/paraio.f90:1007-1085: pack every active particle (mode 0) or the tracers with a positive ID
+// (mode 1) of one rank in (isp, k, j, i) order; returns the number of packed records, lcount[isp] as in the reference
+long long orc3_pack_particles(void* h, int rank, int mode, double* buf, long long* lcount) {
+  World3& w = *(World3*)h;
+  Rank3& R = w.ranks[rank];
+  long long ip = 0;
+  for (int isp = 1; isp <= w.nsp; ++isp) {
+    lcount[isp - 1] = 0;
+    for (int k = R.nzs; k <= R.nze; ++k)
+      for (int j = R.nys; j <= R.nye; ++j)
+        for (int i = 1; i <= R.np2[R.in2(j, k, isp)]; ++i) {
+          const double* u = &R.up[R.ip(1, i, j, k, isp)];
+          int64_t pid;
+          std::memcpy(&pid, &u[w.ndim - 1], 8);
+          if (mode == 0 || pid > 0) {
+            lcount[isp - 1] += 1;
+            if (buf) for (int jp = 0; jp < w.ndim; ++jp) buf[ip * w.ndim + jp] = u[jp];
+            ip += 1;
+          }
+        }
+  }
+  return ip;
+}
 void orc3_set_pusher(void* h, int kind) { ((World3*)h)->pusher = kind; }
 void orc3_shock_inject(void* h, const orc::ShockPrm* sp, const int* nlinj_rows, unsigned epoch) { shock_inject(*(World3*)h, *sp, nlinj_rows, epoch); }
 void orc3_shock_relocate(void* h, const orc::ShockPrm* sp, unsigned epoch) { shock_relocate(*(World3*)h, *sp, epoch); }

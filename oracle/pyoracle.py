@@ -54,6 +54,8 @@ def lib(fast=False):
         L.orc3_field_fdtd_i.argtypes = [C.c_void_p, C.c_int]
         L.orc3_mom_calc.argtypes = [C.c_void_p]
         for d in (2, 3):
+            getattr(L, f"orc{d}_pack_particles").argtypes = [C.c_void_p, C.c_int, C.c_int, dp, C.POINTER(C.c_longlong)]
+            getattr(L, f"orc{d}_pack_particles").restype = C.c_longlong
             getattr(L, f"orc{d}_shock_inject").argtypes = [C.c_void_p, C.POINTER(ShockPrm), ip, C.c_uint]
             getattr(L, f"orc{d}_shock_relocate").argtypes = [C.c_void_p, C.POINTER(ShockPrm), C.c_uint]
             getattr(L, f"orc{d}_nxe").argtypes = [C.c_void_p]
@@ -182,6 +184,14 @@ class World3:
 
     def shock_relocate(self, prm, epoch):
         self.L.orc3_shock_relocate(self.h, C.byref(prm), epoch)
+
+    def pack_particles(self, mode, rank=0):
+        """get_particle_count of paraio (3d/common/paraio.f90:1007-1085): (records[n, ndim], lcount[nsp])"""
+        lc = (C.c_longlong * 2)()
+        n = self.L.orc3_pack_particles(self.h, rank, mode, None, lc)
+        buf = np.zeros((max(n, 1), self.ndim))
+        self.L.orc3_pack_particles(self.h, rank, mode, buf.ctypes.data_as(C.POINTER(C.c_double)), lc)
+        return buf[:n], np.array([lc[0], lc[1]], dtype=np.int64)
 
     @property
     def nxe_now(self):
@@ -317,6 +327,14 @@ class World2:
 
     def shock_relocate(self, prm, epoch):
         self.L.orc2_shock_relocate(self.h, C.byref(prm), epoch)
+
+    def pack_particles(self, mode, rank=0):
+        """get_particle_count of paraio (3d/common/paraio.f90:1007-1085): (records[n, ndim], lcount[nsp])"""
+        lc = (C.c_longlong * 2)()
+        n = self.L.orc2_pack_particles(self.h, rank, mode, None, lc)
+        buf = np.zeros((max(n, 1), self.ndim))
+        self.L.orc2_pack_particles(self.h, rank, mode, buf.ctypes.data_as(C.POINTER(C.c_double)), lc)
+        return buf[:n], np.array([lc[0], lc[1]], dtype=np.int64)
 
     @property
     def nxe_now(self):

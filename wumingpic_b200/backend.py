@@ -54,7 +54,7 @@ ABI_SYMBOLS = [
     "wm_bc_particle_x", "wm_bc_injection", "wm_bc_particle_yz", "wm_sort_bucket", "wm_step", "wm_set_fused",
     "wm_h_particle_solv", "wm_h_field_fdtd_i", "wm_h_step", "wm_load_weibel", "wm_energy", "wm_gauss",
     "wm_get_stats", "wm_sync", "wm_set_timing", "wm_launch_count", "wm_stream", "wm_mom_calc",
-    "wm_particle_solv_vay", "wm_h_particle_solv_vay", "wm_set_pusher", "wm_shock_inject", "wm_shock_relocate", "wm_settle",
+    "wm_particle_solv_vay", "wm_h_particle_solv_vay", "wm_set_pusher", "wm_shock_inject", "wm_shock_relocate", "wm_settle", "wm_pack_particles",
 ]
 
 
@@ -98,6 +98,7 @@ def load_library():
         L.wm_set_fused.argtypes = [vp, C.c_int]
         L.wm_set_pusher.argtypes = [vp, C.c_int]
         L.wm_settle.argtypes = [vp]
+        L.wm_pack_particles.argtypes = [vp, C.c_int, dp, C.c_longlong, C.POINTER(C.c_longlong)]
         lp = C.POINTER(C.c_longlong)
         L.wm_shock_inject.argtypes = [vp, C.POINTER(ShockParams), C.c_int, ip, lp, C.c_longlong]
         L.wm_shock_relocate.argtypes = [vp, C.POINTER(ShockParams), C.c_int, lp, C.c_longlong]
@@ -328,6 +329,17 @@ class Backend:
         id_first = np.ascontiguousarray(id_first, dtype=np.int64).ravel()
         assert id_first.size == self.nsp * self.nyl * self.nzl
         self._ck(self.L.wm_shock_relocate(self.h, C.byref(prm), nxe_new, id_first.ctypes.data_as(C.POINTER(C.c_longlong)), epoch))
+
+    def pack_particles(self, mode):
+        """paraio's get_particle_count (3d/common/paraio.f90:1007-1085): mode 0 all active particles, mode 1 tracers (ID > 0);
+        returns (records[n, ndim], lcount[nsp]) packed species-major in pencil order"""
+        lc = (C.c_longlong * 2)()
+        self._ck(self.L.wm_pack_particles(self.h, mode, None, 0, lc))
+        n = int(lc[0] + lc[1])
+        buf = np.zeros((max(n, 1), self.ndim))
+        if n:
+            self._ck(self.L.wm_pack_particles(self.h, mode, _dptr(buf), n, lc))
+        return buf[:n], np.array([lc[0], lc[1]], dtype=np.int64)
 
     def energy(self):
         out = np.zeros(4)
