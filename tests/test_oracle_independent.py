@@ -514,3 +514,34 @@ def test_wall_cg_matches_a_dense_numpy_solve(bc):
     else:
         assert not d5[:, X(nxe + 1), :].any()
     w.close()
+
+
+def test_moments_match_a_periodic_numpy_cic_sum():
+    """mom_calc__nvt (3d/common/mom_calc.f90:218-332: CIC weights about the cell centres, N, V = u/gamma, T = u^2/gamma) followed by
+    boundary_periodic__mom (3d/common/boundary_periodic.f90:1102-1235: ghost layer folded into the periodic image, x then y then z)
+    equals, on the interior cells, one CIC sum with periodic index arithmetic.  The momenta are the re-centred ones mom_calc__accl
+    leaves in gp (its gather and half-step rotation are the push's, checked above)."""
+    w = make_world3(10, 6, 5, 5, steps=2)
+    nx, ny, nz = w.nx, w.ny, w.nz
+    w.mom_calc()
+    np2 = w.arr("np2")
+    m = active_mask(np2, w.np)
+    isp = np.nonzero(m)[0]
+    g = w.arr("gp")[m]
+    c = w.c
+    ih = np.floor(g[:, 0] / w.delx - 5e-1).astype(int); jh = np.floor(g[:, 1] / w.delx - 5e-1).astype(int)
+    kh = np.floor(g[:, 2] / w.delx - 5e-1).astype(int)
+    dx = g[:, 0] - 5e-1 - ih; dy = g[:, 1] - 5e-1 - jh; dz = g[:, 2] - 5e-1 - kh
+    gam = 1e0 / np.sqrt(1e0 + (g[:, 3] ** 2 + g[:, 4] ** 2 + g[:, 5] ** 2) / (c * c))
+    vals = [np.ones_like(gam), g[:, 3] * gam, g[:, 4] * gam, g[:, 5] * gam, g[:, 3] ** 2 * gam, g[:, 4] ** 2 * gam, g[:, 5] ** 2 * gam]
+    M = np.zeros((2, nz, ny, nx, 7))
+    for ok, wz in ((0, 1 - dz), (1, dz)):
+        for oj, wy in ((0, 1 - dy), (1, dy)):
+            for oi, wx in ((0, 1 - dx), (1, dx)):
+                wgt = wx * wy * wz
+                for l in range(7):
+                    np.add.at(M[..., l], (isp, (kh + ok - 2) % nz, (jh + oj - 2) % ny, (ih + oi - 2) % nx), vals[l] * wgt)
+    ref = w.arr("mom")[:, 1:-1, 1:-1, 1:-1, :]                 # (nsp, nz, ny, nx, 7) interior
+    assert np.abs(ref - M).max() <= 1e-12 * np.abs(M).max()
+    assert abs(M[..., 0].sum() - np2.sum()) < 1e-9              # every particle's weights sum to one
+    w.close()
