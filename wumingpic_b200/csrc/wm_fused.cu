@@ -21,8 +21,12 @@
 //     instructions per particle and strip instead of 31) and the full 4x5 loop only over the crossers.
 //   * the next batch's particle loads are issued before the current batch is processed (register prefetch), so the
 //     global-load latency hides behind ~1.5 k instructions of phase A/B work instead of stalling 4 warps per scheduler.
-//   * a CTA owns 16 consecutive x cells of one (j,k) pencil: their particles are one contiguous run of the
-//     cell-sorted SoA (coalesced 128-byte loads per half-warp) and share an 18x3x3 field tile.
+//   * a CTA owns G = 8 consecutive x cells of one (j,k) pencil (16 lanes per cell): their particles are one contiguous run
+//     of the cell-sorted SoA (coalesced 128-byte loads per half-warp) and share a 10x3x3 field tile, loaded by 9 TMA bulk
+//     row copies, plus a second tile of its x differences (the x sum of the gather is f(i) + sx(+1) d(i) - sx(-1) d(i-1)).
+//   * lazy sort (wm_sort.cu): between two steps the sort's permutation stays pending and this kernel reads its particle
+//     through inv[sorted position] (a two-stage prefetch requests the index one batch before the particle), so the
+//     particle store is read and written once per step.
 //   * the kernel also counts, per source cell, how many particles go to each of the 27 neighbour cells.
 //     |dx| < c dt <= 1 cell, so that count matrix is all the sort needs: destination offsets follow from a
 //     per-cell prefix over the 27 sources and ranks from the (stable) order inside the source cell, which
@@ -34,9 +38,8 @@
 
 namespace {
 
-// G = cells per CTA (template parameter): 16 threads per cell, so a CTA has 16*G threads.  G = 8 gives four
-// 128-thread CTAs per SM in different phases of their batch loop (better overlap of phase-A load latency with
-// phase-B math than two 256-thread CTAs); G = 16 halves the field-tile halo overhead.
+// G = cells per CTA (template parameter): 16 threads per cell, so a CTA has 16*G threads.  G = 8 gives three
+// 128-thread CTAs per SM (168 registers, 57.5 KB of shared memory each) in different phases of their batch loop.
 constexpr int SLOTS = 16;     // particles per cell and batch
 constexpr int NF = 21;        // double2 fields per particle record
 #ifndef WM_CSTR
