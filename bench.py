@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--ny", type=int, default=256)
     ap.add_argument("--nz", type=int, default=64, help="z cells PER GPU")
     ap.add_argument("--ppc", type=int, default=64, help="particles per cell and species")
+    ap.add_argument("--strong-nz", type=int, default=0,
+                    help="strong scaling: TOTAL z cells of a fixed box split over the GPUs (e.g. 128 = the 256x256x128 box of SURVEY.md "
+                         "8d); 0 (default): weak scaling with --nz cells per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -208,6 +211,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     nx, ny, n0 = args.nx, args.ny, args.ppc
+    if args.strong_nz:                                  # strong scaling: the box is fixed, the slabs shrink
+        if args.strong_nz % world:
+            raise SystemExit(f"--strong-nz {args.strong_nz} is not a multiple of {world} GPUs")
+        args.nz = args.strong_nz // world
     nz_glob = args.nz * world                           # weak scaling: z-slabs, per-GPU work fixed
     q, r, _ = wm.weibel_constants(n0)
     np_cap = int(n0 * nx * 1.25)
@@ -349,7 +356,8 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong" if args.strong_nz else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": (f"3-D Weibel {nx}x{ny}x{args.nz} cells/GPU, {n0} ppc x 2 species "
                                         f"({npart_rank} particles/GPU), periodic, cfl=1, gfac=0.501") if args.dim == 3 else
