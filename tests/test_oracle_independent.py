@@ -545,3 +545,57 @@ def test_moments_match_a_periodic_numpy_cic_sum():
     assert np.abs(ref - M).max() <= 1e-12 * np.abs(M).max()
     assert abs(M[..., 0].sum() - np2.sum()) < 1e-9              # every particle's weights sum to one
     w.close()
+
+
+def test_2d_field_solve_matches_numpy_fft_restatement():
+    """2d/common/field.f90:124-174 + cgm :319-461 on a periodic box: right-hand side, exact FFT inversion of (f4 - four shifts) with
+    f4 = 4 + f5, explicit dE -- the 2-D counterpart of test_field_solve_matches_numpy_fft_restatement"""
+    from tests.util import make_world2
+    w = make_world2(16, 10, 5, steps=3)
+    c, delt, delx, gfac = w.c, w.delt, w.delx, w.gfac
+    f1 = c * delt / delx
+    f2 = gfac * f1 * f1
+    f3 = 4.0 * np.pi * delx / c
+    f5 = (delx / (c * delt * gfac)) ** 2
+    f4 = 4.0 + f5
+    w.particle_solv()
+    w.field_fdtd_i(1)
+    w.field_fdtd_i(2)
+    inner = (slice(2, -2),) * 2
+    uf = w.arr("uf")[inner].copy()                 # (j, i, 6)
+    uj = w.arr("uj")[inner].copy()
+    sh = lambda a, dj, di: np.roll(a, (-dj, -di), axis=(0, 1))       # a(i+di, j+dj)  # noqa: E731
+    lap = lambda a: sh(a, -1, 0) + sh(a, 0, -1) - 4. * a + sh(a, 0, 1) + sh(a, 1, 0)   # noqa: E731
+    B = [uf[..., n] for n in range(3)]; E = [uf[..., 3 + n] for n in range(3)]; J = [uj[..., n] for n in range(3)]
+    gkl = [
+        f2 * (lap(B[0]) + f3 * (-sh(J[2], -1, 0) + J[2])) - f1 * (-sh(E[2], -1, 0) + E[2]),
+        f2 * (lap(B[1]) - f3 * (-sh(J[2], 0, -1) + J[2])) + f1 * (-sh(E[2], 0, -1) + E[2]),
+        f2 * (lap(B[2]) + f3 * (-sh(J[1], 0, -1) + J[1] + sh(J[0], -1, 0) - J[0])) - f1 * (-sh(E[1], 0, -1) + E[1] + sh(E[0], -1, 0) - E[0]),
+    ]
+    w.field_fdtd_i(3)
+    got = w.arr("gkl")
+    for n in range(3):
+        assert np.abs(got[..., n] - gkl[n]).max() <= 1e-13 * np.abs(gkl[n]).max(), n
+    ny, nx = gkl[0].shape
+    ky, kx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    symbol = f4 - 2 * np.cos(2 * np.pi * kx / nx) - 2 * np.cos(2 * np.pi * ky / ny)
+    w.field_fdtd_i(4)
+    w.field_fdtd_i(5)
+    df = w.arr("df")[inner]
+    dB = []
+    for n in range(3):
+        b = f5 * gkl[n]
+        exact = np.real(np.fft.ifft2(np.fft.fft2(b) / symbol))
+        assert np.linalg.norm(df[..., n] - exact) <= 1.5e-6 * np.linalg.norm(b) / f5, n
+        dB.append(df[..., n].copy())
+    w.field_fdtd_i(6)
+    w.field_fdtd_i(7)
+    df = w.arr("df")[inner]
+    dE = [
+        +f1 * (gfac * (-dB[2] + sh(dB[2], 1, 0)) + (-B[2] + sh(B[2], 1, 0))) - 4. * np.pi * delt * J[0],
+        -f1 * (gfac * (-dB[2] + sh(dB[2], 0, 1)) + (-B[2] + sh(B[2], 0, 1))) - 4. * np.pi * delt * J[1],
+        +f1 * (gfac * (-dB[1] + sh(dB[1], 0, 1) + dB[0] - sh(dB[0], 1, 0)) + (-B[1] + sh(B[1], 0, 1) + B[0] - sh(B[0], 1, 0))) - 4. * np.pi * delt * J[2],
+    ]
+    for n in range(3):
+        assert np.abs(df[..., 3 + n] - dE[n]).max() <= 1e-13 * max(np.abs(dE[n]).max(), 1e-300), n
+    w.close()
