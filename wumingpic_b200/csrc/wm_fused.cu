@@ -143,15 +143,10 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
   const int i0 = nxs + gx * G;
   const int ncg = min(G, nxe - i0 + 1);  // cells in this group
 
-  if (t == 0) mbar_init(&S.bar, 1);
-  if (t < 2 * (G + 1)) {
-    const int isp = t / (G + 1), ii = t % (G + 1);
-    const int* row = cs + (size_t)g.pen(j, k, isp) * (g.nx + 1) + (i0 - g.nxgs);
-    S.beg[isp][ii] = row[min(ii, ncg)];
-  }
-  for (int e = t; e < 2 * 27 * G; e += TPB) (&S.cnt27[0][0][0])[e] = 0;
-  __syncthreads();
+  // prologue order: the tile (TMA), the index rows and the first particles are three independent global round trips --
+  // all three are in flight before anything waits (the tile is waited for after the first particle loads were issued)
   if (t == 0) {
+    mbar_init(&S.bar, 1);
     // field tile by TMA bulk copies: 9 rows of (ncg+2) cells x 6 doubles (48 B per cell keeps 16-B alignment)
     const uint32_t row_bytes = (uint32_t)(ncg + 2) * 48u;
     mbar_expect_tx(&S.bar, 9u * row_bytes);
@@ -161,6 +156,13 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
       tma_bulk_g2s(&S.tile[r * TILE_ROW], tmpf + g.box(i0 - 1, j + jj, k + kk) * 6, row_bytes, &S.bar);
     }
   }
+  if (t < 2 * (G + 1)) {
+    const int isp = t / (G + 1), ii = t % (G + 1);
+    const int* row = cs + (size_t)g.pen(j, k, isp) * (g.nx + 1) + (i0 - g.nxgs);
+    S.beg[isp][ii] = row[min(ii, ncg)];
+  }
+  for (int e = t; e < 2 * 27 * G; e += TPB) (&S.cnt27[0][0][0])[e] = 0;
+  __syncthreads();
 
   // phase-A identity: (cell, slot); phase-B identity: (cell, component, transverse index m)
   const int ca = t >> 4, sa = t & 15;
@@ -189,15 +191,6 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
   const double len_x = (g.nxge - g.nxgs + 1) * g.delx;
   const double len_y = (g.nyge - g.nygs + 1) * g.delx;
   const double len_z = (g.nzge - g.nzgs + 1) * g.delx;
-
-  mbar_wait(&S.bar, 0);
-  // x differences of the field tile, once per CTA (shared by the ~128 particles of every cell): the x sum of the gather
-  // becomes f(i) + sx(+1) d(i) - sx(-1) d(i-1), two DFMA instead of DMUL + two DFMA (sx(-1) + sx(0) + sx(+1) = 1)
-  for (int e = t; e < 9 * (G + 1) * 6; e += TPB) {
-    const int r = e / ((G + 1) * 6), q = e % ((G + 1) * 6);
-    S.dtile[r * TILE_ROW + q] = S.tile[r * TILE_ROW + q + 6] - S.tile[r * TILE_ROW + q];
-  }
-  __syncthreads();
 
   int ns0 = 0, nl0 = 0, ns1 = 0, nl1 = 0;   // stayers / leavers of this thread's cell written so far, per species
   // register prefetch of the next batch's particle (index -1: none)
@@ -231,6 +224,16 @@ k_fused3(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
   prep(0);
   fetch();
   prep(1);
+
+  mbar_wait(&S.bar, 0);
+  // x differences of the field tile, once per CTA (shared by the ~128 particles of every cell): the x sum of the gather
+  // becomes f(i) + sx(+1) d(i) - sx(-1) d(i-1), two DFMA instead of DMUL + two DFMA (sx(-1) + sx(0) + sx(+1) = 1)
+  for (int e = t; e < 9 * (G + 1) * 6; e += TPB) {
+    const int r = e / ((G + 1) * 6), q = e % ((G + 1) * 6);
+    S.dtile[r * TILE_ROW + q] = S.tile[r * TILE_ROW + q + 6] - S.tile[r * TILE_ROW + q];
+  }
+  __syncthreads();
+
   for (int batch = 0; batch < nbatch; ++batch) {
     int nst = 0, ncr = 0;   // stayer / crosser records of this half-warp's cell in this batch
     // ------------------------------ phase A ------------------------------
