@@ -599,3 +599,67 @@ def test_2d_field_solve_matches_numpy_fft_restatement():
     for n in range(3):
         assert np.abs(df[..., 3 + n] - dE[n]).max() <= 1e-13 * max(np.abs(dE[n]).max(), 1e-300), n
     w.close()
+
+
+@pytest.mark.parametrize("bc", [1, 2], ids=["reconnection", "shock"])
+def test_3d_wall_cg_matches_a_dense_numpy_solve(bc):
+    """the 3-D counterpart of test_wall_cg_matches_a_dense_numpy_solve: cgm (3d/common/field.f90:409-560) with
+    boundary_reconnection__phi (3d/proj/reconnection/boundary_reconnection.f90:1094-1116) or boundary_shock__phi
+    (3d/proj/shock/boundary_shock.f90:1086-1108) as a dense solve, and the x ghost fills of boundary_*__dfield (:672-682 / :674-686)"""
+    w = make_world3(9, 5, 4, 5, steps=2, bc=bc, order=bc, u0=0.3 if bc == 2 else 0.0)
+    nx, ny, nz = w.nx, w.ny, w.nz
+    nxs, nxe = 2, nx + 1
+    f5 = (w.delx / (w.c * w.delt * w.gfac)) ** 2
+    f4 = 6.0 + f5
+    w.particle_solv()
+    if bc == 1:
+        w.bc_particle_x()
+    else:
+        w.bc_injection(0.3)
+    for st in (1, 2, 3):
+        w.field_fdtd_i(st)
+    gkl = w.arr("gkl").copy()                      # (k, j, i, 3)
+    w.field_fdtd_i(4)
+    df = w.arr("df").copy()
+    nxr = nxe - nxs + 1
+    idx = lambda i, j, k: ((k % nz) * ny + (j % ny)) * nxr + (i - nxs)   # noqa: E731
+    n = nxr * ny * nz
+    for l in (1, 2, 3):
+        A = np.zeros((n, n))
+        for k in range(nz):
+            for j in range(ny):
+                for i in range(nxs, nxe + 1):
+                    row = idx(i, j, k)
+                    A[row, row] += f4
+                    for dj, dk in ((-1, 0), (1, 0), (0, -1), (0, 1)):
+                        A[row, idx(i, j + dj, k + dk)] -= 1.0
+                    if i > nxs:
+                        A[row, idx(i - 1, j, k)] -= 1.0
+                    elif l == 1:
+                        A[row, idx(nxs, j, k)] += 1.0          # phi(nxs-1) = -phi(nxs)
+                    else:
+                        A[row, idx(nxs + 1, j, k)] -= 1.0      # phi(nxs-1) = phi(nxs+1)
+                    if i < nxe:
+                        A[row, idx(i + 1, j, k)] -= 1.0
+                    elif bc == 1:
+                        if l == 1:
+                            A[row, idx(nxe - 2, j, k)] += 1.0  # phi(nxe+1) = -phi(nxe-2)
+                        else:
+                            A[row, idx(nxe - 1, j, k)] -= 1.0  # phi(nxe+1) = phi(nxe-1)
+        b = (f5 * gkl[..., l - 1]).reshape(-1)
+        exact = np.linalg.solve(A, b).reshape(nz, ny, nxr)
+        got = df[2:-2, 2:-2, 2:-2, l - 1]
+        lam_min = np.linalg.eigvalsh(0.5 * (A + A.T)).min()
+        assert np.linalg.norm(got - exact) <= 1.5e-6 * np.linalg.norm(b) / lam_min, (bc, l)
+    w.field_fdtd_i(5)
+    d5 = w.arr("df")                               # (k, j, i, 6), box x index = global index
+    assert np.array_equal(d5[:, :, nxs - 1, 0], -d5[:, :, nxs, 0])
+    assert np.array_equal(d5[:, :, nxs - 1, 1:4], d5[:, :, nxs + 1, 1:4])
+    assert np.array_equal(d5[:, :, nxs - 1, 4:6], -d5[:, :, nxs, 4:6])
+    if bc == 1:
+        assert np.array_equal(d5[:, :, nxe, 0], -d5[:, :, nxe - 1, 0])
+        assert np.array_equal(d5[:, :, nxe + 1, 1:4], d5[:, :, nxe - 1, 1:4])
+        assert np.array_equal(d5[:, :, nxe, 4:6], -d5[:, :, nxe - 1, 4:6])
+    else:
+        assert not d5[:, :, nxe + 1, :].any()
+    w.close()
