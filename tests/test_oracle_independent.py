@@ -663,3 +663,71 @@ def test_3d_wall_cg_matches_a_dense_numpy_solve(bc):
     else:
         assert not d5[:, :, nxe + 1, :].any()
     w.close()
+
+
+def test_deposit_plus_current_fold_is_a_periodic_sum():
+    """ele_cur over all particles (3d/common/field.f90:238-404) followed by boundary_periodic__curre (3d/common/boundary_periodic.f90:
+    676-978: the two ghost layers folded onto their periodic images, x then y then z) equals, on the interior, the sum of the
+    single-particle stencils of numpy_deposit_one placed with periodic index arithmetic."""
+    w = make_world3(8, 4, 4, 3, steps=2)
+    nx, ny, nz = w.nx, w.ny, w.nz
+    w.particle_solv()
+    w.field_fdtd_i(1)
+    w.field_fdtd_i(2)
+    np2, cc, up, gp = w.arr("np2"), w.arr("cumcnt"), w.arr("up"), w.arr("gp")
+    J = np.zeros((nz, ny, nx, 3))
+    m, ci = _cells_of(w)
+    isp, kk, jj, ii = np.nonzero(m)
+    for n in range(len(isp)):
+        s, k, j, t = isp[n], kk[n], jj[n], ii[n]
+        cell = (int(ci[s, k, j, t]), j + 2, k + 2)
+        st = numpy_deposit_one(up[s, k, j, t, :3], gp[s, k, j, t, :3], cell, w.q[s] * w.delx / w.delt)     # [kp, jp, ip, comp]
+        for kp in range(5):
+            for jp in range(5):
+                for ip in range(5):
+                    J[(cell[2] + kp - 2 - 2) % nz, (cell[1] + jp - 2 - 2) % ny, (cell[0] + ip - 2 - 2) % nx] += st[kp, jp, ip]
+    got = w.arr("uj")[2:-2, 2:-2, 2:-2]
+    assert np.abs(got - J).max() <= 1e-12 * np.abs(J).max()
+    w.close()
+
+
+def test_wall_particle_rules_match_numpy():
+    """boundary_reconnection__particle_x (3d/proj/reconnection/boundary_reconnection.f90:69-110: reflect about (nxs+1) delx and
+    (nxe-1) delx, all three momenta negated on the left, ux,uy,uz on the right) and boundary_shock__injection
+    (3d/proj/shock/boundary_shock.f90:424-469: left wall as above, moving right wall xend = nxe delx + v0 delt with ux -> 2 u0 - ux)"""
+    for bc, u0 in ((1, 0.0), (2, 0.3)):
+        w = make_world3(10, 4, 4, 6, steps=1, bc=bc, order=bc, u0=u0)
+        nxs, nxe = 2, w.nx + 1
+        w.particle_solv()
+        m = active_mask(w.arr("np2"), w.np)
+        # push some particles through both walls
+        gp = w.arr("gp")
+        rng = np.random.default_rng(2)
+        sel = rng.random(gp.shape[:-1]) < 0.3
+        beyond = (nxe - 1 + rng.random(gp.shape[:-1])) if bc == 1 else (nxe + 0.3 + 0.5 * rng.random(gp.shape[:-1]))
+        gp[..., 0] = np.where(m & sel, np.where(rng.random(gp.shape[:-1]) < 0.5, nxs + 1 - rng.random(gp.shape[:-1]), beyond), gp[..., 0])
+        before = gp[m].copy()
+        if bc == 1:
+            w.bc_particle_x()
+        else:
+            w.bc_injection(u0)
+        after = w.arr("gp")[m]
+        x, u = before[:, 0].copy(), before[:, 3:6].copy()
+        ipos = np.trunc(x / w.delx).astype(int)
+        left = ipos < nxs + 1
+        if bc == 1:
+            right = ~left & (ipos >= nxe - 1)
+            xr = 2.0 * (nxe - 1) * w.delx - x
+            ur = -u
+        else:
+            v0 = u0 / np.sqrt(1.0 + u0 * u0 / (w.c * w.c))
+            xend = nxe * w.delx + v0 * w.delt
+            right = ~left & (x > xend)
+            xr = 2.0 * xend - x
+            ur = np.stack([2.0 * u0 - u[:, 0], -u[:, 1], -u[:, 2]], axis=1)
+        xn = np.where(left, 2.0 * (nxs + 1) * w.delx - x, np.where(right, xr, x))
+        un = np.where(left[:, None], -u, np.where(right[:, None], ur, u))
+        assert left.any() and right.any()
+        assert np.array_equal(after[:, 0], xn) and np.array_equal(after[:, 3:6], un)
+        assert np.array_equal(after[:, 1:3], before[:, 1:3])
+        w.close()
