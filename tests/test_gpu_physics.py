@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def test_gpu_cold_plasma_oscillates_at_the_plasma_frequency():
-    n0, nx, ny, nz = 8, 32, 2, 2
+    n0, nx, ny, nz = 8, 32, 4, 4
     q, r, _ = weibel_constants(n0)
     w = World3(nx, ny, nz, n0 * nx * 3, q=q, r=r)          # the oracle world only builds the initial state
     w.load_weibel(n0, v_thi=0.0, v_the=0.0, t_ani=1.0)
