@@ -20,9 +20,28 @@ class ShockPrm(C.Structure):
 _LIBS = {}
 
 
+def _host_cpu_tag():
+    """the CPU feature flags of this host: liboracle_fast.so is built with -march=native, so a copy built on another machine (the
+    .so travels from the build container to the GPU box) must be rebuilt when the instruction sets differ"""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(" ".join(sorted(line.split(":", 1)[1].split())).encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(fast=False):
     target = "liboracle_fast.so" if fast else "liboracle.so"
-    subprocess.run(["make", "-s", "-C", _HERE, target], check=True)
+    if fast:
+        subprocess.run(["make", "-s", "-B", "-C", _HERE, target], check=True)
+        with open(os.path.join(_HERE, "liboracle_fast.host"), "w") as f:
+            f.write(_host_cpu_tag())
+    else:
+        subprocess.run(["make", "-s", "-C", _HERE, target], check=True)
     return os.path.join(_HERE, target)
 
 
@@ -33,6 +52,12 @@ def lib(fast=False):
         src_newer = (not os.path.exists(path)) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(path)
             for f in ("oracle3d.cpp", "oracle2d.cpp", "oracle_common.h"))
+        if fast and not src_newer:
+            try:
+                with open(os.path.join(_HERE, "liboracle_fast.host")) as f:
+                    src_newer = f.read().strip() != _host_cpu_tag()
+            except OSError:
+                src_newer = True
         if src_newer:
             path = build(fast)
         L = C.CDLL(path)
