@@ -6,9 +6,13 @@ end-to-end (host-buffer) number.  Contract: see the repo's task description; one
   python bench.py [--gpus N --steps K --warmup W]          this backend (N > 1: launched by torchrun)
   python bench.py --impl reference [--steps K --warmup W]  the reference's CPU algorithm (oracle port) on host cores
 
-Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): 3-D Weibel, uniform Maxwellian pair plasma,
-256 x 256 x 64 cells per GPU, 64 particles per cell and species (536.9 M particles per GPU), z-slabs
-across GPUs (weak scaling: nz = 64 N).  Inputs are synthetic (device-side Philox Maxwellian load).
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): 3-D Weibel, uniform Maxwellian pair plasma, 64 particles per cell
+and species, z-slabs across GPUs.  Default = STRONG scaling, the north star's target: the fixed 256 x 256 x 128 box
+(1.07 G particles; 120 GB double-buffered, fits one B200) split over the N GPUs as the reference splits a fixed box over its
+ranks (3d/common/mpi_set.f90:45-94).  --weak: 256 x 256 x 64 cells PER GPU (536.9 M particles per GPU, nz = 64 N).
+Inputs are synthetic (device-side Philox Maxwellian load).  Before the timed region every rank runs the committed golden
+case of tests/golden/bench_parity3d.npz (oracle output; no oracle code is imported) through the same wm_step path and reports
+the comparison in `checks.parity`.
 """
 import argparse
 import json
@@ -35,16 +39,22 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=256)
     ap.add_argument("--ny", type=int, default=256)
-    ap.add_argument("--nz", type=int, default=64, help="z cells PER GPU")
+    ap.add_argument("--nz", type=int, default=64, help="z cells PER GPU (with --weak)")
     ap.add_argument("--ppc", type=int, default=64, help="particles per cell and species")
-    ap.add_argument("--strong-nz", type=int, default=0,
-                    help="strong scaling: TOTAL z cells of a fixed box split over the GPUs (e.g. 128 = the 256x256x128 box of SURVEY.md "
-                         "8d); 0 (default): weak scaling with --nz cells per GPU")
+    ap.add_argument("--strong-nz", type=int, default=128,
+                    help="strong scaling (default): TOTAL z cells of the fixed box split over the GPUs (128 = the 256x256x128 box of "
+                         "SURVEY.md 8d)")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: --nz cells per GPU, the box grows with N")
+    ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity run before the timed region")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-nz", type=int, default=4, help="z cells of the bounded CPU sample")
-    ap.add_argument("--unfused", action="store_true", help="time the per-procedure kernels instead of the fused step")
+    ap.add_argument("--unfused", "--five-calls", dest="unfused", action="store_true",
+                    help="drive the reference's five procedure calls per step (particle__solv, field__fdtd_i, bc__particle_x, "
+                         "bc__particle_yz, sort__bucket: what an unmodified driver does) instead of the one-call wm_step")
+    ap.add_argument("--slow-kernels", action="store_true",
+                    help="wm_set_fused(0): the separate per-procedure kernels (push, RED deposit, classify, eager sort)")
     ap.add_argument("--dim", type=int, default=3, choices=[2, 3],
                     help="3 (default): the C2 3-D Weibel workload of the metric; 2: a 2-D Weibel sheet nx x (ny per GPU) for the "
                          "2-D code path (not a bench line of BASELINE.json; ndim = 6 -> 192 B per particle-step)")
@@ -128,9 +138,16 @@ def host_memory_available():
 def cpu_baseline(args, steps=2, warmup=1):
     """The oracle (a C++ port of the reference loop nests, -O3 -march=native -fopenmp) on the host cores,
     on a bounded sample of the same workload: same nx, ny, ppc and physics, only nz reduced."""
+    from oracle import pyoracle
     from oracle.pyoracle import World3, weibel_constants
     import numpy as np
     nx, ny, nz, n0 = args.nx, args.ny, args.cpu_nz, args.ppc
+    # every host thread this process may use -- set explicitly: launchers (torch.distributed.run) export OMP_NUM_THREADS=1 and
+    # the OpenMP runtime obeys it.  `cores` below is the team a parallel region of the oracle library REALLY gets.
+    want = len(os.sched_getaffinity(0))
+    team = pyoracle.set_num_threads(want, fast=True)
+    if team != want or pyoracle.num_threads(fast=True) != want:
+        raise RuntimeError(f"oracle OpenMP team is {team} threads, {want} host threads are available: refusing to report a CPU baseline")
     q, r, _ = weibel_constants(n0)
     w = World3(nx, ny, nz, int(n0 * nx * 1.5), q=q, r=r, fast=True)
     w.load_weibel(n0)
@@ -142,7 +159,7 @@ def cpu_baseline(args, steps=2, warmup=1):
         w.step()
     dt = time.perf_counter() - t0
     assert w.error() == 0
-    cores = len(os.sched_getaffinity(0))
+    cores = team
     w.close()
     return {"value": npart * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"3-D Weibel {nx}x{ny}x{nz}, {n0} ppc x 2 species = {npart} particles, {steps} steps "
@@ -157,15 +174,63 @@ def run_reference(args):
         return
     cb = cpu_baseline(args, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
     line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak" if args.weak else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"3-D Weibel {args.nx}x{args.ny}x{args.nz} cells/GPU, {args.ppc} ppc x 2 species; "
-                                   f"CPU arm runs the bounded sample nz={args.cpu_nz}",
+            "config": {"workload": (f"3-D Weibel {args.nx}x{args.ny}x{args.nz} cells/GPU" if args.weak else
+                                    f"3-D Weibel, fixed {args.nx}x{args.ny}x{args.strong_nz} box") +
+                                   f", {args.ppc} ppc x 2 species; the CPU arm runs the bounded sample nz={args.cpu_nz} "
+                                   "(same nx, ny, ppc, physics: a per-particle rate)",
                        "parallelism": f"openmp{cb['cores']}"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def golden_parity(wm, dist, world, rank, local_rank, fused=True, five_calls=False):
+    """Every rank runs its z-slab of the committed golden case (tests/golden/bench_parity3d.npz: oracle output, 8 x 6 x 32 cells,
+    9216 particles, 3 steps) through the path that is timed below -- wm_step: fused kernel, lazy sort, peer-memory cgm, NCCL halos
+    and migration -- and compares with the oracle's end state: fields (relative to the max-norm), np2 / cumcnt and the particle-ID
+    sets per cell (exact).  No oracle code runs here: the golden file is its committed output."""
+    import numpy as np
+    import torch
+    from tests import fixture_slabs as fs
+    fx = fs.load()
+    nx, ny, nz = int(fx["nx"]), int(fx["ny"]), int(fx["nz"])
+    lay = wm.SlabLayout(2, ny + 1, 2, nz + 1, 1, world, rank)
+    b = wm.Backend(3, int(fx["np_cap"]), 2, nx + 1, 2, ny + 1, 2, nz + 1, nys=lay.nys, nye=lay.nye, nzs=lay.nzs, nze=lay.nze,
+                   q=fx["q"], r=fx["r"], nproc_j=1, nproc_k=world, rank_j=0, rank_k=rank, device=local_rank)
+    if world > 1:
+        box = [b.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        b.comm_init(world, rank, box[0])
+    b.set_fused(fused)
+    st = fs.slab_state(fx, lay.nzs, lay.nze)
+    b.upload(st["up"], st["np2"], st["cumcnt"], st["uf"])
+    b.upload_work("df", st["df"])
+    worst_gauss = 0.0
+    for _ in range(int(fx["steps"])):
+        (b.time_loop if five_calls else b.step)(2, nx + 1, 1, wm.backend.WM_ORDER_WEIBEL)
+        res, rho = b.gauss()
+        worst_gauss = max(worst_gauss, res / max(rho, 1.0))
+    up, np2, cc, uf = b.empty("up"), b.empty("np2"), b.empty("cumcnt"), b.empty("uf")
+    b.download(up, np2, cc, uf)
+    r = fs.compare_slab(fx, lay.nzs, lay.nze, up, np2, cc, uf)
+    cg = b.stats()["cg_iterations"]
+    flags = b.stats()["error_flags"]
+    b.close()
+    ok_local = r["np2_equal"] and r["cumcnt_equal"] and r["ids_equal"] and flags == 0
+    t = torch.tensor([r["uf_rel_err"], worst_gauss, 0.0 if ok_local else 1.0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = t.tolist()
+    return {"case": f"golden 3-D Weibel {nx}x{ny}x{nz}, {len(fx['rec0'])} particles, {int(fx['steps'])} steps, {world} z-slab(s), "
+                    f"{'wm_step (fused, lazy sort)' if fused else 'per-procedure kernels'}; oracle output committed under tests/golden/",
+            "uf_rel_err_max_over_ranks": t[0], "gauss_rel_residual_max": t[1],
+            "np2_cumcnt_id_sets_exact_all_ranks": t[2] == 0.0,
+            "cg_iterations": cg, "cg_iterations_oracle": [int(v) for v in fx["cg_1"]],
+            "pass": bool(t[2] == 0.0 and t[0] < 1e-9 and t[1] < 1e-13 and list(cg) == [int(v) for v in fx["cg_1"]])}
 
 
 _REAL_STDOUT = None
@@ -211,11 +276,15 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     nx, ny, n0 = args.nx, args.ny, args.ppc
-    if args.strong_nz:                                  # strong scaling: the box is fixed, the slabs shrink
+    strong = not args.weak and args.dim == 3 and args.strong_nz > 0
+    if strong:                                          # strong scaling: the box is fixed, the slabs shrink
         if args.strong_nz % world:
             raise SystemExit(f"--strong-nz {args.strong_nz} is not a multiple of {world} GPUs")
         args.nz = args.strong_nz // world
     nz_glob = args.nz * world                           # weak scaling: z-slabs, per-GPU work fixed
+    parity = None
+    if not args.no_parity and args.dim == 3:
+        parity = golden_parity(wm, dist, world, rank, local_rank, fused=not args.slow_kernels, five_calls=args.unfused)
     q, r, _ = wm.weibel_constants(n0)
     np_cap = int(n0 * nx * 1.25)
     if args.dim == 3:
@@ -237,9 +306,12 @@ def main():
     npart = npart_rank * world
     stream = torch.cuda.ExternalStream(b.stream(), device=torch.device("cuda", local_rank))
     order = wm.backend.WM_ORDER_WEIBEL
-    if args.unfused:
-        b.set_fused(False)      # wm_step then sequences the per-procedure kernels, like a driver calling the five entry points
-    step = lambda n: b.step(2, nx + 1, n, order)  # noqa: E731
+    if args.slow_kernels:
+        b.set_fused(False)      # the separate per-procedure kernels: nothing is deferred or fused
+    if args.unfused:            # the driver's five calls per step; on resident state they reach the same fused kernel + lazy sort
+        step = lambda n: b.time_loop(2, nx + 1, n, order)  # noqa: E731
+    else:
+        step = lambda n: b.step(2, nx + 1, n, order)  # noqa: E731
 
     def barrier():
         torch.cuda.synchronize()
@@ -357,18 +429,22 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "strong" if args.strong_nz else "weak",
+                "scaling": "strong" if strong else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": (f"3-D Weibel {nx}x{ny}x{args.nz} cells/GPU, {n0} ppc x 2 species "
+                "config": {"workload": (f"3-D Weibel, fixed {nx}x{ny}x{nz_glob} box ({npart} particles) split into {world} z-slab(s) of "
+                                        f"{args.nz} planes, {n0} ppc x 2 species ({npart_rank} particles/GPU), periodic, cfl=1, gfac=0.501"
+                                        if strong else
+                                        f"3-D Weibel {nx}x{ny}x{args.nz} cells/GPU, {n0} ppc x 2 species "
                                         f"({npart_rank} particles/GPU), periodic, cfl=1, gfac=0.501") if args.dim == 3 else
                                        (f"2-D Weibel {nx}x{ny} cells/GPU, {n0} ppc x 2 species ({npart_rank} particles/GPU), "
                                         "periodic (NOT the metric's workload: 2-D code path check)"),
                            "parallelism": f"{'z' if args.dim == 3 else 'y'}-slabs x{world}",
                            "l2": "inputs (particle arrays, >= 30 GB) far exceed the 126 MB L2; no flush needed",
-                           "particles": npart, "path": "per-procedure kernels" if args.unfused else "wm_step"},
+                           "particles": npart, "path": ("five reference procedure calls per step" if args.unfused else "wm_step") +
+                                   (", per-procedure kernels (wm_set_fused 0)" if args.slow_kernels else "")},
                 "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "checks": {"gauss_residual": res, "max_4pi_rho": rho, "cg_iterations": st["cg_iterations"],
-                           "error_flags": st["error_flags"]}}
+                           "error_flags": st["error_flags"], "parity": parity}}
         emit(line)
     b.close()
     if world > 1:

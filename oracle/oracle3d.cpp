@@ -1382,6 +1382,20 @@ void* orc3_create(int nx, int ny, int nz, int np, int nproc_j, int nproc_k, doub
 void orc3_destroy(void* h) { delete (World3*)h; }
 
 int orc3_nranks(void* h) { return (int)((World3*)h)->ranks.size(); }
+// the OpenMP team the parallel regions of this library will really use (what bench.py reports as `cores`): a launcher such as
+// torch.distributed.run exports OMP_NUM_THREADS=1, which the runtime obeys -- the count must be set and read back, not assumed
+int orc_num_threads(void) { return omp_get_max_threads(); }
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+// threads that actually entered a parallel region (a cgroup / nested-parallelism limit can cut the team below the request)
+int orc_team_size(void) {
+  int n = 1;
+#pragma omp parallel
+  {
+#pragma omp single
+    n = omp_get_num_threads();
+  }
+  return n;
+}
 int orc3_error(void* h) { return ((World3*)h)->err; }
 void orc3_clear_error(void* h) { ((World3*)h)->err = 0; }
 

@@ -114,8 +114,20 @@ def lib(fast=False):
         L.orc2_cg_iterations.argtypes = [C.c_void_p, ip]
         L.orc2_energy.argtypes = [C.c_void_p, dp]
         L.orc2_gauss.argtypes = [C.c_void_p, C.c_int, dp]
+        L.orc_set_num_threads.argtypes = [C.c_int]
         _LIBS[key] = L
     return _LIBS[key]
+
+
+def set_num_threads(n, fast=False):
+    """size the OpenMP team of the oracle library explicitly and return the team a parallel region really gets"""
+    L = lib(fast)
+    L.orc_set_num_threads(int(n))
+    return L.orc_team_size()
+
+
+def num_threads(fast=False):
+    return lib(fast).orc_num_threads()
 
 
 def weibel_constants(n0, mass_ratio=1.0, sigma_e=0.0, omega_pe=0.1, c=1.0):

@@ -40,3 +40,16 @@ def test_b200_arm_fails_loudly_without_a_device():
                         "--nz", "4", "--ppc", "2", "--no-e2e", "--no-cpu"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0
     assert r.stdout.strip() == ""            # no JSON line from a run that could not use the GPU
+
+
+def test_reference_arm_uses_all_host_threads_under_a_launcher():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the reference arm must size its OpenMP team itself and report the team
+    it really got (VERDICT r01 weak #7: an N > 1 reference arm ran single-threaded while labelled with the core count)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1", "--nx", "32", "--ny", "16", "--cpu-nz", "4", "--ppc", "4"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["config"]["parallelism"] == f"openmp{len(os.sched_getaffinity(0))}"

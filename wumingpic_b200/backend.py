@@ -289,6 +289,22 @@ class Backend:
     def step(self, nxs, nxe, nsteps=1, order=WM_ORDER_WEIBEL, u0=0.0):
         self._ck(self.L.wm_step(self.h, nxs, nxe, order, u0, nsteps))
 
+    def time_loop(self, nxs, nxe, nsteps=1, order=WM_ORDER_WEIBEL, u0=0.0, vay=False):
+        """nsteps iterations of the reference drivers' time loop, procedure by procedure, in the order of the set-up's app.f90
+        (Weibel 3d/proj/weibel/app.f90:100-108; reconnection 3d/proj/reconnection/app.f90:103-108; shock 2d/proj/shock/app.f90:112-118).
+        On resident state these five calls run the same fused kernel + lazy sort as step() (wm_api.cu: deferred particle__solv)."""
+        for _ in range(nsteps):
+            (self.particle__solv_vay if vay else self.particle__solv)(nxs, nxe)
+            if order == WM_ORDER_RECONNECTION:
+                self.bc__particle_x(nxs, nxe)
+            elif order == WM_ORDER_SHOCK:
+                self.bc__injection(nxs, nxe, u0)
+            self.field__fdtd_i(nxs, nxe)
+            if order == WM_ORDER_WEIBEL:
+                self.bc__particle_x(nxs, nxe)
+            self.bc__particle_yz()
+            self.sort__bucket(nxs, nxe)
+
     def set_fused(self, on=True):
         self._ck(self.L.wm_set_fused(self.h, 1 if on else 0))
 

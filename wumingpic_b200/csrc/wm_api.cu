@@ -98,6 +98,8 @@ bool range_ok(const wm_ctx* c, int nxs, int nxe) {
 void wm_set_error(const std::string& msg) { g_err = msg; }
 
 extern "C" {
+static int flush_deferred(wm_ctx* c);
+static int fold_timing(wm_ctx* c);
 
 const char* wm_last_error(void) { return g_err.c_str(); }
 int wm_version(void) { return 100; }
@@ -218,7 +220,7 @@ int wm_create(const wm_params* prm, wm_ctx** out) {
   c->hbuf_elems = (size_t)2 * 6 * g.bx * std::max(g.by, g.bz);
   WM_CUDA(cudaMalloc(&c->hbuf[0], c->hbuf_elems * sizeof(double)));
   WM_CUDA(cudaMalloc(&c->hbuf[2], c->hbuf_elems * sizeof(double)));
-  for (int e = 0; e < 8; ++e) WM_CUDA(cudaEventCreate(&c->ev[e]));
+  for (int e = 0; e < 5 * wm_ctx::EV_STEPS; ++e) WM_CUDA(cudaEventCreate(&c->ev[e]));
   WM_CUDA(cudaStreamSynchronize(c->stream));
   *out = c;
   return WM_OK;
@@ -245,7 +247,7 @@ int wm_destroy(wm_ctx* c) {
   for (int* p : ii) if (p) cudaFree(p);
   if (c->scan_tmp) cudaFree(c->scan_tmp);
   if (c->red_host) cudaFreeHost(c->red_host);
-  for (int e = 0; e < 8; ++e) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
+  for (int e = 0; e < 5 * wm_ctx::EV_STEPS; ++e) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
   cudaStreamDestroy(c->stream);
   delete c;
   return WM_OK;
@@ -261,6 +263,9 @@ int wm_upload(wm_ctx* c, const double* up, const int* np2, const int* cumcnt, co
   if (uf) WM_CUDA(cudaMemcpyAsync(c->uf, uf, g.nbox() * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (up) {
     c->lazy = false;   // the uploaded state supersedes a pending (lazy) sort permutation
+    c->defer_push = false;   // ... and whatever was deferred on the old state
+    c->defer_xbc = 0;
+    c->fused_done = false;
     if (!np2 || !cumcnt) {
       wm_set_error("wm_upload: up needs np2 and cumcnt");
       return WM_ERR_ARG;
@@ -279,8 +284,17 @@ int wm_upload(wm_ctx* c, const double* up, const int* np2, const int* cumcnt, co
     c->n_sp0 = poff[g.npen / g.nsp];
     WM_TRY(reserve_particles(c, (size_t)c->ntot));
     std::vector<int> cs((size_t)g.npen * (g.nx + 1) + 1);
-    for (int pen = 0; pen < g.npen; ++pen)
-      for (int i = 0; i <= g.nx; ++i) cs[(size_t)pen * (g.nx + 1) + i] = poff[pen] + cumcnt[(size_t)pen * (g.nx + 1) + i];
+    // Cell i of a pencil holds the records (cumcnt(i), cumcnt(i+1)] (particle.f90:100-108); the pencil population is np2, NOT
+    // cumcnt(nxe+1): the shock driver leaves cumcnt above nxe stale (inject / relocate bump np2 and cumcnt(nxe) only,
+    // 2d/proj/shock/app.f90:836-838; init never fills cumcnt(nxe+1:), :346-359), and a stale entry below its predecessor is an
+    // empty cell in the reference's loops.  The device index is the same membership made monotone and closed with np2.
+    for (int pen = 0; pen < g.npen; ++pen) {
+      int run = 0;
+      for (int i = 0; i <= g.nx; ++i) {
+        run = std::min(std::max(run, cumcnt[(size_t)pen * (g.nx + 1) + i]), np2[pen]);
+        cs[(size_t)pen * (g.nx + 1) + i] = poff[pen] + run;
+      }
+    }
     cs.back() = poff[g.npen];
     c->keys_valid = false;
     WM_CUDA(cudaMemcpyAsync(c->cs, cs.data(), cs.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -311,6 +325,14 @@ int wm_download(wm_ctx* c, double* up, int* np2, int* cumcnt, double* uf, double
   if (!c) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
   const Geo& g = c->g;
+  if (gp) {
+    if (c->fused_done) {
+      wm_set_error("wm_download: after field__fdtd_i took the push over (fused kernel) gp holds the wrapped, re-binned set; "
+                   "read gp between particle__solv and field__fdtd_i, or call wm_set_fused(ctx, 0)");
+      return WM_ERR_STATE;
+    }
+    WM_TRY(flush_deferred(c));   // somebody wants the pushed set itself: run the deferred push now
+  }
   WM_TRY(wm_materialize(c));
   WM_TRY(check_flags(c));
   if (uf) WM_CUDA(cudaMemcpyAsync(uf, c->uf, g.nbox() * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -403,21 +425,55 @@ static int particle_solv_with(wm_ctx* c, int nxs, int nxe, int pusher) {
   WM_TRY(rc);
   c->gp_valid = true;
   c->keys_valid = false;
+  c->fused_done = false;
   c->last_nxs = nxs;
   c->last_nxe = nxe;
   return WM_OK;
 }
-int wm_particle_solv(wm_ctx* c, int nxs, int nxe) { return particle_solv_with(c, nxs, nxe, WM_PUSHER_BORIS); }
-int wm_particle_solv_vay(wm_ctx* c, int nxs, int nxe) { return particle_solv_with(c, nxs, nxe, WM_PUSHER_VAY); }
+
+// run what was deferred with the per-procedure kernels (somebody wants gp itself, or the call order is not one of the three
+// time loops the fused kernel covers)
+static int flush_deferred(wm_ctx* c) {
+  if (!c->defer_push) return WM_OK;
+  c->defer_push = false;
+  WM_TRY(particle_solv_with(c, c->defer_nxs, c->defer_nxe, c->defer_pusher));
+  const int xbc = c->defer_xbc;
+  c->defer_xbc = 0;
+  if (xbc == WM_ORDER_RECONNECTION) WM_TRY(wm_k_bc_x(c, c->defer_nxs, c->defer_nxe, WM_BC_RECONNECTION, 0.0));
+  if (xbc == WM_ORDER_SHOCK) WM_TRY(wm_k_bc_x(c, c->defer_nxs, c->defer_nxe, WM_BC_SHOCK, c->defer_u0));
+  return WM_OK;
+}
+
+// particle__solv / particle__solv_vay on device-resident state: deferred when the fused kernel may take it over
+static int particle_solv_entry(wm_ctx* c, int nxs, int nxe, int pusher) {
+  if (!c || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling particle__init()"); return WM_ERR_ARG; }
+  WM_CUDA(cudaSetDevice(c->device));
+  WM_TRY(flush_deferred(c));     // two pushes in a row: the first one really happens
+  if (!c->use_fused || c->ntot == 0) return particle_solv_with(c, nxs, nxe, pusher);
+  c->defer_push = true;
+  c->defer_pusher = pusher;
+  c->defer_nxs = nxs;
+  c->defer_nxe = nxe;
+  c->defer_xbc = 0;
+  c->gp_valid = true;            // logically the pushed set exists from here on
+  c->keys_valid = false;
+  c->fused_done = false;
+  c->last_nxs = nxs;
+  c->last_nxe = nxe;
+  return WM_OK;
+}
+int wm_particle_solv(wm_ctx* c, int nxs, int nxe) { return particle_solv_entry(c, nxs, nxe, WM_PUSHER_BORIS); }
+int wm_particle_solv_vay(wm_ctx* c, int nxs, int nxe) { return particle_solv_entry(c, nxs, nxe, WM_PUSHER_VAY); }
 
 int wm_field_stage(wm_ctx* c, int nxs, int nxe, int stage) {
   if (!c || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling field__init()"); return WM_ERR_ARG; }
   WM_CUDA(cudaSetDevice(c->device));
+  if (stage == 1) WM_TRY(flush_deferred(c));
   c->last_nxs = nxs;
   c->last_nxe = nxe;
   switch (stage) {
     case 1:
-      if (!c->gp_valid || c->keys_valid) {
+      if (!c->gp_valid || c->keys_valid || c->fused_done) {
         wm_set_error("field__fdtd_i needs the pushed particles: call it after particle__solv and before bc__particle_y[z]");
         return WM_ERR_STATE;
       }
@@ -441,8 +497,8 @@ static int field_stages(wm_ctx* c, int nxs, int nxe, int first) {
     for (int s = first; s <= 8; ++s) WM_TRY(wm_field_stage(c, nxs, nxe, s));
     return WM_OK;
   }
-  static cudaEvent_t ev[9] = {};
-  if (!ev[0]) for (auto& e : ev) cudaEventCreate(&e);
+  cudaEvent_t ev[9];   // created per call on the context's device (a measurement aid: the cost does not matter)
+  for (auto& e : ev) cudaEventCreate(&e);
   cudaEventRecord(ev[first - 1], c->stream);
   for (int s = first; s <= 8; ++s) {
     WM_TRY(wm_field_stage(c, nxs, nxe, s));
@@ -450,15 +506,62 @@ static int field_stages(wm_ctx* c, int nxs, int nxe, int first) {
   }
   cudaEventSynchronize(ev[8]);
   for (int s = first; s <= 8; ++s) { float ms = 0; cudaEventElapsedTime(&ms, ev[s - 1], ev[s]); g_stage_ms[s] += ms; }
+  for (auto& e : ev) cudaEventDestroy(e);
   g_stage_calls++;
   return WM_OK;
 }
-int wm_field_fdtd_i(wm_ctx* c, int nxs, int nxe) { return field_stages(c, nxs, nxe, 1); }
+// K1 + ONE kernel for push + boundaries + deposit + destination counting (wm_fused.cu); the pending lazy permutation of the
+// previous sort is consumed by it when it covered the same x range
+static int fused_push_deposit(wm_ctx* c, int nxs, int nxe, int order, double u0) {
+  if (c->lazy && (nxs != c->lazy_nxs || nxe != c->lazy_nxe)) WM_TRY(wm_materialize(c));
+  WM_TRY(wm_k_tmpf(c, nxs, nxe));
+  WM_TRY(wm_k_zero_uj(c, nxs, nxe));
+  WM_TRY(wm_k_push_deposit_fused(c, nxs, nxe, order, u0));
+  c->gp_valid = true;
+  c->keys_valid = false;
+  c->fused_done = true;
+  c->fused_order = order;
+  c->last_nxs = nxs;
+  c->last_nxe = nxe;
+  return WM_OK;
+}
+
+int wm_field_fdtd_i(wm_ctx* c, int nxs, int nxe) {
+  if (!c || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling field__init()"); return WM_ERR_ARG; }
+  WM_CUDA(cudaSetDevice(c->device));
+  if (c->defer_push) {
+    // which of the reference's three time loops this call sequence is: nothing between solv and fdtd_i (Weibel / beam,
+    // 3d/proj/weibel/app.f90:100-108), the reflecting bc__particle_x (reconnection :103-108) or bc__injection (shock)
+    const int order = c->defer_xbc;
+    const int saved = c->pusher;
+    if (nxs == c->defer_nxs && nxe == c->defer_nxe && wm_fused_supported(c, order)) {
+      c->defer_push = false;
+      c->defer_xbc = 0;
+      c->pusher = c->defer_pusher;
+      const int rc = fused_push_deposit(c, nxs, nxe, order, c->defer_u0);
+      c->pusher = saved;
+      WM_TRY(rc);
+      return field_stages(c, nxs, nxe, 2);
+    }
+  }
+  return field_stages(c, nxs, nxe, 1);
+}
 
 int wm_bc_particle_x(wm_ctx* c, int nxs, int nxe) {
   if (!c) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
   if (!c->gp_valid) { wm_set_error("bc__particle_x acts on the pushed particles (call particle__solv first)"); return WM_ERR_STATE; }
+  if (c->fused_done) {
+    // Weibel loop: the periodic wrap was applied by the fused kernel after its deposit (ORDER 0); in the wall loops the fused
+    // kernel already reflected before the deposit and a second call of the driver would be a no-op in the reference too
+    // (a reflected particle lies inside the walls)
+    return WM_OK;
+  }
+  if (c->defer_push && c->defer_xbc == 0 && c->g.bc != WM_BC_PERIODIC && nxs == c->defer_nxs && nxe == c->defer_nxe) {
+    c->defer_xbc = WM_ORDER_RECONNECTION;    // reflecting walls before the field step: the reconnection loop
+    return WM_OK;
+  }
+  WM_TRY(flush_deferred(c));
   // boundary_shock__particle_x is the same reflecting-wall rule as boundary_reconnection__particle_x
   return wm_k_bc_x(c, nxs, nxe, c->g.bc == WM_BC_PERIODIC ? WM_BC_PERIODIC : WM_BC_RECONNECTION, 0.0);
 }
@@ -467,6 +570,13 @@ int wm_bc_injection(wm_ctx* c, int nxs, int nxe, double u0) {
   if (!c) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
   if (!c->gp_valid) { wm_set_error("bc__injection acts on the pushed particles"); return WM_ERR_STATE; }
+  if (c->fused_done) { wm_set_error("bc__injection after field__fdtd_i: not a call order of the reference"); return WM_ERR_STATE; }
+  if (c->defer_push && c->defer_xbc == 0 && c->g.bc == WM_BC_SHOCK && nxs == c->defer_nxs && nxe == c->defer_nxe) {
+    c->defer_xbc = WM_ORDER_SHOCK;
+    c->defer_u0 = u0;
+    return WM_OK;
+  }
+  WM_TRY(flush_deferred(c));
   return wm_k_bc_x(c, nxs, nxe, WM_BC_SHOCK, u0);
 }
 
@@ -474,6 +584,8 @@ int wm_bc_particle_yz(wm_ctx* c) {
   if (!c) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
   if (!c->gp_valid) { wm_set_error("bc__particle_yz acts on the pushed particles"); return WM_ERR_STATE; }
+  if (c->fused_done) { c->keys_valid = true; return WM_OK; }   // wrapped and counted by the fused kernel
+  WM_TRY(flush_deferred(c));
   // re-binning is classification here; the movers travel inside sort__bucket's scatter (wm_sort.cu)
   WM_TRY(wm_k_classify(c, c->last_nxs, c->last_nxe));
   c->keys_valid = true;
@@ -484,57 +596,78 @@ int wm_sort_bucket(wm_ctx* c, int nxs, int nxe) {
   if (!c || !range_ok(c, nxs, nxe)) { wm_set_error("Initialize first by calling sort__init()"); return WM_ERR_ARG; }
   WM_CUDA(cudaSetDevice(c->device));
   if (!c->gp_valid) { wm_set_error("sort__bucket sorts the pushed particles"); return WM_ERR_STATE; }
-  if (!c->keys_valid) WM_TRY(wm_k_classify(c, nxs, nxe));
-  WM_TRY(wm_k_sort(c, nxs, nxe));
+  WM_TRY(flush_deferred(c));
+  if (c->fused_done) {
+    // the permutation stays pending for the next fused kernel (lazy sort), exactly as inside wm_step
+    c->allow_lazy = 1;
+    const int rc = wm_k_sort(c, nxs, nxe);
+    c->allow_lazy = 0;
+    WM_TRY(rc);
+  } else {
+    if (!c->keys_valid) WM_TRY(wm_k_classify(c, nxs, nxe));
+    WM_TRY(wm_k_sort(c, nxs, nxe));
+  }
   c->gp_valid = false;
   c->keys_valid = false;
+  c->fused_done = false;
+  return WM_OK;
+}
+
+// fold the recorded (not yet read) phase events into the sums: the only host synchronisation of the timing mode
+static int fold_timing(wm_ctx* c) {
+  if (c->ev_used == 0) return WM_OK;
+  WM_CUDA(cudaEventSynchronize(c->ev[5 * (c->ev_used - 1) + 4]));
+  for (int s = 0; s < c->ev_used; ++s) {
+    for (int e = 0; e < 4; ++e) {
+      cudaEventElapsedTime(&c->ms_phase[e], c->ev[5 * s + e], c->ev[5 * s + e + 1]);
+      c->ms_sum[e] += c->ms_phase[e];
+    }
+    c->timed_steps++;
+  }
+  c->ev_used = 0;
   return WM_OK;
 }
 
 int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
   if (!c || !range_ok(c, nxs, nxe)) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
+  WM_TRY(flush_deferred(c));
   const bool fused = c->use_fused && wm_fused_supported(c, order);
   // a pending lazy sort is consumed by the fused kernel only if it covered the same x range
   if (c->lazy && (!fused || nxs != c->lazy_nxs || nxe != c->lazy_nxe)) WM_TRY(wm_materialize(c));
   for (int it = 0; it < nsteps; ++it) {
-    if (c->timing) WM_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    if (c->timing && c->ev_used == wm_ctx::EV_STEPS) WM_TRY(fold_timing(c));
+    cudaEvent_t* ev = c->ev + 5 * c->ev_used;
+    if (c->timing) WM_CUDA(cudaEventRecord(ev[0], c->stream));
     if (fused) {
       // K1, then ONE kernel for push + boundaries + deposit + destination counting (wm_fused.cu)
-      WM_TRY(wm_k_tmpf(c, nxs, nxe));
-      WM_TRY(wm_k_zero_uj(c, nxs, nxe));
-      WM_TRY(wm_k_push_deposit_fused(c, nxs, nxe, order, u0));
-      c->gp_valid = true;
-      if (c->timing) { WM_CUDA(cudaEventRecord(c->ev[1], c->stream)); WM_CUDA(cudaEventRecord(c->ev[2], c->stream)); }
+      WM_TRY(fused_push_deposit(c, nxs, nxe, order, u0));
+      if (c->timing) { WM_CUDA(cudaEventRecord(ev[1], c->stream)); WM_CUDA(cudaEventRecord(ev[2], c->stream)); }
       WM_TRY(field_stages(c, nxs, nxe, 2));
-      if (c->timing) WM_CUDA(cudaEventRecord(c->ev[3], c->stream));
+      if (c->timing) WM_CUDA(cudaEventRecord(ev[3], c->stream));
       c->allow_lazy = 1;      // the next fused kernel (or wm_materialize) applies the permutation
       const int rc_sort = wm_k_sort(c, nxs, nxe);
       c->allow_lazy = 0;
       WM_TRY(rc_sort);
       c->gp_valid = false;
       c->keys_valid = false;
+      c->fused_done = false;
     } else {
       WM_TRY(particle_solv_with(c, nxs, nxe, c->pusher));
-      if (c->timing) WM_CUDA(cudaEventRecord(c->ev[1], c->stream));
+      if (c->timing) WM_CUDA(cudaEventRecord(ev[1], c->stream));
       if (order == WM_ORDER_RECONNECTION) WM_TRY(wm_bc_particle_x(c, nxs, nxe));
       if (order == WM_ORDER_SHOCK) WM_TRY(wm_bc_injection(c, nxs, nxe, u0));
       WM_TRY(wm_field_stage(c, nxs, nxe, 1));
-      if (c->timing) WM_CUDA(cudaEventRecord(c->ev[2], c->stream));
+      if (c->timing) WM_CUDA(cudaEventRecord(ev[2], c->stream));
       WM_TRY(field_stages(c, nxs, nxe, 2));
-      if (c->timing) WM_CUDA(cudaEventRecord(c->ev[3], c->stream));
+      if (c->timing) WM_CUDA(cudaEventRecord(ev[3], c->stream));
       if (order == WM_ORDER_WEIBEL) WM_TRY(wm_bc_particle_x(c, nxs, nxe));
       WM_TRY(wm_bc_particle_yz(c));
       WM_TRY(wm_sort_bucket(c, nxs, nxe));
     }
     if (c->timing) {
-      WM_CUDA(cudaEventRecord(c->ev[4], c->stream));
-      WM_CUDA(cudaEventSynchronize(c->ev[4]));
-      for (int e = 0; e < 4; ++e) {
-        cudaEventElapsedTime(&c->ms_phase[e], c->ev[e], c->ev[e + 1]);
-        c->ms_sum[e] += c->ms_phase[e];
-      }
-      c->timed_steps++;
+      WM_CUDA(cudaEventRecord(ev[4], c->stream));
+      c->ev_used++;
     }
   }
   return WM_OK;
@@ -627,6 +760,9 @@ int wm_load_weibel(wm_ctx* c, int n0, double v_thi, double v_the, double t_ani, 
   if (!c || n0 <= 0) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
   c->lazy = false;
+  c->defer_push = false;
+  c->defer_xbc = 0;
+  c->fused_done = false;
   const Geo& g = c->g;
   if ((long long)n0 * g.nx > g.np) {
     wm_set_error("Error: Too large number of particles");  // 3d/proj/weibel/app.f90:315-320
@@ -694,6 +830,7 @@ int wm_get_stats(wm_ctx* c, wm_stats* out) {
   if (c->cg_ite_on_device)
     WM_CUDA(cudaMemcpyAsync(c->cg_ite, c->totals + 6, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   WM_CUDA(cudaStreamSynchronize(c->stream));
+  WM_TRY(fold_timing(c));
   for (int l = 0; l < 3; ++l) out->cg_iterations[l] = c->cg_ite[l];
   out->n_particles = c->ntot;
   out->max_np2 = 0;
@@ -717,6 +854,7 @@ int wm_sync(wm_ctx* c) {
 int wm_set_timing(wm_ctx* c, int on) {
   if (!c) return WM_ERR_ARG;
   c->timing = on;
+  c->ev_used = 0;
   for (int e = 0; e < 4; ++e) c->ms_sum[e] = 0;
   c->timed_steps = 0;
   return WM_OK;

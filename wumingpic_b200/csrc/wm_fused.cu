@@ -764,11 +764,8 @@ k_fused2(Geo g, Ptcl A, Ptcl B, const double* __restrict__ id_in, double* __rest
 template <int ORDER, int G, bool VAY>
 int launch_fused2(wm_ctx* ctx, int nxs, int nxe, double u0) {
   const Geo& g = ctx->g;
-  static bool attr_set = false;
-  if (!attr_set) {
-    WM_CUDA(cudaFuncSetAttribute(k_fused2<ORDER, G, VAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem2<G>)));
-    attr_set = true;
-  }
+  // per device / context, so not cached in a process-wide static (a process may drive several devices, wm_params.device)
+  WM_CUDA(cudaFuncSetAttribute(k_fused2<ORDER, G, VAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem2<G>)));
   const int ngx = (nxe - nxs + 1 + G - 1) / G;
   const int blocks = ngx * g.nyl;
   const double xend = nxe * g.delx + u0 / sqrt(1 + (u0 * u0) / (g.c * g.c)) * g.delt;   // 2d/proj/shock/boundary_shock.f90:271
@@ -782,11 +779,7 @@ int launch_fused2(wm_ctx* ctx, int nxs, int nxe, double u0) {
 template <int ORDER, int G, bool VAY>
 int launch_fused(wm_ctx* ctx, int nxs, int nxe, double u0) {
   const Geo& g = ctx->g;
-  static bool attr_set = false;
-  if (!attr_set) {
-    WM_CUDA(cudaFuncSetAttribute(k_fused3<ORDER, G, VAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<G>)));
-    attr_set = true;
-  }
+  WM_CUDA(cudaFuncSetAttribute(k_fused3<ORDER, G, VAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<G>)));
   const int ngx = (nxe - nxs + 1 + G - 1) / G;
   const int blocks = ngx * g.nyl * g.nzl;
   const double xend = nxe * g.delx + u0 / sqrt(1.0 + (u0 * u0) / (g.c * g.c)) * g.delt;   // boundary_shock.f90:438

@@ -124,6 +124,17 @@ struct wm_ctx {
   bool gp_valid = false;     // set B holds the pushed state
   bool keys_valid = false;   // migration pass done (histogram in cs_new)
   int last_nxs = 0, last_nxe = 0;  // x range of the last particle__solv (bc__particle_y[z] has no range argument)
+  // The reference's five calls on the fast kernels (wm_api.cu): particle__solv on resident state is DEFERRED (nobody reads gp
+  // between it and field__fdtd_i: 3d/proj/weibel/app.f90:102-104) together with a following reflecting-wall bc__particle_x /
+  // bc__injection (reconnection and shock loops); field__fdtd_i then launches the fused push + boundary + deposit kernel, and the
+  // later bc__particle_x (Weibel loop) / bc__particle_y[z] find their work done.  Any other reader of gp runs the deferred
+  // procedures with the per-procedure kernels first (flush_deferred).
+  bool defer_push = false;       // a particle__solv is pending
+  int defer_pusher = 0, defer_nxs = 0, defer_nxe = 0;
+  int defer_xbc = 0;             // 0 none, WM_ORDER_RECONNECTION: reflecting bc__particle_x pending, WM_ORDER_SHOCK: bc__injection
+  double defer_u0 = 0.0;
+  bool fused_done = false;       // the fused kernel ran for this step: set B is pushed, wrapped and counted
+  int fused_order = 0;
   // comm
   PeerCG peer = {};
   bool peer_ok = false;            // the peer-memory cgm is usable (all ranks agreed)
@@ -135,7 +146,11 @@ struct wm_ctx {
   // bookkeeping
   long long launches = 0;
   int timing = 0;
-  cudaEvent_t ev[8] = {};
+  // phase timing: five events per timed step from a pool, resolved (one host sync) only when the pool is full or the sums are
+  // read -- wm_step never waits on the host between steps
+  static constexpr int EV_STEPS = 64;
+  cudaEvent_t ev[5 * EV_STEPS] = {};
+  int ev_used = 0;               // timed steps recorded and not yet folded into ms_sum
   float ms_phase[4] = {0, 0, 0, 0};
   double ms_sum[4] = {0, 0, 0, 0};
   int timed_steps = 0;
