@@ -110,10 +110,12 @@ def test_upload_with_shock_shaped_cumcnt():
         up, np2, c2, uf = b.empty("up"), b.empty("np2"), b.empty("cumcnt"), b.empty("uf")
         b.download(up, np2, c2, uf)
         assert b.stats()["error_flags"] == 0 and b.stats()["n_particles"] == int(w.arr("np2").sum())
-        outs.append((up[active_mask(np2, w.np)].view(np.int64).copy(), np2.copy(), c2[..., :nxe - 1].copy(), uf.copy()))
+        outs.append((up[active_mask(np2, w.np)].copy(), np2.copy(), c2[..., :nxe - 1].copy(), uf.copy()))
         b.close()
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
-    assert np.array_equal(outs[0][0], outs[1][0])
+    # same particles in the same (deterministic) order; coordinates to round-off (the J sums of step 1 are RED.F64 in any order)
+    assert np.array_equal(outs[0][0][:, -1].view(np.int64), outs[1][0][:, -1].view(np.int64))
+    assert np.abs(outs[0][0][:, :-1] - outs[1][0][:, :-1]).max() < 1e-12
     assert rel_err(outs[1][3], outs[0][3]) < 1e-12
     w.step(2, U0); w.step(2, U0)
     assert np.array_equal(outs[1][1], w.arr("np2"))
