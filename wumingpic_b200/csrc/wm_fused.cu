@@ -812,6 +812,7 @@ int wm_k_push_deposit_fused(wm_ctx* ctx, int nxs, int nxe, int order, double u0)
     if (order == WM_ORDER_SHOCK) return WM_DISPATCH(launch_fused2, 2, u0);
     return WM_DISPATCH(launch_fused2, 0, 0.0);
   }
+  // (round 2 measured a one-warp-per-cell form of this kernel: slower, see profiles/r02_fused_experiments.md)
   if (order == WM_ORDER_RECONNECTION) return WM_DISPATCH(launch_fused, 1, 0.0);
   if (order == WM_ORDER_SHOCK) return WM_DISPATCH(launch_fused, 2, u0);
   return WM_DISPATCH(launch_fused, 0, 0.0);
