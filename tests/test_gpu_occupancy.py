@@ -77,15 +77,15 @@ def test_64ppc_eight_batches_per_cell(path):
 
 
 def test_ragged_cells():
-    """x -> 2 + nx ((x - 2)/nx)^3 piles the load up near the low-x edge: cells with several hundred particles (> 32 batches of a
-    half-warp) next to empty ones; the Weibel loop then runs as usual"""
+    """x -> 2 + (nx - 4) ((x - 2)/nx)^3 piles the load up near the low-x edge: cells with a hundred particles and more next to
+    thinly filled and empty ones; the Weibel loop then runs as usual"""
     nx, ny, nz, n0 = 24, 6, 6, 12
     w = make_world3(nx, ny, nz, n0, np_factor=3)
     up, gp, np2 = w.arr("up"), w.arr("gp"), w.arr("np2")
     gp[...] = up
     m = active_mask(np2, w.np)
     x = gp[..., 0]
-    x[m] = 2.0 + nx * ((x[m] - 2.0) / nx) ** 3
+    x[m] = 2.0 + (nx - 4) * ((x[m] - 2.0) / nx) ** 3
     w.sort_bucket()
     w.arr("gp")[...] = w.arr("up")
     cc = w.arr("cumcnt")

@@ -141,7 +141,13 @@ int wm_create(const wm_params* prm, wm_ctx** out) {
     cudaGetDevice(&c->device);
   }
   WM_CUDA(cudaSetDevice(c->device));
-  WM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    // the main stream (push, field solve) outranks the second stream (the sort that may run beside the field solve)
+    int lo = 0, hi = 0;
+    WM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    WM_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+    WM_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, lo));
+  }
   Geo& g = c->g;
   g.dim = p.dim; g.ndim = p.ndim; g.nsp = p.nsp; g.np = p.np;
   g.nxgs = p.nxgs; g.nxge = p.nxge; g.nygs = p.nygs; g.nyge = p.nyge;
@@ -220,7 +226,10 @@ int wm_create(const wm_params* prm, wm_ctx** out) {
   c->hbuf_elems = (size_t)2 * 6 * g.bx * std::max(g.by, g.bz);
   WM_CUDA(cudaMalloc(&c->hbuf[0], c->hbuf_elems * sizeof(double)));
   WM_CUDA(cudaMalloc(&c->hbuf[2], c->hbuf_elems * sizeof(double)));
-  for (int e = 0; e < 5 * wm_ctx::EV_STEPS; ++e) WM_CUDA(cudaEventCreate(&c->ev[e]));
+  for (int e = 0; e < wm_ctx::EV_PER * wm_ctx::EV_STEPS; ++e) WM_CUDA(cudaEventCreate(&c->ev[e]));
+  WM_CUDA(cudaEventCreateWithFlags(&c->ev_fused, cudaEventDisableTiming));
+  WM_CUDA(cudaEventCreateWithFlags(&c->ev_sort, cudaEventDisableTiming));
+  if (const char* e = getenv("WM_OVERLAP_SORT")) c->overlap = atoi(e);
   WM_CUDA(cudaStreamSynchronize(c->stream));
   *out = c;
   return WM_OK;
@@ -247,7 +256,10 @@ int wm_destroy(wm_ctx* c) {
   for (int* p : ii) if (p) cudaFree(p);
   if (c->scan_tmp) cudaFree(c->scan_tmp);
   if (c->red_host) cudaFreeHost(c->red_host);
-  for (int e = 0; e < 5 * wm_ctx::EV_STEPS; ++e) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
+  for (int e = 0; e < wm_ctx::EV_PER * wm_ctx::EV_STEPS; ++e) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
+  if (c->ev_fused) cudaEventDestroy(c->ev_fused);
+  if (c->ev_sort) cudaEventDestroy(c->ev_sort);
+  if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
   cudaStreamDestroy(c->stream);
   delete c;
   return WM_OK;
@@ -517,6 +529,7 @@ static int fused_push_deposit(wm_ctx* c, int nxs, int nxe, int order, double u0)
   WM_TRY(wm_k_tmpf(c, nxs, nxe));
   WM_TRY(wm_k_zero_uj(c, nxs, nxe));
   WM_TRY(wm_k_push_deposit_fused(c, nxs, nxe, order, u0));
+  WM_CUDA(cudaEventRecord(c->ev_fused, c->stream));   // what the sort waits for (not for the field solve that follows)
   c->gp_valid = true;
   c->keys_valid = false;
   c->fused_done = true;
@@ -524,6 +537,32 @@ static int fused_push_deposit(wm_ctx* c, int nxs, int nxe, int order, double u0)
   c->last_nxs = nxs;
   c->last_nxe = nxe;
   return WM_OK;
+}
+
+// The sort that follows a fused push kernel (lazy: its permutation stays pending).  With overlap on it is enqueued on the second
+// stream behind the fused kernel only, so it runs concurrently with the field solve the caller enqueued on the main stream; the main
+// stream then waits for it.  t0 / t1: optional timing events recorded around it on the stream it runs on.
+static int sort_after_fused(wm_ctx* c, int nxs, int nxe, cudaEvent_t t0, cudaEvent_t t1) {
+  const bool ov = wm_overlap_bps(c, (long long)(nxe - nxs + 1) * c->g.nyl * c->g.nzl) > 0;
+  cudaStream_t main_stream = c->stream;
+  void* main_comm = c->nccl_comm;
+  if (ov) {
+    c->stream = c->stream2;
+    if (c->nccl_comm2) c->nccl_comm = c->nccl_comm2;
+    cudaStreamWaitEvent(c->stream, c->ev_fused, 0);
+  }
+  if (t0) cudaEventRecord(t0, c->stream);
+  c->allow_lazy = 1;      // the next fused kernel (or wm_materialize) applies the permutation
+  const int rc = wm_k_sort(c, nxs, nxe);
+  c->allow_lazy = 0;
+  if (t1) cudaEventRecord(t1, c->stream);
+  if (ov) {
+    cudaEventRecord(c->ev_sort, c->stream);
+    c->stream = main_stream;
+    c->nccl_comm = main_comm;
+    cudaStreamWaitEvent(c->stream, c->ev_sort, 0);
+  }
+  return rc;
 }
 
 int wm_field_fdtd_i(wm_ctx* c, int nxs, int nxe) {
@@ -598,11 +637,9 @@ int wm_sort_bucket(wm_ctx* c, int nxs, int nxe) {
   if (!c->gp_valid) { wm_set_error("sort__bucket sorts the pushed particles"); return WM_ERR_STATE; }
   WM_TRY(flush_deferred(c));
   if (c->fused_done) {
-    // the permutation stays pending for the next fused kernel (lazy sort), exactly as inside wm_step
-    c->allow_lazy = 1;
-    const int rc = wm_k_sort(c, nxs, nxe);
-    c->allow_lazy = 0;
-    WM_TRY(rc);
+    // the permutation stays pending for the next fused kernel (lazy sort), exactly as inside wm_step; the field solve this
+    // driver enqueued with field__fdtd_i may still be running on the main stream: the sort overlaps it
+    WM_TRY(sort_after_fused(c, nxs, nxe, nullptr, nullptr));
   } else {
     if (!c->keys_valid) WM_TRY(wm_k_classify(c, nxs, nxe));
     WM_TRY(wm_k_sort(c, nxs, nxe));
@@ -616,12 +653,12 @@ int wm_sort_bucket(wm_ctx* c, int nxs, int nxe) {
 // fold the recorded (not yet read) phase events into the sums: the only host synchronisation of the timing mode
 static int fold_timing(wm_ctx* c) {
   if (c->ev_used == 0) return WM_OK;
-  WM_CUDA(cudaEventSynchronize(c->ev[5 * (c->ev_used - 1) + 4]));
+  constexpr int P = wm_ctx::EV_PER;
+  WM_CUDA(cudaEventSynchronize(c->ev[P * (c->ev_used - 1) + 4]));   // the step end: recorded after the main stream joined the sort
   for (int s = 0; s < c->ev_used; ++s) {
-    for (int e = 0; e < 4; ++e) {
-      cudaEventElapsedTime(&c->ms_phase[e], c->ev[5 * s + e], c->ev[5 * s + e + 1]);
-      c->ms_sum[e] += c->ms_phase[e];
-    }
+    for (int e = 0; e < 3; ++e) cudaEventElapsedTime(&c->ms_phase[e], c->ev[P * s + e], c->ev[P * s + e + 1]);
+    cudaEventElapsedTime(&c->ms_phase[3], c->ev[P * s + 5], c->ev[P * s + 6]);   // the sort, on whichever stream it ran
+    for (int e = 0; e < 4; ++e) c->ms_sum[e] += c->ms_phase[e];
     c->timed_steps++;
   }
   c->ev_used = 0;
@@ -637,7 +674,7 @@ int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
   if (c->lazy && (!fused || nxs != c->lazy_nxs || nxe != c->lazy_nxe)) WM_TRY(wm_materialize(c));
   for (int it = 0; it < nsteps; ++it) {
     if (c->timing && c->ev_used == wm_ctx::EV_STEPS) WM_TRY(fold_timing(c));
-    cudaEvent_t* ev = c->ev + 5 * c->ev_used;
+    cudaEvent_t* ev = c->ev + wm_ctx::EV_PER * c->ev_used;
     if (c->timing) WM_CUDA(cudaEventRecord(ev[0], c->stream));
     if (fused) {
       // K1, then ONE kernel for push + boundaries + deposit + destination counting (wm_fused.cu)
@@ -645,10 +682,7 @@ int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
       if (c->timing) { WM_CUDA(cudaEventRecord(ev[1], c->stream)); WM_CUDA(cudaEventRecord(ev[2], c->stream)); }
       WM_TRY(field_stages(c, nxs, nxe, 2));
       if (c->timing) WM_CUDA(cudaEventRecord(ev[3], c->stream));
-      c->allow_lazy = 1;      // the next fused kernel (or wm_materialize) applies the permutation
-      const int rc_sort = wm_k_sort(c, nxs, nxe);
-      c->allow_lazy = 0;
-      WM_TRY(rc_sort);
+      WM_TRY(sort_after_fused(c, nxs, nxe, c->timing ? ev[5] : nullptr, c->timing ? ev[6] : nullptr));
       c->gp_valid = false;
       c->keys_valid = false;
       c->fused_done = false;
@@ -661,9 +695,11 @@ int wm_step(wm_ctx* c, int nxs, int nxe, int order, double u0, int nsteps) {
       if (c->timing) WM_CUDA(cudaEventRecord(ev[2], c->stream));
       WM_TRY(field_stages(c, nxs, nxe, 2));
       if (c->timing) WM_CUDA(cudaEventRecord(ev[3], c->stream));
+      if (c->timing) WM_CUDA(cudaEventRecord(ev[5], c->stream));
       if (order == WM_ORDER_WEIBEL) WM_TRY(wm_bc_particle_x(c, nxs, nxe));
       WM_TRY(wm_bc_particle_yz(c));
       WM_TRY(wm_sort_bucket(c, nxs, nxe));
+      if (c->timing) WM_CUDA(cudaEventRecord(ev[6], c->stream));
     }
     if (c->timing) {
       WM_CUDA(cudaEventRecord(ev[4], c->stream));

@@ -25,6 +25,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;   // NCCL >= 2.18
   ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -45,6 +46,7 @@ NcclApi& api() {
   LOAD(GetUniqueId, "ncclGetUniqueId");
   LOAD(CommInitRank, "ncclCommInitRank");
   LOAD(CommDestroy, "ncclCommDestroy");
+  LOAD(CommSplit, "ncclCommSplit");
   LOAD(Send, "ncclSend");
   LOAD(Recv, "ncclRecv");
   LOAD(AllReduce, "ncclAllReduce");
@@ -243,6 +245,13 @@ extern "C" int wm_comm_init(wm_ctx* ctx, int nranks, int rank, const char* id_by
   WM_CUDA(cudaSetDevice(ctx->device));
   WM_NCCL(a.CommInitRank(&comm, nranks, id, rank));
   ctx->nccl_comm = comm;
+  // a second communicator over the same ranks for the sort / migration stream (wm_api.cu sort_after_fused): operations of one
+  // communicator must not run concurrently from two streams
+  ctx->nccl_comm2 = nullptr;
+  if (a.CommSplit && ctx->overlap) {
+    ncclComm_t comm2 = nullptr;
+    if (a.CommSplit(comm, 0, rank, &comm2, nullptr) == 0 && comm2) ctx->nccl_comm2 = comm2;
+  }
   WM_TRY(peer_setup(ctx));
   return wm_enable_slab_migration(ctx);
 }
@@ -256,6 +265,8 @@ int wm_comm_destroy(wm_ctx* ctx) {
     ctx->phi = ctx->pcg = ctx->pcg2 = ctx->rcg = nullptr;   // they lived in the arena
     ctx->peer_ok = false;
   }
+  if (ctx->nccl_comm2 && api().CommDestroy) api().CommDestroy((ncclComm_t)ctx->nccl_comm2);
+  ctx->nccl_comm2 = nullptr;
   if (ctx->nccl_comm && api().CommDestroy) api().CommDestroy((ncclComm_t)ctx->nccl_comm);
   ctx->nccl_comm = nullptr;
   return WM_OK;

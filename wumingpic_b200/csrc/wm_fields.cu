@@ -1050,7 +1050,13 @@ int wm_k_cgm(wm_ctx* ctx, int nxs, int nxe) {
     if (per_sm[peer] == 0) WM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[peer], kern, TPB, 0));
     int nsm = 0;
     WM_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
-    int nb = (int)std::min<long long>((long long)nsm * per_sm[peer], (n + TPB - 1) / TPB);
+    // blocks per SM: all that fit -- unless the sort runs beside this kernel on the second stream (wm_overlap_bps, wm_internal.cuh)
+    int bps = per_sm[peer];
+    static const int bps_env = getenv("WM_CG_BPS") ? atoi(getenv("WM_CG_BPS")) : 0;
+    const int ov_bps = wm_overlap_bps(ctx, n);
+    if (ov_bps > 0) bps = std::min(bps, ov_bps);
+    if (bps_env > 0) bps = std::min(bps, bps_env);
+    int nb = (int)std::min<long long>((long long)nsm * bps, (n + TPB - 1) / TPB);
     nb = std::max(1, std::min(nb, 1024));   // 2 ping-pong partial buffers of 2*nb doubles in ctx->red
     double *df = ctx->df, *gkl = ctx->gkl, *phi = ctx->phi, *p = ctx->pcg, *p2 = ctx->pcg2, *r = ctx->rcg, *b = ctx->bcg, *ap = ctx->apcg;
     double* part = ctx->red;

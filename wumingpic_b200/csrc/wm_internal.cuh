@@ -70,6 +70,14 @@ struct wm_ctx {
   Geo g;
   int device = 0;
   cudaStream_t stream = nullptr;
+  // The sort / re-binning / migration of a step needs only what the fused push kernel left behind, the field solve only J: inside
+  // wm_step (and the five-call sequence that reaches the same kernels) the sort runs on a second stream -- with its own NCCL
+  // communicator -- concurrently with the field solve, and the main stream joins it before anything else touches the particles.
+  // Both phases are latency-bound on thin slabs (strong scaling), so overlapping them is where 8-GPU efficiency comes from.
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fused = nullptr, ev_sort = nullptr;
+  void* nccl_comm2 = nullptr;
+  int overlap = 1;
   // particles
   size_t cap = 0;      // capacity (particles) of each SoA array
   long long ntot = 0;  // active particles
@@ -148,13 +156,27 @@ struct wm_ctx {
   int timing = 0;
   // phase timing: five events per timed step from a pool, resolved (one host sync) only when the pool is full or the sums are
   // read -- wm_step never waits on the host between steps
-  static constexpr int EV_STEPS = 64;
-  cudaEvent_t ev[5 * EV_STEPS] = {};
+  static constexpr int EV_STEPS = 64, EV_PER = 7;   // per step: start, fused end, field start, field end, step end, sort start, sort end
+  cudaEvent_t ev[EV_PER * EV_STEPS] = {};
   int ev_used = 0;               // timed steps recorded and not yet folded into ms_sum
   float ms_phase[4] = {0, 0, 0, 0};
   double ms_sum[4] = {0, 0, 0, 0};
   int timed_steps = 0;
 };
+
+// Sort-beside-field-solve policy (wm_api.cu sort_after_fused, wm_fields.cu wm_k_cgm): returns 0 when the sort stays on the main
+// stream, else the blocks per SM the cooperative cgm may take while the sort runs beside it.  The overlap pays where both phases
+// are latency-bound, i.e. on thin slabs of a multi-GPU run (measured on 8 x B200, fixed 256x256x128 box: 20.2 -> 18.6 ms per step;
+// on 4.2 M cells per rank it costs time).  The cgm grid is capped at <= 4 blocks of 256 threads per SM so that the sort's NCCL
+// transfer kernels can always become resident beside it: a cooperative grid that fills every SM while the neighbours' solves wait
+// for this rank's reductions and this rank's transfer kernel waits for the neighbours' would be a cross-rank dependency cycle.
+static inline int wm_overlap_bps(const wm_ctx* c, long long ncells) {
+  if (!c->overlap || c->nranks == 1 || !c->nccl_comm2 || !c->stream2) return 0;
+  const long long per_bps = 148LL * 256 * 16;            // ~16 cells per thread and sweep
+  const long long bps = (ncells + per_bps - 1) / per_bps;
+  if (bps > 4) return 0;
+  return (int)(bps < 2 ? 2 : bps);
+}
 
 // error plumbing -------------------------------------------------------------------------------
 void wm_set_error(const std::string& msg);
