@@ -328,6 +328,30 @@ int wm_upload(wm_ctx* c, const double* up, const int* np2, const int* cumcnt, co
       }
     }
     c->gp_valid = false;
+    // The cell index must agree with the particles (cell = int(x), sort.f90:65): the kernels' re-binning moves a particle at most
+    // one cell from the cell the index puts it in.  Every state the reference passes around satisfies this EXCEPT the shock driver's
+    // freshly loaded box, whose cumcnt is nominal (n0 per cell, 2d/proj/shock/app.f90:346-359) while the particles are spread
+    // evenly over one more cell (:436-441), so that some sit one cell below their nominal cell.  The reference evaluates its first
+    // step about the nominal cells (and loses the charge of the particles that end up two cells away); here the index is repaired
+    // on upload by one sort__bucket of the uploaded set, i.e. the first step already runs on consistent cells.
+    int bad = 0;
+    WM_TRY(wm_k_cells_consistent(c, &bad));
+    if (c->nranks > 1 && c->nccl_comm) {           // the repair sort exchanges counts with the neighbours: decide it together
+      double v = bad ? 1.0 : 0.0;
+      WM_CUDA(cudaMemcpyAsync(c->red, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      WM_TRY(wm_comm_allreduce_sum(c, c->red, 1));
+      WM_CUDA(cudaMemcpyAsync(&v, c->red, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      WM_CUDA(cudaStreamSynchronize(c->stream));
+      bad = v > 0.0;
+    }
+    if (bad) {
+      std::swap(c->A, c->B);                       // the uploaded set plays the pushed set of a sort
+      c->gp_valid = true;
+      WM_TRY(wm_k_classify(c, g.nxgs, g.nxge));
+      WM_TRY(wm_k_sort(c, g.nxgs, g.nxge));
+      c->gp_valid = false;
+      c->keys_valid = false;
+    }
   }
   WM_CUDA(cudaStreamSynchronize(c->stream));
   return WM_OK;

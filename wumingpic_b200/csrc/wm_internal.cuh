@@ -218,6 +218,7 @@ int wm_k_classify(wm_ctx* ctx, int nxs, int nxe);
 int wm_k_sort(wm_ctx* ctx, int nxs, int nxe);
 int wm_enable_slab_migration(wm_ctx* ctx);
 int wm_k_refresh_np2(wm_ctx* ctx);
+int wm_k_cells_consistent(wm_ctx* ctx, int* inconsistent);
 int wm_materialize(wm_ctx* ctx);   // apply a pending (lazy) sort permutation: set A becomes the sorted set again
 int wm_k_energy(wm_ctx* ctx, double* out_host);
 int wm_k_gauss(wm_ctx* ctx, double* out_host);

@@ -461,7 +461,33 @@ int scan_ints(wm_ctx* ctx, int* data, size_t n) {
   return WM_OK;
 }
 
+// flags[1] |= 1 if some particle's int(x) is not the cell the index puts it in (one thread per (pencil, cell); runs once per upload)
+__global__ void k_cells_consistent(Geo g, const double* __restrict__ x, const int* __restrict__ cs, int* flags) {
+  const long long n = (long long)g.npen * g.nx;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int pen = (int)(e / g.nx), ci = (int)(e % g.nx);
+    const int* row = cs + (size_t)pen * (g.nx + 1) + ci;
+    bool bad = false;
+    for (int p = row[0]; p < row[1]; ++p) bad |= (int)x[p] != g.nxgs + ci;     // sort.f90:65: the cell of a particle is int(x)
+    if (bad) atomicOr(flags + 1, 1);
+  }
+}
+
 }  // namespace
+
+// Does the uploaded cell index agree with the particles?  It always does after a sort__bucket; the one state of the reference where
+// it does not is the shock driver's freshly loaded box (nominal cumcnt).  *inconsistent = 1 if not.
+int wm_k_cells_consistent(wm_ctx* ctx, int* inconsistent) {
+  const Geo& g = ctx->g;
+  *inconsistent = 0;
+  if (ctx->ntot == 0) return WM_OK;
+  WM_CUDA(cudaMemsetAsync(ctx->flags + 1, 0, sizeof(int), ctx->stream));
+  k_cells_consistent<<<grid_for((long long)g.npen * g.nx), TPB, 0, ctx->stream>>>(g, ctx->A.c[0], ctx->cs, ctx->flags);
+  WM_LAUNCH_CHECK(ctx);
+  WM_CUDA(cudaMemcpyAsync(inconsistent, ctx->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  WM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return WM_OK;
+}
 
 // called by the producers (fused push kernel, k_classify) before they accumulate the histogram
 int wm_sort_prepare(wm_ctx* ctx) {
