@@ -55,6 +55,10 @@ def parse():
                          "bc__particle_yz, sort__bucket: what an unmodified driver does) instead of the one-call wm_step")
     ap.add_argument("--slow-kernels", action="store_true",
                     help="wm_set_fused(0): the separate per-procedure kernels (push, RED deposit, classify, eager sort)")
+    ap.add_argument("--setup", default="weibel", choices=["weibel", "shock", "reconnection"],
+                    help="weibel (default): the metric's workload.  shock / reconnection: BASELINE.json configs[2..4] -- the drivers' own loads "
+                         "(wumingpic_b200/setups.py) on y-slabs (2-D) / z-slabs (3-D), sizes --nx (shock: box capacity) --ny --nz PER GPU, --ppc "
+                         "(shock: n_ppc; reconnection: scales nbg = ppc, ncs = 5 ppc); not the metric's bench line")
     ap.add_argument("--dim", type=int, default=3, choices=[2, 3],
                     help="3 (default): the C2 3-D Weibel workload of the metric; 2: a 2-D Weibel sheet nx x (ny per GPU) for the "
                          "2-D code path (not a bench line of BASELINE.json; ndim = 6 -> 192 B per particle-step)")
@@ -233,6 +237,179 @@ def golden_parity(wm, dist, world, rank, local_rank, fused=True, five_calls=Fals
             "pass": bool(t[2] == 0.0 and t[0] < 1e-9 and t[1] < 1e-13 and list(cg) == [int(v) for v in fx["cg_1"]])}
 
 
+def run_setup(args):
+    """BASELINE.json configs[2..4]: the shock and reconnection set-ups end to end on N GPUs -- the drivers' initial loads (every rank
+    builds its own slab, wumingpic_b200/setups.py), then the set-up's own time loop on device-resident state: reconnection = wm_step with
+    the reflecting walls before the field solve; shock = wm_step with the injection wall + wm_shock_inject + wm_shock_relocate every
+    step (intvl_expand = 1 as in the sample config), the host keeping only the integer bookkeeping of inject()."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import wumingpic_b200 as wm
+    from wumingpic_b200 import setups
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dim = args.dim
+    ny = args.ny * world if dim == 2 else args.ny
+    nz = None if dim == 2 else args.nz * world
+    if args.setup == "reconnection":
+        s = setups.reconnection_constants(args.nx, ny, nz, nbg=args.ppc, ncs=5 * args.ppc)
+        load, cap = setups.reconnection_slab, int(s.extra["np_row"] * 1.3) + 64
+    else:
+        s = setups.shock_constants(args.nx, args.nx // 2, ny, nz, n_ppc=args.ppc)   # cold upstream, as config_sample.json
+        load, cap = setups.shock_slab, int(args.ppc * args.nx * 1.3) + 64
+    s.np_cap = cap                     # pencil capacity of the HOST arrays: the drivers allocate n0 nx (x5); only the populated part travels
+    if dim == 2:
+        lay = wm.SlabLayout(2, ny + 1, 0, 0, world, 1, rank)
+        b = wm.Backend(2, cap, 2, s.nx + 1, 2, ny + 1, nys=lay.nys, nye=lay.nye, delt=s.delt, c=s.c, gfac=s.gfac, q=s.q, r=s.r,
+                       bc_kind=s.bc, nproc_j=world, nproc_k=1, rank_j=rank, rank_k=0, device=local_rank)
+        nzs = nze = 2
+    else:
+        lay = wm.SlabLayout(2, ny + 1, 2, nz + 1, 1, world, rank)
+        b = wm.Backend(3, cap, 2, s.nx + 1, 2, ny + 1, 2, nz + 1, nys=lay.nys, nye=lay.nye, nzs=lay.nzs, nze=lay.nze, delt=s.delt,
+                       c=s.c, gfac=s.gfac, q=s.q, r=s.r, bc_kind=s.bc, nproc_j=1, nproc_k=world, rank_j=0, rank_k=rank, device=local_rank)
+        nzs, nze = lay.nzs, lay.nze
+    if world > 1:
+        box = [b.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        b.comm_init(world, rank, box[0])
+    t_load = time.perf_counter()
+    up, np2, cc, uf = load(s, lay.nys, lay.nye, nzs, nze)
+    b.upload(up, np2, cc, uf)
+    del up
+    t_load = time.perf_counter() - t_load
+    stream = torch.cuda.ExternalStream(b.stream(), device=torch.device("cuda", local_rank))
+    nrows_glob = s.ny * s.nz
+    if dim == 2:
+        rows = np.arange(lay.nys - 2, lay.nye - 1)
+    else:
+        rows = ((np.arange(nzs, nze + 1) - 2)[:, None] * s.ny + (np.arange(lay.nys, lay.nye + 1) - 2)[None, :]).ravel()
+    prm = setups.shock_params(s) if args.setup == "shock" else None
+    state = {"nxe": s.nxe, "it": 0}
+
+    def count_global():
+        t = torch.tensor(b_counts(), device="cuda", dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(t)
+        return t.tolist()
+
+    def b_counts():
+        n = b.empty("np2")
+        b.download(np2=n)
+        return n.reshape(2, -1).sum(axis=1).astype(np.int64)
+
+    def one_step():
+        state["it"] += 1
+        it = state["it"]
+        if args.setup == "reconnection":
+            b.step(s.nxs, s.nxe, 1, s.order)
+            return
+        b.step(s.nxs, state["nxe"], 1, s.order, s.u0)
+        # inject(): the host's integer bookkeeping (2d/proj/shock/app.f90:711-781); the particle totals it needs for the IDs are
+        # tracked from the counts themselves (every injected / relocated particle is known to the host), no read-back per step
+        counts = setups.shock_inject_counts(s, it, nproc=world)
+        excl = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+        idf = np.stack([excl[rows] + state["ntot"][0], excl[rows] + state["ntot"][1]])
+        b.shock_inject(prm, state["nxe"], counts[rows], idf, it)
+        state["ntot"] = state["ntot"] + int(counts.sum())
+        if state["nxe"] < s.nx + 1:
+            state["nxe"] += 1
+            g = np.asarray(rows, dtype=np.int64)
+            b.shock_relocate(prm, state["nxe"], np.stack([g * s.n0 + state["ntot"][0], g * s.n0 + state["ntot"][1]]), it)
+            state["ntot"] = state["ntot"] + nrows_glob * s.n0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    state["ntot"] = np.array(count_global(), dtype=np.int64)
+    n_start = int(state["ntot"].sum())
+    e0 = b.energy().sum()
+    for _ in range(args.warmup):
+        one_step()
+    b.sync()
+    b.set_timing(True)
+    launches0 = b.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n_before = sum(count_global())
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        one_step()
+    b.settle()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = b.launch_count() - launches0
+    st = b.stats()
+    b.set_timing(False)
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    n_after = sum(count_global())
+    per_rank = torch.tensor([float(st["n_particles"])], device="cuda", dtype=torch.float64)
+    pr = [torch.zeros_like(per_rank) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(pr, per_rank)
+    else:
+        pr = [per_rank]
+    pr = [float(x.item()) for x in pr]
+    res, rho = b.gauss()
+    e1 = b.energy().sum()
+    et = torch.tensor([e0, e1, res / max(rho, 1.0)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        tmp = et.clone()
+        dist.all_reduce(tmp[:2])
+        gm = et[2:].clone()
+        dist.all_reduce(gm, op=dist.ReduceOp.MAX)
+        et = torch.cat([tmp[:2], gm])
+    et = et.tolist()
+    updates = 0.5 * (n_before + n_after) * args.steps            # the shock box fills up while it is timed: mean population
+    peak, peak_src = measured_peak()
+    bytes_step = 192 if dim == 2 else 224
+    k_ms = (st["ms_push"] + st["ms_deposit"]) / max(1, st["timed_steps"])
+    npart_rank = max(pr)
+    if rank == 0:
+        line = {"metric": f"particle-updates/sec (push+deposit+solve+migrate+sort), {dim}-D {args.setup}", "value": updates / (ms * 1e-3),
+                "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{dim}-D {args.setup} (BASELINE.json configs[{2 if args.setup == 'shock' else (3 if dim == 2 else 4)}]): "
+                                       f"{s.nx} x {s.ny}" + (f" x {s.nz}" if dim == 3 else "") + f" cells, {n_start} particles at the start, "
+                                       + (f"Harris sheet, mass ratio {s.r[0]:g}, nbg {s.extra['nbg']}, ncs {s.extra['ncs']}, cfl 0.5"
+                                          if args.setup == "reconnection" else
+                                          f"n_ppc {s.n0}, u_inject {abs(s.u0):g}, injection wall + inject() + relocate() every step, "
+                                          f"box {s.nxe - s.nxs} -> {state['nxe'] - s.nxs} cells"),
+                           "parallelism": f"{'y' if dim == 2 else 'z'}-slabs x{world}", "particles": int(n_after),
+                           "l2": "particle arrays exceed the 126 MB L2", "loader_s": t_load,
+                           "note": "not the metric's bench line (that is --setup weibel); the drivers' loads restated in wumingpic_b200/setups.py"},
+                "roofline": {"bound": "hbm", "kernel": "push+deposit", "kernel_ms": k_ms, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                             "achieved": npart_rank * (bytes_step / 2) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None,
+                             "frac": npart_rank * (bytes_step / 2) / (k_ms * 1e-3) / 1e9 / peak if k_ms > 0 else None, "traffic": None,
+                             "step": {"bytes_per_update": bytes_step, "frac": updates / args.steps / world * bytes_step / (ms / args.steps * 1e-3) / 1e9 / peak},
+                             "phases_ms": {k: st[k] / max(1, st["timed_steps"]) for k in ("ms_push", "ms_deposit", "ms_field", "ms_sort")}},
+                "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+                "checks": {"gauss_rel_residual_max": et[2], "energy_start": et[0], "energy_end": et[1], "cg_iterations": st["cg_iterations"],
+                           "error_flags": st["error_flags"], "particles_per_rank": pr,
+                           "imbalance_max_over_mean": max(pr) / (sum(pr) / len(pr)),
+                           "particles_before_after_timed_region": [int(n_before), int(n_after)]}}
+        emit(line)
+    b.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -259,6 +436,8 @@ def main():
     quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
+    if args.setup != "weibel":
+        return run_setup(args)
 
     import numpy as np
     import torch

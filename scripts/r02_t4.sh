@@ -1,0 +1,3 @@
+set -x
+mkdir -p gpurun_out
+( timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -8 ) 2>&1 | tail -10

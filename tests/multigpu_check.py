@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--n0", type=int, default=8)
     ap.add_argument("--dim", type=int, default=3, help="3: z-slabs; 2: y-slabs (2d/common/mpi_set.f90:36-47)")
     ap.add_argument("--bc", type=int, default=0, help="0 periodic (Weibel loop), 1 reconnection walls, 2 shock walls")
+    ap.add_argument("--yslab", type=int, default=0, help="1 (3-D): decompose along y (nproc_j = WORLD_SIZE, nproc_k = 1) like the reference's "
+                                                           "shipped 3-D samples, instead of z-slabs")
     ap.add_argument("--source", type=int, default=0, help="1 (with --bc 2): the shock driver's inject()/relocate() run on the device "
                                                             "after every step (wm_shock_inject / wm_shock_relocate), box grows from nx-6")
     args = ap.parse_args()
@@ -41,7 +43,10 @@ def main():
     order, u0 = args.bc, (0.3 if args.bc == 2 else 0.0)     # each boundary module with its own time loop
     if args.source:
         return shock_source_check(args, rank, world, local)
-    if args.dim == 3:
+    if args.dim == 3 and args.yslab:
+        w = make_world3(args.nx, args.ny, args.nz, args.n0, steps=2, nproc_j=world, nproc_k=1, bc=args.bc, order=order, u0=u0)
+        b = backend_for(w, rank=rank, device=local, nproc_j=world, nproc_k=1)
+    elif args.dim == 3:
         w = make_world3(args.nx, args.ny, args.nz, args.n0, steps=2, nproc_k=world, bc=args.bc, order=order, u0=u0)
         b = backend_for(w, rank=rank, device=local, nproc_k=world)
     else:
@@ -85,7 +90,7 @@ def main():
     ref = w.arr("mom", rank)
     inner = (slice(None),) + (slice(1, -1),) * args.dim
     assert rel_err(got[inner], ref[inner]) < 1e-9, "moments differ"
-    print(f"rank {rank}/{world} ok: dim={args.dim} bc={args.bc} fused={args.fused} np2/cumcnt/IDs exact, max|dx| {worst:.2e}, uf rel {worst_uf:.2e}",
+    print(f"rank {rank}/{world} ok: dim={args.dim}{' y-slabs' if args.yslab else ''} bc={args.bc} fused={args.fused} np2/cumcnt/IDs exact, max|dx| {worst:.2e}, uf rel {worst_uf:.2e}",
           flush=True)
     b.close()
     dist.destroy_process_group()

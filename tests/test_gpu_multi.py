@@ -22,7 +22,7 @@ def _keep_log(name, text):
     d = os.path.join(ROOT, "gpurun_out")
     try:
         os.makedirs(d, exist_ok=True)
-        with open(os.path.join(d, "multigpu_parity.log"), "a") as f:
+        with open(os.path.join(d, f"multigpu_parity_{_ngpu()}gpu_box.log"), "a") as f:
             f.write(f"== {name}\n" + "\n".join(l for l in text.splitlines() if " ok: " in l) + "\n")
     except OSError:
         pass
@@ -54,6 +54,7 @@ def test_slab_parity_variants(dim, bc):
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" ok: ") == 2
+    _keep_log(f"slab_parity_variant_dim{dim}_bc{bc}_2ranks", r.stdout)
 
 
 @pytest.mark.parametrize("dim", [3, 2])
@@ -81,3 +82,19 @@ def test_slab_parity_uneven_slabs():
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" ok: ") == 2
+
+
+@pytest.mark.parametrize("bc", [0, 1], ids=["periodic", "reconnection"])
+def test_yslab_parity(bc):
+    """3-D y-slabs (nproc_j = 2, nproc_k = 1: how every shipped 3-D sample of the reference decomposes, 3d/proj/weibel/config_sample.json
+    :12-13) against the oracle's nproc_j = 2 emulation; the device runs them as z-slabs of the relabelled system (tests/test_gpu_yslab.py)"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(29620 + bc),
+           os.path.join(ROOT, "tests", "multigpu_check.py"), "--fused", "1", "--yslab", "1", "--bc", str(bc),
+           "--nx", "18", "--ny", "12", "--nz", "6"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok: ") == 2
+    _keep_log(f"yslab_parity_bc{bc}_2ranks", r.stdout)

@@ -90,6 +90,33 @@ int check_flags(wm_ctx* c) {
   return WM_OK;
 }
 
+// y-slab relabelling (wm_ctx::swap_yz): caller pencil (isp, k, j) <-> device pencil (isp, k' = j, j' = k)
+int pen_host_to_dev(const wm_ctx* c, int pen_h) {
+  const Geo& g = c->g;
+  const int nyl_h = g.nzl, nzl_h = g.nyl;
+  const int jj = pen_h % nyl_h, kk = (pen_h / nyl_h) % nzl_h, isp = pen_h / (nyl_h * nzl_h);
+  return (isp * g.nzl + jj) * g.nyl + kk;
+}
+// rows of `w` ints per pencil from the caller's pencil order into the device's (to_dev) or back
+void permute_pencil_rows(const wm_ctx* c, const int* in, int* out, int w, bool to_dev) {
+  for (int ph = 0; ph < c->g.npen; ++ph) {
+    const int pd = pen_host_to_dev(c, ph);
+    const int* s = in + (size_t)(to_dev ? ph : pd) * w;
+    int* d = out + (size_t)(to_dev ? pd : ph) * w;
+    for (int i = 0; i < w; ++i) d[i] = s[i];
+  }
+}
+int need_swapbuf(wm_ctx* c) {
+  if (!c->swapbuf) WM_CUDA(cudaMalloc(&c->swapbuf, c->g.nbox() * 6 * sizeof(double)));
+  return WM_OK;
+}
+int no_swap(const wm_ctx* c, const char* what) {
+  if (!c->swap_yz) return WM_OK;
+  wm_set_error(std::string(what) + " is not available with 3-D y-slabs (the device works in the relabelled (x, z, y) system): "
+               "use z-slabs (nproc_j = 1), or the host form of this procedure between wm_download and wm_upload");
+  return WM_ERR_STATE;
+}
+
 bool range_ok(const wm_ctx* c, int nxs, int nxe) {
   return nxs >= c->g.nxgs && nxe <= c->g.nxge && nxs <= nxe;
 }
@@ -118,6 +145,7 @@ int wm_para_range(int n1, int n2, int isize, int irank, int* ns, int* ne) {
 int wm_create(const wm_params* prm, wm_ctx** out) {
   if (!prm || !out) return WM_ERR_ARG;
   *out = nullptr;
+  {
   const wm_params& p = *prm;
   if (!((p.dim == 3 && p.ndim == 7) || (p.dim == 2 && p.ndim == 6)) || p.nsp != 2 || p.np <= 0) {
     wm_set_error("wm_create: need (dim,ndim) = (3,7) or (2,6), nsp = 2, np > 0");
@@ -132,7 +160,19 @@ int wm_create(const wm_params* prm, wm_ctx** out) {
     wm_set_error("wm_create: no CUDA device (this backend has no CPU fallback)");
     return WM_ERR_CUDA;
   }
+  }
   wm_ctx* c = new wm_ctx();
+  c->hprm = *prm;
+  // 3-D y-slabs (nproc_j > 1, nproc_k = 1) -> z'-slabs of the relabelled system (wm_internal.cuh, wm_ctx::swap_yz); WM_SWAP_YZ=1
+  // forces the relabelling on any 3-D run (how the single-GPU tests exercise it)
+  wm_params pp = *prm;
+  if (pp.dim == 3 && pp.nproc_k == 1 && (pp.nproc_j > 1 || getenv("WM_SWAP_YZ") != nullptr)) {
+    std::swap(pp.nygs, pp.nzgs); std::swap(pp.nyge, pp.nzge);
+    std::swap(pp.nys, pp.nzs);   std::swap(pp.nye, pp.nze);
+    std::swap(pp.nproc_j, pp.nproc_k); std::swap(pp.rank_j, pp.rank_k);
+    c->swap_yz = true;
+  }
+  const wm_params& p = pp;
   c->prm = p;
   for (int k = 0; k < 6; ++k) c->A.c[k] = c->B.c[k] = nullptr;
   if (p.device >= 0) {
@@ -248,7 +288,7 @@ int wm_destroy(wm_ctx* c) {
   }
   wm_comm_destroy(c);   // also releases the peer arena (and nulls the CG arrays that lived in it)
   free_particles(c);
-  double* d[] = {c->mom, c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->pcg2, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
+  double* d[] = {c->swapbuf, c->mom, c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->pcg2, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
                  c->hbuf[2], c->stage};
   for (double* p : d) if (p) cudaFree(p);
   int* ii[] = {c->cs, c->cs_new, c->np2, c->poff, c->flags, c->cnt27, c->inc, c->inc_off, c->totals, c->inv, c->goff};
@@ -272,7 +312,16 @@ int wm_upload(wm_ctx* c, const double* up, const int* np2, const int* cumcnt, co
   if (!c) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
   const Geo& g = c->g;
-  if (uf) WM_CUDA(cudaMemcpyAsync(c->uf, uf, g.nbox() * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  std::vector<int> np2_d, cumcnt_d;      // y-slab relabelling: the caller's small integer arrays in the device's pencil order
+  if (c->swap_yz) {
+    if (np2) { np2_d.resize(g.npen); permute_pencil_rows(c, np2, np2_d.data(), 1, true); np2 = np2_d.data(); }
+    if (cumcnt) { cumcnt_d.resize((size_t)g.npen * (g.nx + 1)); permute_pencil_rows(c, cumcnt, cumcnt_d.data(), g.nx + 1, true); cumcnt = cumcnt_d.data(); }
+  }
+  if (uf && c->swap_yz) {
+    WM_TRY(need_swapbuf(c));
+    WM_CUDA(cudaMemcpyAsync(c->swapbuf, uf, g.nbox() * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    WM_TRY(wm_k_swap_box6(c, c->swapbuf, c->uf, true));
+  } else if (uf) WM_CUDA(cudaMemcpyAsync(c->uf, uf, g.nbox() * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (up) {
     c->lazy = false;   // the uploaded state supersedes a pending (lazy) sort permutation
     c->defer_push = false;   // ... and whatever was deferred on the old state
@@ -371,21 +420,31 @@ int wm_download(wm_ctx* c, double* up, int* np2, int* cumcnt, double* uf, double
   }
   WM_TRY(wm_materialize(c));
   WM_TRY(check_flags(c));
-  if (uf) WM_CUDA(cudaMemcpyAsync(uf, c->uf, g.nbox() * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (uf && c->swap_yz) {
+    WM_TRY(need_swapbuf(c));
+    WM_TRY(wm_k_swap_box6(c, c->uf, c->swapbuf, false));
+    WM_CUDA(cudaMemcpyAsync(uf, c->swapbuf, g.nbox() * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  } else if (uf) WM_CUDA(cudaMemcpyAsync(uf, c->uf, g.nbox() * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   std::vector<int> h_np2(g.npen);
   WM_CUDA(cudaMemcpyAsync(h_np2.data(), c->np2, (size_t)g.npen * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   WM_CUDA(cudaStreamSynchronize(c->stream));
   int maxcnt = 0;
   for (int v : h_np2) maxcnt = std::max(maxcnt, v);
-  if (np2) std::memcpy(np2, h_np2.data(), (size_t)g.npen * sizeof(int));
+  if (np2) {
+    if (c->swap_yz) permute_pencil_rows(c, h_np2.data(), np2, 1, false);
+    else std::memcpy(np2, h_np2.data(), (size_t)g.npen * sizeof(int));
+  }
   if (cumcnt) {
     std::vector<int> cs((size_t)g.npen * (g.nx + 1));
     WM_CUDA(cudaMemcpyAsync(cs.data(), c->cs, cs.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     WM_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<int> rel(c->swap_yz ? cs.size() : 0);
+    int* dst = c->swap_yz ? rel.data() : cumcnt;
     for (int pen = 0; pen < g.npen; ++pen) {
       const int base = cs[(size_t)pen * (g.nx + 1)];
-      for (int i = 0; i <= g.nx; ++i) cumcnt[(size_t)pen * (g.nx + 1) + i] = cs[(size_t)pen * (g.nx + 1) + i] - base;
+      for (int i = 0; i <= g.nx; ++i) dst[(size_t)pen * (g.nx + 1) + i] = cs[(size_t)pen * (g.nx + 1) + i] - base;
     }
+    if (c->swap_yz) permute_pencil_rows(c, rel.data(), cumcnt, g.nx + 1, false);
   }
   for (int which = 0; which < 2; ++which) {
     double* dst = which == 0 ? up : gp;
@@ -414,6 +473,7 @@ int wm_download(wm_ctx* c, double* up, int* np2, int* cumcnt, double* uf, double
 
 int wm_download_work(wm_ctx* c, int which, double* out) {
   if (!c || !out) return WM_ERR_ARG;
+  WM_TRY(no_swap(c, "wm_download_work"));
   WM_CUDA(cudaSetDevice(c->device));
   const Geo& g = c->g;
   const size_t nb = g.nbox();
@@ -441,7 +501,13 @@ int wm_download_work(wm_ctx* c, int which, double* out) {
 int wm_upload_work(wm_ctx* c, int which, const double* in) {
   if (!c || !in || which != 1) return WM_ERR_ARG;
   WM_CUDA(cudaSetDevice(c->device));
-  WM_CUDA(cudaMemcpyAsync(c->df, in, c->g.nbox() * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (c->swap_yz) {      // df is a field increment: it translates like uf
+    WM_TRY(need_swapbuf(c));
+    WM_CUDA(cudaMemcpyAsync(c->swapbuf, in, c->g.nbox() * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    WM_TRY(wm_k_swap_box6(c, c->swapbuf, c->df, true));
+  } else {
+    WM_CUDA(cudaMemcpyAsync(c->df, in, c->g.nbox() * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
   WM_CUDA(cudaStreamSynchronize(c->stream));
   return WM_OK;
 }
@@ -818,6 +884,7 @@ int wm_h_step(wm_ctx* c, double* up, double* uf, int* np2, int* cumcnt, int nxs,
 // ---------------------------------------------------------------------------------------------
 int wm_load_weibel(wm_ctx* c, int n0, double v_thi, double v_the, double t_ani, double b0, unsigned long long seed) {
   if (!c || n0 <= 0) return WM_ERR_ARG;
+  WM_TRY(no_swap(c, "wm_load_weibel"));
   WM_CUDA(cudaSetDevice(c->device));
   c->lazy = false;
   c->defer_push = false;
@@ -854,6 +921,18 @@ int wm_mom_calc(wm_ctx* c, int nxs, int nxe, double* mom) {
   WM_CUDA(cudaMemcpyAsync(tmp.data(), c->mom, nel * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   WM_CUDA(cudaStreamSynchronize(c->stream));
   size_t t = 0;
+  if (c->swap_yz) {
+    // caller's mom(7, x, y, z, nsp) from the device's (x, y' = z, z' = y): V = (Vx, Vz', Vy'), T = (Txx, Tz'z', Ty'y')
+    static const int lmap[7] = {0, 1, 3, 2, 4, 6, 5};
+    for (int isp = 0; isp < g.nsp; ++isp)
+      for (int kh = g.nys - 1; kh <= g.nye + 1; ++kh)          // the caller's z range is the device's y' range
+        for (int jh = g.nzs - 1; jh <= g.nze + 1; ++jh)
+          for (int i = g.nxgs - 1; i <= g.nxge + 1; ++i) {
+            const double* s = &tmp[((size_t)isp * nb + g.box(i, kh, jh)) * 7];
+            for (int l = 0; l < 7; ++l) mom[t++] = s[lmap[l]];
+          }
+    return check_flags(c);
+  }
   const int k0 = g.dim == 3 ? g.nzs - 1 : 0, k1 = g.dim == 3 ? g.nze + 1 : 0;
   for (int isp = 0; isp < g.nsp; ++isp)
     for (int k = k0; k <= k1; ++k)

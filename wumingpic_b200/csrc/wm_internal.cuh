@@ -66,7 +66,16 @@ struct PeerCG {
 };
 
 struct wm_ctx {
-  wm_params prm;
+  wm_params prm;       // what the kernels run on (y and z exchanged when swap_yz)
+  // 3-D y-slabs (the reference's nproc_j > 1, nproc_k = 1: every shipped 3-D sample, 3d/proj/*/config_sample.json) run on the z-slab
+  // machinery through an exact relabelling at the host boundary: the device works in (x, y' = z, z' = y).  An axis exchange is a
+  // reflection, so the axial vector changes sign: B' = -(Bx, Bz, By), E' = (Ex, Ez, Ey), u' = (ux, uz, uy), J' = (Jx, Jz, Jy) -- with
+  // these every equation of the loop (Lorentz force, Faraday, Ampere, the Yee staggering, the Esirkepov factors) is the same code in
+  // the primed system; only the order of floating-point sums changes.  wm_upload / wm_download / wm_mom_calc translate pencil
+  // order, record columns and field components; hprm keeps the caller's view.
+  wm_params hprm;
+  bool swap_yz = false;
+  double* swapbuf = nullptr;   // nbox x 6 staging of the field translation
   Geo g;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -225,6 +234,7 @@ int wm_k_gauss(wm_ctx* ctx, double* out_host);
 int wm_k_load_weibel(wm_ctx* ctx, int n0, double v_thi, double v_the, double t_ani, double b0, unsigned long long seed);
 int wm_k_aos_to_soa(wm_ctx* ctx, const double* stage, Ptcl dst, double* dst_id, int pen0, int npens, int maxcnt);
 int wm_k_soa_to_aos(wm_ctx* ctx, double* stage, Ptcl src, const double* src_id, int pen0, int npens, int maxcnt);
+int wm_k_swap_box6(wm_ctx* ctx, const double* in, double* out, bool to_device);
 int wm_k_cs_from_cumcnt(wm_ctx* ctx, const int* cumcnt_dev);
 int wm_k_cumcnt_from_cs(wm_ctx* ctx, int* cumcnt_dev);
 // fields (wm_fields.cu)

@@ -46,6 +46,10 @@ __global__ void k_count_below(const int* __restrict__ sel, int nsel, long long b
 }  // namespace
 
 extern "C" int wm_pack_particles(wm_ctx* c, int mode, double* buf, long long cap_records, long long* lcount) {
+  if (c && c->swap_yz) {
+    wm_set_error("wm_pack_particles is not available with 3-D y-slabs (relabelled device system): use z-slabs, or wm_download");
+    return WM_ERR_STATE;
+  }
   if (!c || !lcount || (mode != 0 && mode != 1)) {
     wm_set_error("Error: invalid mode specified for get_particle_count");   // paraio.f90:1065-1069
     return WM_ERR_ARG;

@@ -429,33 +429,55 @@ __global__ void k_bc_x_walls(Geo g, Ptcl P, long long n, int nxs, int nxe, int k
 // host <-> device layout conversion: the reference's padded AoS pencils <-> SoA
 // stage holds [pencil][slot < maxcnt][ndim]
 // ---------------------------------------------------------------------------------------------
+// swap (3-D y-slabs, wm_internal.cuh): the stage holds the CALLER's pencils (order (isp, k, j), columns x y z ux uy uz id); the device
+// pencil of caller pencil (isp, k, j) is (isp, k' = j, j' = k) and the record columns y <-> z, uy <-> uz change places
+__device__ __forceinline__ int wm_host_pen_to_dev(const Geo& g, int pen_h) {
+  const int nyl_h = g.nzl, nzl_h = g.nyl;                      // the caller's slab extents
+  const int jj = pen_h % nyl_h, kk = (pen_h / nyl_h) % nzl_h, isp = pen_h / (nyl_h * nzl_h);
+  return (isp * g.nzl + jj) * g.nyl + kk;
+}
+__device__ __forceinline__ int wm_swap_col(int c) { return c == 1 ? 2 : (c == 2 ? 1 : (c == 4 ? 5 : (c == 5 ? 4 : c))); }
+
 __global__ void k_aos_to_soa(Geo g, const double* __restrict__ stage, Ptcl dst, double* __restrict__ dst_id,
-                             const int* __restrict__ poff, const int* __restrict__ np2, int pen0, int npens, int maxcnt) {
+                             const int* __restrict__ poff, const int* __restrict__ np2, int pen0, int npens, int maxcnt, int swap) {
   const long long n = (long long)npens * maxcnt;
   const int nd = g.ndim;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     int pl = (int)(e / maxcnt), ii = (int)(e % maxcnt);
-    int pen = pen0 + pl;
+    int pen = swap ? wm_host_pen_to_dev(g, pen0 + pl) : pen0 + pl;
     if (ii >= np2[pen]) continue;
     const double* s = stage + e * nd;
     size_t d = (size_t)poff[pen] + ii;
-    for (int c = 0; c < nd - 1; ++c) dst.c[c][d] = s[c];
+    for (int c = 0; c < nd - 1; ++c) dst.c[swap ? wm_swap_col(c) : c][d] = s[c];
     dst_id[d] = s[nd - 1];
   }
 }
 
 __global__ void k_soa_to_aos(Geo g, double* __restrict__ stage, Ptcl src, const double* __restrict__ src_id,
-                             const int* __restrict__ poff, const int* __restrict__ np2, int pen0, int npens, int maxcnt) {
+                             const int* __restrict__ poff, const int* __restrict__ np2, int pen0, int npens, int maxcnt, int swap) {
   const long long n = (long long)npens * maxcnt;
   const int nd = g.ndim;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     int pl = (int)(e / maxcnt), ii = (int)(e % maxcnt);
-    int pen = pen0 + pl;
+    int pen = swap ? wm_host_pen_to_dev(g, pen0 + pl) : pen0 + pl;
     if (ii >= np2[pen]) continue;
     double* s = stage + e * nd;
     size_t d = (size_t)poff[pen] + ii;
-    for (int c = 0; c < nd - 1; ++c) s[c] = src.c[c][d];
+    for (int c = 0; c < nd - 1; ++c) s[c] = src.c[swap ? wm_swap_col(c) : c][d];
     s[nd - 1] = src_id[d];
+  }
+}
+
+// field translation of the y-slab relabelling, both directions (it is an involution): out(c', i, a, b) = sign(c') in(c, i, b, a) with
+// c' = (0 2 1 3 5 4)[c], minus on the three B components; `in` has the OTHER system's box extents (its y extent = our z extent)
+__global__ void k_swap_box6(const double* __restrict__ in, double* __restrict__ out, int bx, int by_out, int bz_out) {
+  const long long n = (long long)bx * by_out * bz_out;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % bx), a = (int)((e / bx) % by_out), b = (int)(e / ((long long)bx * by_out));
+    const double* s = in + (((long long)a * bz_out + b) * bx + i) * 6;       // (i, y_in = b, z_in = a): in's y extent is bz_out
+    double* d = out + e * 6;
+    d[0] = -s[0]; d[1] = -s[2]; d[2] = -s[1];
+    d[3] = s[3];  d[4] = s[5];  d[5] = s[4];
   }
 }
 
@@ -533,7 +555,16 @@ int wm_k_bc_x(wm_ctx* ctx, int nxs, int nxe, int kind, double u0) {
 int wm_k_aos_to_soa(wm_ctx* ctx, const double* stage, Ptcl dst, double* dst_id, int pen0, int npens, int maxcnt) {
   const long long n = (long long)npens * maxcnt;
   if (n == 0) return WM_OK;
-  k_aos_to_soa<<<grid_for(n), TPB, 0, ctx->stream>>>(ctx->g, stage, dst, dst_id, ctx->poff, ctx->np2, pen0, npens, maxcnt);
+  k_aos_to_soa<<<grid_for(n), TPB, 0, ctx->stream>>>(ctx->g, stage, dst, dst_id, ctx->poff, ctx->np2, pen0, npens, maxcnt, ctx->swap_yz ? 1 : 0);
+  WM_LAUNCH_CHECK(ctx);
+  return WM_OK;
+}
+
+// field box between the caller's (x, y, z) and the device's (x, z, y) system (see wm_ctx::swap_yz); to_device: in = caller layout
+int wm_k_swap_box6(wm_ctx* ctx, const double* in, double* out, bool to_device) {
+  const Geo& g = ctx->g;
+  const int by_out = to_device ? g.by : g.bz, bz_out = to_device ? g.bz : g.by;
+  k_swap_box6<<<grid_for((long long)g.nbox()), TPB, 0, ctx->stream>>>(in, out, g.bx, by_out, bz_out);
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
 }
@@ -541,7 +572,7 @@ int wm_k_aos_to_soa(wm_ctx* ctx, const double* stage, Ptcl dst, double* dst_id, 
 int wm_k_soa_to_aos(wm_ctx* ctx, double* stage, Ptcl src, const double* src_id, int pen0, int npens, int maxcnt) {
   const long long n = (long long)npens * maxcnt;
   if (n == 0) return WM_OK;
-  k_soa_to_aos<<<grid_for(n), TPB, 0, ctx->stream>>>(ctx->g, stage, src, src_id, ctx->poff, ctx->np2, pen0, npens, maxcnt);
+  k_soa_to_aos<<<grid_for(n), TPB, 0, ctx->stream>>>(ctx->g, stage, src, src_id, ctx->poff, ctx->np2, pen0, npens, maxcnt, ctx->swap_yz ? 1 : 0);
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
 }

@@ -265,11 +265,21 @@ extern "C" {
 
 int wm_shock_inject(wm_ctx* c, const wm_shock_params* sp, int nxe, const int* nlinj, const long long* id_first, long long epoch) {
   if (!c || !sp || !nlinj || !id_first) return WM_ERR_ARG;
+  if (c->swap_yz) {
+    wm_set_error("the device-side shock source is not available with 3-D y-slabs (relabelled device system): use z-slabs, or the "
+                 "driver's own inject() / relocate() between wm_download and wm_upload");
+    return WM_ERR_STATE;
+  }
   return shock_source(c, sp, nxe, nlinj, id_first, epoch, false);
 }
 
 int wm_shock_relocate(wm_ctx* c, const wm_shock_params* sp, int nxe_new, const long long* id_first, long long epoch) {
   if (!c || !sp || !id_first) return WM_ERR_ARG;
+  if (c->swap_yz) {
+    wm_set_error("the device-side shock source is not available with 3-D y-slabs (relabelled device system): use z-slabs, or the "
+                 "driver's own inject() / relocate() between wm_download and wm_upload");
+    return WM_ERR_STATE;
+  }
   return shock_source(c, sp, nxe_new, nullptr, id_first, epoch, true);
 }
 
