@@ -542,9 +542,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": "push+deposit", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": npart_rank * bytes_push,
-                "co_limiters": "ncu (profiles/r01_s4_fused_v6.md): fp64 pipe 48 % active, LSU data-pipe wavefronts 77 %, issue slots "
-                               "52 % (fp64 instructions hold their scheduler two cycles: ~76 % of an issue-bound model), DRAM 24 % -- "
-                               "the kernel is issue/shared-memory bound, not HBM bound; measured DFMA peak 1.71e13/s "
+                "co_limiters": "ncu (profiles/r01_s4_fused_v6.md; round-2 restructuring experiments: profiles/r02_fused_experiments.md): "
+                               "shared-memory wavefronts (LSU data pipe) 77 %, fp64 pipe 48 %, issue slots 52 %, DRAM 24 % -- the kernel is "
+                               "bound by shared-memory wavefronts and fp64 issue, not by HBM; measured DFMA peak 1.71e13/s "
                                "(profiles/r01_fp64_peak.json)",
                 "kernel_ms": k_ms,
                 "step": {"bytes_per_update": bytes_step,
