@@ -5,18 +5,13 @@ mkdir -p gpurun_out; rm -f gpurun_out/multigpu_parity_*.log
 ( timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -x -k "test_slab_parity and fused and not 2-" 2>&1 | tail -4 ) 2>&1 | tail -6
 cat gpurun_out/multigpu_parity_*.log
 tr() { n=$1; shift; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29700+RANDOM%200)) bench.py --gpus $n "$@"; }
-for n in 8 4 2; do
+for n in 8 4; do
   tr $n --no-e2e --no-cpu > gpurun_out/r02_final_strong$n.json 2> gpurun_out/r02_final_strong$n.err || tail -3 gpurun_out/r02_final_strong$n.err
   python - <<PY
 import json
 d=json.load(open('gpurun_out/r02_final_strong$n.json')); print('strong N=$n', round(d['value']/1e9,2),'G/s', round(d['ms_per_step'],3),'ms', {k:round(v,2) for k,v in d['roofline']['phases_ms'].items()}, d['checks']['parity']['pass'], d['checks']['gauss_residual'], d['clocks'])
 PY
 done
-tr 8 --weak --no-e2e --no-cpu > gpurun_out/r02_final_weak8.json 2> gpurun_out/r02_final_weak8.err || tail -3 gpurun_out/r02_final_weak8.err
-python - <<PY
-import json
-d=json.load(open('gpurun_out/r02_final_weak8.json')); print('weak N=8', round(d['value']/1e9,2),'G/s', round(d['ms_per_step'],3),'ms', {k:round(v,2) for k,v in d['roofline']['phases_ms'].items()}, d['checks']['parity']['pass'])
-PY
 st() { name=$1; shift; tr 8 "$@" > gpurun_out/r02_final_$name.json 2> gpurun_out/r02_final_$name.err || tail -4 gpurun_out/r02_final_$name.err
 python - <<PY
 import json
