@@ -11,3 +11,4 @@ PY
 run equal WM_STREAM_PRIO=0
 run sorthigh WM_STREAM_PRIO=2
 run equal_bps3 WM_STREAM_PRIO=0 WM_CG_BPS=3
+WM_OVERLAP_SORT=0 WM_SORT_TIMING=1 WM_FIELD_TIMING=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29950 bench.py --gpus 8 --no-e2e --no-cpu --no-parity --steps 10 2>&1 >/dev/null | grep "wuming_b200\] rank [03]" | cut -c1-400

@@ -62,13 +62,39 @@ def test_steps_match_oracle(swapped, bc, order, u0):
     b.close(); w.close()
 
 
-def test_unavailable_entry_points_say_so(swapped):
+def test_device_weibel_loader_under_relabelling(swapped):
+    """wm_load_weibel generates the CALLER's load: same Philox stream per caller pencil, y / z and the anisotropic uz in the caller's
+    columns -- positions bit-identical to the oracle's loader, Maxwellian momenta to libm ulp"""
+    w = make_world3(NX, NY, NZ, N0, b0=0.3)
+    b = backend_for(w)
+    b.load_weibel(N0, b0=0.3)
+    up, np2, cc, uf = b.empty("up"), b.empty("np2"), b.empty("cumcnt"), b.empty("uf")
+    b.download(up, np2, cc, uf)
+    m = active_mask(np2, w.np)
+    assert np.array_equal(np2, w.arr("np2")) and np.array_equal(cc, w.arr("cumcnt")) and np.array_equal(uf, w.arr("uf"))
+    assert np.array_equal(up[m][:, :3], w.arr("up")[m][:, :3])
+    assert np.array_equal(up[m][:, 6].view(np.int64), w.arr("up")[m][:, 6].view(np.int64))
+    np.testing.assert_allclose(up[m][:, 3:6], w.arr("up")[m][:, 3:6], rtol=0, atol=1e-15)
+    b.close(); w.close()
+
+
+def test_pack_and_unavailable_entry_points(swapped):
+    """particle packing gives the caller's records (as a set per species: the pencil order is (j, k) under y-slabs); the device-side
+    shock source and the stage-wise work arrays answer WM_ERR_STATE with a message"""
     import wumingpic_b200 as wm
-    w = make_world3(NX, NY, NZ, N0)
+    w = make_world3(NX, NY, NZ, N0, steps=1)
     b = backend_for(w)
     upload_from_world(b, w)
+    rec, lc = b.pack_particles(0)
+    ref, lcr = w.pack_particles(0)
+    assert np.array_equal(lc, lcr)
+    for lo, hi in ((0, lc[0]), (lc[0], lc[0] + lc[1])):
+        a, r = rec[lo:hi], ref[lo:hi]
+        a, r = a[np.argsort(a[:, 6].view(np.int64))], r[np.argsort(r[:, 6].view(np.int64))]
+        assert np.array_equal(a.view(np.int64), r.view(np.int64))
     with pytest.raises(wm.WmError, match="y-slabs"):
-        b.load_weibel(N0)
+        b.download_work("uj")
+    prm = wm.ShockParams(n0=N0, v0=-0.3, v_thi=0.0, v_the=0.0, b0=0.0, theta_bn=0.0, phi_bn=0.0, l_damp_ini=4.0, seed=1)
     with pytest.raises(wm.WmError, match="y-slabs"):
-        b.pack_particles(0)
+        b.shock_inject(prm, NX, np.zeros(NY * NZ, dtype=np.int32), np.zeros((2, NY * NZ), dtype=np.int64), 1)
     b.close(); w.close()

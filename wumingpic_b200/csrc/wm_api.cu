@@ -12,6 +12,7 @@
 #include <vector>
 
 int wm_comm_destroy(wm_ctx* ctx);
+void wm_sort_timing_report(int rank);
 static double g_stage_ms[9] = {0};   // WM_FIELD_TIMING (see field_stages)
 static long g_stage_calls = 0;
 
@@ -291,6 +292,7 @@ int wm_destroy(wm_ctx* c) {
             g_stage_ms[8] / g_stage_calls);
     g_stage_calls = 0;
   }
+  wm_sort_timing_report(c->rank);
   wm_comm_destroy(c);   // also releases the peer arena (and nulls the CG arrays that lived in it)
   free_particles(c);
   double* d[] = {c->swapbuf, c->mom, c->uf, c->df, c->uj, c->gkl, c->tmpf, c->phi, c->pcg, c->pcg2, c->rcg, c->bcg, c->apcg, c->red, c->hbuf[0],
@@ -889,7 +891,6 @@ int wm_h_step(wm_ctx* c, double* up, double* uf, int* np2, int* cumcnt, int nxs,
 // ---------------------------------------------------------------------------------------------
 int wm_load_weibel(wm_ctx* c, int n0, double v_thi, double v_the, double t_ani, double b0, unsigned long long seed) {
   if (!c || n0 <= 0) return WM_ERR_ARG;
-  WM_TRY(no_swap(c, "wm_load_weibel"));
   WM_CUDA(cudaSetDevice(c->device));
   c->lazy = false;
   c->defer_push = false;

@@ -41,8 +41,10 @@ __device__ inline void box_muller(double x1, double x2, double& ns, double& nc) 
   nc = rr * cos(2.0 * kPi * x2);
 }
 
+// swap: 3-D y-slabs -- the device works in (x, y' = z, z' = y) (wm_internal.cuh, wm_ctx::swap_yz): the CALLER's pencil (j, k) = (k', j')
+// keys the random stream, its y goes to our z column and its anisotropic uz to our uy column, so that the state is the caller's load
 __global__ void k_load_weibel(Geo g, Ptcl A, double* __restrict__ id, int n0, double v_thi, double v_the, double t_ani,
-                              unsigned long long seed) {
+                              unsigned long long seed, int swap) {
   const int npp = n0 * g.nx;  // particles per pencil and species
   const long long n = (long long)npp * g.nyl * g.nzl;
   const int U = g.dim;
@@ -50,12 +52,13 @@ __global__ void k_load_weibel(Geo g, Ptcl A, double* __restrict__ id, int n0, do
     const int ii = (int)(e % npp) + 1;
     const int jk = (int)(e / npp);
     const int j = g.nys + jk % g.nyl, k = g.dim == 3 ? g.nzs + jk / g.nyl : 0;
-    const uint32_t pencil = (uint32_t)((j - g.nygs) + (g.dim == 3 ? (size_t)g.ny * (k - g.nzgs) : 0));
+    const uint32_t pencil = swap ? (uint32_t)((k - g.nzgs) + (size_t)g.nz * (j - g.nygs))     // caller's (j_h, k_h) = (k, j), ny_h = nz
+                                 : (uint32_t)((j - g.nygs) + (g.dim == 3 ? (size_t)g.ny * (k - g.nzgs) : 0));
     double u0, u1;
     uniform2(seed, pencil, (uint32_t)ii, 0u, u0, u1);
     const double x = (g.nxgs + (g.nxge - g.nxgs + 1) * (ii - 5e-1) / npp) * g.delx;
-    const double y = (j + u0) * g.delx;
-    const double z = (k + u1) * g.delx;
+    const double y = (j + (swap ? u1 : u0)) * g.delx;
+    const double z = (k + (swap ? u0 : u1)) * g.delx;
     for (int isp = 0; isp < 2; ++isp) {
       const size_t d = (size_t)g.pen(j, k, isp) * npp + (ii - 1);
       const double sd = isp == 0 ? v_thi : v_the;
@@ -68,8 +71,8 @@ __global__ void k_load_weibel(Geo g, Ptcl A, double* __restrict__ id, int n0, do
       A.c[1][d] = y;
       if (g.dim == 3) A.c[2][d] = z;
       A.c[U][d] = sd * ns;
-      A.c[U + 1][d] = sd * nc;
-      A.c[U + 2][d] = t_ani * sd * ms;
+      A.c[U + (swap ? 2 : 1)][d] = sd * nc;
+      A.c[U + (swap ? 1 : 2)][d] = t_ani * sd * ms;
       long long pid = (long long)isp * ((long long)npp * g.ny * g.nz) + (long long)pencil * npp + ii;
       id[d] = __longlong_as_double(-pid);
     }
@@ -90,11 +93,11 @@ __global__ void k_load_index(Geo g, int* __restrict__ cs, int* __restrict__ np2,
   }
 }
 
-__global__ void k_load_uf(Geo g, double* __restrict__ uf, double b0) {
+__global__ void k_load_uf(Geo g, double* __restrict__ uf, double b0, int swap) {
   const long long n = (long long)g.nbox();
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     double* f = uf + e * 6;
-    f[0] = 0; f[1] = 0; f[2] = b0; f[3] = 0; f[4] = 0; f[5] = 0;
+    f[0] = 0; f[1] = swap ? -b0 : 0; f[2] = swap ? 0 : b0; f[3] = 0; f[4] = 0; f[5] = 0;     // Bz = b0; relabelled: B'y' = -Bz
   }
 }
 
@@ -197,11 +200,12 @@ int grid_for(long long n) {
 int wm_k_load_weibel(wm_ctx* ctx, int n0, double v_thi, double v_the, double t_ani, double b0, unsigned long long seed) {
   const Geo& g = ctx->g;
   const long long n = (long long)n0 * g.nx * g.nyl * g.nzl;
-  k_load_uf<<<grid_for((long long)g.nbox()), TPB, 0, ctx->stream>>>(g, ctx->uf, b0);
+  const int swap = ctx->swap_yz ? 1 : 0;
+  k_load_uf<<<grid_for((long long)g.nbox()), TPB, 0, ctx->stream>>>(g, ctx->uf, b0, swap);
   WM_LAUNCH_CHECK(ctx);
   k_load_index<<<grid_for((long long)g.npen * (g.nx + 1)), TPB, 0, ctx->stream>>>(g, ctx->cs, ctx->np2, ctx->poff, n0);
   WM_LAUNCH_CHECK(ctx);
-  k_load_weibel<<<grid_for(n), TPB, 0, ctx->stream>>>(g, ctx->A, ctx->id[ctx->cid], n0, v_thi, v_the, t_ani, seed);
+  k_load_weibel<<<grid_for(n), TPB, 0, ctx->stream>>>(g, ctx->A, ctx->id[ctx->cid], n0, v_thi, v_the, t_ani, seed, swap);
   WM_LAUNCH_CHECK(ctx);
   return WM_OK;
 }

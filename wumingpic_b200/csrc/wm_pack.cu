@@ -25,13 +25,17 @@ struct IsTracer {
 };
 
 // records sel[first .. first+n) -> stage (ndim doubles each)
+// swap: 3-D y-slabs (wm_ctx::swap_yz): the caller's y, uy are the device's z', uz' columns and vice versa
 __global__ void k_pack_records(Geo g, Ptcl A, const double* __restrict__ id, const int* __restrict__ sel, long long first,
-                               long long n, double* __restrict__ stage) {
+                               long long n, double* __restrict__ stage, int swap) {
   const int ncomp = g.ndim - 1;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const long long p = sel ? sel[first + e] : first + e;
     double* o = stage + e * g.ndim;
-    for (int c = 0; c < ncomp; ++c) o[c] = A.c[c][p];
+    for (int c = 0; c < ncomp; ++c) {
+      const int cs = !swap ? c : (c == 1 ? 2 : (c == 2 ? 1 : (c == 4 ? 5 : (c == 5 ? 4 : c))));
+      o[c] = A.c[cs][p];
+    }
     o[ncomp] = id[p];
   }
 }
@@ -46,10 +50,8 @@ __global__ void k_count_below(const int* __restrict__ sel, int nsel, long long b
 }  // namespace
 
 extern "C" int wm_pack_particles(wm_ctx* c, int mode, double* buf, long long cap_records, long long* lcount) {
-  if (c && c->swap_yz) {
-    wm_set_error("wm_pack_particles is not available with 3-D y-slabs (relabelled device system): use z-slabs, or wm_download");
-    return WM_ERR_STATE;
-  }
+  // 3-D y-slabs: the records come out in the caller's columns but in (species, j, k, cell) pencil order instead of paraio's
+  // (species, k, j, cell) -- the readers of the _ptcl / _orb files identify particles by ID (see the header of this file)
   if (!c || !lcount || (mode != 0 && mode != 1)) {
     wm_set_error("Error: invalid mode specified for get_particle_count");   // paraio.f90:1065-1069
     return WM_ERR_ARG;
@@ -107,7 +109,7 @@ extern "C" int wm_pack_particles(wm_ctx* c, int mode, double* buf, long long cap
       WM_CUDA(cudaMalloc(&stage, (size_t)chunk * g.ndim * sizeof(double)));
       for (long long first = 0; first < nsel; first += chunk) {
         const long long n = std::min(chunk, nsel - first);
-        k_pack_records<<<std::min(wm_blocks(n, TPB), 148 * 16), TPB, 0, st>>>(g, c->A, c->id[c->cid], sel, first, n, stage);
+        k_pack_records<<<std::min(wm_blocks(n, TPB), 148 * 16), TPB, 0, st>>>(g, c->A, c->id[c->cid], sel, first, n, stage, c->swap_yz ? 1 : 0);
         WM_LAUNCH_CHECK(c);
         WM_CUDA(cudaMemcpyAsync(buf + first * g.ndim, stage, (size_t)n * g.ndim * sizeof(double), cudaMemcpyDeviceToHost, st));
         WM_CUDA(cudaStreamSynchronize(st));

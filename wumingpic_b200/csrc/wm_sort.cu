@@ -516,9 +516,26 @@ int wm_k_classify(wm_ctx* ctx, int nxs, int nxe) {
 }
 
 // sort__bucket (+ the migration half of bc__particle_y[z]): needs dst_off / cnt27 of the pushed set B
+// WM_SORT_TIMING=1 (measurement aid): device time of the phases of wm_k_sort, summed per rank and printed by wm_sort_timing_report
+static double g_sort_ms[8] = {0};
+static long g_sort_calls = 0;
+void wm_sort_timing_report(int rank) {
+  if (g_sort_calls == 0) return;
+  fprintf(stderr, "[wuming_b200] rank %d sort phases over %ld calls (ms/call): counts-exchange %.3f scans+totals(host sync) %.3f goff+mark+perm %.3f "
+                  "apply(ghost rows) %.3f payload-exchange %.3f insert+np2 %.3f\n", rank, g_sort_calls, g_sort_ms[0] / g_sort_calls,
+          g_sort_ms[1] / g_sort_calls, g_sort_ms[2] / g_sort_calls, g_sort_ms[3] / g_sort_calls, g_sort_ms[4] / g_sort_calls,
+          g_sort_ms[5] / g_sort_calls);
+  g_sort_calls = 0;
+}
+
 int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
   const Geo& g = ctx->g;
   cudaStream_t st = ctx->stream;
+  static const bool timing = getenv("WM_SORT_TIMING") != nullptr;
+  cudaEvent_t tev[7] = {};
+  int tn = 0;
+  auto mark = [&]() { if (timing && tn < 7) { if (!tev[tn]) cudaEventCreate(&tev[tn]); cudaEventRecord(tev[tn++], st); } };
+  mark();
   const int w = g.nx + 1;
   const size_t ncs = (size_t)g.nrows * w;
   const int per_side = g.nsp * g.ngrow * w;
@@ -542,6 +559,7 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
     WM_CUDA(cudaMemsetAsync(ctx->inc_off + 2 * per_side, 0, sizeof(int), st));
     WM_TRY(scan_ints(ctx, ctx->inc_off, (size_t)2 * per_side + 1));
   }
+  mark();
   WM_TRY(scan_ints(ctx, ctx->cs_new, ncs + 1));
   if (g.multi) {
     k_totals<<<1, 32, 0, st>>>(g, ctx->cs_new, ctx->inc_off, ctx->totals);
@@ -554,6 +572,7 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
       return WM_ERR_MEMORY_OVER;
     }
   }
+  mark();
   const int old_cid = 1 - ctx->cid;   // the producers moved the IDs along with the particles into the spare array
   static const bool no_lazy = getenv("WM_NO_LAZY_SORT") != nullptr;   // measurement switch
   const bool lazy = ctx->allow_lazy && !no_lazy;
@@ -570,6 +589,7 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
     }
     k_perm<<<g.npen * nch, TPB, 0, st>>>(g, ctx->cs, ctx->cnt27, ctx->goff, ctx->dst_off, ctx->inv, ctx->flags, nxs, nxe, nch);
     WM_LAUNCH_CHECK(ctx);
+    mark();
     // the permutation is applied now -- or, inside wm_step, left to the next fused kernel (which reads through inv); a slab
     // run still materialises its outgoing ghost rows, behind the local particles of the free set
     const int row0 = lazy ? g.npen : 0;
@@ -584,6 +604,7 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
       WM_LAUNCH_CHECK(ctx);
     }
   }
+  mark();
   if (g.multi) {
     // payload: ghost rows of A (behind the local particles) -> neighbours; arrivals land in B / the old ID array,
     // which are free once the scatter has read them (stream order) -- or, lazy, in the arrival store R
@@ -610,6 +631,7 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
       WM_TRY(wm_comm_recv(ctx, ctx->rank_down[ax], dst, (size_t)tot[4] * sizeof(double)));
     }
     WM_TRY(wm_comm_group_end(ctx));
+    mark();
     if (!lazy && tot[4] + tot[5] > 0) {
       const int blocks = std::min(wm_blocks((long long)2 * per_side * 32, TPB), 148 * 8);
       if (g.dim == 3)
@@ -641,6 +663,13 @@ int wm_k_sort(wm_ctx* ctx, int nxs, int nxe) {
   k_np2_poff<<<wm_blocks(g.npen + 1, TPB), TPB, 0, st>>>(g, ctx->cs, ctx->np2, ctx->poff, ctx->flags,
                                                            g.multi ? -1LL : ctx->ntot);
   WM_LAUNCH_CHECK(ctx);
+  if (timing) {
+    mark();
+    cudaEventSynchronize(tev[tn - 1]);
+    for (int e = 0; e + 1 < tn; ++e) { float ms = 0; cudaEventElapsedTime(&ms, tev[e], tev[e + 1]); g_sort_ms[tn == 7 ? e : (e < 4 ? e : e + 1)] += ms; }
+    for (int e = 0; e < tn; ++e) cudaEventDestroy(tev[e]);
+    g_sort_calls++;
+  }
   return WM_OK;
 }
 
