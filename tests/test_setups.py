@@ -64,6 +64,26 @@ def test_shock_loader_and_injection_counts():
     assert abs(tot / (200 * s.n0 * abs(v0) * s.delt * 12) - 1) < 0.01       # the particle flux n0 |v0| dt per row and step
 
 
+def test_3d_loaders_extend_the_2d_ones():
+    """the 3-D drivers load the same distributions with a uniform z added (3d/proj/reconnection/app.f90:436-455, 3d/proj/shock/app.f90
+    :452-457): field planes identical along z, z inside the pencil's cell, pencils independent of the slab they are built in"""
+    s = setups.reconnection_constants(41, 10, 6, **REC)
+    up, np2, cc, uf = setups.reconnection_slab(s, 2, 11, 2, 7)
+    assert up.shape == (2, 6, 10, s.np_cap, 7) and uf.shape == (10, 14, 45, 6)
+    assert all(np.array_equal(uf[0], uf[k]) for k in range(1, 10))
+    m = np.arange(s.np_cap)[None, None, None, :] < np2[..., None]
+    kk = np.broadcast_to(np.arange(2, 8)[None, :, None, None], m.shape)
+    z = up[..., 2]
+    assert ((z >= kk) & (z < kk + 1))[m].all()
+    up2, _, _, _ = setups.reconnection_slab(s, 4, 6, 5, 6)
+    assert np.array_equal(up2.view(np.int64), up[:, 3:5, 2:5].view(np.int64))
+    t = setups.shock_constants(64, 20, 6, 4, n_ppc=3)
+    up, np2, cc, uf = setups.shock_slab(t, 2, 7, 2, 5)
+    assert up.shape == (2, 4, 6, t.np_cap, 7) and (np2 == 3 * (22 - 2 - 1)).all()
+    assert (up[..., 4] == 0).all() and (up[..., 5] == 0).all()           # cold upstream: no transverse momentum
+    assert np.array_equal(up[0][..., :3], up[1][..., :3])
+
+
 def _compare(b, w, nxe, tol_x=1e-8):
     up, np2, cc = b.empty("up"), b.empty("np2"), b.empty("cumcnt")
     b.download(up, np2, cc)
