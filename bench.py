@@ -66,18 +66,27 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  nvidia-smi needs up to a second
+    before its first line, and a strong-scaling step on 8 GPUs is 18 ms: the sampler is therefore started BEFORE the warm-up and
+    every row is stamped on arrival; begin() / end() bracket the timed region and stop() reports the rows that fell inside it.
+    If the region was shorter than one sampling period, the rows closest to it (the warm-up steps right before it: same kernels,
+    same load) are reported instead, and `window` says so."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 100
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        # nvidia-smi numbers the physical devices; CUDA's ordinal goes through CUDA_VISIBLE_DEVICES (indices or UUIDs)
+        self.index = ids[index] if index < len(ids) else str(index)
+        self.rows, self.proc, self.t0, self.t1 = [], None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -86,27 +95,47 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.monotonic()
+
+    def end(self):
+        self.t1 = time.monotonic()
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        t0 = self.t0 if self.t0 is not None else float("-inf")
+        t1 = self.t1 if self.t1 is not None else time.monotonic()
+        if t1 - t0 < 2.5 * self.PERIOD_MS * 1e-3:      # a very short region: wait for the row that was sampled at its end
+            time.sleep(1.5 * self.PERIOD_MS * 1e-3)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        self.t.join(timeout=2)
+        ok = [(t, r) for t, r in list(self.rows) if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in ok if t0 <= t <= t1]
+        window = "timed region"
+        if not rows and ok:
+            # no row landed inside the region: the rows sampled within one period of its ends, else the three closest (warm-up)
+            near = [r for t, r in ok if t0 - self.PERIOD_MS * 1e-3 <= t <= t1 + self.PERIOD_MS * 1e-3]
+            if near:
+                rows, window = near, f"timed region +- {self.PERIOD_MS} ms (the region is shorter than the sampling period)"
+            else:
+                ok.sort(key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t1)))
+                rows, window = [r for _, r in ok[:3]], "closest samples: warm-up steps (no sample fell into the timed region)"
+        sm = sorted(float(r[1]) for r in rows)
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) < 9:
-                continue
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window, "period_ms": self.PERIOD_MS}
 
 
 def measured_peak():
@@ -333,22 +362,24 @@ def run_setup(args):
     state["ntot"] = np.array(count_global(), dtype=np.int64)
     n_start = int(state["ntot"].sum())
     e0 = b.energy().sum()
+    sampler = ClockSampler(local_rank)
+    sampler.start()                       # before the warm-up: nvidia-smi is up and printing when the timed region starts
     for _ in range(args.warmup):
         one_step()
     b.sync()
     b.set_timing(True)
     launches0 = b.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     n_before = sum(count_global())
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
     ev0.record(stream)
     for _ in range(args.steps):
         one_step()
     b.settle()
     ev1.record(stream)
     barrier()
+    sampler.end()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = b.launch_count() - launches0
@@ -499,19 +530,21 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident steady state: W warm-up steps, then exactly K timed steps --------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()             # before the warm-up: nvidia-smi is up and printing when the timed region starts
     step(args.warmup)
     b.sync()
     b.set_timing(True)
     launches0 = b.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
     ev0.record(stream)
     step(args.steps)
     b.settle()      # the last sort's permutation is applied inside the timed region (wm_step leaves it pending for the next step)
     ev1.record(stream)
     barrier()
+    sampler.end()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = b.launch_count() - launches0

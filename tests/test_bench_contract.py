@@ -53,3 +53,54 @@ def test_reference_arm_uses_all_host_threads_under_a_launcher():
     d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
     assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert d["config"]["parallelism"] == f"openmp{len(os.sched_getaffinity(0))}"
+
+
+def _fake_nvidia_smi(tmp_path, startup_s):
+    """an `nvidia-smi` that needs `startup_s` before its first row, then prints one row every 100 ms like `-lms 100`"""
+    p = tmp_path / "nvidia-smi"
+    p.write_text("#!/bin/sh\nsleep %g\nwhile true; do echo '0, 1965, 1965, 612.3, 0x0000000000000000, Not Active, Not Active, "
+                 "Not Active, Active'; sleep 0.1; done\n" % startup_s)
+    p.chmod(0o755)
+    return str(tmp_path)
+
+
+def test_clock_sampler_windows_rows_on_the_timed_region(tmp_path, monkeypatch):
+    """The sampler is started before the warm-up and reports the rows that arrived between begin() and end(); a region shorter
+    than the sampling period (18 ms steps on 8 GPUs) falls back to the closest rows and says so -- never `samples: 0` while
+    nvidia-smi is printing."""
+    import importlib
+    import time
+    monkeypatch.setenv("PATH", _fake_nvidia_smi(tmp_path, 0.3) + os.pathsep + os.environ["PATH"])
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES", raising=False)
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.8)                 # "warm-up": nvidia-smi starts up meanwhile
+    s.begin()
+    time.sleep(0.45)
+    s.end()
+    c = s.stop()
+    assert c["window"] == "timed region" and 3 <= c["samples"] <= 6, c
+    assert c["sm_mhz"] == 1965.0 and c["sm_max_mhz"] == 1965.0 and c["reasons"] == ["sw_power_cap"]
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.8)
+    s.begin()
+    time.sleep(0.005)               # a timed region far shorter than the sampling period
+    s.end()
+    c = s.stop()
+    assert c["samples"] >= 1 and c["sm_mhz"] == 1965.0 and c["window"] != "timed region", c
+
+
+def test_clock_sampler_without_nvidia_smi(tmp_path, monkeypatch):
+    import importlib
+    monkeypatch.setenv("PATH", str(tmp_path))
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    s = bench.ClockSampler(0)
+    s.start()
+    s.begin()
+    s.end()
+    c = s.stop()
+    assert c["sm_mhz"] is None and c["samples"] == 0 and c["reasons"] == ["nvidia-smi unavailable"]
