@@ -1,0 +1,1283 @@
+#!/usr/bin/env python
+"""f2cxx.py -- a mechanical Fortran 90 -> C++ translator for the language subset WumingPIC's hot path is written in.
+
+TEST INFRASTRUCTURE ONLY (lives under oracle/): this image has no Fortran compiler, so the reference's own source files
+(`/root/reference/{2d,3d}/common/{particle,field,sort,boundary_periodic,mom_calc}.f90` and the `boundary_{reconnection,shock}.f90`
+of the set-ups) are translated statement by statement into C++ and compiled with g++ into `oracle/_ref/` (git-ignored; nothing
+of the reference is copied into the repository -- the translation is regenerated from the sources where they lie).  The result is
+"the reference itself, run here" in the only form this environment allows, and it is what pins the hand-written oracle
+(tests/test_ref_transpiled.py, tests/golden/make_ref_fixtures.py).
+
+What is translated, and how (one Fortran statement -> one C++ statement, no optimisation, no re-ordering):
+  * free-form source: `!` comments (incl. `!$OMP`, `!$ ` conditional lines and `!OCL`: the translation is the SERIAL program),
+    `&` continuations, case-insensitive names (everything outside strings is lower-cased)
+  * modules: `use`, `implicit none`, `private/public`, module variables (`save`, `parameter`, `allocatable`), `contains`
+  * subroutines with explicit-shape / assumed-shape dummies, procedure dummies declared by `interface` blocks, automatic arrays,
+    `save`d locals; every argument is passed by reference (the gfortran ABI without hidden arguments, except one trailing
+    `int*` extent per assumed-shape dummy)
+  * statements: assignment (scalar, element, array section, whole array), `call`, `if/else if/else/endif`, one-line `if`,
+    `do` (with step), `do while`, named `do` + `exit/cycle [name]`, `select case`, `allocate/deallocate`, `write` (message to
+    stderr), `stop` (C++ exception caught at the entry point; `f90rt_stop_count()` tells the caller), `return`
+  * expressions: Fortran precedence incl. `**` (integer powers by repeated multiplication as gfortran expands them, real powers
+    by pow), `.and./.or./.not.`, relational operators in both spellings, literal kinds (`1d0` double, `1.` / `0.5` / `1e0` SINGLE
+    precision as the standard says -- `sqrt(2.)` is a float32 square root), integer division, mixed-mode promotion (C++'s usual
+    arithmetic conversions coincide with Fortran's for int / real(4) / real(8)); every binary operation is parenthesised exactly as
+    the Fortran parse tree associates it, and the C++ is compiled with -ffp-contract=off, so the arithmetic is the reference's
+  * intrinsics: int, dble, real, sqrt, dsqrt, abs, max, min, mod, floor, atan, exp, log, sin, cos, size, sum (of one section or of
+    an elemental expression of sections), `ieee_set_rounding_mode(ieee_down|ieee_nearest|...)` -> fesetround
+  * `use mpi`: MPI_SENDRECV / MPI_ALLREDUCE / MPI_BARRIER... become calls into f90rt.h's transport hooks (a single rank copies; N
+    ranks are N private copies of the library on N threads with a rendezvous provided by the test driver, oracle/f2cxx/pyref.py)
+
+Anything outside this subset raises TranslateError with the file and line -- the translator never guesses.
+"""
+import re
+import sys
+
+
+class TranslateError(Exception):
+    pass
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# source -> logical lines
+# ----------------------------------------------------------------------------------------------------------------------
+def _strip_comment(line):
+    out, q = [], None
+    for ch in line:
+        if q:
+            out.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            out.append(ch)
+        elif ch == "!":
+            break
+        else:
+            out.append(ch)
+    return "".join(out).rstrip()
+
+
+def _lower_outside_strings(s):
+    out, q = [], None
+    for ch in s:
+        if q:
+            out.append(ch)
+            if ch == q:
+                q = None
+        else:
+            if ch in "'\"":
+                q = ch
+            out.append(ch.lower())
+    return "".join(out)
+
+
+def logical_lines(text):
+    """[(first physical line number, statement text)] -- comments dropped, continuations joined, lower-cased"""
+    res, cur, start = [], "", 0
+    for no, raw in enumerate(text.splitlines(), 1):
+        line = _strip_comment(raw)
+        if not line.strip():
+            continue
+        s = line.strip()
+        if cur:
+            if s.startswith("&"):
+                s = s[1:].lstrip()
+            cur += " " + s
+        else:
+            cur, start = s, no
+        if cur.endswith("&"):
+            cur = cur[:-1].rstrip()
+            continue
+        for part in _split_top(cur, ";"):
+            if part.strip():
+                res.append((start, _lower_outside_strings(part.strip())))
+        cur = ""
+    if cur:
+        res.append((start, _lower_outside_strings(cur)))
+    return res
+
+
+def _split_top(s, sep):
+    """split on `sep` outside parentheses and strings"""
+    out, depth, q, cur = [], 0, None, []
+    i = 0
+    while i < len(s):
+        ch = s[i]
+        if q:
+            cur.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            cur.append(ch)
+        elif ch in "([":
+            depth += 1
+            cur.append(ch)
+        elif ch in ")]":
+            depth -= 1
+            cur.append(ch)
+        elif depth == 0 and s.startswith(sep, i):
+            out.append("".join(cur))
+            cur = []
+            i += len(sep)
+            continue
+        else:
+            cur.append(ch)
+        i += 1
+    out.append("".join(cur))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# expressions
+# ----------------------------------------------------------------------------------------------------------------------
+_TOKEN = re.compile(r"""
+    (?P<num>(?:\d+\.(?![a-z]+\.)\d*|\.\d+|\d+)(?:[de][+-]?\d+)?(?:_\w+)?)
+  | (?P<dotop>\.(?:and|or|not|eq|ne|lt|le|gt|ge|eqv|neqv|true|false)\.)
+  | (?P<name>[a-z_]\w*)
+  | (?P<str>'(?:[^']|'')*'|"(?:[^"]|"")*")
+  | (?P<op>\*\*|==|/=|<=|>=|//|[-+*/<>(),:=%])
+  | (?P<ws>\s+)
+""", re.X)
+
+_DOTOPS = {".eq.": "==", ".ne.": "/=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">="}
+
+
+def tokenize(s, where=""):
+    toks, pos = [], 0
+    while pos < len(s):
+        m = _TOKEN.match(s, pos)
+        if not m:
+            raise TranslateError(f"{where}: cannot tokenize {s[pos:pos + 20]!r} in {s!r}")
+        pos = m.end()
+        kind = m.lastgroup
+        if kind == "ws":
+            continue
+        txt = m.group()
+        if kind == "num":
+            # `1.eq.2`-style ambiguity does not occur in this code base; `1.d0` does not either
+            toks.append(("num", txt))
+        elif kind == "dotop":
+            if txt in (".true.", ".false."):
+                toks.append(("logical", txt))
+            else:
+                toks.append(("op", _DOTOPS.get(txt, txt)))
+        elif kind == "name":
+            toks.append(("name", txt))
+        elif kind == "str":
+            toks.append(("str", txt))
+        else:
+            toks.append(("op", txt))
+    return toks
+
+
+class Parser:
+    """precedence climbing over Fortran's operator table"""
+
+    def __init__(self, toks, where=""):
+        self.t, self.i, self.where = toks, 0, where
+
+    def peek(self):
+        return self.t[self.i] if self.i < len(self.t) else ("eof", "")
+
+    def next(self):
+        tok = self.peek()
+        self.i += 1
+        return tok
+
+    def accept(self, kind, val=None):
+        k, v = self.peek()
+        if k == kind and (val is None or v == val):
+            self.i += 1
+            return True
+        return False
+
+    def expect(self, kind, val=None):
+        if not self.accept(kind, val):
+            raise TranslateError(f"{self.where}: expected {val or kind}, found {self.peek()} in {self.t}")
+
+    def done(self):
+        return self.i >= len(self.t)
+
+    # lowest: .eqv./.neqv.  <  .or.  <  .and.  <  .not.  <  relational  <  +,- (binary and unary)  <  *,/  <  **
+    def expr(self):
+        return self.p_or()
+
+    def p_or(self):
+        a = self.p_and()
+        while self.peek() == ("op", ".or."):
+            self.next()
+            a = ("bin", "||", a, self.p_and())
+        return a
+
+    def p_and(self):
+        a = self.p_not()
+        while self.peek() == ("op", ".and."):
+            self.next()
+            a = ("bin", "&&", a, self.p_not())
+        return a
+
+    def p_not(self):
+        if self.peek() == ("op", ".not."):
+            self.next()
+            return ("un", "!", self.p_not())
+        return self.p_rel()
+
+    def p_rel(self):
+        a = self.p_add()
+        k, v = self.peek()
+        if k == "op" and v in ("==", "/=", "<", "<=", ">", ">="):
+            self.next()
+            b = self.p_add()
+            return ("bin", "!=" if v == "/=" else v, a, b)
+        return a
+
+    def p_add(self):
+        k, v = self.peek()
+        if k == "op" and v in "+-" and len(v) == 1:
+            self.next()
+            a = self.p_mul()
+            a = ("un", v, a)
+        else:
+            a = self.p_mul()
+        while True:
+            k, v = self.peek()
+            if k == "op" and v in ("+", "-"):
+                self.next()
+                a = ("bin", v, a, self.p_mul())
+            else:
+                return a
+
+    def p_mul(self):
+        a = self.p_pow()
+        while True:
+            k, v = self.peek()
+            if k == "op" and v in ("*", "/"):
+                self.next()
+                a = ("bin", v, a, self.p_pow())
+            else:
+                return a
+
+    def p_pow(self):
+        a = self.p_primary()
+        if self.peek() == ("op", "**"):
+            self.next()
+            # right associative; the exponent may carry a sign:  a**-b
+            k, v = self.peek()
+            if k == "op" and v in ("+", "-"):
+                self.next()
+                b = ("un", v, self.p_pow())
+            else:
+                b = self.p_pow()
+            return ("pow", a, b)
+        return a
+
+    def p_primary(self):
+        k, v = self.next()
+        if k == "num":
+            return ("num", v)
+        if k == "logical":
+            return ("logical", v == ".true.")
+        if k == "str":
+            return ("str", v)
+        if k == "op" and v == "(":
+            e = self.expr()
+            self.expect("op", ")")
+            return ("paren", e)
+        if k == "name":
+            if self.accept("op", "("):
+                args = []
+                if not self.accept("op", ")"):
+                    while True:
+                        args.append(self.subscript())
+                        if self.accept("op", ")"):
+                            break
+                        self.expect("op", ",")
+                return ("call", v, args)
+            return ("name", v)
+        raise TranslateError(f"{self.where}: unexpected token {(k, v)} in {self.t}")
+
+    def subscript(self):
+        """expr | [expr] : [expr] [: expr]"""
+        lo = hi = st = None
+        if self.peek() != ("op", ":"):
+            lo = self.expr()
+            if self.peek() != ("op", ":"):
+                return lo
+        self.expect("op", ":")
+        if self.peek() not in (("op", ","), ("op", ")"), ("op", ":")):
+            hi = self.expr()
+        if self.accept("op", ":"):
+            st = self.expr()
+        return ("range", lo, hi, st)
+
+
+def parse_expr(s, where=""):
+    p = Parser(tokenize(s, where), where)
+    e = p.expr()
+    if not p.done():
+        raise TranslateError(f"{where}: trailing tokens in expression {s!r}")
+    return e
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# symbols
+# ----------------------------------------------------------------------------------------------------------------------
+CTYPE = {"integer": "int", "real8": "double", "real4": "float", "logical": "bool", "integer8": "long long"}
+
+
+class Sym:
+    def __init__(self, name, ftype, dims=None, attrs=(), init=None, intent=None):
+        self.name, self.ftype, self.dims, self.attrs, self.init, self.intent = name, ftype, dims, set(attrs), init, intent
+        self.is_dummy = False
+        self.proc_sig = None        # for procedure dummies: list of (ctype, is_array)
+
+    @property
+    def ctype(self):
+        return CTYPE[self.ftype]
+
+    @property
+    def rank(self):
+        return len(self.dims) if self.dims else 0
+
+    @property
+    def deferred(self):             # (:,:) -- allocatable or assumed shape
+        return bool(self.dims) and all(d == (None, None) for d in self.dims)
+
+
+def parse_type(spec, where):
+    s = spec.replace(" ", "")
+    if s == "integer":
+        return "integer"
+    if s in ("integer(8)", "integer(kind=8)"):
+        return "integer8"
+    if s in ("real(8)", "real(kind=8)", "doubleprecision"):
+        return "real8"
+    if s in ("real", "real(4)", "real(kind=4)"):
+        return "real4"
+    if s == "logical":
+        return "logical"
+    raise TranslateError(f"{where}: unsupported type {spec!r}")
+
+
+def parse_decl(stmt, where):
+    """'real(8), intent(in) :: a(n), b' -> [Sym]   (None if the statement is not a type declaration)"""
+    m = re.match(r"(integer|real|logical|double\s+precision)\b", stmt)
+    if not m or "::" not in stmt:
+        return None
+    left, right = stmt.split("::", 1)
+    parts = [p.strip() for p in _split_top(left, ",")]
+    ftype = parse_type(parts[0], where)
+    attrs, intent, dimattr = [], None, None
+    for a in parts[1:]:
+        a2 = a.replace(" ", "")
+        if a2.startswith("intent("):
+            intent = a2[7:-1]
+        elif a2.startswith("dimension("):
+            dimattr = a2[10:-1]
+        elif a2 in ("save", "parameter", "allocatable"):
+            attrs.append(a2)
+        else:
+            raise TranslateError(f"{where}: unsupported attribute {a!r}")
+    syms = []
+    for ent in _split_top(right, ","):
+        ent = ent.strip()
+        init = None
+        if "=" in ent:
+            # entity initialisation (not ==)
+            eq = _find_top_assign(ent)
+            if eq >= 0:
+                init = ent[eq + 1:].strip()
+                ent = ent[:eq].strip()
+        m2 = re.match(r"([a-z_]\w*)\s*(\((.*)\))?$", ent)
+        if not m2:
+            raise TranslateError(f"{where}: cannot parse entity {ent!r}")
+        name, dimtxt = m2.group(1), m2.group(3) if m2.group(2) else dimattr
+        dims = None
+        if dimtxt is not None:
+            dims = []
+            for d in _split_top(dimtxt, ","):
+                d = d.strip()
+                if d == ":":
+                    dims.append((None, None))
+                elif d == "*":
+                    raise TranslateError(f"{where}: assumed-size arrays are not supported")
+                else:
+                    lohi = _split_top(d, ":")
+                    if len(lohi) == 1:
+                        dims.append(("1", lohi[0].strip()))
+                    else:
+                        dims.append((lohi[0].strip(), lohi[1].strip()))
+        syms.append(Sym(name, ftype, dims, attrs, init, intent))
+    return syms
+
+
+def _find_top_assign(s):
+    depth, q = 0, None
+    for i, ch in enumerate(s):
+        if q:
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+        elif ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+        elif ch == "=" and depth == 0:
+            if s[i + 1:i + 2] == "=" or s[i - 1:i] in ("=", "/", "<", ">"):
+                continue
+            return i
+    return -1
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# program structure
+# ----------------------------------------------------------------------------------------------------------------------
+class Subroutine:
+    def __init__(self, name, args, line):
+        self.name, self.args, self.line = name, args, line
+        self.syms = {}          # name -> Sym
+        self.order = []         # declaration order
+        self.body = []          # [(line, stmt)]
+        self.uses = []
+
+
+class Module:
+    def __init__(self, name):
+        self.name, self.syms, self.order, self.subs, self.uses = name, {}, [], [], []
+
+
+MPI_CONSTANTS = {"mpi_status_size": "6"}
+
+
+def parse_module(text, fname):
+    lines = logical_lines(text)
+    i, mod = 0, None
+
+    def where(no):
+        return f"{fname}:{no}"
+
+    def parse_sub(i, interface=False):
+        no, st = lines[i]
+        m = re.match(r"subroutine\s+([a-z_]\w*)\s*(\((.*)\))?\s*$", st)
+        if not m:
+            raise TranslateError(f"{where(no)}: cannot parse {st!r}")
+        args = [a.strip() for a in m.group(3).split(",")] if m.group(3) and m.group(3).strip() else []
+        sub = Subroutine(m.group(1), args, no)
+        i += 1
+        in_spec = True
+        while True:
+            no, st = lines[i]
+            if re.match(r"end\s*subroutine\b", st) or st == "end":
+                i += 1
+                break
+            if in_spec:
+                if st.startswith("use ") or st.startswith("use,"):
+                    sub.uses.append(st)
+                    i += 1
+                    continue
+                if st.startswith("implicit"):
+                    i += 1
+                    continue
+                if st == "interface":
+                    i += 1
+                    while lines[i][1] not in ("end interface", "endinterface"):
+                        isub, i = parse_sub(i, interface=True)
+                        sig = []
+                        for a in isub.args:
+                            s = isub.syms.get(a)
+                            if s is None:
+                                raise TranslateError(f"{where(isub.line)}: interface argument {a} undeclared")
+                            sig.append((s.ctype, s.rank > 0))
+                        ps = Sym(isub.name, "integer")
+                        ps.proc_sig = sig
+                        sub.syms[isub.name] = ps
+                        sub.order.append(isub.name)
+                    i += 1
+                    continue
+                d = parse_decl(st, where(no))
+                if d is not None:
+                    for s in d:
+                        sub.syms[s.name] = s
+                        sub.order.append(s.name)
+                    i += 1
+                    continue
+                in_spec = False
+            sub.body.append((no, st))
+            i += 1
+        for a in sub.args:
+            if a not in sub.syms:
+                raise TranslateError(f"{where(sub.line)}: dummy argument {a} of {sub.name} is not declared")
+            sub.syms[a].is_dummy = True
+        return sub, i
+
+    while i < len(lines):
+        no, st = lines[i]
+        m = re.match(r"module\s+([a-z_]\w*)$", st)
+        if m and mod is None:
+            mod = Module(m.group(1))
+            i += 1
+            continue
+        if mod is None:
+            raise TranslateError(f"{where(no)}: statement outside a module: {st!r}")
+        if re.match(r"end\s*module\b", st):
+            i += 1
+            continue
+        if st.startswith("use ") or st.startswith("use,"):
+            mod.uses.append(st)
+            i += 1
+            continue
+        if st.startswith("implicit") or st.startswith("private") or st.startswith("public"):
+            i += 1
+            continue
+        if st == "contains":
+            i += 1
+            while i < len(lines) and not re.match(r"end\s*module\b", lines[i][1]):
+                sub, i = parse_sub(i)
+                mod.subs.append(sub)
+            continue
+        d = parse_decl(st, where(no))
+        if d is None:
+            raise TranslateError(f"{where(no)}: unsupported module-level statement {st!r}")
+        for s in d:
+            mod.syms[s.name] = s
+            mod.order.append(s.name)
+        i += 1
+    return mod
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# code generation
+# ----------------------------------------------------------------------------------------------------------------------
+INTRINSIC_1 = {"sqrt": "f90::sqrt_", "dsqrt": "f90::sqrt_", "abs": "f90::abs_", "dabs": "f90::abs_", "atan": "f90::atan_",
+               "exp": "f90::exp_", "log": "f90::log_", "sin": "f90::sin_", "cos": "f90::cos_", "tanh": "f90::tanh_",
+               "cosh": "f90::cosh_", "floor": "f90::floor_", "nint": "f90::nint_"}
+
+EXTERNALS = {   # name -> C symbol in f90rt.h   (every argument by reference)
+    "mpi_sendrecv": "f90rt_mpi_sendrecv", "mpi_allreduce": "f90rt_mpi_allreduce", "mpi_barrier": "f90rt_mpi_barrier",
+    "mpi_bcast": "f90rt_mpi_bcast", "mpi_abort": "f90rt_mpi_abort", "mpi_finalize": "f90rt_mpi_finalize",
+}
+
+ROUNDING = {"ieee_down": "FE_DOWNWARD", "ieee_up": "FE_UPWARD", "ieee_nearest": "FE_TONEAREST", "ieee_to_zero": "FE_TOWARDZERO"}
+
+
+def mangle(name):
+    return name + "_"
+
+
+class Gen:
+    def __init__(self, modules, known_subs):
+        self.modules = modules
+        self.known_subs = known_subs            # name -> Subroutine (all translated modules)
+        self.out = []
+        self.tmp = 0
+
+    # ---- scopes ----
+    def lookup(self, name):
+        if self.sub is not None and name in self.sub.syms:
+            return self.sub.syms[name]
+        if name in self.mod.syms:
+            return self.mod.syms[name]
+        for u in self.used_modules:
+            if name in u.syms:
+                return u.syms[name]
+        return None
+
+    def W(self, no):
+        return f"{self.fname}:{no}"
+
+    # ---- literals ----
+    @staticmethod
+    def number(txt):
+        t = txt
+        kind = None
+        if "_" in t:
+            t, kind = t.split("_", 1)
+        if re.fullmatch(r"\d+", t):
+            return t + ("LL" if kind == "8" else "")
+        if "d" in t:
+            t = t.replace("d", "e")
+            if "." not in t.split("e")[0]:
+                t = t.split("e")[0] + ".0e" + t.split("e")[1]
+            return t                          # double
+        if kind == "8":
+            return t if ("." in t or "e" in t) else t + ".0"
+        # default real: SINGLE precision
+        if t.endswith("."):
+            t += "0"
+        if "e" in t and "." not in t.split("e")[0]:
+            t = t.split("e")[0] + ".0e" + t.split("e")[1]
+        return t + "f"
+
+    # ---- expressions ----
+    def is_array(self, name):
+        s = self.lookup(name)
+        return s is not None and s.rank > 0
+
+    def has_section(self, e):
+        """does the expression contain an array-valued reference (a section or a bare array name)?"""
+        k = e[0]
+        if k == "name":
+            return self.is_array(e[1])
+        if k == "call":
+            if self.is_array(e[1]):
+                return any(a[0] == "range" for a in e[2]) or any(self.has_section(a) for a in e[2] if a[0] != "range")
+            if e[1] in ("sum", "size", "maxval", "minval") and self.lookup(e[1]) is None:
+                return False                 # reductions are scalar
+            return any(self.has_section(a) for a in e[2])
+        if k in ("bin",):
+            return self.has_section(e[2]) or self.has_section(e[3])
+        if k == "pow":
+            return self.has_section(e[1]) or self.has_section(e[2])
+        if k in ("un",):
+            return self.has_section(e[2])
+        if k == "paren":
+            return self.has_section(e[1])
+        return False
+
+    def section_dims(self, e, no):
+        """for an array-valued reference: [(lo_cxx, hi_cxx)] of its ranged dimensions"""
+        if e[0] == "name":
+            s = self.lookup(e[1])
+            return [(f"{mangle(e[1])}.lb({d})", f"{mangle(e[1])}.ub({d})") for d in range(s.rank)]
+        s = self.lookup(e[1])
+        dims = []
+        for d, a in enumerate(e[2]):
+            if a[0] == "range":
+                if a[3] is not None:
+                    raise TranslateError(f"{self.W(no)}: strided sections are not supported")
+                lo = self.ex(a[1], no) if a[1] is not None else f"{mangle(e[1])}.lb({d})"
+                hi = self.ex(a[2], no) if a[2] is not None else f"{mangle(e[1])}.ub({d})"
+                dims.append((lo, hi))
+        if len(e[2]) != s.rank:
+            raise TranslateError(f"{self.W(no)}: rank mismatch in reference to {e[1]}")
+        return dims
+
+    def ex(self, e, no, secvars=None):
+        """expression -> C++.  secvars: loop variables of the enclosing elemental context (array assignment / sum)"""
+        k = e[0]
+        if k == "num":
+            return self.number(e[1])
+        if k == "logical":
+            return "true" if e[1] else "false"
+        if k == "str":
+            body = e[1][1:-1].replace("\\", "\\\\").replace('"', '\\"')
+            return f'"{body}"'
+        if k == "paren":
+            return "(" + self.ex(e[1], no, secvars) + ")"
+        if k == "un":
+            return f"({e[1]}{self.ex(e[2], no, secvars)})"
+        if k == "bin":
+            return f"({self.ex(e[2], no, secvars)} {e[1]} {self.ex(e[3], no, secvars)})"
+        if k == "pow":
+            return f"f90::pow_({self.ex(e[1], no, secvars)}, {self.ex(e[2], no, secvars)})"
+        if k == "name":
+            name = e[1]
+            s = self.lookup(name)
+            if s is None:
+                if name in MPI_CONSTANTS:
+                    return MPI_CONSTANTS[name]
+                raise TranslateError(f"{self.W(no)}: unknown name {name!r}")
+            if s.rank > 0:
+                if secvars is None:
+                    raise TranslateError(f"{self.W(no)}: whole array {name!r} in a scalar context")
+                idx = [f"{mangle(name)}.lb({d}) + {secvars[d]}" for d in range(s.rank)]
+                if s.rank > len(secvars):
+                    raise TranslateError(f"{self.W(no)}: rank of {name!r} exceeds the elemental context")
+                return f"{mangle(name)}({', '.join(idx)})"
+            return mangle(name)
+        if k == "call":
+            name, args = e[1], e[2]
+            s = self.lookup(name)
+            if s is not None and s.rank > 0:
+                if len(args) != s.rank:
+                    raise TranslateError(f"{self.W(no)}: {name} has rank {s.rank}, {len(args)} subscripts given")
+                idx, nsec = [], 0
+                for d, a in enumerate(args):
+                    if a[0] == "range":
+                        if secvars is None:
+                            raise TranslateError(f"{self.W(no)}: array section of {name!r} in a scalar context")
+                        if a[3] is not None:
+                            raise TranslateError(f"{self.W(no)}: strided sections are not supported")
+                        lo = self.ex(a[1], no) if a[1] is not None else f"{mangle(name)}.lb({d})"
+                        if nsec >= len(secvars):
+                            raise TranslateError(f"{self.W(no)}: section rank of {name!r} exceeds the elemental context")
+                        idx.append(f"({lo}) + {secvars[nsec]}")
+                        nsec += 1
+                    else:
+                        idx.append(self.ex(a, no, secvars))
+                return f"{mangle(name)}({', '.join(idx)})"
+            if s is not None:
+                raise TranslateError(f"{self.W(no)}: {name!r} is a scalar but is subscripted")
+            # intrinsics
+            if name == "int":
+                return f"f90::int_({self.ex(args[0], no, secvars)})"
+            if name in ("dble", "dfloat"):
+                return f"((double)({self.ex(args[0], no, secvars)}))"
+            if name == "real":
+                if len(args) == 2:
+                    kind = self.ex(args[1], no)
+                    if kind not in ("8", "4"):
+                        raise TranslateError(f"{self.W(no)}: real(x, kind) with kind {kind}")
+                    return f"(({'double' if kind == '8' else 'float'})({self.ex(args[0], no, secvars)}))"
+                return f"((float)({self.ex(args[0], no, secvars)}))"
+            if name in INTRINSIC_1:
+                if len(args) != 1:
+                    raise TranslateError(f"{self.W(no)}: {name} takes one argument")
+                return f"{INTRINSIC_1[name]}({self.ex(args[0], no, secvars)})"
+            if name in ("max", "min", "dmax1", "dmin1", "mod", "sign", "atan2"):
+                fn = {"dmax1": "max", "dmin1": "min"}.get(name, name)
+                return f"f90::{fn}_({', '.join(self.ex(a, no, secvars) for a in args)})"
+            if name == "size":
+                if args[0][0] != "name" or not self.is_array(args[0][1]):
+                    raise TranslateError(f"{self.W(no)}: size() of a non-array")
+                if len(args) == 2:
+                    return f"((int){mangle(args[0][1])}.extent(({self.ex(args[1], no)}) - 1))"
+                return f"((int){mangle(args[0][1])}.size())"
+            if name in ("sum", "maxval", "minval"):
+                return self.reduction(name, args, no)
+            raise TranslateError(f"{self.W(no)}: unknown function or array {name!r}")
+        raise TranslateError(f"{self.W(no)}: cannot translate expression node {e!r}")
+
+    def find_shape(self, e, no):
+        """the section dims of the first array-valued reference inside e (defines the elemental shape)"""
+        k = e[0]
+        if k == "name" and self.is_array(e[1]):
+            return self.section_dims(e, no)
+        if k == "call":
+            if self.is_array(e[1]):
+                if any(a[0] == "range" for a in e[2]):
+                    return self.section_dims(e, no)
+                for a in e[2]:
+                    r = self.find_shape(a, no)
+                    if r:
+                        return r
+                return None
+            if e[1] in ("sum", "maxval", "minval", "size") and self.lookup(e[1]) is None:
+                return None
+            for a in e[2]:
+                r = self.find_shape(a, no)
+                if r:
+                    return r
+            return None
+        for sub in e[1:]:
+            if isinstance(sub, tuple):
+                r = self.find_shape(sub, no)
+                if r:
+                    return r
+        return None
+
+    def reduction(self, name, args, no):
+        if len(args) != 1:
+            raise TranslateError(f"{self.W(no)}: {name}() with dim/mask arguments is not supported")
+        shape = self.find_shape(args[0], no)
+        if not shape:
+            raise TranslateError(f"{self.W(no)}: {name}() of a scalar expression")
+        self.tmp += 1
+        t = self.tmp
+        vs = [f"_r{t}_{d}" for d in range(len(shape))]
+        body = self.ex(args[0], no, vs)
+        zero = [f"{lo}" for lo, hi in shape]
+        # the element type comes from evaluating the elemental expression once symbolically (decltype: unevaluated)
+        first = self.ex(args[0], no, ["0L"] * len(shape))
+        code = f"[&]() {{ typedef std::decay<decltype({first})>::type _T{t}; "
+        if name == "sum":
+            code += f"_T{t} _s = 0; "
+        else:
+            code += f"bool _first = true; _T{t} _s = 0; "
+        for d in reversed(range(len(shape))):
+            lo, hi = shape[d]
+            code += f"for (long {vs[d]} = 0, _n{t}_{d} = (long)({hi}) - (long)({lo}) + 1; {vs[d]} < _n{t}_{d}; ++{vs[d]}) "
+        if name == "sum":
+            code += f"{{ _s = _s + ({body}); }} "
+        elif name == "maxval":
+            code += f"{{ _T{t} _v = ({body}); if (_first || _v > _s) _s = _v; _first = false; }} "
+        else:
+            code += f"{{ _T{t} _v = ({body}); if (_first || _v < _s) _s = _v; _first = false; }} "
+        code += "return _s; }()"
+        del zero
+        return code
+
+    # ---- statements ----
+    def emit(self, s):
+        self.out.append("  " * self.ind + s)
+
+    def assignment(self, lhs_txt, rhs_txt, no):
+        lhs = parse_expr(lhs_txt, self.W(no))
+        rhs = parse_expr(rhs_txt, self.W(no))
+        lhs_is_arr = (lhs[0] == "name" and self.is_array(lhs[1])) or \
+                     (lhs[0] == "call" and self.is_array(lhs[1]) and any(a[0] == "range" for a in lhs[2]))
+        if not lhs_is_arr:
+            if lhs[0] == "call" and not self.is_array(lhs[1]):
+                raise TranslateError(f"{self.W(no)}: assignment to {lhs[1]!r}, which is not an array")
+            if self.has_section(rhs):
+                raise TranslateError(f"{self.W(no)}: array-valued right-hand side assigned to a scalar")
+            self.emit(f"{self.ex(lhs, no)} = {self.ex(rhs, no)};")
+            return
+        shape = self.section_dims(lhs, no)
+        self.tmp += 1
+        t = self.tmp
+        vs = [f"_a{t}_{d}" for d in range(len(shape))]
+        lname = lhs[1]
+        # Fortran evaluates the whole right-hand side before storing: if the target array also appears on the right, go through a copy
+        alias = self.mentions(rhs, lname)
+        loops = ""
+        for d in reversed(range(len(shape))):
+            loops += f"for (long {vs[d]} = 0; {vs[d]} < _n{t}_{d}; ++{vs[d]}) "
+        self.emit("{")
+        self.ind += 1
+        for d, (lo, hi) in enumerate(shape):
+            self.emit(f"const long _n{t}_{d} = (long)({hi}) - (long)({lo}) + 1;")
+        L = self.ex(lhs, no, vs)
+        R = self.ex(rhs, no, vs)
+        if alias:
+            tot = " * ".join(f"(_n{t}_{d} > 0 ? _n{t}_{d} : 0)" for d in range(len(shape)))
+            self.emit(f"std::vector<std::decay<decltype({self.ex(lhs, no, ['0L'] * len(shape))})>::type> _tmp{t}({tot});")
+            self.emit(f"{{ long _q = 0; {loops}{{ _tmp{t}[_q++] = {R}; }} }}")
+            self.emit(f"{{ long _q = 0; {loops}{{ {L} = _tmp{t}[_q++]; }} }}")
+        else:
+            self.emit(f"{loops}{{ {L} = {R}; }}")
+        self.ind -= 1
+        self.emit("}")
+
+    def mentions(self, e, name):
+        if e[0] == "name":
+            return e[1] == name
+        if e[0] == "call":
+            return e[1] == name or any(self.mentions(a, name) for a in e[2] if a is not None and a[0] != "range") or \
+                any(self.mentions(x, name) for a in e[2] if a[0] == "range" for x in a[1:] if x is not None)
+        return any(self.mentions(x, name) for x in e[1:] if isinstance(x, tuple))
+
+    def actual_arg(self, a_txt, no):
+        """an actual argument -> a C++ pointer expression (everything is passed by reference)"""
+        e = parse_expr(a_txt, self.W(no))
+        if e[0] == "name":
+            s = self.lookup(e[1])
+            if s is not None:
+                if s.proc_sig is not None:
+                    return mangle(e[1])
+                if s.rank > 0:
+                    return f"{mangle(e[1])}.data()"
+                if "parameter" in s.attrs:
+                    return f"f90::tmp({mangle(e[1])}).ptr()"
+                return f"&{mangle(e[1])}"
+            if e[1] in self.known_subs:
+                return e[1]                       # a procedure passed as an actual argument
+            if e[1] in MPI_CONSTANTS:
+                return f"f90::tmp({MPI_CONSTANTS[e[1]]}).ptr()"
+            raise TranslateError(f"{self.W(no)}: unknown actual argument {e[1]!r}")
+        if e[0] == "call" and self.is_array(e[1]):
+            if any(a[0] == "range" for a in e[2]):
+                raise TranslateError(f"{self.W(no)}: array sections as actual arguments are not supported")
+            return f"&{self.ex(e, no)}"
+        return f"f90::tmp({self.ex(e, no)}).ptr()"
+
+    def call_stmt(self, st, no):
+        m = re.match(r"call\s+([a-z_]\w*)\s*(\((.*)\))?\s*$", st)
+        if not m:
+            raise TranslateError(f"{self.W(no)}: cannot parse {st!r}")
+        name = m.group(1)
+        args = [a.strip() for a in _split_top(m.group(3), ",")] if m.group(3) and m.group(3).strip() else []
+        if name == "ieee_set_rounding_mode":
+            mode = args[0]
+            if mode not in ROUNDING:
+                raise TranslateError(f"{self.W(no)}: rounding mode {mode!r}")
+            self.emit(f"f90::set_rounding({ROUNDING[mode]});")
+            return
+        if name.startswith("omp_"):
+            return
+        ptrs = [self.actual_arg(a, no) for a in args]
+        s = self.lookup(name)
+        if s is not None and s.proc_sig is not None:
+            self.emit(f"{mangle(name)}({', '.join(ptrs)});")
+            return
+        if name in EXTERNALS:
+            self.emit(f"{EXTERNALS[name]}({', '.join(ptrs)});")
+            return
+        if name in self.known_subs:
+            callee = self.known_subs[name]
+            if len(callee.args) != len(args):
+                raise TranslateError(f"{self.W(no)}: {name} takes {len(callee.args)} arguments, {len(args)} given")
+            # assumed-shape dummies take a trailing extent each
+            extra = []
+            for a, d in zip(args, callee.args):
+                ds = callee.syms[d]
+                if ds.rank > 0 and ds.deferred and "allocatable" not in ds.attrs:
+                    e = parse_expr(a, self.W(no))
+                    if e[0] != "name" or not self.is_array(e[1]):
+                        raise TranslateError(f"{self.W(no)}: assumed-shape dummy {d} needs a whole array actual")
+                    extra.append(f"f90::tmp((int){mangle(e[1])}.size()).ptr()")
+            self.emit(f"{name}({', '.join(ptrs + extra)});")
+            return
+        raise TranslateError(f"{self.W(no)}: call to unknown procedure {name!r}")
+
+    def bounds_list(self, sym, no):
+        return ", ".join(f"{{(long)({self.ex(parse_expr(lo, self.W(no)), no)}), (long)({self.ex(parse_expr(hi, self.W(no)), no)})}}"
+                         for lo, hi in sym.dims)
+
+    def block(self, body):
+        """translate a list of (line, stmt) with nesting"""
+        stack = []          # ("if"|"do"|"select", label, extra)
+        for no, st in body:
+            # ---- block ends
+            if re.match(r"end\s*if$", st):
+                self.ind -= 1
+                self.emit("}")
+                stack.pop()
+                continue
+            m = re.match(r"end\s*do(\s+([a-z_]\w*))?$", st)
+            if m:
+                kind, label, uniq = stack.pop()
+                if label:
+                    self.emit(f"_cycle_{uniq}: ;")
+                self.ind -= 1
+                self.emit("}")
+                if label:
+                    self.emit(f"_exit_{uniq}: ;")
+                if kind == "dowrap":
+                    self.ind -= 1
+                    self.emit("}")
+                continue
+            if re.match(r"end\s*select$", st):
+                kind, _, state = stack.pop()
+                if state["open"]:
+                    self.ind -= 1
+                    self.emit("}")
+                self.ind -= 1
+                self.emit("}")
+                continue
+            # ---- if family
+            m = re.match(r"else\s*if\s*\((.*)\)\s*then$", st)
+            if m:
+                self.ind -= 1
+                self.emit(f"}} else if ({self.ex(parse_expr(m.group(1), self.W(no)), no)}) {{")
+                self.ind += 1
+                continue
+            if st == "else":
+                self.ind -= 1
+                self.emit("} else {")
+                self.ind += 1
+                continue
+            m = re.match(r"if\s*\((.*)\)\s*then$", st)
+            if m:
+                self.emit(f"if ({self.ex(parse_expr(m.group(1), self.W(no)), no)}) {{")
+                self.ind += 1
+                stack.append(("if", None, None))
+                continue
+            if st.startswith("if") and re.match(r"if\s*\(", st):
+                # one-line if: find the matching parenthesis
+                p = st.index("(")
+                depth, j = 0, p
+                while True:
+                    if st[j] == "(":
+                        depth += 1
+                    elif st[j] == ")":
+                        depth -= 1
+                        if depth == 0:
+                            break
+                    j += 1
+                cond, rest = st[p + 1:j], st[j + 1:].strip()
+                self.emit(f"if ({self.ex(parse_expr(cond, self.W(no)), no)}) {{")
+                self.ind += 1
+                self.simple(rest, no, stack)
+                self.ind -= 1
+                self.emit("}")
+                continue
+            # ---- select case
+            m = re.match(r"select\s*case\s*\((.*)\)$", st)
+            if m:
+                self.tmp += 1
+                self.emit("{")
+                self.ind += 1
+                self.emit(f"const auto _sel{self.tmp} = {self.ex(parse_expr(m.group(1), self.W(no)), no)};")
+                stack.append(("select", None, {"var": f"_sel{self.tmp}", "open": False}))
+                continue
+            m = re.match(r"case\s*(\((.*)\)|default)$", st)
+            if m:
+                state = stack[-1][2]
+                if m.group(1) == "default":
+                    cond = None
+                else:
+                    alts = []
+                    for v in _split_top(m.group(2), ","):
+                        v = v.strip()
+                        if ":" in v:
+                            lo, hi = [x.strip() for x in v.split(":")]
+                            c = []
+                            if lo:
+                                c.append(f"{state['var']} >= {self.ex(parse_expr(lo, self.W(no)), no)}")
+                            if hi:
+                                c.append(f"{state['var']} <= {self.ex(parse_expr(hi, self.W(no)), no)}")
+                            alts.append("(" + " && ".join(c) + ")")
+                        else:
+                            alts.append(f"{state['var']} == {self.ex(parse_expr(v, self.W(no)), no)}")
+                    cond = " || ".join(alts)
+                if state["open"]:
+                    self.ind -= 1
+                    self.emit("} else " + (f"if ({cond}) {{" if cond else "{"))
+                else:
+                    self.emit(f"if ({cond}) {{" if cond else "{")
+                    state["open"] = True
+                self.ind += 1
+                continue
+            # ---- do family
+            m = re.match(r"(?:([a-z_]\w*)\s*:\s*)?do\s+while\s*\((.*)\)$", st)
+            if m:
+                label = m.group(1)
+                self.emit(f"while ({self.ex(parse_expr(m.group(2), self.W(no)), no)}) {{")
+                self.ind += 1
+                self.tmp += 1
+                stack.append(("do", label, f"{label}_{self.tmp}"))
+                continue
+            m = re.match(r"(?:([a-z_]\w*)\s*:\s*)?do\s+([a-z_]\w*)\s*=\s*(.*)$", st)
+            if m:
+                label, var = m.group(1), m.group(2)
+                parts = [p.strip() for p in _split_top(m.group(3), ",")]
+                if len(parts) not in (2, 3):
+                    raise TranslateError(f"{self.W(no)}: cannot parse do statement {st!r}")
+                vs = self.lookup(var)
+                if vs is None or vs.rank:
+                    raise TranslateError(f"{self.W(no)}: do variable {var!r}")
+                self.tmp += 1
+                t = self.tmp
+                lo = self.ex(parse_expr(parts[0], self.W(no)), no)
+                hi = self.ex(parse_expr(parts[1], self.W(no)), no)
+                stp = self.ex(parse_expr(parts[2], self.W(no)), no) if len(parts) == 3 else "1"
+                self.emit("{")
+                self.ind += 1
+                self.emit(f"const long _lo{t} = {lo}, _hi{t} = {hi}, _st{t} = {stp};")
+                self.emit(f"long _n{t} = f90::trip_count(_lo{t}, _hi{t}, _st{t});")
+                self.emit(f"for ({mangle(var)} = _lo{t}; _n{t} > 0; --_n{t}, {mangle(var)} += _st{t}) {{")
+                self.ind += 1
+                stack.append(("dowrap", label, f"{label}_{t}"))
+                continue
+            if re.match(r"(?:([a-z_]\w*)\s*:\s*)?do$", st):
+                raise TranslateError(f"{self.W(no)}: unbounded do loops are not supported")
+            self.simple(st, no, stack)
+        if stack:
+            raise TranslateError(f"{self.fname}: unterminated block {stack[-1][0]} in {self.sub.name if self.sub else '?'}")
+
+    def simple(self, st, no, stack):
+        """a non-block statement"""
+        if st.startswith("call "):
+            self.call_stmt(st, no)
+            return
+        m = re.match(r"(exit|cycle)(\s+([a-z_]\w*))?$", st)
+        if m:
+            kind, label = m.group(1), m.group(3)
+            if label:
+                uniq = [u for k2, l2, u in stack if k2 in ("do", "dowrap") and l2 == label]
+                if not uniq:
+                    raise TranslateError(f"{self.W(no)}: {kind} {label}: no enclosing loop of that name")
+                self.emit(f"goto _{kind}_{uniq[-1]};")
+            else:
+                # innermost loop: its C++ counterpart is the innermost for/while as well (ifs and selects are not loops)
+                self.emit("break;" if kind == "exit" else "continue;")
+            return
+        if st == "return":
+            self.emit("return;")
+            return
+        if st == "continue":
+            self.emit(";")
+            return
+        if st.startswith("stop"):
+            self.emit(f'f90::stop("{self.W(no)}");')
+            return
+        if re.match(r"(write|print)\b", st):
+            txt = st.replace("\\", "\\\\").replace('"', '\\"')
+            self.emit(f'f90::message("{self.W(no)}: {txt}");')
+            return
+        m = re.match(r"allocate\s*\((.*)\)$", st)
+        if m:
+            for ent in _split_top(m.group(1), ","):
+                ent = ent.strip()
+                if ent.startswith("stat="):
+                    continue
+                m2 = re.match(r"([a-z_]\w*)\s*\((.*)\)$", ent)
+                if not m2:
+                    raise TranslateError(f"{self.W(no)}: cannot parse allocate entity {ent!r}")
+                name = m2.group(1)
+                s = self.lookup(name)
+                if s is None or "allocatable" not in s.attrs:
+                    raise TranslateError(f"{self.W(no)}: allocate of non-allocatable {name!r}")
+                b = []
+                for d in _split_top(m2.group(2), ","):
+                    lohi = _split_top(d.strip(), ":")
+                    lo = "1" if len(lohi) == 1 else self.ex(parse_expr(lohi[0], self.W(no)), no)
+                    hi = self.ex(parse_expr(lohi[-1], self.W(no)), no)
+                    b.append(f"{{(long)({lo}), (long)({hi})}}")
+                if len(b) != s.rank:
+                    raise TranslateError(f"{self.W(no)}: allocate rank mismatch for {name!r}")
+                self.emit(f"{mangle(name)}.allocate({{{', '.join(b)}}});")
+            return
+        m = re.match(r"deallocate\s*\((.*)\)$", st)
+        if m:
+            for ent in _split_top(m.group(1), ","):
+                self.emit(f"{mangle(ent.strip())}.deallocate();")
+            return
+        eq = _find_top_assign(st)
+        if eq > 0:
+            self.assignment(st[:eq].strip(), st[eq + 1:].strip(), no)
+            return
+        raise TranslateError(f"{self.W(no)}: unsupported statement {st!r}")
+
+    # ---- declarations ----
+    def proc_ptr_type(self, sig):
+        return "void (*)(" + ", ".join(f"{ct}*" for ct, _ in sig) + ")"
+
+    def sub_signature(self, sub):
+        ps = []
+        for a in sub.args:
+            s = sub.syms[a]
+            if s.proc_sig is not None:
+                ps.append("void (*" + mangle(a) + ")(" + ", ".join(f"{ct}*" for ct, _ in s.proc_sig) + ")")
+            elif s.rank > 0:
+                ps.append(f"{s.ctype}* {a}_p")
+            else:
+                ps.append(f"{s.ctype}* {a}_p")
+        for a in sub.args:
+            s = sub.syms[a]
+            if s.rank > 0 and s.deferred:
+                ps.append(f"int* {a}_n")
+        return f'extern "C" void {sub.name}({", ".join(ps)})'
+
+    def gen_sub(self, sub):
+        self.sub = sub
+        self.emit(self.sub_signature(sub) + " {")
+        self.ind += 1
+        self.emit(f"using namespace mod_{self.mod.name};")
+        for u in self.used_modules:
+            self.emit(f"using namespace mod_{u.name};")
+        self.emit("F90_ENTRY_BEGIN")
+        if any("ieee_arithmetic" in u for u in sub.uses + self.mod.uses):
+            # Fortran 2003 14.4: a procedure that changes the rounding mode gets the caller's mode back on return
+            self.emit("f90::RoundingScope _rounding_scope;")
+        # 1. scalar dummies (arrays' bounds may use them)
+        for a in sub.args:
+            s = sub.syms[a]
+            if s.proc_sig is None and s.rank == 0:
+                self.emit(f"{s.ctype}& {mangle(a)} = *{a}_p;")
+        # 2. everything else in declaration order
+        for name in sub.order:
+            s = sub.syms[name]
+            if s.proc_sig is not None:
+                continue
+            if s.is_dummy:
+                if s.rank == 0:
+                    continue
+                if s.deferred:
+                    if s.rank != 1:
+                        raise TranslateError(f"{self.W(sub.line)}: assumed-shape dummy {name} of rank > 1")
+                    self.emit(f"f90::Arr<{s.ctype}, 1> {mangle(name)}({name}_p, {{{{1L, (long)*{name}_n}}}});")
+                else:
+                    self.emit(f"f90::Arr<{s.ctype}, {s.rank}> {mangle(name)}({name}_p, {{{self.bounds_list(s, sub.line)}}});")
+                continue
+            static = "static " if ("save" in s.attrs or s.init is not None) and "parameter" not in s.attrs else ""
+            if "parameter" in s.attrs:
+                if s.rank:
+                    raise TranslateError(f"{self.W(sub.line)}: array parameters are not supported")
+                self.emit(f"const {s.ctype} {mangle(name)} = {self.ex(parse_expr(s.init, self.W(sub.line)), sub.line)};")
+            elif s.rank == 0:
+                init = f" = {self.ex(parse_expr(s.init, self.W(sub.line)), sub.line)}" if s.init is not None else \
+                    (" = 0" if s.ftype != "logical" else " = false")
+                self.emit(f"{static}{s.ctype} {mangle(name)}{init};")
+            elif "allocatable" in s.attrs:
+                if static:
+                    # SAVEd allocatable locals (df, gkl, uj of field__fdtd_i; flag, bff_ptcl of the migration) live at file scope
+                    # so that the test driver can read and seed them: f2cxx_saved__<procedure>__<name>(bounds[2 rank]) -> data
+                    self.saved.append((sub.name, name, s))
+                    self.emit(f"f90::Arr<{s.ctype}, {s.rank}>& {mangle(name)} = f2cxx_saved::{sub.name}__{name};")
+                else:
+                    self.emit(f"f90::Arr<{s.ctype}, {s.rank}> {mangle(name)};")
+            else:
+                if static:
+                    raise TranslateError(f"{self.W(sub.line)}: saved explicit-shape local arrays are not supported")
+                self.emit(f"f90::Arr<{s.ctype}, {s.rank}> {mangle(name)}(nullptr, {{{self.bounds_list(s, sub.line)}}});")
+        self.block(sub.body)
+        self.emit("F90_ENTRY_END")
+        self.ind -= 1
+        self.emit("}")
+        self.emit("")
+        self.sub = None
+
+    def gen_module(self, mod, fname):
+        self.mod, self.fname, self.sub, self.ind = mod, fname, None, 0
+        self.used_modules = []
+        for u in mod.uses:
+            m = re.match(r"use\s*(?:,\s*intrinsic\s*::)?\s*([a-z_]\w*)", u)
+            if m and m.group(1) in self.modules:
+                self.used_modules.append(self.modules[m.group(1)])
+        self.emit(f"// ---- module {mod.name}  <-  {fname}")
+        self.emit(f"namespace mod_{mod.name} {{")
+        self.ind += 1
+        for name in mod.order:
+            s = mod.syms[name]
+            if "parameter" in s.attrs:
+                self.emit(f"static const {s.ctype} {mangle(name)} = {self.ex(parse_expr(s.init, fname), 0)};")
+            elif s.rank == 0:
+                init = f" = {self.ex(parse_expr(s.init, fname), 0)}" if s.init is not None else \
+                    (" = 0" if s.ftype != "logical" else " = false")
+                self.emit(f"static {s.ctype} {mangle(name)}{init};")
+            elif "allocatable" in s.attrs:
+                self.emit(f"static f90::Arr<{s.ctype}, {s.rank}> {mangle(name)};")
+            else:
+                raise TranslateError(f"{fname}: explicit-shape module array {name!r} is not supported")
+        self.ind -= 1
+        self.emit("}")
+        self.emit("")
+        for sub in mod.subs:
+            saved = self.used_modules
+            extra = []
+            for u in sub.uses:
+                m = re.match(r"use\s*(?:,\s*intrinsic\s*::)?\s*([a-z_]\w*)", u)
+                if m and m.group(1) in self.modules and self.modules[m.group(1)] not in saved:
+                    extra.append(self.modules[m.group(1)])
+            self.used_modules = saved + extra
+            self.gen_sub(sub)
+            self.used_modules = saved
+
+
+def translate(files):
+    """files: [(display name, text)] -> C++ source of one translation unit"""
+    mods, order = {}, []
+    for fname, text in files:
+        m = parse_module(text, fname)
+        mods[m.name] = m
+        order.append((m, fname))
+    known = {}
+    for m, _ in order:
+        for s in m.subs:
+            if s.name in known:
+                raise TranslateError(f"duplicate subroutine {s.name}")
+            known[s.name] = s
+    g = Gen(mods, known)
+    g.ind = 0
+    g.emit("// GENERATED by oracle/f2cxx/f2cxx.py from the reference's Fortran sources -- do not edit, do not commit")
+    g.emit('#include "f90rt.h"')
+    g.emit("")
+    # forward declarations of every subroutine (cross-module calls, procedures as actual arguments)
+    for m, fname in order:
+        g.mod, g.fname, g.sub, g.used_modules = m, fname, None, []
+        for s in m.subs:
+            g.emit(g.sub_signature(s) + ";")
+    g.emit("")
+    g.emit("// @@SAVED@@")
+    g.saved = []
+    for m, fname in order:
+        g.gen_module(m, fname)
+    decl = ["namespace f2cxx_saved {"]
+    for subname, name, s in g.saved:
+        decl.append(f"static f90::Arr<{s.ctype}, {s.rank}> {subname}__{name};")
+    decl.append("}")
+    for subname, name, s in g.saved:
+        decl.append(f'extern "C" {s.ctype}* f2cxx_saved__{subname}__{name}(long* bounds) {{ auto& a = f2cxx_saved::{subname}__{name}; '
+                    f"for (int d = 0; d < {s.rank}; ++d) {{ bounds[2 * d] = a.lb(d); bounds[2 * d + 1] = a.ub(d); }} return a.data(); }}")
+    text = "\n".join(g.out) + "\n"
+    return text.replace("// @@SAVED@@", "\n".join(decl))
+
+
+if __name__ == "__main__":
+    srcs = sys.argv[1:]
+    sys.stdout.write(translate([(p, open(p).read()) for p in srcs]))
