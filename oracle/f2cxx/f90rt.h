@@ -185,7 +185,14 @@ inline double pow_(float x, double y) { return std::pow((double)x, y); }
 inline float pow_(float x, float y) { return std::pow(x, y); }
 inline double pow_(int x, double y) { return std::pow((double)x, y); }
 
-inline void set_rounding(int mode) { std::fesetround(mode); }
+// gcc does not model the rounding mode as state (no FENV_ACCESS): -frounding-math stops constant folding, and the memory clobber
+// keeps every value that is LOADED after the call from being computed before it -- which covers the reference's use (the
+// operands of its ieee_down sections are particle coordinates read from `up` inside the loops that follow the call)
+inline void set_rounding(int mode) {
+  asm volatile("" ::: "memory");
+  std::fesetround(mode);
+  asm volatile("" ::: "memory");
+}
 struct RoundingScope {              // IEEE modes are restored when the procedure that changed them returns (F2003 14.4)
   int saved;
   RoundingScope() : saved(std::fegetround()) {}
@@ -204,7 +211,9 @@ const char* f90rt_last_stop();
 void f90rt_note_stop(const char* what);
 }
 namespace f90 {
-inline int g_depth = 0;            // nesting of translated procedures: only the outermost one swallows a STOP
+// nesting of translated procedures: only the outermost one swallows a STOP.  Internal linkage on purpose: an `inline` variable
+// is a GNU-unique symbol, i.e. ONE object shared by all the private copies of the library that emulate the MPI ranks
+static thread_local int g_depth = 0;
 struct EntryGuard {
   EntryGuard() { ++g_depth; }
   ~EntryGuard() { --g_depth; }
