@@ -2,7 +2,7 @@
 //
 // CPU restatement of WumingPIC's 2-D per-timestep loop, following the reference loop nests and
 // array shapes 1:1 (Fortran index bases are kept through the accessor functions below).
-// PARITY UNPINNED by reference goldens (none exist for this path); see oracle_common.h.
+// Pinned bit for bit to the translated reference (oracle/f2cxx, tests/test_ref_transpiled.py); see oracle_common.h.
 //
 //   particle__solv                 2d/common/particle.f90:48-179
 //   field__init / fdtd_i           2d/common/field.f90:22-63, 66-186

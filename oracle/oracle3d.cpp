@@ -2,8 +2,8 @@
 //
 // CPU restatement of WumingPIC's 3-D per-timestep loop, following the reference
 // loop nests and array shapes 1:1 (Fortran index bases are kept through the
-// accessor functions below).  PARITY UNPINNED by reference goldens (none exist
-// for this path); see oracle_common.h.
+// accessor functions below).  Pinned bit for bit to the translated reference
+// (oracle/f2cxx, tests/test_ref_transpiled.py); see oracle_common.h.
 //
 //   particle__solv                3d/common/particle.f90:52-233
 //   field__init / fdtd_i          3d/common/field.f90:22-67, 70-208

@@ -5,16 +5,25 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load it, and only as the checker / timed CPU baseline.
 //
-// PARITY UNPINNED: the reference ships no golden vectors, known-answer tests or
+// PARITY PIN: the reference ships no golden vectors, known-answer tests or
 // fixtures for push / deposit / field solve / migration / sort (SURVEY.md §4,
-// §8c), and no Fortran compiler or MPI exists in this image, so the reference
-// itself cannot be run here.  The oracle is a line-by-line restatement of the
-// Fortran loop nests (each function cites the file:line it follows) and is
-// additionally checked through the physics invariants the algorithm guarantees
-// (Gauss-law residual at round-off, particle-count / ID-multiset conservation,
-// Boris |u| conservation, N-slab == 1-slab equivalence) and against a second,
-// independent numpy restatement of push / deposit / field solve
-// (tests/test_oracle_independent.py).
+// §8c), and no Fortran compiler or MPI exists in this image, so a gfortran
+// build of the reference cannot be run here.  What pins the oracle instead is
+// THE REFERENCE'S OWN SOURCE run through another front end: oracle/f2cxx
+// translates the 14 hot-path Fortran files mechanically into C++ (oracle/_ref,
+// built from /root/reference, never committed) and the oracle equals that
+// translated reference BIT FOR BIT -- fields, np2, cumcnt, particle records in
+// order, every step, 2-D and 3-D, periodic / reconnection / shock modules,
+// both pushers, moments, 1 rank and y, z, y x z rank grids
+// (tests/test_ref_transpiled.py; committed vectors tests/golden/ref_cases.npz,
+// tests/test_ref_golden.py).  Not covered by that pin: OpenMP / a real MPI
+// library's reduction order, and the drivers' loaders (random_number).
+// The oracle is a line-by-line restatement of the Fortran loop nests (each
+// function cites the file:line it follows) and is additionally checked through
+// the physics invariants the algorithm guarantees (Gauss-law residual at
+// round-off, particle-count / ID-multiset conservation, Boris |u| conservation,
+// N-slab == 1-slab equivalence) and against a second, independent numpy
+// restatement of push / deposit / field solve (tests/test_oracle_independent.py).
 #pragma once
 #include <cstdint>
 #include <cmath>

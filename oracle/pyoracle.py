@@ -2,7 +2,7 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 legs may import this module; the product path (wumingpic_b200) never does.
-PARITY UNPINNED by reference goldens -- see oracle/oracle_common.h.
+Pinned bit for bit to the reference's own source, translated (oracle/f2cxx -> oracle/_ref) -- see oracle/oracle_common.h.
 """
 import ctypes as C
 import os

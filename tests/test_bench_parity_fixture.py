@@ -1,16 +1,27 @@
-"""The golden state bench.py checks every rank against (tests/golden/bench_parity3d.npz): (1) it is what the oracle produces
-today; (2) the slab cutting / comparing logic of tests/fixture_slabs.py is right -- the oracle's OWN N-slab emulation, started
+"""The golden state bench.py checks every rank against (tests/golden/bench_parity3d.npz): (1) it is what the translated
+reference produces today, bit for bit, and what the oracle produces to the round-off of its threaded deposit; (2) the slab cutting / comparing logic of tests/fixture_slabs.py is right -- the oracle's OWN N-slab emulation, started
 from the slabs cut out of the global state, must land on the global end state."""
 import numpy as np
 import pytest
 
 from tests import fixture_slabs as fs
-from tests.golden.make_bench_parity_fixture import build
+from oracle.f2cxx import pyref
+from tests.golden.make_bench_parity_fixture import build_from_oracle, build_from_reference
 from tests.util import make_world3
 
 
+@pytest.mark.skipif(not pyref.available(3), reason="the translated reference cannot be built here")
+def test_fixture_is_the_translated_reference_output():
+    fx, now = fs.load(), build_from_reference()
+    assert sorted(fx) == sorted(now)
+    for k in now:
+        a, b = np.asarray(now[k]), np.asarray(fx[k])
+        assert a.shape == b.shape, k
+        assert np.array_equal(a.view(np.int64) if a.dtype == np.float64 else a, b.view(np.int64) if b.dtype == np.float64 else b), k
+
+
 def test_fixture_is_current_oracle_output():
-    fx, now = fs.load(), build()
+    fx, now = fs.load(), build_from_oracle()
     for k in ("np2_0", "cumcnt_0", "np2_1", "cumcnt_1", "ids_1"):
         assert np.array_equal(fx[k], now[k]), k
     assert np.array_equal(fx["rec0"][:, -1].view(np.int64), now["rec0"][:, -1].view(np.int64))   # the IDs, bit-cast

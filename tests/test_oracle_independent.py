@@ -1,7 +1,8 @@
 """A second, independent restatement of the two particle kernels of the reference -- written in numpy straight from the Fortran text,
 sharing no code with oracle/*.cpp -- checked against the C++ oracle.  The reference ships no golden vectors for this path and cannot
-be built here (parity unpinned), so this does not pin the oracle to the reference's OUTPUT; it does rule out
-transcription slips in the oracle, which would have to be made identically twice, in two languages, to go unnoticed.
+be built by a Fortran compiler here; the pin to the reference's output is tests/test_ref_transpiled.py (the reference's
+own source, translated).  This file is the independent second reading: it rules out transcription slips in the oracle, which would
+have to be made identically twice, in two languages, to go unnoticed -- and it does not depend on the translator.
 
     push    3d/common/particle.f90:75-91 (tmpf staging), :108-184 (shape factors, 27-point gather), :186-222 (Buneman-Boris, move)
             3d/common/particle.f90:369-406 (Vay)

@@ -1,5 +1,6 @@
 """Physics known-answer tests of the oracle: results that follow from the equations the reference solves, not from its code.
-The reference ships no golden vectors for this path (parity unpinned); these pin the normalisation of the whole
+The reference ships no golden vectors for this path (the pin to its own translated source is
+tests/test_ref_transpiled.py); these tie the normalisation of the whole
 loop -- the 4 pi factors of the field update, q = sqrt(m / (4 pi n0)) omega_p of the loaders (3d/proj/weibel/app.f90:298-305),
 the deposit, the push -- to analytic values."""
 import numpy as np
