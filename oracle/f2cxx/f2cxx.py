@@ -290,7 +290,13 @@ class Parser:
                 args = []
                 if not self.accept("op", ")"):
                     while True:
-                        args.append(self.subscript())
+                        # keyword argument  name = expr  (sum(a, dim=1))
+                        if self.peek()[0] == "name" and self.i + 1 < len(self.t) and self.t[self.i + 1] == ("op", "="):
+                            kw = self.next()[1]
+                            self.next()
+                            args.append(("kw", kw, self.expr()))
+                        else:
+                            args.append(self.subscript())
                         if self.accept("op", ")"):
                             break
                         self.expect("op", ",")
@@ -436,8 +442,10 @@ def _find_top_assign(s):
 # program structure
 # ----------------------------------------------------------------------------------------------------------------------
 class Subroutine:
-    def __init__(self, name, args, line):
+    def __init__(self, name, args, line, kind="subroutine", result=None):
         self.name, self.args, self.line = name, args, line
+        self.kind, self.result = kind, result        # function: the name of the result variable
+        self.stmt_funcs = {}    # statement functions: name -> (dummy names, expression text, line)
         self.syms = {}          # name -> Sym
         self.order = []         # declaration order
         self.body = []          # [(line, stmt)]
@@ -449,7 +457,9 @@ class Module:
         self.name, self.syms, self.order, self.subs, self.uses = name, {}, [], [], []
 
 
-MPI_CONSTANTS = {"mpi_status_size": "6"}
+# `use mpi`: a datatype handle is the element size in bytes (f90rt.h)
+MPI_CONSTANTS = {"mpi_status_size": "6", "mpi_integer": "4", "mpi_integer8": "8", "mpi_double_precision": "8", "mpi_real8": "8",
+                 "mpi_sum": "1", "mpi_comm_world": "0"}
 
 
 def parse_module(text, fname):
@@ -461,16 +471,16 @@ def parse_module(text, fname):
 
     def parse_sub(i, interface=False):
         no, st = lines[i]
-        m = re.match(r"subroutine\s+([a-z_]\w*)\s*(\((.*)\))?\s*$", st)
+        m = re.match(r"(subroutine|function)\s+([a-z_]\w*)\s*(\(([^()]*)\))?\s*(?:result\s*\(\s*([a-z_]\w*)\s*\))?\s*$", st)
         if not m:
             raise TranslateError(f"{where(no)}: cannot parse {st!r}")
-        args = [a.strip() for a in m.group(3).split(",")] if m.group(3) and m.group(3).strip() else []
-        sub = Subroutine(m.group(1), args, no)
+        args = [a.strip() for a in m.group(4).split(",")] if m.group(4) and m.group(4).strip() else []
+        sub = Subroutine(m.group(2), args, no, kind=m.group(1), result=(m.group(5) or m.group(2)) if m.group(1) == "function" else None)
         i += 1
         in_spec = True
         while True:
             no, st = lines[i]
-            if re.match(r"end\s*subroutine\b", st) or st == "end":
+            if re.match(r"end\s*(subroutine|function)\b", st) or st == "end":
                 i += 1
                 break
             if in_spec:
@@ -502,6 +512,13 @@ def parse_module(text, fname):
                     for s in d:
                         sub.syms[s.name] = s
                         sub.order.append(s.name)
+                    i += 1
+                    continue
+                # statement function:  f(x, y) = expression,  f a declared scalar of this procedure
+                msf = re.match(r"([a-z_]\w*)\s*\(([a-z_0-9,\s]*)\)\s*=(?!=)(.*)$", st)
+                if msf and msf.group(1) in sub.syms and not sub.syms[msf.group(1)].dims and not sub.syms[msf.group(1)].is_dummy \
+                        and msf.group(1) not in sub.args:
+                    sub.stmt_funcs[msf.group(1)] = ([a.strip() for a in msf.group(2).split(",") if a.strip()], msf.group(3).strip(), no)
                     i += 1
                     continue
                 in_spec = False
@@ -557,8 +574,13 @@ INTRINSIC_1 = {"sqrt": "f90::sqrt_", "dsqrt": "f90::sqrt_", "abs": "f90::abs_", 
 
 EXTERNALS = {   # name -> C symbol in f90rt.h   (every argument by reference)
     "mpi_sendrecv": "f90rt_mpi_sendrecv", "mpi_allreduce": "f90rt_mpi_allreduce", "mpi_barrier": "f90rt_mpi_barrier",
-    "mpi_bcast": "f90rt_mpi_bcast", "mpi_abort": "f90rt_mpi_abort", "mpi_finalize": "f90rt_mpi_finalize",
+    "mpi_bcast": "f90rt_mpi_bcast", "mpi_finalize": "f90rt_mpi_finalize", "mpi_allgather": "f90rt_mpi_allgather",
+    "mpi_reduce": "f90rt_mpi_reduce",
 }
+# procedures of the reference's utility module that consume the (non-reproducible) Fortran random_number: they are INPUTS of a
+# comparison, provided by the test driver through hooks (f90rt.h) -- not translated
+EXTERNAL_FUNCS = {"uniform_rand": "f90rt_uniform_rand", "normal_rand": "f90rt_normal_rand"}
+EXTERNALS_SIZED = {"shuffle": "f90rt_shuffle"}        # whole-array actuals are followed by their extent
 
 ROUNDING = {"ieee_down": "FE_DOWNWARD", "ieee_up": "FE_UPWARD", "ieee_nearest": "FE_TONEAREST", "ieee_to_zero": "FE_TOWARDZERO"}
 
@@ -625,8 +647,8 @@ class Gen:
             if self.is_array(e[1]):
                 return any(a[0] == "range" for a in e[2]) or any(self.has_section(a) for a in e[2] if a[0] != "range")
             if e[1] in ("sum", "size", "maxval", "minval") and self.lookup(e[1]) is None:
-                return False                 # reductions are scalar
-            return any(self.has_section(a) for a in e[2])
+                return any(a[0] == "kw" and a[1] == "dim" for a in e[2])     # reductions are scalar unless taken along a dim
+            return any(self.has_section(a) for a in e[2] if a[0] != "kw")
         if k in ("bin",):
             return self.has_section(e[2]) or self.has_section(e[3])
         if k == "pow":
@@ -709,8 +731,28 @@ class Gen:
                     else:
                         idx.append(self.ex(a, no, secvars))
                 return f"{mangle(name)}({', '.join(idx)})"
+            if self.sub is not None and name in self.sub.stmt_funcs:
+                dummies = self.sub.stmt_funcs[name][0]
+                if len(dummies) != len(args):
+                    raise TranslateError(f"{self.W(no)}: statement function {name} takes {len(dummies)} arguments")
+                return f"{mangle(name)}sf({', '.join(self.ex(a, no, secvars) for a in args)})"
             if s is not None:
                 raise TranslateError(f"{self.W(no)}: {name!r} is a scalar but is subscripted")
+            if name in self.known_subs and self.known_subs[name].kind == "function":
+                callee = self.known_subs[name]
+                if len(callee.args) != len(args):
+                    raise TranslateError(f"{self.W(no)}: {name} takes {len(callee.args)} arguments, {len(args)} given")
+                return f"{name}({', '.join(self.actual_arg_ast(a, no) for a in args)})"
+            if name in EXTERNAL_FUNCS:
+                if args:
+                    raise TranslateError(f"{self.W(no)}: {name} takes no arguments")
+                return f"{EXTERNAL_FUNCS[name]}()"
+            if name == "transfer":
+                if len(args) != 2 or args[1][0] != "num":
+                    raise TranslateError(f"{self.W(no)}: transfer() needs a literal mold")
+                lit = args[1][1].split("_")[0]
+                to = "double" if ("." in lit or "d" in lit or "e" in lit) else "i64"
+                return f"f90::transfer_{to}({self.ex(args[0], no, secvars)})"
             # intrinsics
             if name == "int":
                 return f"f90::int_({self.ex(args[0], no, secvars)})"
@@ -737,7 +779,7 @@ class Gen:
                     return f"((int){mangle(args[0][1])}.extent(({self.ex(args[1], no)}) - 1))"
                 return f"((int){mangle(args[0][1])}.size())"
             if name in ("sum", "maxval", "minval"):
-                return self.reduction(name, args, no)
+                return self.reduction(name, args, no, secvars)
             raise TranslateError(f"{self.W(no)}: unknown function or array {name!r}")
         raise TranslateError(f"{self.W(no)}: cannot translate expression node {e!r}")
 
@@ -769,7 +811,9 @@ class Gen:
                     return r
         return None
 
-    def reduction(self, name, args, no):
+    def reduction(self, name, args, no, secvars=None):
+        if len(args) == 2 and args[1][0] == "kw" and args[1][1] == "dim" and name == "sum":
+            return self.sum_dim(args[0], args[1][2], no, secvars)
         if len(args) != 1:
             raise TranslateError(f"{self.W(no)}: {name}() with dim/mask arguments is not supported")
         shape = self.find_shape(args[0], no)
@@ -799,6 +843,34 @@ class Gen:
         code += "return _s; }()"
         del zero
         return code
+
+    def sum_dim(self, arr, dim_e, no, secvars):
+        """sum(section, dim=k) inside an elemental context: the k-th ranged dimension is summed, the others follow the context"""
+        if secvars is None:
+            raise TranslateError(f"{self.W(no)}: sum(..., dim=) outside an array assignment")
+        k = self.ex(dim_e, no)
+        if not re.fullmatch(r"\d+", k):
+            raise TranslateError(f"{self.W(no)}: sum(..., dim=) needs a literal dim")
+        k = int(k) - 1
+        if arr[0] == "name":
+            arr = ("call", arr[1], [("range", None, None, None)] * self.lookup(arr[1]).rank)
+        if arr[0] != "call" or not self.is_array(arr[1]):
+            raise TranslateError(f"{self.W(no)}: sum(..., dim=) of an expression is not supported")
+        shape = self.section_dims(arr, no)
+        if not 0 <= k < len(shape):
+            raise TranslateError(f"{self.W(no)}: dim out of range")
+        self.tmp += 1
+        t = self.tmp
+        inner = f"_d{t}"
+        vs, it = [], iter(secvars)
+        for d in range(len(shape)):
+            vs.append(inner if d == k else next(it))
+        lo, hi = shape[k]
+        body = self.ex(arr, no, vs)
+        first = self.ex(arr, no, ["0L"] * len(shape))
+        return (f"[&]() {{ typedef std::decay<decltype({first})>::type _T{t}; _T{t} _s = 0; "
+                f"for (long {inner} = 0, _n{t} = (long)({hi}) - (long)({lo}) + 1; {inner} < _n{t}; ++{inner}) {{ _s = _s + ({body}); }} "
+                f"return _s; }}()")
 
     # ---- statements ----
     def emit(self, s):
@@ -852,7 +924,9 @@ class Gen:
 
     def actual_arg(self, a_txt, no):
         """an actual argument -> a C++ pointer expression (everything is passed by reference)"""
-        e = parse_expr(a_txt, self.W(no))
+        return self.actual_arg_ast(parse_expr(a_txt, self.W(no)), no)
+
+    def actual_arg_ast(self, e, no):
         if e[0] == "name":
             s = self.lookup(e[1])
             if s is not None:
@@ -896,8 +970,19 @@ class Gen:
         if name in EXTERNALS:
             self.emit(f"{EXTERNALS[name]}({', '.join(ptrs)});")
             return
+        if name in EXTERNALS_SIZED:
+            full = []
+            for a, ptr in zip(args, ptrs):
+                e = parse_expr(a, self.W(no))
+                full.append(ptr)
+                if e[0] == "name" and self.is_array(e[1]):
+                    full.append(f"f90::tmp((int){mangle(e[1])}.size()).ptr()")
+            self.emit(f"{EXTERNALS_SIZED[name]}({', '.join(full)});")
+            return
         if name in self.known_subs:
             callee = self.known_subs[name]
+            if callee.kind != "subroutine":
+                raise TranslateError(f"{self.W(no)}: call of the function {name}")
             if len(callee.args) != len(args):
                 raise TranslateError(f"{self.W(no)}: {name} takes {len(callee.args)} arguments, {len(args)} given")
             # assumed-shape dummies take a trailing extent each
@@ -1077,8 +1162,10 @@ class Gen:
                 self.emit("break;" if kind == "exit" else "continue;")
             return
         if st == "return":
-            self.emit("return;")
+            self.emit(f"return {mangle(self.sub.result)};" if self.sub.kind == "function" else "return;")
             return
+        if re.match(r"(open|close)\s*\(", st):
+            return                                    # file handling is outside the path; formatted output is captured below
         if st == "continue":
             self.emit(";")
             return
@@ -1086,6 +1173,20 @@ class Gen:
             self.emit(f'f90::stop("{self.W(no)}");')
             return
         if re.match(r"(write|print)\b", st):
+            mw = re.match(r"write\s*\(\s*([a-z_]\w*)\s*,", st)
+            if mw and self.lookup(mw.group(1)) is not None:
+                # write(unit, fmt) numeric items: a record of a data file (energy.dat) -- handed to the test driver
+                depth, j = 0, st.index("(")
+                while True:
+                    depth += st[j] == "("
+                    depth -= st[j] == ")"
+                    if depth == 0:
+                        break
+                    j += 1
+                items = [x.strip() for x in _split_top(st[j + 1:], ",") if x.strip()]
+                vals = ", ".join(f"(double)({self.ex(parse_expr(x, self.W(no)), no)})" for x in items)
+                self.emit(f"f90rt_capture({len(items)}, std::vector<double>{{{vals}}}.data());")
+                return
             txt = st.replace("\\", "\\\\").replace('"', '\\"')
             self.emit(f'f90::message("{self.W(no)}: {txt}");')
             return
@@ -1141,7 +1242,12 @@ class Gen:
             s = sub.syms[a]
             if s.rank > 0 and s.deferred:
                 ps.append(f"int* {a}_n")
-        return f'extern "C" void {sub.name}({", ".join(ps)})'
+        ret = "void"
+        if sub.kind == "function":
+            if sub.result not in sub.syms:
+                raise TranslateError(f"{self.W(sub.line)}: result variable {sub.result} of {sub.name} is not declared")
+            ret = sub.syms[sub.result].ctype
+        return f'extern "C" {ret} {sub.name}({", ".join(ps)})'
 
     def gen_sub(self, sub):
         self.sub = sub
@@ -1150,7 +1256,8 @@ class Gen:
         self.emit(f"using namespace mod_{self.mod.name};")
         for u in self.used_modules:
             self.emit(f"using namespace mod_{u.name};")
-        self.emit("F90_ENTRY_BEGIN")
+        if sub.kind == "subroutine":
+            self.emit("F90_ENTRY_BEGIN")             # functions are only called from translated code: exceptions pass through
         if any("ieee_arithmetic" in u for u in sub.uses + self.mod.uses):
             # Fortran 2003 14.4: a procedure that changes the rounding mode gets the caller's mode back on return
             self.emit("f90::RoundingScope _rounding_scope;")
@@ -1195,8 +1302,24 @@ class Gen:
                 if static:
                     raise TranslateError(f"{self.W(sub.line)}: saved explicit-shape local arrays are not supported")
                 self.emit(f"f90::Arr<{s.ctype}, {s.rank}> {mangle(name)}(nullptr, {{{self.bounds_list(s, sub.line)}}});")
+        # statement functions: lambdas over the procedure's variables (their dummies shadow same-named locals)
+        for fname_, (dummies, expr_txt, fno) in sub.stmt_funcs.items():
+            saved = {}
+            params = []
+            for dmy in dummies:
+                ds = sub.syms.get(dmy)
+                if ds is None or ds.rank:
+                    raise TranslateError(f"{self.W(fno)}: dummy {dmy} of statement function {fname_} must be a declared scalar")
+                params.append(f"{ds.ctype} {mangle(dmy)}")
+            body = self.ex(parse_expr(expr_txt, self.W(fno)), fno)
+            rt = sub.syms[fname_].ctype
+            self.emit(f"auto {mangle(fname_)}sf = [&]({', '.join(params)}) -> {rt} {{ return {body}; }};")
+            del saved
         self.block(sub.body)
-        self.emit("F90_ENTRY_END")
+        if sub.kind == "subroutine":
+            self.emit("F90_ENTRY_END")
+        else:
+            self.emit(f"return {mangle(sub.result)};")
         self.ind -= 1
         self.emit("}")
         self.emit("")
@@ -1223,9 +1346,20 @@ class Gen:
             elif "allocatable" in s.attrs:
                 self.emit(f"static f90::Arr<{s.ctype}, {s.rank}> {mangle(name)};")
             else:
-                raise TranslateError(f"{fname}: explicit-shape module array {name!r} is not supported")
+                # explicit shape with constant bounds (parameters declared above it)
+                self.emit(f"static f90::Arr<{s.ctype}, {s.rank}> {mangle(name)}(nullptr, {{{self.bounds_list(s, 0)}}});")
         self.ind -= 1
         self.emit("}")
+        # the test driver reads and seeds module variables through these (the drivers' state lives in module `app`)
+        for name in mod.order:
+            s = mod.syms[name]
+            if "parameter" in s.attrs:
+                continue
+            if s.rank == 0:
+                self.emit(f'extern "C" void* f2cxx_modvar__{mod.name}__{name}() {{ return &mod_{mod.name}::{mangle(name)}; }}')
+            else:
+                self.emit(f'extern "C" {s.ctype}* f2cxx_modarr__{mod.name}__{name}(long* bounds) {{ auto& a = mod_{mod.name}::{mangle(name)}; '
+                          f"for (int d = 0; d < {s.rank}; ++d) {{ bounds[2 * d] = a.lb(d); bounds[2 * d + 1] = a.ub(d); }} return a.data(); }}")
         self.emit("")
         for sub in mod.subs:
             saved = self.used_modules

@@ -50,4 +50,54 @@ void f90rt_mpi_allreduce(const void* sbuf, void* rbuf, int* count, int* type, in
 void f90rt_mpi_barrier(int*, int* ierr) {
   if (ierr) *ierr = 0;
 }
+// the driver-level collectives are used by single-rank tests only: one rank gathers / reduces / broadcasts to itself
+static void need_one_rank(const char* what) {
+  if (g_sr) throw std::runtime_error(std::string(what) + " is implemented for one rank only");
+}
+void f90rt_mpi_bcast(void*, int*, int*, int*, int*, int* ierr) {
+  need_one_rank("MPI_BCAST");
+  if (ierr) *ierr = 0;
+}
+void f90rt_mpi_allgather(const void* sbuf, int* scount, int* stype, void* rbuf, int*, int*, int*, int* ierr) {
+  need_one_rank("MPI_ALLGATHER");
+  std::memmove(rbuf, sbuf, (size_t)(*scount * *stype));
+  if (ierr) *ierr = 0;
+}
+void f90rt_mpi_reduce(const void* sbuf, void* rbuf, int* count, int* type, int*, int*, int*, int* ierr) {
+  need_one_rank("MPI_REDUCE");
+  std::memmove(rbuf, sbuf, (size_t)(*count * *type));
+  if (ierr) *ierr = 0;
+}
+void f90rt_mpi_finalize(int* ierr) {
+  if (ierr) *ierr = 0;
+}
+
+static f90rt_rand_fn g_uniform = nullptr, g_normal = nullptr;
+static f90rt_shuffle_fn g_shuffle = nullptr;
+void f90rt_set_random(f90rt_rand_fn u, f90rt_rand_fn n, f90rt_shuffle_fn s) {
+  g_uniform = u;
+  g_normal = n;
+  g_shuffle = s;
+}
+double f90rt_uniform_rand() {
+  if (!g_uniform) throw std::runtime_error("uniform_rand() called but the test driver provided no stream");
+  return g_uniform();
+}
+double f90rt_normal_rand() {
+  if (!g_normal) throw std::runtime_error("normal_rand() called but the test driver provided no stream");
+  return g_normal();
+}
+void f90rt_shuffle(int* a, int* n) {
+  if (!g_shuffle) throw std::runtime_error("shuffle() called but the test driver provided no permutation");
+  g_shuffle(a, *n);
+}
+
+static std::vector<double> g_cap;
+void f90rt_capture(int n, const double* v) { g_cap.insert(g_cap.end(), v, v + n); }
+int f90rt_captured(double* out, int max) {
+  int n = (int)g_cap.size() < max ? (int)g_cap.size() : max;
+  for (int i = 0; i < n; ++i) out[i] = g_cap[i];
+  g_cap.clear();
+  return n;
+}
 }

@@ -120,6 +120,7 @@ inline int int_(double x) { return (int)x; }
 inline float sqrt_(float x) { return std::sqrt(x); }
 inline double sqrt_(double x) { return std::sqrt(x); }
 inline int abs_(int x) { return x < 0 ? -x : x; }
+inline long long abs_(long long x) { return x < 0 ? -x : x; }
 inline float abs_(float x) { return std::fabs(x); }
 inline double abs_(double x) { return std::fabs(x); }
 inline float atan_(float x) { return std::atan(x); }
@@ -129,9 +130,13 @@ inline float exp_(float x) { return std::exp(x); }
 inline double log_(double x) { return std::log(x); }
 inline float log_(float x) { return std::log(x); }
 inline double sin_(double x) { return std::sin(x); }
+inline float sin_(float x) { return std::sin(x); }
 inline double cos_(double x) { return std::cos(x); }
+inline float cos_(float x) { return std::cos(x); }
 inline double tanh_(double x) { return std::tanh(x); }
+inline float tanh_(float x) { return std::tanh(x); }
 inline double cosh_(double x) { return std::cosh(x); }
+inline float cosh_(float x) { return std::cosh(x); }
 inline int floor_(float x) { return (int)std::floor(x); }
 inline int floor_(double x) { return (int)std::floor(x); }
 inline int nint_(double x) { return (int)std::lround(x); }
@@ -159,6 +164,20 @@ inline int mod_(int a, int b) { return a % b; }       // sign of the dividend, l
 inline double mod_(double a, double b) { return std::fmod(a, b); }
 inline double sign_(double a, double b) { return std::signbit(b) ? -std::fabs(a) : std::fabs(a); }
 inline int sign_(int a, int b) { return b < 0 ? -abs_(a) : abs_(a); }
+inline long long sign_(long long a, long long b) { return b < 0 ? -abs_(a) : abs_(a); }
+// TRANSFER(source, mold) between the two 8-byte kinds the reference uses it for (the particle ID bit-cast into a real(8) slot)
+inline double transfer_double(long long v) {
+  double d;
+  std::memcpy(&d, &v, 8);
+  return d;
+}
+inline double transfer_double(double v) { return v; }
+inline long long transfer_i64(double v) {
+  long long i;
+  std::memcpy(&i, &v, 8);
+  return i;
+}
+inline long long transfer_i64(long long v) { return v; }
 
 // x ** n with an integer exponent: repeated multiplication by squaring, the expansion gfortran emits for small constant
 // exponents (x**2 = x*x, x**3 = (x*x)*x, x**4 = (x*x)*(x*x)); real exponents go through pow
@@ -249,5 +268,20 @@ void f90rt_mpi_sendrecv(const void* sbuf, int* scount, int* stype, int* dest, in
                         int* src, int* rtag, int* comm, int* status, int* ierr);
 void f90rt_mpi_allreduce(const void* sbuf, void* rbuf, int* count, int* type, int* op, int* comm, int* ierr);
 void f90rt_mpi_barrier(int* comm, int* ierr);
+void f90rt_mpi_bcast(void* buf, int* count, int* type, int* root, int* comm, int* ierr);
+void f90rt_mpi_allgather(const void* sbuf, int* scount, int* stype, void* rbuf, int* rcount, int* rtype, int* comm, int* ierr);
+void f90rt_mpi_reduce(const void* sbuf, void* rbuf, int* count, int* type, int* op, int* root, int* comm, int* ierr);
+void f90rt_mpi_finalize(int* ierr);
+// inputs the test driver provides in place of the reference's random_number consumers (utils/wuming_utils.f90: uniform_rand,
+// normal_rand, shuffle): values are handed out in call order
+typedef double (*f90rt_rand_fn)();
+typedef void (*f90rt_shuffle_fn)(int* a, int n);
+void f90rt_set_random(f90rt_rand_fn uniform, f90rt_rand_fn normal, f90rt_shuffle_fn shuffle);
+double f90rt_uniform_rand();
+double f90rt_normal_rand();
+void f90rt_shuffle(int* a, int* n);
+// records written by `write(unit, fmt) ...` to data files (energy.dat): the values, in order
+void f90rt_capture(int n, const double* v);
+int f90rt_captured(double* out, int max);       // -> number of values; clears the buffer
 void f90rt_set_rounding_nearest();
 }

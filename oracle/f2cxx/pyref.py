@@ -12,6 +12,7 @@ The call sequences are the drivers': `*__init` as in 3d/proj/weibel/app.f90:341-
 import ctypes as C
 import os
 import queue
+import re
 import shutil
 import tempfile
 import threading
@@ -271,3 +272,92 @@ class RefWorld:
             R.call("mom_calc__nvt", a["mom"], a["gp"], a["np2"])
             R.call(self._bcname("mom"), a["mom"])
         self._all(one)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# the drivers' own procedures (proj/*/app.f90), assembled and translated by app_harness.py
+# ------------------------------------------------------------------------------------------------------------------------------
+class RefApp:
+    """one rank of a driver's module `app`: harness__configure / harness__init wrap the statement blocks of load_config / init,
+    every other procedure (set_initial_condition, inject, relocate, energy_history, ...) is the reference's text.  The random
+    inputs (`uniform_rand`, `normal_rand`, `shuffle` of utils/wuming_utils.f90) are handed out IN CALL ORDER from the sequences
+    given to feed(); running out of values raises."""
+
+    def __init__(self, name):
+        from . import app_harness
+        path = app_harness.build(name)
+        if path is None:
+            raise RuntimeError("the translated driver procedures are not built and /root/reference is absent")
+        self.name, self.cfg = name, app_harness.APPS[name]
+        self.R = _Rank(2 if "2d" in name else 3, path)
+        self.L = self.R.L
+        self._u, self._n, self._perm = [], [], []
+        self.calls = {"uniform": 0, "normal": 0, "shuffle": 0}
+        RAND, SHUF = C.CFUNCTYPE(C.c_double), C.CFUNCTYPE(None, C.POINTER(C.c_int), C.c_int)
+
+        def uniform():
+            self.calls["uniform"] += 1
+            return self._pop(self._u, "uniform_rand")
+
+        def normal():
+            self.calls["normal"] += 1
+            return self._pop(self._n, "normal_rand")
+
+        def shuffle(a, n):
+            self.calls["shuffle"] += 1
+            perm = self._pop(self._perm, "shuffle")
+            vals = [a[i] for i in range(n)]
+            assert sorted(perm) == list(range(n))
+            for i in range(n):
+                a[i] = vals[perm[i]]
+
+        self.R.keep += [RAND(uniform), RAND(normal), SHUF(shuffle)]
+        self.L.f90rt_set_random(*self.R.keep[-3:])
+
+    @staticmethod
+    def _pop(seq, what):
+        if not seq:
+            raise RuntimeError(f"{what}() called more often than the test provided values")   # -> std::terminate is avoided: ctypes prints it
+        return seq.pop(0)
+
+    def feed(self, uniform=(), normal=(), shuffles=()):
+        self._u, self._n, self._perm = list(map(float, uniform)), list(map(float, normal)), [list(p) for p in shuffles]
+
+    def leftover(self):
+        return len(self._u), len(self._n), len(self._perm)
+
+    def call(self, name, *args):
+        self.R.call(name, *args)
+
+    def scalar(self, name, ctype=None):
+        """a ctypes view of a module scalar (read .value, assign .value)"""
+        f = getattr(self.L, f"f2cxx_modvar__app__{name}")
+        f.restype = C.c_void_p
+        if ctype is None:
+            ctype = C.c_int if re.match(r"(n|i|mpi)", name) else C.c_double
+        return ctype.from_address(f())
+
+    def array(self, name, dtype=np.float64):
+        """numpy view (index order reversed) of a module array; None while unallocated"""
+        f = getattr(self.L, f"f2cxx_modarr__app__{name}")
+        f.restype = C.c_void_p
+        b = (C.c_long * 16)()
+        p = f(b)
+        if not p:
+            return None
+        rank = {"np2": self.R_dim(), "cumcnt": self.R_dim() + 1, "uf": self.R_dim() + 1, "up": self.R_dim() + 2, "gp": self.R_dim() + 2,
+                "mom": self.R_dim() + 2, "r": 1, "q": 1}[name]
+        ext = [b[2 * d + 1] - b[2 * d] + 1 for d in range(rank)]
+        ct = C.c_double if dtype == np.float64 else C.c_int
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(int(np.prod(ext)),)).reshape(ext[::-1])
+
+    def R_dim(self):
+        return 2 if "2d" in self.name else 3
+
+    def configure(self, rank_args, **params):
+        """harness__configure(<the "parameter" section of config.json>, nrank, nys, nye[, nzs, nze, nrank_j, nrank_k])"""
+        vals = []
+        for c in self.cfg["config"]:
+            v = params[c]
+            vals.append(int(v) if re.match(r"(num_|n_)", c) else float(v))
+        self.call("harness__configure", *vals, *[int(v) for v in rank_args])

@@ -1396,6 +1396,12 @@ int orc_team_size(void) {
   }
   return n;
 }
+// the keyed draws of the oracle's loaders and particle source, for tests that feed the TRANSLATED reference's uniform_rand() /
+// normal_rand() (utils/wuming_utils.f90) the values the oracle gives the same particle (tests/test_ref_driver_procs.py)
+void orc_philox_uniform2(unsigned long long seed, unsigned stream, unsigned idx, unsigned purpose, unsigned epoch, double* out) {
+  orc::Philox::uniform2(seed, stream, idx, purpose, out[0], out[1], epoch);
+}
+void orc_box_muller(double x1, double x2, double* out) { orc::box_muller(x1, x2, out[0], out[1]); }
 int orc3_error(void* h) { return ((World3*)h)->err; }
 void orc3_clear_error(void* h) { ((World3*)h)->err = 0; }
 

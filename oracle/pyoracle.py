@@ -115,6 +115,8 @@ def lib(fast=False):
         L.orc2_energy.argtypes = [C.c_void_p, dp]
         L.orc2_gauss.argtypes = [C.c_void_p, C.c_int, dp]
         L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_philox_uniform2.argtypes = [C.c_ulonglong, C.c_uint, C.c_uint, C.c_uint, C.c_uint, dp]
+        L.orc_box_muller.argtypes = [C.c_double, C.c_double, dp]
         _LIBS[key] = L
     return _LIBS[key]
 
@@ -128,6 +130,29 @@ def set_num_threads(n, fast=False):
 
 def num_threads(fast=False):
     return lib(fast).orc_num_threads()
+
+
+def philox_uniform2(seed, stream, idx, purpose, epoch=0):
+    """the two uniforms of the oracle's keyed stream (oracle_common.h Philox::uniform2)"""
+    out = (C.c_double * 2)()
+    lib().orc_philox_uniform2(seed, stream, idx, purpose, epoch, out)
+    return out[0], out[1]
+
+
+def box_muller(x1, x2):
+    """(rr sin, rr cos) in the reference's form (utils/wuming_utils.f90:72-90), evaluated by the oracle's libm"""
+    out = (C.c_double * 2)()
+    lib().orc_box_muller(x1, x2, out)
+    return out[0], out[1]
+
+
+def keyed_normals(seed, row, ii, isp, base, epoch=0):
+    """the three normal deviates the oracle gives particle (row, ii) of species isp (oracle_common.h shock_velocity / the loaders)"""
+    a0, a1 = philox_uniform2(seed, row, ii, base + 2 * isp - 1, epoch)
+    b0, b1 = philox_uniform2(seed, row, ii, base + 2 * isp, epoch)
+    ns, nc = box_muller(a0, a1)
+    ms, _ = box_muller(b0, b1)
+    return ns, nc, ms
 
 
 def weibel_constants(n0, mass_ratio=1.0, sigma_e=0.0, omega_pe=0.1, c=1.0):
