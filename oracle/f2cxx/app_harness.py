@@ -54,54 +54,113 @@ def block(text, first, last, inside=None):
 
 
 # ---- per-application assembly --------------------------------------------------------------------------------------------------
-# DECL: the declaration part of the wrapper module (written here).  CONFIG: dummy list of harness__configure = the "parameter"
-# section of the driver's config.json.  The executable text comes from the reference through procedure() / block().
-def _shock(dim):
-    f = f"{dim}d/proj/shock/app.f90"
+# decl: the declaration part of the wrapper module (written here).  config: the "parameter" section of the driver's config.json =
+# the dummy list of harness__configure.  Everything executable comes from the reference through procedure() / block().
+_MPI = "  integer :: mnpr = 8, opsum = 1, ncomw = 0, nerr = 0      ! what `use mpi_set` provides; datatype handle = element size\n"
+
+
+def _common(dim, cfl):
     yz = "nys, nye" if dim == 2 else "nys, nye, nzs, nze, nrank_j, nrank_k"
     sizes = "ny, nygs, nyge" if dim == 2 else "ny, nygs, nyge, nz, nzgs, nzge, nproc_j, nproc_k"
-    cfgi = "num_process, n_ppc, n_x, n_x_ini, n_y" if dim == 2 else "num_process, num_process_j, n_ppc, n_x, n_x_ini, n_y, n_z"
     arr = ("np2(:,:), cumcnt(:,:,:)", "uf(:,:,:), up(:,:,:,:), gp(:,:,:,:), mom(:,:,:,:)") if dim == 2 else \
         ("np2(:,:,:), cumcnt(:,:,:,:)", "uf(:,:,:,:), up(:,:,:,:,:), gp(:,:,:,:,:), mom(:,:,:,:,:)")
     decl = f"""
-  integer :: {cfgi}
-  real(8) :: u_inject, mass_ratio, sigma_e, omega_pe, v_the, v_thi, theta_bn, phi_bn, l_damp_ini
   integer :: nproc, nrank, it0, np, n0, nx, nxgs, nxge, nxs, nxe, {sizes}, {yz}, mpierr
   integer, parameter :: ndim = {6 if dim == 2 else 7}, nsp = 2, nroot = 0
-  real(8), parameter :: c = 1.0d0, gfac = 0.501d0, cfl = 1.0d0, delx = 1.0d0, pi = 4.0d0*atan(1.0d0)
-  real(8), parameter :: xrs = 450.0d0, xre = 500.0d0
+  real(8), parameter :: c = 1.0d0, gfac = 0.501d0, cfl = {cfl}, delx = 1.0d0, pi = 4.0d0*atan(1.0d0)
   integer, allocatable :: {arr[0]}
   real(8), allocatable :: {arr[1]}
+""" + _MPI
+    return decl, ["nrank"] + yz.split(", ")
+
+
+def _shock(dim):
+    decl, rank = _common(dim, "1.0d0")
+    cfgi = ["num_process", "n_ppc", "n_x", "n_x_ini", "n_y"] if dim == 2 else ["num_process", "num_process_j", "n_ppc", "n_x", "n_x_ini", "n_y", "n_z"]
+    cfgr = ["u_inject", "mass_ratio", "sigma_e", "omega_pe", "v_the", "v_thi", "theta_bn", "phi_bn", "l_damp_ini"]
+    decl += f"""  integer :: {', '.join(cfgi)}
+  real(8) :: {', '.join(cfgr)}
+  real(8), parameter :: xrs = 450.0d0, xre = 500.0d0
   real(8) :: r(nsp), q(nsp), delt, b0, u0, v0, gam0
 """
-    return dict(file=f, decl=decl, config=(cfgi + ", u_inject, mass_ratio, sigma_e, omega_pe, v_the, v_thi, theta_bn, phi_bn, l_damp_ini").split(", "),
-                rank=["nrank"] + yz.split(", "),
+    return dict(file=f"{dim}d/proj/shock/app.f90", decl=decl, config=[(c, "i") for c in cfgi] + [(c, "r") for c in cfgr], rank=rank,
                 sizes=("load_config", r"^\s*nproc\s*=\s*num_process", r"phi_bn\s*=\s*phi_bn"),
                 init_locals="integer :: isp, i, j" + (", k" if dim == 3 else "") + "\n    real(8) :: wpe, wpi, wge, wgi, vte, vti",
-                init_blocks=[("init", r"allocate\(np2", r"^\s*mom\b.*=\s*0"), ("init", r"^\s*delt\s*=\s*cfl", r"^\s*b0\s*=")],
-                init_blocks2=[("init", r"! number of particles", r"! initialize modules")],
+                init_blocks=[("init", r"allocate\(np2", r"^\s*mom\b.*=\s*0"), ("init", r"^\s*delt\s*=\s*cfl", r"^\s*b0\s*="),
+                             ("init", r"! number of particles", r"! initialize modules")],
+                init_tail=["call set_initial_condition()", "it0 = 0", "gp = up"],
                 procs=["set_initial_condition", "set_particle_ids", "relocate", "inject", "get_global_cumsum", "vprofile"])
 
 
-APPS = {"shock2d": _shock(2), "shock3d": _shock(3)}
+def _weibel(dim):
+    decl, rank = _common(dim, "1.0d0")
+    cfgi = ["num_process", "n_ppc", "n_x", "n_y"] if dim == 2 else ["num_process", "num_process_j", "n_ppc", "n_x", "n_y", "n_z"]
+    cfgr = ["mass_ratio", "sigma_e", "omega_pe", "v_the", "v_thi", "t_ani"]
+    decl += f"""  integer :: {', '.join(cfgi)}
+  real(8) :: {', '.join(cfgr)}
+  real(8) :: r(nsp), q(nsp), delt, b0
+"""
+    return dict(file=f"{dim}d/proj/weibel/app.f90", decl=decl, config=[(c, "i") for c in cfgi] + [(c, "r") for c in cfgr], rank=rank,
+                sizes=("load_config", r"^\s*nproc\s*=\s*num_process", r"^\s*nxe\s*=\s*nxge"),
+                init_locals="integer :: isp, i, j" + (", k" if dim == 3 else "") + "\n    real(8) :: wpe, wpi, wge, wgi, vte, vti",
+                init_blocks=[("init", r"allocate\(np2", r"^\s*mom\b.*=\s*0"), ("init", r"^\s*delt\s*=\s*cfl", r"^\s*b0\s*="),
+                             ("init", r"! number of particles", r"! initialize modules")],
+                init_tail=["call set_initial_condition()", "it0 = 0", "gp = up"],
+                procs=["set_initial_condition", "set_particle_ids", "get_global_cumsum", "energy_history"])
+
+
+def _reconnection(dim):
+    decl, rank = _common(dim, "0.5d0")
+    cfgi = ["num_process", "n_x", "n_y"] if dim == 2 else ["num_process", "num_process_j", "n_x", "n_y", "n_z"]
+    cfgr = ["mass_ratio", "alpha", "rtemp", "lcs"]
+    decl += f"""  integer :: {', '.join(cfgi)}, nbg, ncs
+  real(8) :: {', '.join(cfgr)}
+  real(8) :: r(nsp), q(nsp), delt, b0, vte, vti, x0, y0{', z0' if dim == 3 else ''}
+"""
+    return dict(file=f"{dim}d/proj/reconnection/app.f90", decl=decl,
+                config=[(c, "i") for c in cfgi] + [(c, "r") for c in cfgr] + [("nbg", "i"), ("ncs", "i")], rank=rank,
+                sizes=("load_config", r"^\s*nproc\s*=\s*num_process", r"^\s*nxe\s*=\s*nxge"),
+                init_locals="integer :: isp, i, j, ii" + (", k" if dim == 3 else "") + "\n    real(8) :: wpe, wpi, wge, wgi, ldb",
+                init_blocks=[("init", r"allocate\(np2", r"^\s*mom\b.*=\s*0"), ("init", r"^\s*r\(1\)\s*=\s*mass_ratio", r"^\s*np2\(.*=\s*nbg")],
+                # the driver sorts the load with sort__bucket (another module: the test calls the translated one) before `up = gp`
+                init_tail=["call set_initial_condition()", "it0 = 0"],
+                procs=["set_initial_condition", "set_particle_ids", "get_global_cumsum", "energy_history"])
+
+
+def _pack(dim):
+    """get_particle_count of paraio (what io__ptcl / io__orb pack and count): the module's geometry variables are set by a harness
+    procedure, the procedure itself is the reference's"""
+    names = ["ndim", "np", "nsp", "nys", "nye"] + (["nzs", "nze"] if dim == 3 else []) + ["nproc"]
+    decl = f"\n  integer :: {', '.join(names)}, mpierr\n"
+    setup = (f"  subroutine harness__set({', '.join(n + '_in' for n in names)})\n"
+             f"    integer, intent(in) :: {', '.join(n + '_in' for n in names)}\n"
+             + "".join(f"    {n} = {n}_in\n" for n in names) + "  end subroutine harness__set\n")
+    return dict(file=f"{dim}d/common/paraio.f90", decl=decl, raw=setup, procs=["get_particle_count"])
+
+
+APPS = {"pack2d": _pack(2), "pack3d": _pack(3), "shock2d": _shock(2), "shock3d": _shock(3), "weibel2d": _weibel(2), "weibel3d": _weibel(3),
+        "reconnection2d": _reconnection(2), "reconnection3d": _reconnection(3)}
 
 
 def assemble(name):
     a = APPS[name]
     text = open(os.path.join(REF, a["file"])).read()
-    cfg = a["config"]
+    if "raw" in a:
+        return "\n".join([f"! ASSEMBLED by oracle/f2cxx/app_harness.py from {a['file']}", "module app", "  implicit none", a["decl"],
+                          "contains", "", a["raw"]] + [procedure(text, p) for p in a["procs"]] + ["end module app"]) + "\n"
+    cfg = [c for c, _ in a["config"]]
     out = [f"! ASSEMBLED by oracle/f2cxx/app_harness.py from {a['file']}: declarations by the harness, every executable statement the reference's",
            "module app", "  implicit none", a["decl"], "contains", "",
            f"  subroutine harness__configure({', '.join(c + '_in' for c in cfg)}, {', '.join(r + '_in' for r in a['rank'])})"]
-    ints = [c for c in cfg if re.match(r"(num_|n_)", c)]
+    ints = [c for c, t in a["config"] if t == "i"]
     out.append(f"    integer, intent(in) :: {', '.join(c + '_in' for c in ints + a['rank'])}")
-    out.append(f"    real(8), intent(in) :: {', '.join(c + '_in' for c in cfg if c not in ints)}")
+    out.append(f"    real(8), intent(in) :: {', '.join(c + '_in' for c, t in a['config'] if t == 'r')}")
     out += [f"    {c} = {c}_in" for c in cfg + a["rank"]]
     out.append(block(text, a["sizes"][1], a["sizes"][2], inside=a["sizes"][0]))
     out += ["  end subroutine harness__configure", "", "  subroutine harness__init()", "    " + a["init_locals"]]
-    for pr, first, last in a["init_blocks"] + a["init_blocks2"]:
+    for pr, first, last in a["init_blocks"]:
         out.append(block(text, first, last, inside=pr))
-    out += ["    call set_initial_condition()", "    it0 = 0", "    gp = up", "  end subroutine harness__init", ""]
+    out += ["    " + t for t in a["init_tail"]] + ["  end subroutine harness__init", ""]
     for p in a["procs"]:
         out.append(procedure(text, p))
     out.append("end module app")

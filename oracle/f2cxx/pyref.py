@@ -357,7 +357,7 @@ class RefApp:
     def configure(self, rank_args, **params):
         """harness__configure(<the "parameter" section of config.json>, nrank, nys, nye[, nzs, nze, nrank_j, nrank_k])"""
         vals = []
-        for c in self.cfg["config"]:
+        for c, t in self.cfg["config"]:
             v = params[c]
-            vals.append(int(v) if re.match(r"(num_|n_)", c) else float(v))
+            vals.append(int(v) if t == "i" else float(v))
         self.call("harness__configure", *vals, *[int(v) for v in rank_args])

@@ -9,8 +9,6 @@ inputs (`uniform_rand`, `normal_rand`, `shuffle` of utils/wuming_utils.f90) are 
 values the restatement under test gives the same particle (the oracle's keyed Philox streams; setups.py's per-pencil generators).
 What is compared is therefore every deterministic statement of these procedures: placement, Lorentz boost, velocity profile, ID
 numbering, np2 / cumcnt bookkeeping, the upstream field columns, the injection counts, the Harris-sheet fields and drifts."""
-import math
-
 import numpy as np
 import pytest
 
@@ -196,3 +194,160 @@ def test_shock_time_loop_with_inject_and_relocate(dim):
         assert w.error() == 0 and w.nxe_now == A.scalar("nxe").value
         same_state(A, w, f"relocate {it}")
     assert grew >= 5 and int(A.array("np2", np.int32).sum()) > 2 * len(rows) * npr
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Weibel: loader, IDs, energy_history
+# ---------------------------------------------------------------------------------------------------------------------------
+WEIBEL_CFG = dict(num_process=1, n_ppc=5, n_x=10, n_y=6, mass_ratio=4.0, sigma_e=0.04, omega_pe=0.1, v_the=0.1, v_thi=0.05, t_ani=5.0)
+
+
+def weibel_app(dim, nz=4):
+    cfg = dict(WEIBEL_CFG)
+    if dim == 3:
+        cfg.update(num_process_j=1, n_z=nz)
+    A = pyref.RefApp(f"weibel{dim}d")
+    ny = cfg["n_y"]
+    A.configure([0, 2, ny + 1] if dim == 2 else [0, 2, ny + 1, 2, nz + 1, 0, 0], **cfg)
+    return A, cfg
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_weibel_loader_ids_and_energy_history(dim):
+    """init constants + set_initial_condition + set_particle_ids (3d/proj/weibel/app.f90:298-338, 391-504; 2d :292-328, 380-474)
+    against the oracle's load_weibel, and energy_history (3d :509-577) against the oracle's energy()"""
+    if not have(f"weibel{dim}d"):
+        pytest.skip("the translated driver procedures cannot be built here")
+    nz = 4
+    A, cfg = weibel_app(dim, nz)
+    nx, ny, n0 = cfg["n_x"], cfg["n_y"], cfg["n_ppc"]
+    rows = rows_of(dim, ny, nz)
+    npr = n0 * nx
+    uni, nrm = [], {1: [], 2: []}
+    for j, k, row in rows:
+        for ii in range(1, npr + 1):
+            a, b = pyoracle.philox_uniform2(SEED, row, ii, 0)
+            uni += [a] if dim == 2 else [a, b]
+            for isp in (1, 2):
+                nrm[isp] += list(pyoracle.keyed_normals(SEED, row, ii, isp, 0))
+    A.feed(uniform=uni, normal=nrm[1] + nrm[2])
+    A.call("harness__init")
+    assert A.leftover() == (0, 0, 0)
+    q, r, b0 = pyoracle.weibel_constants(n0, mass_ratio=cfg["mass_ratio"], sigma_e=cfg["sigma_e"], omega_pe=cfg["omega_pe"])
+    assert np.allclose(A.array("q"), q, rtol=2e-16, atol=0) and np.array_equal(A.array("r"), r)
+    assert A.scalar("b0").value == pytest.approx(b0, rel=2e-16) and A.scalar("np").value == n0 * nx * (5 if dim == 2 else 3)
+    W = World2 if dim == 2 else World3
+    w = W(*((nx, ny) if dim == 2 else (nx, ny, nz)), A.scalar("np").value, q=A.array("q").copy(), r=A.array("r").copy())
+    w.load_weibel(n0, v_thi=cfg["v_thi"], v_the=cfg["v_the"], t_ani=cfg["t_ani"], b0=A.scalar("b0").value, seed=SEED)
+    assert np.array_equal(w.arr("np2"), A.array("np2", np.int32)) and np.array_equal(w.arr("cumcnt"), A.array("cumcnt", np.int32))
+    assert np.array_equal(w.arr("uf"), A.array("uf"))
+    m = active_mask(w.arr("np2"), w.np)
+    got, want = A.array("up")[m], w.arr("up")[m]
+    assert np.array_equal(got[:, :-1], want[:, :-1])                 # positions and momenta: bit for bit
+    # IDs: the reference numbers every species from 1 (set_particle_ids: -(particles before this pencil + i)); the oracle's
+    # loader adds (isp - 1) x the species population so that IDs are unique across species -- a label convention of the oracle
+    ntot = len(rows) * npr
+    ref_ids = -got[:, -1].view(np.int64)
+    orc_ids = -want[:, -1].view(np.int64)
+    assert np.array_equal(ref_ids[:ntot], orc_ids[:ntot]) and np.array_equal(ref_ids[ntot:], orc_ids[ntot:] - ntot)
+    assert np.array_equal(ref_ids[:ntot], np.arange(1, ntot + 1))
+    # energy_history: the record written to energy.dat = (it delt, kinetic ion, kinetic electron, E^2/8pi, B^2/8pi, total)
+    it = 3
+    A.call("energy_history", A.array("up"), A.array("uf"), A.array("np2", np.int32), it)
+    rec = (pyref.C.c_double * 16)()
+    n = A.L.f90rt_captured(rec, 16)
+    e = w.energy()
+    total = ((e[0] + e[1]) + e[2]) + e[3]
+    assert rec[0] == it * A.scalar("delt").value
+    if dim == 3:      # 3d/proj/weibel/app.f90:566-571: both species separately
+        assert n == 6 and [rec[1], rec[2], rec[3], rec[4], rec[5]] == [e[0], e[1], e[2], e[3], total]
+    else:             # 2d/proj/weibel/app.f90:539-541: the species summed
+        assert n == 5 and [rec[1], rec[2], rec[3], rec[4]] == [e[0] + e[1], e[2], e[3], total]
+    w.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# reconnection: Harris sheet
+# ---------------------------------------------------------------------------------------------------------------------------
+REC_CFG = dict(num_process=1, n_x=33, n_y=6, mass_ratio=16.0, alpha=2.0, rtemp=0.2, lcs=0.5, nbg=6, ncs=30)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_harris_sheet_loader_equals_setups_py(dim):
+    """init constants + set_initial_condition with its statement functions (b_harris, bx_pert, by_pert, density, jz) and the
+    single-precision `sqrt(2.)` (2d/proj/reconnection/app.f90:286-307, 362-452; 3d :298-322, 395-470), then the driver's
+    sort__bucket -- against wumingpic_b200.setups.reconnection_constants / reconnection_slab"""
+    if not have(f"reconnection{dim}d"):
+        pytest.skip("the translated driver procedures cannot be built here")
+    nz = 3
+    cfg = dict(REC_CFG)
+    if dim == 3:
+        cfg.update(num_process_j=1, n_z=nz)
+    A = pyref.RefApp(f"reconnection{dim}d")
+    nx, ny = cfg["n_x"], cfg["n_y"]
+    A.configure([0, 2, ny + 1] if dim == 2 else [0, 2, ny + 1, 2, nz + 1, 0, 0], **cfg)
+    s = setups.reconnection_constants(nx, ny, nz if dim == 3 else None, mass_ratio=cfg["mass_ratio"], alpha=cfg["alpha"],
+                                      rtemp=cfg["rtemp"], lcs=cfg["lcs"], nbg=cfg["nbg"], ncs=cfg["ncs"])
+    npr, ibg = s.extra["np_row"], s.extra["ibg"]
+    # setups.py draws per pencil: x of the background, x of the sheet, y, (z,) then 3 normals per particle for the ions and for the
+    # electrons; the reference interleaves them per particle (x, y[, z]; ion normals, electron normals)
+    uni, nrm = [], []
+    for j, k, row in rows_of(dim, ny, nz):
+        rng = setups._rng(SEED, row)
+        xbg, xcs, y = rng.random(ibg), rng.random(npr - ibg), rng.random(npr)
+        z = rng.random(npr) if dim == 3 else None
+        n1, n2 = setups._normal(rng, 3 * npr).reshape(npr, 3), setups._normal(rng, 3 * npr).reshape(npr, 3)
+        x = np.concatenate([xbg, xcs])
+        uni.append(np.stack([x, y] + ([z] if dim == 3 else []), axis=1).ravel())
+        nrm.append(np.concatenate([n1, n2], axis=1).ravel())
+    A.feed(uniform=np.concatenate(uni), normal=np.concatenate(nrm))
+    A.call("harness__init")
+    assert A.leftover() == (0, 0, 0)
+    assert A.scalar("np").value == s.np_cap and int(A.array("np2", np.int32)[0].flat[0]) == npr
+    for name, want in (("delt", s.delt), ("b0", s.extra["b0"]), ("vte", s.extra["vte"]), ("vti", s.extra["vti"]), ("x0", s.extra["x0"]),
+                       ("y0", s.extra["y0"]), ("lcs", s.extra["lcs"])):
+        assert A.scalar(name).value == pytest.approx(want, rel=4e-16, abs=0), name
+    assert np.allclose(A.array("q"), s.q, rtol=4e-16, atol=0) and np.array_equal(A.array("r"), s.r)
+    # the driver's `call sort__bucket(gp, up, cumcnt, np2, nxs, nxe); up = gp` with the translated sort
+    R = pyref.RefWorld(dim, nx, ny, nz, s.np_cap, q=s.q, r=s.r, delt=s.delt, bc=1, bounds=True)
+    R.ranks[0].call("sort__bucket", A.array("gp"), A.array("up"), A.array("cumcnt", np.int32), A.array("np2", np.int32), 2, nx + 1)
+    up, np2, cc, uf = setups.reconnection_slab(s, 2, ny + 1, 2, nz + 1 if dim == 3 else 2, seed=SEED)
+    assert np.array_equal(A.array("np2", np.int32), np2) and np.array_equal(A.array("cumcnt", np.int32), cc)
+    assert np.abs(A.array("uf") - uf).max() <= 1e-15 * np.abs(uf).max()               # tanh / exp: numpy vs libm
+    m = active_mask(np2, s.np_cap)
+    got, want = A.array("gp")[m], up[m]
+    assert np.array_equal(got[:, -1].view(np.int64), want[:, -1].view(np.int64))       # same particles in the same sorted order
+    assert np.abs(got[:, :dim] - want[:, :dim]).max() <= 4e-15 * nx                    # logistic placement: log / tanh
+    assert np.abs(got[:, dim:-1] - want[:, dim:-1]).max() <= 1e-15                     # Maxwellian + drift  f jz(x, y) / density(x)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# paraio: get_particle_count (what io__ptcl / io__orb pack)
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+def test_get_particle_count_equals_the_oracle_packing(dim):
+    """3d/common/paraio.f90:1007-1085 (2d/common/paraio.f90): mode 0 packs every active particle, mode 1 the tracers (positive
+    64-bit ID bit-cast in the last slot), both in (species, k, j, particle) order, and the per-species counts -> cumsum"""
+    if not have(f"pack{dim}d"):
+        pytest.skip("the translated procedure cannot be built here")
+    from tests.util import make_world2, make_world3
+    w = make_world2(9, 6, 5, steps=2) if dim == 2 else make_world3(8, 5, 4, 4, steps=2)
+    up, np2 = w.arr("up"), w.arr("np2")
+    m = active_mask(np2, w.np)
+    ids = up[..., -1].view(np.int64)
+    tracer = m & (np.abs(ids) % 7 == 3)
+    ids[tracer] = np.abs(ids[tracer])                               # tracers carry positive IDs (app.f90 set_particle_ids)
+    A = pyref.RefApp(f"pack{dim}d")
+    g = w.geom(0)
+    geo = [g["nys"], g["nye"]] + ([g["nzs"], g["nze"]] if dim == 3 else [])
+    A.call("harness__set", w.ndim, w.np, 2, *geo, 1)
+    for mode in (0, 1):
+        buf = np.zeros(int(np2.sum()) * w.ndim + 1)
+        cumsum = np.zeros((2, 2), np.int64)                         # cumsum(nproc+1, nsp), nproc = 1
+        A.call("get_particle_count", up, np2, buf, cumsum, mode, len(buf))
+        rec, lcount = w.pack_particles(mode)
+        assert np.array_equal(cumsum[:, 0], [0, 0]) and np.array_equal(cumsum[:, 1], lcount)
+        n = int(lcount.sum())
+        assert n == (int(tracer.sum()) if mode else int(np2.sum())) and n > 0
+        assert np.array_equal(buf[:n * w.ndim].view(np.int64), rec.reshape(-1).view(np.int64))
+    w.close()
