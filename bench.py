@@ -4,7 +4,9 @@
 end-to-end (host-buffer) number.  Contract: see the repo's task description; one JSON line on rank 0.
 
   python bench.py [--gpus N --steps K --warmup W]          this backend (N > 1: launched by torchrun)
-  python bench.py --impl reference [--steps K --warmup W]  the reference's CPU algorithm (oracle port) on host cores
+  python bench.py --impl reference [--steps K --warmup W]  the reference's own source on the host cores: oracle/_ref (the Fortran
+                                                           hot path translated to C++, flat MPI with one rank per host thread); the
+                                                           OpenMP oracle port where oracle/_ref is absent
 
 Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): 3-D Weibel, uniform Maxwellian pair plasma, 64 particles per cell
 and species, z-slabs across GPUs.  Default = STRONG scaling, the north star's target: the fixed 256 x 256 x 128 box
@@ -168,7 +170,17 @@ def host_memory_available():
     return avail
 
 
-def cpu_baseline(args, steps=2, warmup=1):
+def rank_grid(cores, ny, nz):
+    """nproc_j x nproc_k for a flat-MPI run with one rank per host thread: y first (what every shipped 3-D sample does,
+    3d/proj/*/config_sample.json), z as well once the y-slabs would get thinner than 4 cells; never more ranks than that allows"""
+    for nk in (1, 2, 4, 8, 16):
+        if cores % nk == 0 and nz % nk == 0 and nz // nk >= 2 and ny // (cores // nk) >= 4:
+            return cores // nk, nk
+    nj = max(1, min(cores, ny // 4))
+    return nj, 1
+
+
+def cpu_port(args, steps=2, warmup=1):
     """The oracle (a C++ port of the reference loop nests, -O3 -march=native -fopenmp) on the host cores,
     on a bounded sample of the same workload: same nx, ny, ppc and physics, only nz reduced."""
     from oracle import pyoracle
@@ -193,12 +205,84 @@ def cpu_baseline(args, steps=2, warmup=1):
     dt = time.perf_counter() - t0
     assert w.error() == 0
     cores = team
+    uf = np.array(w.arr("uf"))
     w.close()
     return {"value": npart * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"3-D Weibel {nx}x{ny}x{nz}, {n0} ppc x 2 species = {npart} particles, {steps} steps "
                       f"({dt:.1f} s) with OMP threads = {cores}; oracle = C++ restatement of the Fortran loop nests "
                       "(no Fortran compiler / MPI in this image)",
-            "seconds": dt, "ms_per_step": dt / steps * 1e3, "particles": npart}
+            "seconds": dt, "ms_per_step": dt / steps * 1e3, "particles": npart, "parallelism": f"openmp{cores}", "uf": uf}
+
+
+def cpu_reference(args, steps=2, warmup=1):
+    """THE REFERENCE'S OWN SOURCE on the host cores: oracle/_ref = the 3-D hot-path Fortran files translated statement by statement
+    to C++ (oracle/f2cxx, pinned bit for bit against the oracle: DESIGN.md 2.1), compiled -O3 -march=native, run as the flat-MPI job
+    the reference is (one rank per host thread on the reference's own y x z rank grid, every rank a private copy of the library on
+    its own thread; MPI_SENDRECV / MPI_ALLREDUCE rendezvous in oracle/f2cxx/mpi_threads.cpp), on the same bounded sample as
+    cpu_port().  The start state is the oracle's Weibel load cut into the ranks' blocks."""
+    from oracle import pyoracle
+    from oracle.f2cxx import pyref
+    from oracle.pyoracle import World3, weibel_constants
+    import numpy as np
+    nx, ny, nz, n0 = args.nx, args.ny, args.cpu_nz, args.ppc
+    cores = len(os.sched_getaffinity(0))
+    nj, nk = rank_grid(cores, ny, nz)
+    q, r, _ = weibel_constants(n0)
+    cap = int(n0 * nx * 1.5)
+    pyoracle.set_num_threads(cores, fast=True)
+    w = World3(nx, ny, nz, cap, nproc_j=nj, nproc_k=nk, q=q, r=r, fast=True)
+    w.load_weibel(n0)
+    R = pyref.RefWorld(3, nx, ny, nz, cap, nproc_j=nj, nproc_k=nk, q=q, r=r, fast=True, native_mpi=nj * nk > 1)
+    npart = 0
+    for rk in range(nj * nk):
+        for k in ("up", "uf", "np2", "cumcnt"):
+            R.arr(k, rk)[...] = w.arr(k, rk)
+        npart += int(w.arr("np2", rk).sum())
+    w.close()
+    R.run_steps(warmup)
+    t0 = time.perf_counter()
+    R.run_steps(steps)
+    dt = time.perf_counter() - t0
+    after = sum(int(R.arr("np2", rk).sum()) for rk in range(nj * nk))
+    if after != npart:
+        raise RuntimeError(f"the translated reference lost particles: {npart} -> {after}")
+    # the global E, B of the interior cells, for the cross-check against the port (ghost layers differ in what they hold)
+    uf = np.zeros((nz + 4, ny + 4, nx + 4, 6))
+    for rk in range(nj * nk):
+        g = R.geom(rk)
+        uf[g["nzs"]:g["nze"] + 1, g["nys"]:g["nye"] + 1, 2:nx + 2] = \
+            R.arr("uf", rk)[2:2 + g["nze"] - g["nzs"] + 1, 2:2 + g["nye"] - g["nys"] + 1, 2:nx + 2]
+    stats = R.mpi_stats()
+    R.close()
+    return {"value": npart * steps / dt, "unit": UNIT, "cores": nj * nk, "kind": "reference",
+            "sample": f"3-D Weibel {nx}x{ny}x{nz}, {n0} ppc x 2 species = {npart} particles, {steps} steps ({dt:.1f} s): the "
+                      f"reference's own Fortran source (3d/common/*.f90) translated to C++ by oracle/f2cxx and compiled with g++ -O3 "
+                      f"-march=native (no Fortran compiler / MPI in this image), run as flat MPI on a {nj} x {nk} (y x z) rank grid, one "
+                      f"rank per host thread ({cores} available), in-process MPI_SENDRECV / MPI_ALLREDUCE"
+                      + (f" ({stats[0] // (steps + warmup) // (nj * nk)} + {stats[1] // (steps + warmup) // (nj * nk)} calls per rank and step)"
+                         if stats else ""),
+            "seconds": dt, "ms_per_step": dt / steps * 1e3, "particles": npart, "parallelism": f"mpi{nj}x{nk}", "uf": uf}
+
+
+def cpu_baseline(args, steps=2, warmup=1):
+    """The CPU baseline of this workload: the translated reference (kind "reference") where oracle/_ref is present, with the OpenMP
+    port timed beside it on the same sample and the two end states compared; the port alone (kind "port") where it is not."""
+    import numpy as np
+    port = cpu_port(args, steps=min(steps, 2), warmup=1)
+    try:
+        ref = cpu_reference(args, steps=steps, warmup=warmup)
+    except Exception as ex:  # noqa: BLE001  -- no prebuilt oracle/_ref, or g++ failed on this host
+        port.pop("uf")
+        port["sample"] += f"; the translated reference was not available here ({type(ex).__name__}: {str(ex)[:200]})"
+        return port
+    nx, ny, nz = args.nx, args.ny, args.cpu_nz
+    ref["port"] = {"value": port["value"], "cores": port["cores"], "parallelism": port["parallelism"]}
+    if min(steps, 2) + 1 == steps + warmup:         # both legs took the same number of steps from the same load: compare E, B
+        a = ref.pop("uf")[2:nz + 2, 2:ny + 2, 2:nx + 2]
+        b = port.pop("uf")[2:nz + 2, 2:ny + 2, 2:nx + 2]
+        ref["port"]["uf_rel_diff"] = float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    ref.pop("uf", None)
+    return ref
 
 
 def run_reference(args):
@@ -214,8 +298,8 @@ def run_reference(args):
                                     f"3-D Weibel, fixed {args.nx}x{args.ny}x{args.strong_nz} box") +
                                    f", {args.ppc} ppc x 2 species; the CPU arm runs the bounded sample nz={args.cpu_nz} "
                                    "(same nx, ny, ppc, physics: a per-particle rate)",
-                       "parallelism": f"openmp{cb['cores']}"},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                       "parallelism": cb["parallelism"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "port") if k in cb},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -634,7 +718,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu and args.dim == 3:
         try:
             cb = cpu_baseline(args)
-            cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "port") if k in cb}
         except Exception as ex:  # noqa: BLE001
             cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
 

@@ -80,10 +80,14 @@ class RefWorld:
     numpy sees them in C order with the index order reversed, exactly like oracle.pyoracle.World2 / World3."""
 
     def __init__(self, dim, nx, ny, nz, np_cap, nproc_j=1, nproc_k=1, delx=1.0, delt=1.0, c=1.0, gfac=0.501, q=(1.0, -1.0),
-                 r=(1.0, 1.0), bc=0, bounds=False):
-        path = build_ref.build(dim, bounds=bounds)
+                 r=(1.0, 1.0), bc=0, bounds=False, fast=False, native_mpi=False):
+        """fast: the -O3 -march=native build of the same generated C++ (timing only, never parity).  native_mpi: the ranks'
+        MPI_SENDRECV / MPI_ALLREDUCE rendezvous in mpi_threads.cpp instead of Python callbacks (same semantics, no interpreter
+        lock on the communication path: what a timed flat-MPI run with one rank per host thread needs)"""
+        path = build_ref.build_fast(dim) if fast else build_ref.build(dim, bounds=bounds)
         if path is None:
             raise RuntimeError("the translated reference is not built and /root/reference is absent")
+        self.native_mpi, self._hub, self._mpi = bool(native_mpi), None, None
         self.dim, self.nx, self.ny, self.nz, self.np, self.bc = dim, nx, ny, nz if dim == 3 else 1, np_cap, bc
         self.ndim, self.nsp = (7 if dim == 3 else 6), 2
         self.q, self.r = np.ascontiguousarray(q, np.float64), np.ascontiguousarray(r, np.float64)
@@ -128,6 +132,19 @@ class RefWorld:
             return self._mail[key]
 
     def _install_transport(self):
+        if self.native_mpi:
+            M = self._mpi = C.CDLL(build_ref.build_mpi())
+            M.f2mpi_create.restype = C.c_void_p
+            M.f2mpi_create.argtypes = [C.c_int, C.c_double]
+            for f in (M.f2mpi_destroy, M.f2mpi_abort, M.f2mpi_aborted):
+                f.argtypes = [C.c_void_p]
+            M.f2mpi_bind.argtypes = [C.c_void_p, C.c_int]
+            M.f2mpi_stats.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
+            self._hub = M.f2mpi_create(self.nranks, 120.0)
+            for R in self.ranks:
+                R.L.f90rt_set_transport.argtypes = [C.c_void_p, C.c_void_p]
+                R.L.f90rt_set_transport(C.cast(M.f2mpi_sendrecv, C.c_void_p), C.cast(M.f2mpi_allreduce, C.c_void_p))
+            return
         SR = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int)
         AR = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int)
         self._barrier = threading.Barrier(self.nranks)
@@ -163,10 +180,15 @@ class RefWorld:
 
         def body(rk):
             try:
+                if self._hub:
+                    self._mpi.f2mpi_bind(self._hub, rk)       # the rank of a native MPI call is the rank its thread is bound to
                 fn(rk)
             except BaseException as e:  # noqa: BLE001
                 err.append(e)
-                self._barrier.abort()
+                if self._hub:
+                    self._mpi.f2mpi_abort(self._hub)
+                else:
+                    self._barrier.abort()
 
         th = [threading.Thread(target=body, args=(rk,)) for rk in range(self.nranks)]
         for t in th:
@@ -263,6 +285,41 @@ class RefWorld:
             self.bc_particle_x()
         self.bc_particle_yz()
         self.sort_bucket()
+
+    def run_steps(self, n, order=ORDER_WEIBEL, u0=0.0, vay=False):
+        """n whole steps with ONE host thread per rank for the whole run (step() starts a thread per rank and procedure): every rank
+        goes through the driver's call sequence on its own and meets its neighbours only inside the MPI calls, as ranks of an MPI
+        job do -- the form the timed CPU baseline uses"""
+        def loop(rk):
+            a, R = self.a[rk], self.ranks[rk]
+            extra = [] if self.bc == 0 else [self.nxs, self.nxe]
+            yz = self._bcname("particle_yz" if self.dim == 3 else "particle_y")
+            for _ in range(n):
+                R.call("particle__solv_vay" if vay else "particle__solv", a["gp"], a["up"], a["uf"], a["cumcnt"], self.nxs, self.nxe)
+                if order == ORDER_RECONNECTION:
+                    R.call(self._bcname("particle_x"), a["gp"], a["np2"], *extra)
+                elif order == ORDER_SHOCK:
+                    R.call(self._bcname("injection"), a["gp"], a["np2"], self.nxs, self.nxe, float(u0))
+                R.call("field__fdtd_i", a["uf"], a["up"], a["gp"], a["cumcnt"], self.nxs, self.nxe, self._bcname("dfield"),
+                       self._bcname("curre"), self._bcname("phi"))
+                if order == ORDER_WEIBEL:
+                    R.call(self._bcname("particle_x"), a["gp"], a["np2"], *extra)
+                R.call(yz, a["gp"], a["np2"])
+                R.call("sort__bucket", a["up"], a["gp"], a["cumcnt"], a["np2"], self.nxs, self.nxe)
+        self._all(loop)
+
+    def mpi_stats(self):
+        """(MPI_SENDRECV calls, MPI_ALLREDUCE calls, payload bytes) of the native transport since the world was made"""
+        if not self._hub:
+            return None
+        out = (C.c_long * 3)()
+        self._mpi.f2mpi_stats(self._hub, out)
+        return tuple(out)
+
+    def close(self):
+        if self._hub:
+            self._mpi.f2mpi_destroy(self._hub)
+            self._hub = None
 
     def mom_calc(self):
         """mom_calc__accl + mom_calc__nvt + bc__mom as the drivers call them (3d/proj/weibel/app.f90:121-124)"""

@@ -1,0 +1,109 @@
+"""The translated reference as a flat-MPI job on host threads -- the form `bench.py --impl reference` times (cpu_baseline.kind
+"reference").  oracle/f2cxx/mpi_threads.cpp replaces the Python rendezvous of pyref.py by an in-process MPI_SENDRECV /
+MPI_ALLREDUCE, run_steps() keeps one thread per rank for the whole run, and libwuming_ref3d_fast.so is the same generated C++
+compiled -O3 -march=native.  Checked here: the native transport changes nothing (bit for bit against the oracle on y x z rank
+grids, all three time loops), the fast build computes the same physics (round-off: FMA contraction), and a rank that dies takes
+the job down instead of hanging its neighbours."""
+import time
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from oracle.f2cxx import pyref
+from tests.util import active_mask, make_world3
+
+pytestmark = pytest.mark.skipif(not pyref.available(3), reason="the translated reference is not built and /root/reference is absent")
+
+
+@pytest.fixture(autouse=True)
+def one_thread():
+    before = pyoracle.num_threads()
+    pyoracle.set_num_threads(1)
+    yield
+    pyoracle.set_num_threads(before)
+
+
+def seed(R, w):
+    for rk in range(w.nranks):
+        for k in ("up", "gp", "uf", "np2", "cumcnt"):
+            R.arr(k, rk)[...] = w.arr(k, rk)
+
+
+@pytest.mark.parametrize("nproc_j,nproc_k", [(2, 2), (3, 2), (4, 1)])
+def test_native_transport_bit_for_bit(nproc_j, nproc_k):
+    nx, ny, nz, n0 = 10, 8, 7, 5
+    w = make_world3(nx, ny, nz, n0, nproc_j=nproc_j, nproc_k=nproc_k)
+    R = pyref.RefWorld(3, nx, ny, nz, w.np, nproc_j=nproc_j, nproc_k=nproc_k, q=w.q, r=w.r, bounds=True, native_mpi=True)
+    seed(R, w)
+    for _ in range(4):
+        w.step()
+    R.run_steps(4)
+    assert w.error() == 0
+    for rk in range(w.nranks):
+        for k in ("np2", "cumcnt", "uf"):
+            assert np.array_equal(w.arr(k, rk), R.arr(k, rk)), (rk, k)
+        m = active_mask(w.arr("np2", rk), w.np)
+        assert np.array_equal(w.arr("up", rk)[m].view(np.int64), R.arr("up", rk)[m].view(np.int64)), rk
+    sr, ar, nbytes = R.mpi_stats()
+    assert sr > 0 and ar > 0 and nbytes > 0 and sr % w.nranks == 0 and ar % w.nranks == 0      # every rank made the same calls
+    R.close()
+
+
+@pytest.mark.parametrize("bc,order,u0", [(1, pyref.ORDER_RECONNECTION, 0.0), (2, pyref.ORDER_SHOCK, -0.2)])
+def test_run_steps_is_the_drivers_sequence(bc, order, u0):
+    """run_steps() (one thread per rank for the whole run, native MPI) against step() (a thread per rank and procedure, Python
+    rendezvous) for the wall-bounded loops on two ranks: identical states"""
+    nx, ny, nz, n0 = 12, 6, 6, 4
+    w = make_world3(nx, ny, nz, n0, nproc_k=2, bc=bc)
+    A = pyref.RefWorld(3, nx, ny, nz, w.np, nproc_k=2, q=w.q, r=w.r, bc=bc, native_mpi=True)
+    B = pyref.RefWorld(3, nx, ny, nz, w.np, nproc_k=2, q=w.q, r=w.r, bc=bc)
+    for R in (A, B):
+        seed(R, w)
+    A.run_steps(3, order=order, u0=u0)
+    for _ in range(3):
+        B.step(order=order, u0=u0)
+    for rk in range(2):
+        for k in ("np2", "cumcnt", "uf"):
+            assert np.array_equal(A.arr(k, rk), B.arr(k, rk)), (rk, k)
+        # the whole store incl. the stale slots, bit-cast: the ID column holds integers whose bit patterns are NaNs as doubles
+        assert np.array_equal(A.arr("up", rk).view(np.int64), B.arr("up", rk).view(np.int64)), rk
+    A.close()
+
+
+def test_fast_build_same_physics():
+    """-O3 -march=native with FMA contraction: round-off differences only, the same particles in the same cells"""
+    nx, ny, nz, n0 = 12, 8, 6, 8
+    w = make_world3(nx, ny, nz, n0, nproc_j=2)
+    A = pyref.RefWorld(3, nx, ny, nz, w.np, nproc_j=2, q=w.q, r=w.r, fast=True, native_mpi=True)
+    B = pyref.RefWorld(3, nx, ny, nz, w.np, nproc_j=2, q=w.q, r=w.r)
+    seed(A, w)
+    seed(B, w)
+    A.run_steps(3)
+    B.run_steps(3)
+    for rk in range(2):
+        assert np.array_equal(A.arr("np2", rk), B.arr("np2", rk)) and np.array_equal(A.arr("cumcnt", rk), B.arr("cumcnt", rk))
+        scale = np.abs(B.arr("uf", rk)).max()
+        assert np.abs(A.arr("uf", rk) - B.arr("uf", rk)).max() <= 1e-12 * scale
+    A.close()
+
+
+def test_a_dead_rank_aborts_the_job():
+    nx, ny, nz, n0 = 10, 6, 6, 3
+    w = make_world3(nx, ny, nz, n0, nproc_k=2)
+    R = pyref.RefWorld(3, nx, ny, nz, w.np, nproc_k=2, q=w.q, r=w.r, native_mpi=True)
+    seed(R, w)
+    R.particle_solv()
+
+    def fn(rk):
+        if rk == 1:
+            raise KeyError("rank 1 dies before its first MPI call")
+        a = R.a[rk]
+        R.ranks[rk].call("field__fdtd_i", a["uf"], a["up"], a["gp"], a["cumcnt"], R.nxs, R.nxe, "boundary_periodic__dfield",
+                         "boundary_periodic__curre", "boundary_periodic__phi")
+
+    t0 = time.perf_counter()
+    with pytest.raises((KeyError, RuntimeError)):
+        R._all(fn)
+    assert time.perf_counter() - t0 < 30.0          # far below the 120 s rendezvous timeout: the abort flag woke rank 0
+    R.close()
