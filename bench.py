@@ -172,11 +172,13 @@ def host_memory_available():
 
 def rank_grid(cores, ny, nz):
     """nproc_j x nproc_k for a flat-MPI run with one rank per host thread: y first (what every shipped 3-D sample does,
-    3d/proj/*/config_sample.json), z as well once the y-slabs would get thinner than 4 cells; never more ranks than that allows"""
+    3d/proj/*/config_sample.json), z as well once the y-slabs would get thinner than 2 cells -- the two ghost layers of the
+    reference's exchanges need two cells per rank and direction (a 1-cell slab runs but computes something else:
+    tests/test_ref_flat_mpi.py) -- and never more ranks than that allows"""
     for nk in (1, 2, 4, 8, 16):
-        if cores % nk == 0 and nz % nk == 0 and nz // nk >= 2 and ny // (cores // nk) >= 4:
+        if cores % nk == 0 and nz % nk == 0 and nz // nk >= 2 and ny // (cores // nk) >= 2:
             return cores // nk, nk
-    nj = max(1, min(cores, ny // 4))
+    nj = max(1, min(cores, ny // 2))
     return nj, 1
 
 

@@ -107,3 +107,51 @@ def test_a_dead_rank_aborts_the_job():
         R._all(fn)
     assert time.perf_counter() - t0 < 30.0          # far below the 120 s rendezvous timeout: the abort flag woke rank 0
     R.close()
+
+
+def test_two_cell_slabs_are_the_thinnest_valid_decomposition():
+    """what bench.rank_grid relies on: ranks that own two cells along a decomposed axis compute the single-rank fields to round-off
+    (the exchanges carry two ghost layers); the translated reference and the oracle agree bit for bit there as everywhere"""
+    nx, ny, nz, n0 = 10, 8, 4, 6
+    one = make_world3(nx, ny, nz, n0, steps=5)
+    w = make_world3(nx, ny, nz, n0, nproc_j=4, nproc_k=2)
+    R = pyref.RefWorld(3, nx, ny, nz, w.np, nproc_j=4, nproc_k=2, q=w.q, r=w.r, bounds=True, native_mpi=True)
+    seed(R, w)
+    for _ in range(5):
+        w.step()
+    R.run_steps(5)
+    ref = one.arr("uf")
+    for rk in range(w.nranks):
+        assert np.array_equal(w.arr("uf", rk), R.arr("uf", rk)) and np.array_equal(w.arr("np2", rk), R.arr("np2", rk))
+        g = w.geom(rk)
+        mine = R.arr("uf", rk)[2:-2, 2:-2, 2:-2]
+        assert np.abs(mine - ref[g["nzs"]:g["nze"] + 1, g["nys"]:g["nye"] + 1, 2:-2]).max() < 1e-13 * np.abs(ref).max()
+    R.close()
+
+
+def test_c1_config_as_the_reference_runs_it():
+    """BASELINE.json configs[0]: 2d/proj/weibel/config_sample.json at FULL size -- 256 x 256 cells, n_ppc 20, np = 5 n_ppc nx
+    (2d/proj/weibel/app.f90:275), `mpiexec -np 4` -- run by the translated reference as four flat-MPI ranks on four threads, against
+    the oracle's four emulated ranks: 2.62 M particles, every record, index and field value bit for bit after each of 3 steps"""
+    if not pyref.available(2):
+        pytest.skip("the translated 2-D reference is not built")
+    from oracle.pyoracle import World2, weibel_constants
+    nx = ny = 256
+    nppc = 20
+    q, r, _ = weibel_constants(nppc, mass_ratio=1.0, sigma_e=0.0, omega_pe=0.1)
+    w = World2(nx, ny, 5 * nppc * nx, nproc=4, q=q, r=r)
+    w.load_weibel(nppc, v_thi=0.1, v_the=0.1, t_ani=5.0, b0=0.0)
+    R = pyref.RefWorld(2, nx, ny, 0, w.np, nproc_j=4, q=q, r=r, native_mpi=True)
+    seed(R, w)
+    assert sum(int(R.arr("np2", rk).sum()) for rk in range(4)) == 2 * nppc * nx * ny
+    for it in range(3):
+        w.step()
+        R.run_steps(1)
+        assert w.error() == 0
+        for rk in range(4):
+            for k in ("np2", "cumcnt", "uf"):
+                assert np.array_equal(w.arr(k, rk), R.arr(k, rk)), (it, rk, k)
+            m = active_mask(w.arr("np2", rk), w.np)
+            assert np.array_equal(w.arr("up", rk)[m].view(np.int64), R.arr("up", rk)[m].view(np.int64)), (it, rk)
+    R.close()
+    w.close()
