@@ -300,9 +300,26 @@ class Parser:
                         if self.accept("op", ")"):
                             break
                         self.expect("op", ",")
-                return ("call", v, args)
-            return ("name", v)
+                return self.components(("call", v, args))
+            return self.components(("name", v))
         raise TranslateError(f"{self.where}: unexpected token {(k, v)} in {self.t}")
+
+    def components(self, base):
+        """base % component [ (subscripts) ] ...  -- derived-type component references (bind(c) types of the ISO_C_BINDING shim)"""
+        while self.accept("op", "%"):
+            k, comp = self.next()
+            if k != "name":
+                raise TranslateError(f"{self.where}: component name expected after %")
+            args = None
+            if self.accept("op", "("):
+                args = []
+                while True:
+                    args.append(self.subscript())
+                    if self.accept("op", ")"):
+                        break
+                    self.expect("op", ",")
+            base = ("comp", base, comp, args)
+        return base
 
     def subscript(self):
         """expr | [expr] : [expr] [: expr]"""
@@ -330,7 +347,11 @@ def parse_expr(s, where=""):
 # ----------------------------------------------------------------------------------------------------------------------
 # symbols
 # ----------------------------------------------------------------------------------------------------------------------
-CTYPE = {"integer": "int", "real8": "double", "real4": "float", "logical": "bool", "integer8": "long long"}
+CTYPE = {"integer": "int", "real8": "double", "real4": "float", "logical": "bool", "integer8": "long long",
+         "cptr": "void*", "cchar": "char"}
+# kind names of ISO_C_BINDING (the C-ABI shim under fortran/) beside the literal kinds the reference uses
+INT_KINDS = {None: "integer", "4": "integer", "c_int": "integer", "8": "integer8", "c_long_long": "integer8", "c_int64_t": "integer8"}
+REAL_KINDS = {None: "real4", "4": "real4", "c_float": "real4", "8": "real8", "c_double": "real8"}
 
 
 class Sym:
@@ -341,6 +362,8 @@ class Sym:
 
     @property
     def ctype(self):
+        if self.ftype.startswith("type:"):          # a bind(c) derived type: the C struct of the same name
+            return self.ftype[5:]
         return CTYPE[self.ftype]
 
     @property
@@ -354,22 +377,29 @@ class Sym:
 
 def parse_type(spec, where):
     s = spec.replace(" ", "")
-    if s == "integer":
-        return "integer"
-    if s in ("integer(8)", "integer(kind=8)"):
-        return "integer8"
-    if s in ("real(8)", "real(kind=8)", "doubleprecision"):
+    m = re.fullmatch(r"integer(?:\((?:kind=)?(\w+)\))?", s)
+    if m and m.group(1) in INT_KINDS:
+        return INT_KINDS[m.group(1)]
+    m = re.fullmatch(r"real(?:\((?:kind=)?(\w+)\))?", s)
+    if m and m.group(1) in REAL_KINDS:
+        return REAL_KINDS[m.group(1)]
+    if s == "doubleprecision":
         return "real8"
-    if s in ("real", "real(4)", "real(kind=4)"):
-        return "real4"
     if s == "logical":
         return "logical"
+    if s == "type(c_ptr)":
+        return "cptr"
+    m = re.fullmatch(r"type\((\w+)\)", s)
+    if m:
+        return "type:" + m.group(1)
+    if s in ("character(kind=c_char)", "character(c_char)"):
+        return "cchar"
     raise TranslateError(f"{where}: unsupported type {spec!r}")
 
 
 def parse_decl(stmt, where):
     """'real(8), intent(in) :: a(n), b' -> [Sym]   (None if the statement is not a type declaration)"""
-    m = re.match(r"(integer|real|logical|double\s+precision)\b", stmt)
+    m = re.match(r"(integer|real|logical|double\s+precision|character)\b|type\s*\(", stmt)
     if not m or "::" not in stmt:
         return None
     left, right = stmt.split("::", 1)
@@ -382,7 +412,7 @@ def parse_decl(stmt, where):
             intent = a2[7:-1]
         elif a2.startswith("dimension("):
             dimattr = a2[10:-1]
-        elif a2 in ("save", "parameter", "allocatable"):
+        elif a2 in ("save", "parameter", "allocatable", "target", "value"):
             attrs.append(a2)
         else:
             raise TranslateError(f"{where}: unsupported attribute {a!r}")
@@ -407,8 +437,8 @@ def parse_decl(stmt, where):
                 d = d.strip()
                 if d == ":":
                     dims.append((None, None))
-                elif d == "*":
-                    raise TranslateError(f"{where}: assumed-size arrays are not supported")
+                elif d == "*":                     # assumed size: only ever handed on (c_loc, an actual argument)
+                    dims.append(("1", "1099511627776"))
                 else:
                     lohi = _split_top(d, ":")
                     if len(lohi) == 1:
@@ -455,14 +485,17 @@ class Subroutine:
 class Module:
     def __init__(self, name):
         self.name, self.syms, self.order, self.subs, self.uses = name, {}, [], [], []
+        self.types = {}         # bind(c) derived types: name -> [Sym] in declaration order
+        self.cfuncs = {}        # bind(c) interface functions: Fortran name -> Subroutine (with .cname)
 
 
 # `use mpi`: a datatype handle is the element size in bytes (f90rt.h)
 MPI_CONSTANTS = {"mpi_status_size": "6", "mpi_integer": "4", "mpi_integer8": "8", "mpi_double_precision": "8", "mpi_real8": "8",
-                 "mpi_sum": "1", "mpi_comm_world": "0"}
+                 "mpi_sum": "1", "mpi_comm_world": "0", "mpi_character": "1"}
 
 
-def parse_module(text, fname):
+def parse_module(text, fname, skip=()):
+    """skip: names of procedures the harness provides natively (their text is not translated)"""
     lines = logical_lines(text)
     i, mod = 0, None
 
@@ -471,11 +504,22 @@ def parse_module(text, fname):
 
     def parse_sub(i, interface=False):
         no, st = lines[i]
-        m = re.match(r"(subroutine|function)\s+([a-z_]\w*)\s*(\(([^()]*)\))?\s*(?:result\s*\(\s*([a-z_]\w*)\s*\))?\s*$", st)
+        m = re.match(r"(subroutine|function)\s+([a-z_]\w*)\s*(\(([^()]*)\))?\s*(.*)$", st)
         if not m:
             raise TranslateError(f"{where(no)}: cannot parse {st!r}")
+        # suffix: result(name) and / or bind(c [, name='...']) in either order
+        suffix, result, cname = m.group(5), None, None
+        mr = re.search(r"result\s*\(\s*([a-z_]\w*)\s*\)", suffix)
+        if mr:
+            result, suffix = mr.group(1), suffix.replace(mr.group(0), "")
+        mb = re.search(r"bind\s*\(\s*c\s*(?:,\s*name\s*=\s*['\"](\w+)['\"]\s*)?\)", suffix)
+        if mb:
+            cname, suffix = mb.group(1) or m.group(2), suffix.replace(mb.group(0), "")
+        if suffix.strip():
+            raise TranslateError(f"{where(no)}: cannot parse {st!r}")
         args = [a.strip() for a in m.group(4).split(",")] if m.group(4) and m.group(4).strip() else []
-        sub = Subroutine(m.group(2), args, no, kind=m.group(1), result=(m.group(5) or m.group(2)) if m.group(1) == "function" else None)
+        sub = Subroutine(m.group(2), args, no, kind=m.group(1), result=(result or m.group(2)) if m.group(1) == "function" else None)
+        sub.cname = cname
         i += 1
         in_spec = True
         while True:
@@ -488,7 +532,17 @@ def parse_module(text, fname):
                     sub.uses.append(st)
                     i += 1
                     continue
-                if st.startswith("implicit"):
+                if st.startswith("implicit") or st.startswith("import"):
+                    i += 1
+                    continue
+                me = re.match(r"external\s*(?:::)?\s*(.*)$", st)
+                if me:
+                    # procedure dummies with an implicit interface: handed on or ignored, never called with arguments here
+                    for nm in [x.strip() for x in me.group(1).split(",")]:
+                        ps = Sym(nm, "integer")
+                        ps.proc_sig = []
+                        sub.syms[nm] = ps
+                        sub.order.append(nm)
                     i += 1
                     continue
                 if st == "interface":
@@ -552,8 +606,36 @@ def parse_module(text, fname):
         if st == "contains":
             i += 1
             while i < len(lines) and not re.match(r"end\s*module\b", lines[i][1]):
+                mh = re.match(r"(?:subroutine|function)\s+([a-z_]\w*)", lines[i][1])
+                if mh and mh.group(1) in skip:
+                    while not re.match(r"end\s*(subroutine|function)\b", lines[i][1]):
+                        i += 1
+                    i += 1
+                    continue
                 sub, i = parse_sub(i)
                 mod.subs.append(sub)
+            continue
+        mt = re.match(r"type\s*,\s*bind\s*\(\s*c\s*\)\s*::\s*([a-z_]\w*)$", st)
+        if mt:
+            comps = []
+            i += 1
+            while not re.match(r"end\s*type\b", lines[i][1]):
+                dc = parse_decl(lines[i][1], where(lines[i][0]))
+                if dc is None:
+                    raise TranslateError(f"{where(lines[i][0])}: unsupported statement inside a type definition")
+                comps += dc
+                i += 1
+            mod.types[mt.group(1)] = comps
+            i += 1
+            continue
+        if st == "interface":
+            i += 1
+            while lines[i][1] not in ("end interface", "endinterface"):
+                isub, i = parse_sub(i, interface=True)
+                if isub.cname is None:
+                    raise TranslateError(f"{where(isub.line)}: module-level interfaces must be bind(c)")
+                mod.cfuncs[isub.name] = isub
+            i += 1
             continue
         d = parse_decl(st, where(no))
         if d is None:
@@ -581,6 +663,9 @@ EXTERNALS = {   # name -> C symbol in f90rt.h   (every argument by reference)
 # comparison, provided by the test driver through hooks (f90rt.h) -- not translated
 EXTERNAL_FUNCS = {"uniform_rand": "f90rt_uniform_rand", "normal_rand": "f90rt_normal_rand"}
 EXTERNALS_SIZED = {"shuffle": "f90rt_shuffle"}        # whole-array actuals are followed by their extent
+# helpers of the ISO_C_BINDING shim that the harness provides natively (character handling is outside the subset): string
+# literals are passed as C strings, everything else by reference
+EXTERNALS_STR = {"wm_check": "f90rt_wm_check"}
 
 ROUNDING = {"ieee_down": "FE_DOWNWARD", "ieee_up": "FE_UPWARD", "ieee_nearest": "FE_TONEAREST", "ieee_to_zero": "FE_TOWARDZERO"}
 
@@ -606,6 +691,28 @@ class Gen:
             if name in u.syms:
                 return u.syms[name]
         return None
+
+    def cfunc(self, name):
+        """a bind(c) interface function visible here -> its Subroutine, else None"""
+        for m in [self.mod] + list(self.used_modules):
+            if name in m.cfuncs:
+                return m.cfuncs[name]
+        return None
+
+    def cfunc_param(self, s):
+        """C parameter type of a bind(c) dummy: `value` -> the type itself, otherwise a pointer to it"""
+        if "value" in s.attrs and not s.rank:
+            return s.ctype
+        return f"{s.ctype}*"
+
+    def cfunc_call(self, f, args, no):
+        if len(args) != len(f.args):
+            raise TranslateError(f"{self.W(no)}: {f.name} takes {len(f.args)} arguments, {len(args)} given")
+        out = []
+        for a, d in zip(args, f.args):
+            ds = f.syms[d]
+            out.append(self.ex(a, no) if ("value" in ds.attrs and not ds.rank) else self.actual_arg_ast(a, no))
+        return f"{f.cname}({', '.join(out)})"
 
     def W(self, no):
         return f"{self.fname}:{no}"
@@ -648,6 +755,8 @@ class Gen:
                 return any(a[0] == "range" for a in e[2]) or any(self.has_section(a) for a in e[2] if a[0] != "range")
             if e[1] in ("sum", "size", "maxval", "minval") and self.lookup(e[1]) is None:
                 return any(a[0] == "kw" and a[1] == "dim" for a in e[2])     # reductions are scalar unless taken along a dim
+            if self.lookup(e[1]) is None and (e[1] == "c_loc" or self.cfunc(e[1]) is not None):
+                return False                                                 # C functions / addresses: scalar whatever they are handed
             return any(self.has_section(a) for a in e[2] if a[0] != "kw")
         if k in ("bin",):
             return self.has_section(e[2]) or self.has_section(e[3])
@@ -657,6 +766,8 @@ class Gen:
             return self.has_section(e[2])
         if k == "paren":
             return self.has_section(e[1])
+        if k == "comp":
+            return False
         return False
 
     def section_dims(self, e, no):
@@ -701,6 +812,8 @@ class Gen:
             if s is None:
                 if name in MPI_CONSTANTS:
                     return MPI_CONSTANTS[name]
+                if name == "c_null_ptr":
+                    return "nullptr"
                 raise TranslateError(f"{self.W(no)}: unknown name {name!r}")
             if s.rank > 0:
                 if secvars is None:
@@ -710,9 +823,43 @@ class Gen:
                     raise TranslateError(f"{self.W(no)}: rank of {name!r} exceeds the elemental context")
                 return f"{mangle(name)}({', '.join(idx)})"
             return mangle(name)
+        if k == "comp":
+            base, comp, cargs = e[1], e[2], e[3]
+            if base[0] != "name":
+                raise TranslateError(f"{self.W(no)}: component of something that is not a plain variable")
+            bs = self.lookup(base[1])
+            if bs is None or not bs.ftype.startswith("type:") or bs.rank:
+                raise TranslateError(f"{self.W(no)}: {base[1]!r} is not a scalar of derived type")
+            comps = None
+            for m in [self.mod] + list(self.used_modules):
+                comps = comps or m.types.get(bs.ftype[5:])
+            cs = next((c for c in comps or [] if c.name == comp), None)
+            if cs is None:
+                raise TranslateError(f"{self.W(no)}: type {bs.ftype[5:]} has no component {comp!r}")
+            if cs.rank == 0:
+                if cargs is not None:
+                    raise TranslateError(f"{self.W(no)}: scalar component {comp!r} is subscripted")
+                return f"{mangle(base[1])}.{comp}"
+            if cs.rank != 1 or cargs is None or len(cargs) != 1 or cargs[0][0] == "range":
+                raise TranslateError(f"{self.W(no)}: array component {comp!r}: only single elements of rank-1 components are supported")
+            lo = self.ex(parse_expr(cs.dims[0][0], self.W(no)), no)
+            return f"{mangle(base[1])}.{comp}[({self.ex(cargs[0], no, secvars)}) - ({lo})]"
         if k == "call":
             name, args = e[1], e[2]
             s = self.lookup(name)
+            if s is None and self.cfunc(name) is not None:
+                return self.cfunc_call(self.cfunc(name), args, no)
+            if s is None and name == "c_loc":
+                if len(args) != 1 or args[0][0] != "name" or self.lookup(args[0][1]) is None:
+                    raise TranslateError(f"{self.W(no)}: c_loc() of something that is not a plain variable")
+                return f"((void*)({self.actual_arg_ast(args[0], no)}))"
+            if s is None and name == "c_associated":
+                return f"(({self.ex(args[0], no)}) != nullptr)"
+            if s is None and name in ("int", "real") and len(args) == 2 and args[1][0] == "name" and \
+                    (args[1][1] in INT_KINDS or args[1][1] in REAL_KINDS) and self.lookup(args[1][1]) is None:
+                to = CTYPE[(INT_KINDS if name == "int" else REAL_KINDS)[args[1][1]]]
+                inner = self.ex(args[0], no, secvars)
+                return f"(({to})(f90::int_({inner})))" if name == "int" and to == "int" else f"(({to})({inner}))"
             if s is not None and s.rank > 0:
                 if len(args) != s.rank:
                     raise TranslateError(f"{self.W(no)}: {name} has rank {s.rank}, {len(args)} subscripts given")
@@ -969,6 +1116,13 @@ class Gen:
             return
         if name in EXTERNALS:
             self.emit(f"{EXTERNALS[name]}({', '.join(ptrs)});")
+            return
+        if name in EXTERNALS_STR and name not in self.known_subs:
+            conv = []
+            for a in args:
+                e = parse_expr(a, self.W(no))
+                conv.append(self.ex(e, no) if e[0] == "str" else self.actual_arg_ast(e, no))
+            self.emit(f"{EXTERNALS_STR[name]}({', '.join(conv)});")
             return
         if name in EXTERNALS_SIZED:
             full = []
@@ -1333,11 +1487,31 @@ class Gen:
             if m and m.group(1) in self.modules:
                 self.used_modules.append(self.modules[m.group(1)])
         self.emit(f"// ---- module {mod.name}  <-  {fname}")
+        # bind(c) derived types are the C structs of the same name; bind(c) interface functions are C prototypes (`value` dummies by
+        # value, everything else by address)
+        for tname, comps in mod.types.items():
+            self.emit(f"struct {tname} {{")
+            for c in comps:
+                if c.rank > 1:
+                    raise TranslateError(f"{fname}: component {c.name} of {tname}: rank > 1")
+                ext = ""
+                if c.rank == 1:
+                    lo, hi = (self.ex(parse_expr(x, fname), 0) for x in c.dims[0])
+                    ext = f"[({hi}) - ({lo}) + 1]"
+                self.emit(f"  {c.ctype} {c.name}{ext};")
+            self.emit("};")
+        for f in mod.cfuncs.values():
+            ret = "void" if f.kind == "subroutine" else f.syms[f.result].ctype
+            self.emit(f'extern "C" {ret} {f.cname}({", ".join(self.cfunc_param(f.syms[a]) for a in f.args)});')
         self.emit(f"namespace mod_{mod.name} {{")
         self.ind += 1
         for name in mod.order:
             s = mod.syms[name]
-            if "parameter" in s.attrs:
+            if s.ftype.startswith("type:"):
+                if s.rank or s.init is not None:
+                    raise TranslateError(f"{fname}: {name}: only scalar, uninitialised variables of derived type are supported")
+                self.emit(f"static {s.ctype} {mangle(name)}{{}};")
+            elif "parameter" in s.attrs:
                 self.emit(f"static const {s.ctype} {mangle(name)} = {self.ex(parse_expr(s.init, fname), 0)};")
             elif s.rank == 0:
                 init = f" = {self.ex(parse_expr(s.init, fname), 0)}" if s.init is not None else \
@@ -1373,13 +1547,27 @@ class Gen:
             self.used_modules = saved
 
 
-def translate(files):
-    """files: [(display name, text)] -> C++ source of one translation unit"""
+def split_modules(text):
+    """a file with several modules -> one text per module, blank-padded so that line numbers stay those of the file"""
+    out, start, lines = [], None, text.splitlines()
+    for no, raw in enumerate(lines):
+        st = _strip_comment(raw).strip().lower()
+        if start is None and re.match(r"module\s+[a-z_]\w*$", st):
+            start = no
+        elif start is not None and re.match(r"end\s*module\b", st):
+            out.append("\n" * start + "\n".join(lines[start:no + 1]) + "\n")
+            start = None
+    return out
+
+
+def translate(files, skip=()):
+    """files: [(display name, text)] -> C++ source of one translation unit; a text may hold several modules"""
     mods, order = {}, []
     for fname, text in files:
-        m = parse_module(text, fname)
-        mods[m.name] = m
-        order.append((m, fname))
+        for part in split_modules(text):
+            m = parse_module(part, fname, skip)
+            mods[m.name] = m
+            order.append((m, fname))
     known = {}
     for m, _ in order:
         for s in m.subs:

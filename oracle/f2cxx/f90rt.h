@@ -284,4 +284,7 @@ void f90rt_shuffle(int* a, int* n);
 void f90rt_capture(int n, const double* v);
 int f90rt_captured(double* out, int max);       // -> number of values; clears the buffer
 void f90rt_set_rounding_nearest();
+// `wm_check` of the ISO_C_BINDING shim (fortran/wuming_b200_c.f90), provided natively by shim_rt.cpp: STOP with the C-ABI
+// library's message when ierr is not 0
+void f90rt_wm_check(int* ierr, const char* where);
 }

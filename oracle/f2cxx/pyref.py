@@ -80,11 +80,14 @@ class RefWorld:
     numpy sees them in C order with the index order reversed, exactly like oracle.pyoracle.World2 / World3."""
 
     def __init__(self, dim, nx, ny, nz, np_cap, nproc_j=1, nproc_k=1, delx=1.0, delt=1.0, c=1.0, gfac=0.501, q=(1.0, -1.0),
-                 r=(1.0, 1.0), bc=0, bounds=False, fast=False, native_mpi=False):
+                 r=(1.0, 1.0), bc=0, bounds=False, fast=False, native_mpi=False, lib=None):
         """fast: the -O3 -march=native build of the same generated C++ (timing only, never parity).  native_mpi: the ranks'
         MPI_SENDRECV / MPI_ALLREDUCE rendezvous in mpi_threads.cpp instead of Python callbacks (same semantics, no interpreter
         lock on the communication path: what a timed flat-MPI run with one rank per host thread needs)"""
-        path = build_ref.build_fast(dim) if fast else build_ref.build(dim, bounds=bounds)
+        self.lib_override = lib
+        # lib: another library with the reference's module interface -- the translated ISO_C_BINDING shim (shim_harness.py), whose
+        # procedures forward to the C ABI: the same driver then runs the CUDA backend (or the recording stub) instead
+        path = lib or (build_ref.build_fast(dim) if fast else build_ref.build(dim, bounds=bounds))
         if path is None:
             raise RuntimeError("the translated reference is not built and /root/reference is absent")
         self.native_mpi, self._hub, self._mpi = bool(native_mpi), None, None

@@ -336,10 +336,90 @@ def test_constructs_outside_the_subset_are_refused():
     with pytest.raises(f2cxx.TranslateError):
         mods = SRC.split("end module helper\n")
         f2cxx.translate([("helper.f90", mods[0] + "end module helper\n"), ("t.f90", mods[1])])
-    for bad in ("subroutine s(a)\n real(8) :: a(*)\n end subroutine s",
-                "subroutine s(a)\n real(8) :: a(4)\n a(1:4:2) = 0d0\n end subroutine s",
+    for bad in ("subroutine s(a)\n real(8) :: a(4)\n a(1:4:2) = 0d0\n end subroutine s",
+                "subroutine s(a)\n type(nosuch) :: a\n a%x = 1\n end subroutine s",
+                "subroutine s(a)\n real(8), pointer :: a(:)\n end subroutine s",
                 "subroutine s(a)\n real(8) :: a(4)\n where(a > 0) a = 0d0\n end subroutine s",
                 "subroutine s(a)\n real(8) :: a(4)\n b = 1d0\n end subroutine s",
                 "subroutine s(a)\n complex :: a\n end subroutine s"):
         with pytest.raises(f2cxx.TranslateError):
             f2cxx.translate([("bad.f90", "module m\n implicit none\ncontains\n" + bad + "\nend module m\n")])
+
+
+# ---- the ISO_C_BINDING subset the C-ABI shim under fortran/ is written in (oracle/f2cxx/shim_harness.py) -------------------------
+CSRC = r"""
+module cbind
+  use iso_c_binding
+  implicit none
+  public
+  type, bind(c) :: rec
+    integer(c_int)       :: n
+    real(c_double)       :: w(3)
+    integer(c_long_long) :: big
+  end type rec
+  type(c_ptr), save :: handle = c_null_ptr
+  type(rec), save   :: r
+  interface
+    function c_fill(p, out) bind(c, name='c_fill_impl') result(ierr)
+      import :: c_int, c_ptr, rec
+      type(rec), intent(in)    :: p
+      type(c_ptr), intent(out) :: out
+      integer(c_int)           :: ierr
+    end function
+    function c_scale(h, a, n, s, tag) bind(c, name='c_scale_impl') result(ierr)
+      import :: c_int, c_ptr, c_double, c_long_long
+      type(c_ptr), value          :: h, a
+      integer(c_int), value       :: n
+      real(c_double), value       :: s
+      integer(c_long_long), value :: tag
+      integer(c_int)              :: ierr
+    end function
+  end interface
+contains
+  subroutine cbind__run(a, n, res)
+    integer, intent(in)            :: n
+    real(8), intent(inout), target :: a(*)
+    integer, intent(out)           :: res(4)
+    integer(c_int) :: ierr
+    res(1) = 0
+    if (.not.c_associated(handle)) res(1) = 1
+    r%n = n; r%w(1) = 1.5d0; r%w(2) = 2.5d0; r%w(3) = r%w(1) + r%w(2); r%big = 4000000000_8
+    ierr = c_fill(r, handle)
+    res(2) = ierr
+    if (c_associated(handle)) res(1) = res(1) + 10
+    ierr = c_scale(handle, c_loc(a), int(n, c_int), real(r%w(3), c_double), int(n, c_long_long) + r%big)
+    res(3) = ierr
+    ierr = c_scale(handle, c_null_ptr, 0, 0d0, 0_8)
+    res(4) = ierr
+  end subroutine cbind__run
+end module cbind
+"""
+
+CIMPL = r"""
+#include <cstring>
+struct rec_c { int n; double w[3]; long long big; };
+static rec_c g_seen;
+extern "C" int c_fill_impl(const rec_c* p, void** out) { g_seen = *p; *out = &g_seen; return (int)sizeof(rec_c); }
+extern "C" int c_scale_impl(void* h, void* a, int n, double s, long long tag) {
+  if (!a) return -7;
+  if (h != &g_seen || g_seen.big != 4000000000LL || tag != 4000000000LL + n) return -1;
+  for (int i = 0; i < n; ++i) ((double*)a)[i] *= s;
+  return g_seen.n * 100 + (int)(g_seen.w[0] + g_seen.w[1] + g_seen.w[2]);
+}
+"""
+
+
+def test_iso_c_binding_subset(tmp_path):
+    """bind(c) derived types are C structs of the same layout, bind(c) interface functions are C calls with `value` dummies by value
+    and the rest by address, c_loc / c_null_ptr / c_associated / int(x, c_int) / real(x, c_double) mean what the standard says"""
+    cpp, impl, so = tmp_path / "cbind.cpp", tmp_path / "impl.cpp", tmp_path / "libcbind.so"
+    cpp.write_text(f2cxx.translate([("cbind.f90", CSRC)]))
+    impl.write_text(CIMPL)
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-I", F2, "-o", str(so), str(cpp), str(impl),
+                        os.path.join(F2, "f90rt.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    L = C.CDLL(str(so))
+    a, res = np.arange(5, dtype=np.float64), np.zeros(4, np.int32)
+    L.cbind__run(_p(a), C.byref(C.c_int(5)), _p(res))
+    assert list(res) == [11, 40, 5 * 100 + 8, -7]            # unassociated, then associated; sizeof(rec) = 4 (+4) + 24 + 8
+    assert np.array_equal(a, np.arange(5) * 4.0)

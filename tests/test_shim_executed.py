@@ -1,0 +1,213 @@
+"""The Fortran ISO_C_BINDING shim (fortran/wuming_b200_c.f90 + wuming_b200_shim{2,3}d.f90 -- what a maintainer links instead of the
+reference's common/*.f90) EXECUTED on CPU.  The image has no Fortran compiler; oracle/f2cxx translates the shim's text like it
+translates the reference's (oracle/f2cxx/shim_harness.py), and the C ABI underneath is oracle/_ref/libwm_stub.so: a recorder compiled
+against include/wuming_b200.h that forwards every call to tests/shim_stub.py, where the CPU oracle plays the device.  The driver on
+top is pyref.RefWorld -- the call sequences of the reference's drivers, unchanged, because the shim's modules have the reference's
+module interface.  Checked: the struct the shim fills, which C functions each procedure calls and in which order, which arrays
+cross the boundary in both synchronisation modes, that the host-visible results of every call are the reference's (bit for bit:
+the oracle does the arithmetic on both sides), the np2 inference from a shock-shaped cumcnt, the error path (a failing C call
+becomes the reference's STOP with the library's message), the moments, the shock source, and the rank-grid / communicator set-up."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from oracle.f2cxx import pyref, shim_harness
+from tests.shim_stub import StubDevice
+from tests.util import active_mask, make_world2, make_world3
+
+NX, NY, NZ, N0 = 12, 6, 5, 4
+
+
+@pytest.fixture(autouse=True)
+def one_thread():
+    before = pyoracle.num_threads()
+    pyoracle.set_num_threads(1)
+    yield
+    pyoracle.set_num_threads(before)
+
+
+def shim_world(dim, w, bc=0):
+    """the reference's driver (pyref.RefWorld) on top of the translated shim; host arrays seeded with the oracle's state"""
+    D = StubDevice()
+    R = pyref.RefWorld(dim, w.nx, w.ny, w.nz if dim == 3 else 0, w.np, q=w.q, r=w.r, bc=bc, lib=shim_harness.build(dim))
+    for k in ("up", "gp", "uf", "np2", "cumcnt"):
+        R.arr(k)[...] = w.arr(k)
+    return D, R
+
+
+def same_state(R, w, what):
+    for k in ("np2", "cumcnt", "uf"):
+        assert np.array_equal(R.arr(k), w.arr(k)), (what, k)
+    m = active_mask(w.arr("np2"), w.np)
+    assert np.array_equal(R.arr("up")[m].view(np.int64), w.arr("up")[m].view(np.int64)), (what, "up")
+
+
+def test_context_is_created_by_the_last_init_with_the_drivers_numbers():
+    w = make_world3(NX, NY, NZ, N0)
+    D, R = shim_world(3, w)
+    assert D.names() == ["wm_create"]                  # bc__init, particle__init, field__init, ... : one context
+    f = D.log[0][1]
+    assert (f["dim"], f["ndim"], f["np"], f["nsp"]) == (3, 7, w.np, 2)
+    assert (f["nxgs"], f["nxge"], f["nygs"], f["nyge"], f["nzgs"], f["nzge"]) == (2, NX + 1, 2, NY + 1, 2, NZ + 1)
+    assert (f["nys"], f["nye"], f["nzs"], f["nze"]) == (2, NY + 1, 2, NZ + 1)
+    assert (f["nproc_j"], f["nproc_k"], f["rank_j"], f["rank_k"], f["bc_kind"], f["device"]) == (1, 1, 0, 0, 0, -1)
+    assert (f["delx"], f["delt"], f["c"], f["gfac"]) == (1.0, 1.0, 1.0, 0.501)
+    assert f["q"] == list(w.q) and f["r"] == list(w.r)
+    # the C struct the translator derived from `type, bind(c) :: wm_params` has the header's size (the values above its layout)
+    from wumingpic_b200.backend import ShockParams, _Params
+    assert D.L.stub_sizeof_params() == C.sizeof(_Params) and D.L.stub_sizeof_shock_params() == C.sizeof(ShockParams)
+
+
+@pytest.mark.parametrize("dim", [3, 2])
+def test_weibel_loop_sync_every_call(dim):
+    """the default mode: an unmodified driver sees the reference's host-visible results after every call"""
+    w = make_world3(NX, NY, NZ, N0) if dim == 3 else make_world2(NX, NY, N0)
+    D, R = shim_world(dim, w)
+    for it in range(3):
+        del D.log[:]
+        w.step()
+        R.step()
+        same_state(R, w, f"step {it}")
+        assert D.log == [("wm_upload", ("up", "np2", "cumcnt", "uf")), ("wm_particle_solv", 2, NX + 1), ("wm_download", ("gp",)),
+                         ("wm_field_fdtd_i", 2, NX + 1), ("wm_download", ("uf",)),
+                         ("wm_bc_particle_x", 2, NX + 1), ("wm_download", ("gp",)),
+                         ("wm_bc_particle_yz",), ("wm_sort_bucket", 2, NX + 1), ("wm_download", ("up", "np2", "cumcnt"))], it
+    # stage-wise: what particle__solv hands back is the pushed set
+    w.particle_solv()
+    R.particle_solv()
+    m = active_mask(w.arr("np2"), w.np)
+    assert np.array_equal(R.arr("gp")[m].view(np.int64), w.arr("gp")[m].view(np.int64))
+
+
+@pytest.mark.parametrize("bc,order,u0", [(1, pyref.ORDER_RECONNECTION, 0.0), (2, pyref.ORDER_SHOCK, -0.2)])
+def test_wall_loops(bc, order, u0):
+    w = make_world3(NX, NY, NZ, N0, bc=bc)
+    D, R = shim_world(3, w, bc=bc)
+    assert D.log[0][1]["bc_kind"] == bc                 # boundary_reconnection__init / boundary_shock__init registered the rules
+    for it in range(3):
+        del D.log[:]
+        w.step(order, u0)
+        R.step(order=order, u0=u0)
+        same_state(R, w, f"bc {bc} step {it}")
+        names = D.names()
+        second = "wm_bc_particle_x" if bc == 1 else "wm_bc_injection.u0"
+        assert names[:3] == ["wm_upload", "wm_particle_solv", "wm_download"] and names[3] == second, names
+        assert "wm_field_fdtd_i" in names and names.index("wm_field_fdtd_i") > names.index(second)
+        if bc == 2:
+            assert ("wm_bc_injection.u0", u0) in D.log and ("wm_bc_injection", 2, NX + 1) in D.log
+
+
+def test_resident_mode_moves_nothing_until_asked():
+    w = make_world3(NX, NY, NZ, N0)
+    D, R = shim_world(3, w)
+    L = R.ranks[0]
+    L.call("wm_shim_set_mode", 1)                        # WM_SHIM_RESIDENT
+    del D.log[:]
+    for _ in range(3):
+        w.step()
+        R.step()
+    assert D.names().count("wm_upload") == 1 and "wm_download" not in D.names()       # the first solv uploads, then nothing
+    assert not np.array_equal(R.arr("uf"), w.arr("uf"))                                  # the host copy is stale by design
+    L.call("wm_shim_sync_to_host", R.arr("up"), R.arr("uf"), R.arr("np2"), R.arr("cumcnt"))
+    assert D.log[-1] == ("wm_download", ("up", "np2", "cumcnt", "uf"))
+    same_state(R, w, "after wm_shim_sync_to_host")
+    # the driver edits the host arrays (shock inject / relocate on the host) and says so: the next solv uploads again
+    del D.log[:]
+    R.step()
+    assert "wm_upload" not in D.names()
+    L.call("wm_shim_host_modified")
+    R.step()
+    assert D.names().count("wm_upload") == 1
+
+
+def test_np2_from_a_shock_shaped_cumcnt():
+    """the shock driver's inject() / relocate() bump np2 and cumcnt(nxe) and leave cumcnt(nxe+1:) stale (3d/proj/shock/app.f90,
+    SURVEY.md App. A.8): the population the shim uploads is the largest prefix count of the active range, not cumcnt(nxe+1)"""
+    w = make_world3(NX, NY, NZ, N0)
+    D, R = shim_world(3, w)
+    nxs, nxe = 2, NX - 2                                 # an active range that ends inside the box
+    cc = R.arr("cumcnt")                                 # (nsp, nz, ny, nx + 1): index i - nxgs
+    cc[...] = np.arange(NX + 1)[None, None, None, :] * 3
+    cc[..., nxe - 2] += 5                                # cumcnt(nxe) bumped by the injection ...
+    cc[..., nxe - 1:] = 0                                # ... cumcnt(nxe+1) and above stale
+    expect = cc[..., :nxe - 1].max(axis=-1)
+    R.ranks[0].call("shim_upload", R.arr("up"), R.arr("uf"), cc, nxs, nxe)
+    assert D.log[-1] == ("wm_upload", ("up", "np2", "cumcnt", "uf"))
+    dev = D.world(next(iter(D.worlds)))
+    assert np.array_equal(dev.arr("np2"), expect) and np.array_equal(dev.arr("cumcnt"), cc)
+    assert (expect == 3 * (nxe - 2) + 5).all()
+
+
+def test_a_failing_call_is_the_references_stop():
+    w = make_world3(NX, NY, NZ, N0)
+    D, R = shim_world(3, w)
+    R.particle_solv()
+    D.fail_next = ("wm_field_fdtd_i", 3, "stop at cgm after ite_max")          # WM_ERR_CG_ITEMAX <-> field.f90:522-525
+    with pytest.raises(RuntimeError, match=r"field__fdtd_i: stop at cgm after ite_max \(code 3\)"):
+        R.field_fdtd_i()
+    assert D.log[-1][0] == "wm_field_fdtd_i"            # nothing was downloaded after the failure
+
+
+def test_procedures_refuse_to_run_before_init():
+    """the reference's own guard: 'Initialize first by calling particle__init()' + stop (3d/common/particle.f90:69-72)"""
+    StubDevice()
+    R = pyref._Rank(3, shim_harness.build(3))
+    z = np.zeros(8)
+    with pytest.raises(RuntimeError, match="STOP"):
+        R.call("particle__solv", z, z, z, np.zeros(8, np.int32), 2, 3)
+
+
+def test_moments_cross_once():
+    w = make_world3(NX, NY, NZ, N0)       # from step 0: the CG warm start (a SAVEd local of field__fdtd_i) is zero on both sides
+    D, R = shim_world(3, w)
+    R.step()
+    w.step()
+    same_state(R, w, "before the moments")
+    del D.log[:]
+    w.mom_calc()
+    R.mom_calc()                                          # mom_calc__accl + mom_calc__nvt + bc__mom, as the drivers call them
+    assert D.log == [("wm_mom_calc", 2, NX + 1)]          # accl only records the range, bc__mom is folded in on the device
+    assert np.array_equal(R.arr("mom"), w.arr("mom"))
+
+
+def test_shock_source_marshalling():
+    w = make_world3(NX, NY, NZ, N0, bc=2)
+    D, R = shim_world(3, w, bc=2)
+    L = R.ranks[0]
+    L.L.shock_source__init.argtypes = None
+    seed = np.array([20240601], dtype=np.int64)
+    L.call("shock_source__init", 7, -0.3, 0.01, 0.02, 0.5, 1.1, 0.2, 4.0, seed)
+    nl = np.arange(NY * NZ, dtype=np.int32)
+    ids = np.arange(2 * NY * NZ, dtype=np.int64) * 1000
+    L.call("shock_source__inject", NX, nl, ids, 17)
+    name, nxe, epoch, prm, got_nl, got_ids = D.log[-1]
+    assert (name, nxe, epoch) == ("wm_shock_inject", NX, 17)
+    assert prm == dict(n0=7, v0=-0.3, v_thi=0.01, v_the=0.02, b0=0.5, theta_bn=1.1, phi_bn=0.2, l_damp_ini=4.0, seed=20240601)
+    assert np.array_equal(got_nl, nl) and np.array_equal(got_ids, ids)
+    L.call("shock_source__relocate", NX + 1, ids, 18)
+    name, nxe, epoch, prm, got_ids = D.log[-1]
+    assert (name, nxe, epoch) == ("wm_shock_relocate", NX + 1, 18) and np.array_equal(got_ids, ids) and prm["n0"] == 7
+
+
+def test_rank_grid_and_communicator_are_set_up_when_the_context_is_created():
+    """wm_shim_comm_init right after mpi_set__init (before the __init calls): the context is created by the last __init WITH the
+    rank grid, and the communicator is connected right behind it -- rank 0 draws the id, MPI_BCAST, wm_comm_init"""
+    D = StubDevice()
+    R = pyref._Rank(3, shim_harness.build(3))
+    R.call("wm_shim_comm_init", 4, 1, 4, 0, 0)           # nproc, nproc_j, nproc_k, nrank, ncomw: rank 0 of a 1 x 4 grid
+    assert D.log == []                                    # nothing can be created yet
+    nstat = np.zeros(6, np.int32)
+    q, r = np.array([1.0, -1.0]), np.array([1.0, 1.0])
+    head = [7, 100, 2, 2, NX + 1, 2, NY + 1, 2, 9, 2, NY + 1, 2, 3]      # ... nzgs, nzge = 2, 9; this rank's nzs, nze = 2, 3
+    R.call("boundary_periodic__init", *head, 0, 0, 1, 3, 4, 8, 0, 0, nstat, 1.0, 1.0, 1.0, len(nstat))
+    R.call("particle__init", *head, 1.0, 1.0, 1.0, q, r)
+    assert D.log == []
+    R.call("field__init", *head, 8, 0, 1, 0, 1.0, 1.0, 1.0, q, r, 0.501)
+    assert D.names() == ["wm_create", "wm_comm_unique_id", "wm_comm_init"]
+    f = D.log[0][1]
+    assert (f["nproc_j"], f["nproc_k"], f["rank_j"], f["rank_k"], f["nzs"], f["nze"], f["nzge"]) == (1, 4, 0, 0, 2, 3, 9)
+    assert D.log[2] == ("wm_comm_init", 4, 0)
+    with pytest.raises(RuntimeError, match="STOP"):      # too late to change the grid of an existing context
+        R.call("wm_shim_comm_init", 4, 2, 2, 0, 0)

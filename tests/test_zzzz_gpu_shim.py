@@ -1,0 +1,106 @@
+"""The Fortran ISO_C_BINDING shim (fortran/*.f90, translated by oracle/f2cxx like the reference itself: oracle/f2cxx/shim_harness.py)
+on top of the REAL libwuming_b200.so: the reference's driver sequences (pyref.RefWorld) call the shim's `particle__solv`,
+`field__fdtd_i`, `bc__*`, `sort__bucket` with the reference's host arrays, the shim calls the C ABI, the CUDA kernels do the work --
+the whole drop-in path a maintainer gets by linking the shim, against the oracle.  The CPU half of this (same driver, same shim,
+a recording stub under the C ABI) is tests/test_shim_executed.py.  Runs last (file name) and skips if the shim library cannot be
+bound to the real backend in this process."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.util import active_mask, canonical_cells, make_world2, make_world3, rel_err
+
+pytestmark = pytest.mark.gpu
+NX = 18
+
+
+@pytest.fixture(scope="module")
+def real_backend():
+    import wumingpic_b200
+    from oracle.f2cxx import shim_harness
+    from wumingpic_b200.backend import library_path
+    wumingpic_b200.load_library()
+    L = C.CDLL(library_path(), mode=C.RTLD_GLOBAL)         # the shim's undefined wm_* symbols resolve against the global scope
+    glob = C.CDLL(None)
+    try:
+        same = C.cast(glob.wm_create, C.c_void_p).value == C.cast(L.wm_create, C.c_void_p).value
+    except AttributeError:
+        same = False
+    if not same:
+        pytest.skip("wm_* in this process do not resolve to libwuming_b200.so (the CPU stub was loaded first: run with -m gpu)")
+    L.wm_destroy.argtypes = [C.c_void_p]
+    return L, shim_harness
+
+
+def shim_world(real_backend, dim, w, bc=0):
+    from oracle.f2cxx import pyref
+    L, shim_harness = real_backend
+    R = pyref.RefWorld(dim, w.nx, w.ny, w.nz if dim == 3 else 0, w.np, q=w.q, r=w.r, bc=bc, lib=shim_harness.build(dim))
+    for k in ("up", "gp", "uf", "np2", "cumcnt"):
+        R.arr(k)[...] = w.arr(k)
+    return R
+
+
+def destroy(real_backend, R):
+    """the shim keeps its context for the life of the program (like the reference's module state); the test releases it"""
+    f = R.ranks[0].L.f2cxx_modvar__wuming_b200_c__ctx
+    f.restype = C.c_void_p
+    ctx = C.c_void_p.from_address(f())
+    if ctx.value:
+        real_backend[0].wm_destroy(ctx)
+        ctx.value = None
+
+
+def compare(R, w, tol_f=1e-8, tol_p=1e-9):      # the tolerances of tests/test_gpu_five_calls.py
+    assert np.array_equal(R.arr("np2"), w.arr("np2")) and np.array_equal(R.arr("cumcnt"), w.arr("cumcnt"))
+    assert rel_err(R.arr("uf"), w.arr("uf")) < tol_f
+    for (cg, rg), (cr, rr) in zip(canonical_cells(R.arr("up"), R.arr("np2"), R.arr("cumcnt")),
+                                  canonical_cells(w.arr("up"), w.arr("np2"), w.arr("cumcnt"))):
+        assert np.array_equal(cg, cr)
+        assert np.array_equal(rg[:, -1].view(np.int64), rr[:, -1].view(np.int64))
+        if len(rg):
+            assert np.abs(rg[:, :-1] - rr[:, :-1]).max() < tol_p
+
+
+@pytest.mark.parametrize("dim,bc,order,u0", [(3, 0, 0, 0.0), (2, 0, 0, 0.0), (3, 1, 1, 0.0), (2, 2, 2, 0.3)],
+                         ids=["3d-weibel", "2d-weibel", "3d-reconnection", "2d-shock"])
+def test_driver_through_the_shim_sync_every_call(real_backend, dim, bc, order, u0):
+    """the default mode of the shim: every procedure hands the reference's host-visible result back (an unmodified driver)"""
+    w = make_world3(NX, 8, 6, 6, bc=bc) if dim == 3 else make_world2(NX, 14, 8, bc=bc)
+    R = shim_world(real_backend, dim, w, bc=bc)
+    try:
+        # one step taken apart: what particle__solv hands back is the pushed set
+        w.particle_solv()
+        R.particle_solv()
+        m = active_mask(w.arr("np2"), w.np)
+        for c in range(w.ndim - 1):
+            assert rel_err(R.arr("gp")[m][:, c], w.arr("gp")[m][:, c]) < 1e-12
+        # ... then whole steps of the set-up's own call order, from the start state again
+        w2 = make_world3(NX, 8, 6, 6, bc=bc) if dim == 3 else make_world2(NX, 14, 8, bc=bc)
+        for k in ("up", "gp", "uf", "np2", "cumcnt"):
+            R.arr(k)[...] = w2.arr(k)
+        for it in range(4):
+            w2.step(order, u0)
+            R.step(order=order, u0=u0)
+            assert w2.error() == 0
+            compare(R, w2)
+    finally:
+        destroy(real_backend, R)
+
+
+def test_driver_through_the_shim_resident(real_backend):
+    """WM_SHIM_RESIDENT: the five calls run the fused kernel + lazy sort on device-resident state; the host arrays are refreshed
+    by wm_shim_sync_to_host only"""
+    w = make_world3(NX, 8, 6, 6)
+    R = shim_world(real_backend, 3, w)
+    try:
+        R.ranks[0].call("wm_shim_set_mode", 1)
+        for _ in range(5):
+            w.step()
+            R.step()
+        assert not np.array_equal(R.arr("uf"), w.arr("uf"))          # nothing came back yet
+        R.ranks[0].call("wm_shim_sync_to_host", R.arr("up"), R.arr("uf"), R.arr("np2"), R.arr("cumcnt"))
+        compare(R, w)
+    finally:
+        destroy(real_backend, R)
