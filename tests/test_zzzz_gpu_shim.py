@@ -104,3 +104,23 @@ def test_driver_through_the_shim_resident(real_backend):
         compare(R, w)
     finally:
         destroy(real_backend, R)
+
+
+def test_moments_through_the_shim(real_backend):
+    """the drivers' output block -- mom_calc__accl, mom_calc__nvt, bc__mom -- through the shim: one wm_mom_calc on the device-resident
+    particles; interior nodes against the oracle (tests/test_gpu_parity_variants.py::test_moments for the tolerance)"""
+    w = make_world3(NX, 8, 6, 6)
+    R = shim_world(real_backend, 3, w)
+    try:
+        for _ in range(2):
+            w.step()
+            R.step()
+        w.mom_calc()
+        R.mom_calc()
+        got, ref = R.arr("mom"), w.arr("mom")
+        inner = (slice(None),) + (slice(1, -1),) * 3
+        for l in range(7):
+            assert rel_err(got[inner][..., l], ref[inner][..., l]) < 1e-9, l
+        assert abs(got[inner][..., 0].sum() - w.arr("np2").sum()) < 1e-9 * w.arr("np2").sum()
+    finally:
+        destroy(real_backend, R)
