@@ -211,3 +211,24 @@ def test_rank_grid_and_communicator_are_set_up_when_the_context_is_created():
     assert D.log[2] == ("wm_comm_init", 4, 0)
     with pytest.raises(RuntimeError, match="STOP"):      # too late to change the grid of an existing context
         R.call("wm_shim_comm_init", 4, 2, 2, 0, 0)
+
+
+def test_a_non_root_rank_of_a_y_slab_grid():
+    """rank 2 of a 4 x 1 grid (y-slabs, what every shipped 3-D sample uses): rank = j nproc_k + k (3d/common/mpi_set.f90:45-60), the
+    id arrives by MPI_BCAST (the root alone draws it), the slab bounds the driver computed travel in wm_params"""
+    D = StubDevice()
+    R = pyref._Rank(3, shim_harness.build(3))
+    R.call("wm_shim_comm_init", 4, 4, 1, 2, 0)
+    nstat = np.zeros(6, np.int32)
+    q, r = np.array([1.0, -1.0]), np.array([1.0, 1.0])
+    head = [7, 100, 2, 2, NX + 1, 2, 17, 2, NZ + 1, 10, 13, 2, NZ + 1]       # ny = 16 in four slabs: this rank owns j = 10 .. 13
+    R.call("boundary_periodic__init", *head, 3, 1, 2, 2, 4, 8, 0, 0, nstat, 1.0, 1.0, 1.0, len(nstat))
+    R.call("field__init", *head, 8, 0, 1, 0, 1.0, 1.0, 1.0, q, r, 0.501)
+    R.call("sort__init", *head)
+    assert D.log == []                                   # charges and masses are still missing
+    R.call("particle__init", *head, 1.0, 1.0, 1.0, q, r)
+    assert D.names() == ["wm_create", "wm_comm_init"]    # no wm_comm_unique_id on a non-root rank
+    f = D.log[0][1]
+    assert (f["nproc_j"], f["nproc_k"], f["rank_j"], f["rank_k"]) == (4, 1, 2, 0)
+    assert (f["nygs"], f["nyge"], f["nys"], f["nye"], f["nzs"], f["nze"]) == (2, 17, 10, 13, 2, NZ + 1)
+    assert D.log[1] == ("wm_comm_init", 4, 2)
