@@ -235,11 +235,15 @@ def cpu_reference(args, steps=2, warmup=1):
     w = World3(nx, ny, nz, cap, nproc_j=nj, nproc_k=nk, q=q, r=r, fast=True)
     w.load_weibel(n0)
     R = pyref.RefWorld(3, nx, ny, nz, cap, nproc_j=nj, nproc_k=nk, q=q, r=r, fast=True, native_mpi=nj * nk > 1)
-    npart = 0
-    for rk in range(nj * nk):
+    # one rank per host CPU, bound to it, and every rank's arrays first touched by that rank (what `mpiexec --bind-to core` gives)
+    R.pin_ranks(sorted(os.sched_getaffinity(0)))
+
+    def seed(rk):
         for k in ("up", "uf", "np2", "cumcnt"):
             R.arr(k, rk)[...] = w.arr(k, rk)
-        npart += int(w.arr("np2", rk).sum())
+        R.arr("gp", rk)[...] = 0.0
+    R._all(seed)
+    npart = sum(int(w.arr("np2", rk).sum()) for rk in range(nj * nk))
     w.close()
     R.run_steps(warmup)
     t0 = time.perf_counter()

@@ -174,15 +174,26 @@ class RefWorld:
             R.keep += [SR(sendrecv), AR(allreduce)]
             R.L.f90rt_set_transport(R.keep[-2], R.keep[-1])
 
+    def pin_ranks(self, cpus):
+        """timed runs: rank r's threads run on host CPU cpus[r % len(cpus)] (like `mpiexec --bind-to core`), so that the memory a
+        rank touches first -- seed its arrays from inside _all() -- is local to the core that works on it"""
+        self._pin = list(cpus)
+
     def _all(self, fn):
         """run fn(rank) on every rank -- concurrently when there is more than one (they exchange messages)"""
-        if self.nranks == 1:
+        pin = getattr(self, "_pin", None)
+        if self.nranks == 1 and not pin:
             fn(0)
             return
         err = []
 
         def body(rk):
             try:
+                if pin:
+                    try:
+                        os.sched_setaffinity(0, {pin[rk % len(pin)]})       # 0 = the calling thread
+                    except OSError:
+                        pass
                 if self._hub:
                     self._mpi.f2mpi_bind(self._hub, rk)       # the rank of a native MPI call is the rank its thread is bound to
                 fn(rk)
@@ -190,7 +201,7 @@ class RefWorld:
                 err.append(e)
                 if self._hub:
                     self._mpi.f2mpi_abort(self._hub)
-                else:
+                elif getattr(self, "_barrier", None) is not None:
                     self._barrier.abort()
 
         th = [threading.Thread(target=body, args=(rk,)) for rk in range(self.nranks)]
