@@ -111,3 +111,44 @@ def test_everything_the_drivers_use_is_provided(patched):
                     assert name in provided[mod], (str(u), mod, name)
         assert {"particle", "field", "sort", "mom_calc", "boundary_periodic", "wuming_b200_c"} <= seen
         assert {"boundary_reconnection", "boundary_shock"} <= seen
+
+
+def test_resident_patch_puts_the_sync_points_where_the_drivers_read_or_edit_the_host_arrays(tmp_path):
+    import make_reference_patch as mp
+    tree = tmp_path / "WumingPIC"
+    shutil.copytree(REF, tree, ignore=shutil.ignore_patterns("*.png", "*.ipynb", ".git"))
+    for d, _, fs in os.walk(tree):
+        os.chmod(d, 0o755)
+        for f in fs:
+            os.chmod(os.path.join(d, f), 0o644)
+    patch = tmp_path / "resident.patch"
+    patch.write_text(mp.make_patch(REF, resident=True))
+    r = subprocess.run(["patch", "-p1", "-d", str(tree), "-i", str(patch)], capture_output=True, text=True)
+    assert r.returncode == 0 and "FAILED" not in r.stdout and "fuzz" not in r.stdout, r.stdout + r.stderr
+    sync = "call wm_shim_sync_to_host(up,uf,np2,cumcnt)"
+    n_drivers = 0
+    for dim in (2, 3):
+        for name in os.listdir(tree / f"{dim}d" / "proj"):
+            n_drivers += 1
+            new = [l.strip() for l in open(tree / f"{dim}d" / "proj" / name / "app.f90").read().splitlines()]
+            old = [l.strip() for l in open(os.path.join(REF, f"{dim}d", "proj", name, "app.f90")).read().splitlines()]
+            a, b = new.index("subroutine app__main()"), new.index("end subroutine app__main")
+            main = new[a:b]
+            assert main[main.index("call init()") + 1] == "call wm_shim_set_mode(WM_SHIM_RESIDENT)"
+            # every reader of the host arrays inside the loop is preceded by the sync, every writer is bracketed
+            for i, l in enumerate(main):
+                if re.match(r"call (io__ptcl|io__orb|mom_calc__accl|save_restart)\(", l):
+                    assert main[i - 1] == sync, (name, l)
+                if l in ("call inject()", "call relocate()"):
+                    assert main[i - 1] == sync and main[i + 1] == "call wm_shim_host_modified()", (name, l)
+            assert sum(l == sync for l in main) == sum(bool(re.match(r"call (io__ptcl|io__orb|mom_calc__accl|save_restart)\(|"
+                                                                         r"call (inject|relocate)\(\)", l)) for l in main)
+            assert ("call inject()" in main) == (name == "shock")
+            # the five calls of the time loop are untouched, and outside app__main only the `use` and the comm_init line were added
+            removed = [l for l in old if l not in new]
+            assert removed == [], (name, removed)
+            outside = new[:a] + new[b:]
+            extra = [l for l in outside if l not in old]
+            assert len(extra) == 3 and extra[0].startswith("use wuming_b200_c, only:") and extra[1] == "WM_SHIM_RESIDENT" \
+                and extra[2].startswith("call wm_shim_comm_init("), (name, extra)
+    assert n_drivers == 7

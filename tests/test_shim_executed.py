@@ -168,8 +168,61 @@ def test_moments_cross_once():
     del D.log[:]
     w.mom_calc()
     R.mom_calc()                                          # mom_calc__accl + mom_calc__nvt + bc__mom, as the drivers call them
-    assert D.log == [("wm_mom_calc", 2, NX + 1)]          # accl only records the range, bc__mom is folded in on the device
+    # default mode: the host arrays may have been edited since the sort, so they travel; then accl only records the range and
+    # bc__mom is folded in on the device: ONE compute call, and mom is all that comes back
+    assert D.log == [("wm_upload", ("up", "np2", "cumcnt", "uf")), ("wm_mom_calc", 2, NX + 1)]
     assert np.array_equal(R.arr("mom"), w.arr("mom"))
+
+
+def test_moments_after_the_driver_edited_the_host_arrays():
+    """the shock driver's order: sort__bucket, inject() / relocate() on the HOST arrays, then the moment block, then the next
+    particle__solv.  In resident mode nothing travels for the moments unless the driver said it edited the arrays
+    (wm_shim_host_modified) -- then they do, and the moments are those of the edited state"""
+    w = make_world3(NX, NY, NZ, N0)
+    D, R = shim_world(3, w)
+    L = R.ranks[0]
+    L.call("wm_shim_set_mode", 1)
+    R.step()
+    w.step()
+    del D.log[:]
+    R.mom_calc()
+    w.mom_calc()
+    assert D.log == [("wm_mom_calc", 2, NX + 1)] and np.array_equal(R.arr("mom"), w.arr("mom"))      # resident: no transfer but mom
+    # the driver's host-side edit: bring the state back, drop the last particle of every pencil, say so
+    L.call("wm_shim_sync_to_host", R.arr("up"), R.arr("uf"), R.arr("np2"), R.arr("cumcnt"))
+    for a in (R, w):
+        cc, n2 = a.arr("cumcnt"), a.arr("np2")
+        last = cc[..., -1].copy()
+        n2[...] = n2 - 1
+        cc[...] = np.minimum(cc, (last - 1)[..., None])
+    L.call("wm_shim_host_modified")
+    del D.log[:]
+    R.mom_calc()
+    w.mom_calc()
+    assert D.log == [("wm_upload", ("up", "np2", "cumcnt", "uf")), ("wm_mom_calc", 2, NX + 1)]
+    assert np.array_equal(R.arr("mom"), w.arr("mom"))
+    assert abs(R.arr("mom")[:, 1:-1, 1:-1, 1:-1, 0].sum() - w.arr("np2").sum()) < 1e-9 * w.arr("np2").sum()
+
+
+def test_sync_to_host_downloads_once_per_step():
+    """resident mode with several outputs firing in the same step (io__ptcl, io__orb, the moment block, save_restart all call
+    wm_shim_sync_to_host in a patched driver): the first call brings the state back, the others find it current"""
+    w = make_world3(NX, NY, NZ, N0)
+    D, R = shim_world(3, w)
+    L = R.ranks[0]
+    L.call("wm_shim_set_mode", 1)
+    R.step()
+    w.step()
+    del D.log[:]
+    for _ in range(3):
+        L.call("wm_shim_sync_to_host", R.arr("up"), R.arr("uf"), R.arr("np2"), R.arr("cumcnt"))
+    assert D.names() == ["wm_download"]
+    same_state(R, w, "after the first sync")
+    R.step()
+    w.step()
+    L.call("wm_shim_sync_to_host", R.arr("up"), R.arr("uf"), R.arr("np2"), R.arr("cumcnt"))
+    assert D.names().count("wm_download") == 2
+    same_state(R, w, "after the next step's sync")
 
 
 def test_shock_source_marshalling():

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """make_reference_patch.py -- the build-system side of the drop-in, as a patch a maintainer applies to a WumingPIC checkout.
 
-    python tools/make_reference_patch.py --ref /path/to/WumingPIC [--out wuming_b200.patch] [--install]
+    python tools/make_reference_patch.py --ref /path/to/WumingPIC [--out wuming_b200.patch] [--install] [--resident]
 
 Reads the checkout's Makefiles and drivers WHERE THEY LIE, derives the edited versions mechanically and writes a unified diff
 (nothing of the reference is stored in this repository; the patch is made from the maintainer's own tree, so it follows whatever
@@ -16,6 +16,14 @@ version they have).  With --install it also copies fortran/wuming_b200_c.f90 and
                                  compiling their own boundary_*.f90 (the shim provides those modules)
   {2d,3d}/proj/*/app.f90         one line after mpi_set__init: call wm_shim_comm_init(nproc, nproc_j, nproc_k, nrank, ncomw)
                                  (+ its `use`): the rank grid and the communicator for the device side
+
+  --resident (optional)          the fast mode: the state stays on the GPU between time steps (WM_SHIM_RESIDENT) and the five calls of the
+                                 loop run the fused kernel + lazy sort.  In app__main: `call wm_shim_set_mode(WM_SHIM_RESIDENT)` after
+                                 init(), `call wm_shim_sync_to_host(up,uf,np2,cumcnt)` in front of everything that reads the host arrays
+                                 (io__ptcl, io__orb, the moment / energy block, save_restart -- one download per step however many of
+                                 them fire), and in the shock drivers the same in front of inject() / relocate() with
+                                 `call wm_shim_host_modified()` behind them (they edit the host arrays).  Without it the default
+                                 WM_SHIM_SYNC_EVERY_CALL mode needs no further edit and hands every result back after every call.
 
 Everything else -- main.f90, the time loops, JSON config, paraio / mpiio output, utils -- is untouched: main.out runs as before,
 with the kernels behind the five calls of the time loop on the GPU.  tests/test_reference_patch.py applies the patch to a copy of
@@ -70,8 +78,19 @@ def edit_proj_makefile(text):
     return text
 
 
-def edit_app(text, dim):
-    text, n = re.subn(rf"^([ \t]*)use wuming{dim}d[ \t]*$", rf"\g<0>\n\1use wuming_b200_c, only: wm_shim_comm_init", text, count=1, flags=re.M | re.I)
+USE_PLAIN = "use wuming_b200_c, only: wm_shim_comm_init"
+USE_RESIDENT = ("use wuming_b200_c, only: wm_shim_comm_init, wm_shim_set_mode, wm_shim_sync_to_host, wm_shim_host_modified, &\n"
+                "{ind}                         WM_SHIM_RESIDENT")
+SYNC = "call wm_shim_sync_to_host(up,uf,np2,cumcnt)"
+READERS = ("io__ptcl", "io__orb", "mom_calc__accl", "save_restart")       # mom_calc__accl opens the moment / io__mom / energy block
+WRITERS = ("inject", "relocate")                                           # shock drivers: edit up, np2, cumcnt, uf, nxe on the host
+
+
+def edit_app(text, dim, resident=False):
+    def use_line(m):
+        extra = USE_RESIDENT.format(ind=m.group(1)) if resident else USE_PLAIN
+        return f"{m.group(0)}\n{m.group(1)}{extra}"
+    text, n = re.subn(rf"^([ \t]*)use wuming{dim}d[ \t]*$", use_line, text, count=1, flags=re.M | re.I)
     if n != 1:
         raise SystemExit("app.f90: `use wuming?d` not found")
     grid = "nproc,nproc_j,nproc_k" if dim == 3 else "nproc,nproc,1"
@@ -79,10 +98,24 @@ def edit_app(text, dim):
                       flags=re.M | re.I)
     if n != 1:
         raise SystemExit("app.f90: call mpi_set__init not found")
-    return text
+    if not resident:
+        return text
+    # the remaining edits live inside app__main
+    m = re.search(r"^[ \t]*subroutine app__main\b.*?^[ \t]*end subroutine app__main\b", text, re.M | re.S | re.I)
+    if not m:
+        raise SystemExit("app.f90: app__main not found")
+    body = m.group(0)
+    body, n = re.subn(r"^([ \t]*)call init\(\)[ \t]*$", r"\g<0>\n\1call wm_shim_set_mode(WM_SHIM_RESIDENT)", body, count=1, flags=re.M | re.I)
+    if n != 1:
+        raise SystemExit("app.f90: call init() not found in app__main")
+    for name in READERS:
+        body = re.sub(rf"^([ \t]*)(call {name}\()", rf"\1{SYNC}\n\1\2", body, flags=re.M | re.I)
+    for name in WRITERS:
+        body = re.sub(rf"^([ \t]*)(call {name}\(\))[ \t]*$", rf"\1{SYNC}\n\1\2\n\1call wm_shim_host_modified()", body, flags=re.M | re.I)
+    return text[:m.start()] + body + text[m.end():]
 
 
-def plan(ref):
+def plan(ref, resident=False):
     """[(relative path, new text)]"""
     out = [("common.mk", edit_common_mk(open(os.path.join(ref, "common.mk")).read()))]
     for dim in (2, 3):
@@ -93,13 +126,13 @@ def plan(ref):
             mk, app = os.path.join(proj, name, "Makefile"), os.path.join(proj, name, "app.f90")
             if os.path.exists(mk) and os.path.exists(app):
                 out.append((f"{dim}d/proj/{name}/Makefile", edit_proj_makefile(open(mk).read())))
-                out.append((f"{dim}d/proj/{name}/app.f90", edit_app(open(app).read(), dim)))
+                out.append((f"{dim}d/proj/{name}/app.f90", edit_app(open(app).read(), dim, resident)))
     return out
 
 
-def make_patch(ref):
+def make_patch(ref, resident=False):
     chunks = []
-    for rel, new in plan(ref):
+    for rel, new in plan(ref, resident):
         old = open(os.path.join(ref, rel)).read()
         chunks += list(difflib.unified_diff(old.splitlines(True), new.splitlines(True), "a/" + rel, "b/" + rel, n=2))
     return "".join(chunks)
@@ -110,8 +143,9 @@ def main():
     ap.add_argument("--ref", required=True, help="a WumingPIC checkout")
     ap.add_argument("--out", default="wuming_b200.patch")
     ap.add_argument("--install", action="store_true", help="also copy the shim sources into {2d,3d}/common/ of the checkout")
+    ap.add_argument("--resident", action="store_true", help="device-resident time loop: mode switch + sync points in app__main")
     a = ap.parse_args()
-    text = make_patch(a.ref)
+    text = make_patch(a.ref, a.resident)
     with open(a.out, "w") as f:
         f.write(text)
     print(f"wrote {a.out}: {text.count(chr(10) + '+++ ')+ (1 if text.startswith('--- ') else 0)} files; apply with  patch -p1 -d {a.ref} < {a.out}")
