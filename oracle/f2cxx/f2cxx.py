@@ -485,6 +485,8 @@ class Subroutine:
 class Module:
     def __init__(self, name):
         self.name, self.syms, self.order, self.subs, self.uses = name, {}, [], [], []
+        self.private_default = False    # a bare `private` statement: only the names of `public ::` lists are visible to users
+        self.public = set()
         self.types = {}         # bind(c) derived types: name -> [Sym] in declaration order
         self.cfuncs = {}        # bind(c) interface functions: Fortran name -> Subroutine (with .cname)
 
@@ -601,6 +603,11 @@ def parse_module(text, fname, skip=()):
             i += 1
             continue
         if st.startswith("implicit") or st.startswith("private") or st.startswith("public"):
+            if st == "private":
+                mod.private_default = True
+            mp_ = re.match(r"public\s*(?:::)?\s*(.+)$", st)
+            if mp_:
+                mod.public |= {x.strip() for x in mp_.group(1).split(",")}
             i += 1
             continue
         if st == "contains":
@@ -680,6 +687,7 @@ class Gen:
         self.known_subs = known_subs            # name -> Subroutine (all translated modules)
         self.out = []
         self.tmp = 0
+        self.renames = {}
 
     # ---- scopes ----
     def lookup(self, name):
@@ -688,7 +696,7 @@ class Gen:
         if name in self.mod.syms:
             return self.mod.syms[name]
         for u in self.used_modules:
-            if name in u.syms:
+            if name in u.syms and (not u.private_default or name in u.public):
                 return u.syms[name]
         return None
 
@@ -1084,8 +1092,8 @@ class Gen:
                 if "parameter" in s.attrs:
                     return f"f90::tmp({mangle(e[1])}).ptr()"
                 return f"&{mangle(e[1])}"
-            if e[1] in self.known_subs:
-                return e[1]                       # a procedure passed as an actual argument
+            if self.renames.get(e[1], e[1]) in self.known_subs:
+                return self.renames.get(e[1], e[1])     # a procedure passed as an actual argument
             if e[1] in MPI_CONSTANTS:
                 return f"f90::tmp({MPI_CONSTANTS[e[1]]}).ptr()"
             raise TranslateError(f"{self.W(no)}: unknown actual argument {e[1]!r}")
@@ -1100,6 +1108,8 @@ class Gen:
         if not m:
             raise TranslateError(f"{self.W(no)}: cannot parse {st!r}")
         name = m.group(1)
+        if self.lookup(name) is None:
+            name = self.renames.get(name, name)
         args = [a.strip() for a in _split_top(m.group(3), ",")] if m.group(3) and m.group(3).strip() else []
         if name == "ieee_set_rounding_mode":
             mode = args[0]
@@ -1141,8 +1151,10 @@ class Gen:
                 raise TranslateError(f"{self.W(no)}: {name} takes {len(callee.args)} arguments, {len(args)} given")
             # assumed-shape dummies take a trailing extent each
             extra = []
-            for a, d in zip(args, callee.args):
+            for k_, (a, d) in enumerate(zip(args, callee.args)):
                 ds = callee.syms[d]
+                if ds.proc_sig == []:            # `external` dummy (implicit interface): any procedure goes
+                    ptrs[k_] = f"(void (*)())({ptrs[k_]})"
                 if ds.rank > 0 and ds.deferred and "allocatable" not in ds.attrs:
                     e = parse_expr(a, self.W(no))
                     if e[0] != "name" or not self.is_array(e[1]):
@@ -1409,7 +1421,12 @@ class Gen:
         self.ind += 1
         self.emit(f"using namespace mod_{self.mod.name};")
         for u in self.used_modules:
-            self.emit(f"using namespace mod_{u.name};")
+            if u.private_default:       # only what the module makes public is visible (its private variables may share names with ours)
+                for nm in u.order:
+                    if nm in u.public:
+                        self.emit(f"using mod_{u.name}::{mangle(nm)};")
+            else:
+                self.emit(f"using namespace mod_{u.name};")
         if sub.kind == "subroutine":
             self.emit("F90_ENTRY_BEGIN")             # functions are only called from translated code: exceptions pass through
         if any("ieee_arithmetic" in u for u in sub.uses + self.mod.uses):
@@ -1482,10 +1499,13 @@ class Gen:
     def gen_module(self, mod, fname):
         self.mod, self.fname, self.sub, self.ind = mod, fname, None, 0
         self.used_modules = []
+        self.renames = {}          # `use m, local => name`: the local name of a procedure of another translated module
         for u in mod.uses:
             m = re.match(r"use\s*(?:,\s*intrinsic\s*::)?\s*([a-z_]\w*)", u)
             if m and m.group(1) in self.modules:
                 self.used_modules.append(self.modules[m.group(1)])
+                for local, remote in re.findall(r"([a-z_]\w*)\s*=>\s*([a-z_]\w*)", u):
+                    self.renames[local] = remote
         self.emit(f"// ---- module {mod.name}  <-  {fname}")
         # bind(c) derived types are the C structs of the same name; bind(c) interface functions are C prototypes (`value` dummies by
         # value, everything else by address)

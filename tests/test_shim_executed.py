@@ -285,3 +285,36 @@ def test_a_non_root_rank_of_a_y_slab_grid():
     assert (f["nproc_j"], f["nproc_k"], f["rank_j"], f["rank_k"]) == (4, 1, 2, 0)
     assert (f["nygs"], f["nyge"], f["nys"], f["nye"], f["nzs"], f["nze"]) == (2, 17, 10, 13, 2, NZ + 1)
     assert D.log[1] == ("wm_comm_init", 4, 2)
+
+
+# ---- the reference's own main loop, patched for the resident mode, on top of the shim ---------------------------------------------
+@pytest.mark.parametrize("setup,dim", [("weibel", 3), ("weibel", 2), ("reconnection", 3), ("reconnection", 2), ("shock", 3), ("shock", 2)])
+def test_patched_main_loop_of_every_driver(setup, dim):
+    """app__main of proj/<setup>/app.f90 after `call init()` -- the text of the reference, with the edits of
+    tools/make_reference_patch.py --resident -- translated and run for 12 steps with outputs every 3 / 4 / 5 steps: every record an
+    output procedure was handed is the state of ITS step (checksums of np2, uf, the particles and the moments against the oracle
+    stepped through the same schedule), although the state left the device only at those steps; in the shock loop the host-side
+    inject() / relocate() see the current state and their edits reach the device before the next push"""
+    from oracle.f2cxx import mainloop_harness
+    from tests.mainloop_util import MainLoop, assert_records_match
+    if mainloop_harness.build(setup, dim) is None:
+        pytest.skip("the main-loop library is not built and /root/reference is absent")
+    bc = {"weibel": 0, "reconnection": 1, "shock": 2}[setup]
+    w = make_world3(NX, NY, NZ, N0, bc=bc) if dim == 3 else make_world2(NX, NY, N0, bc=bc)
+    D = StubDevice()
+    ml = MainLoop(setup, dim, w, max_it=12, intvl_ptcl=5, intvl_orb=4, intvl_mom=3, intvl_expand=2, u0=-0.2 if setup == "shock" else 0.0)
+    assert D.names() == ["wm_create"]
+    got = ml.run()
+    want = ml.expected()
+    assert_records_match(got, want)
+    names = D.names()
+    if setup == "shock":
+        # the host arrays are edited every step: one download (in front of inject(); the later syncs of the step and the final
+        # save_restart find the host current) and one upload (in front of the moment block if there is one, else of the next push)
+        # uploads: the initial state, then once behind each of the 12 edits that something on the device still follows (the pushes
+        # of steps 2 .. 12 and the moment block of step 12)
+        assert names.count("wm_download") == 12 and names.count("wm_upload") == 13
+    else:
+        # steps with an output: 3 4 5 6 8 9 10 12 -> eight downloads, and the final save_restart finds the host current; ONE upload
+        assert names.count("wm_download") == 8 and names.count("wm_upload") == 1
+    assert names.count("wm_mom_calc") == 4

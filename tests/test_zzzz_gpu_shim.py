@@ -124,3 +124,29 @@ def test_moments_through_the_shim(real_backend):
         assert abs(got[inner][..., 0].sum() - w.arr("np2").sum()) < 1e-9 * w.arr("np2").sum()
     finally:
         destroy(real_backend, R)
+
+
+@pytest.mark.parametrize("setup,dim", [("weibel", 3), ("reconnection", 2), ("shock", 3)])
+def test_patched_main_loop_on_the_gpu(real_backend, setup, dim):
+    """the reference's OWN main loop (app__main after `call init()`, with the edits of tools/make_reference_patch.py --resident),
+    translated, on top of the shim and the real library: 12 steps device-resident, outputs every 3 / 4 / 5 steps -- every record an
+    output procedure is handed is the oracle's state of that step (checksums; the CPU twin with exact transfer counts is
+    tests/test_shim_executed.py::test_patched_main_loop_of_every_driver)"""
+    from oracle.f2cxx import mainloop_harness
+    from tests.mainloop_util import MainLoop, assert_records_match
+    if mainloop_harness.build(setup, dim) is None:
+        pytest.skip("the main-loop library is not built and /root/reference is absent")
+    bc = {"weibel": 0, "reconnection": 1, "shock": 2}[setup]
+    w = make_world3(NX, 8, 6, 6, bc=bc) if dim == 3 else make_world2(NX, 14, 8, bc=bc)
+    ml = MainLoop(setup, dim, w, max_it=12, intvl_ptcl=5, intvl_orb=4, intvl_mom=3, intvl_expand=2, u0=0.3 if setup == "shock" else 0.0)
+    try:
+        got = ml.run()
+        want = ml.expected()
+        assert_records_match(got, want, rtol=1e-7)
+    finally:
+        f = ml.R.L.f2cxx_modvar__wuming_b200_c__ctx
+        f.restype = C.c_void_p
+        ctx = C.c_void_p.from_address(f())
+        if ctx.value:
+            real_backend[0].wm_destroy(ctx)
+            ctx.value = None
