@@ -75,7 +75,8 @@ def _standins(dim):
              "    allocate(uf(6,nxgs-2:nxge+2,nys-2:nye+2)); allocate(up(ndim,np,nys:nye,nsp))\n"
              "    allocate(gp(ndim,np,nys:nye,nsp)); allocate(mom(7,nxgs-1:nxge+1,nys-1:nye+1,nsp))")
     psum = _pencil_loops(dim, "      do ii = 1, np2(@P)\n        s = s + up(1,ii,@P) + 3d0*up(ndim-1,ii,@P)\n      enddo")
-    edit = _pencil_loops(dim, "      np2(@P) = np2(@P) - 1\n      do i = nxgs, nxge+1\n        cumcnt(i,@P) = min(cumcnt(i,@P), np2(@P))\n      enddo")
+    # the edit must not depend on the ORDER of the particles inside a cell (the device's order is deterministic but not the oracle's)
+    edit = _pencil_loops(dim, "      do ii = 1, np2(@P)\n        up(ndim-1,ii,@P) = 0.999d0*up(ndim-1,ii,@P)\n      enddo")
     momin = ":,nxgs:nxge,nys:nye,nzs:nze,:" if dim == 3 else ":,nxgs:nxge,nys:nye,:"
     return f"""
   subroutine harness__alloc(ndim_in,np_in,nsp_in,nxgs_in,nxge_in,nygs_in,nyge_in,nzgs_in,nzge_in,nys_in,nye_in,nzs_in,nze_in)
@@ -130,15 +131,15 @@ def _standins(dim):
   subroutine finalize()
   end subroutine finalize
 
-  ! stand-ins for the shock driver's host-side particle source: they EDIT the host arrays (the last particle of every pencil goes),
+  ! stand-ins for the shock driver's host-side particle source: they EDIT the host arrays (uz of every particle shrinks by 0.1 %),
   ! which is all that matters to the shim -- the state must have been brought back before, and must travel again afterwards
   subroutine inject()
-    integer :: isp, {jk}, i
+    integer :: isp, {jk}, ii
     write(hunit,*) {MAGIC:.3e}_8, 6d0, 0d0, 2d0, 1d0*sum(np2), particle_checksum()
 {edit}  end subroutine inject
 
   subroutine relocate()
-    integer :: isp, {jk}, i
+    integer :: isp, {jk}, ii
     write(hunit,*) {MAGIC:.3e}_8, 7d0, 0d0, 2d0, 1d0*sum(np2), particle_checksum()
 {edit}  end subroutine relocate
 """.replace("@MOMIN", momin)

@@ -83,9 +83,10 @@ class MainLoop:
 
     def host_edit(self):
         """what the harness's inject() / relocate() stand-ins do to the host arrays"""
-        n2, cc = self.w.arr("np2"), self.w.arr("cumcnt")
-        n2[...] = n2 - 1
-        cc[...] = np.minimum(cc, n2[..., None])
+        w = self.w
+        uz = w.arr("up")[..., w.ndim - 2]
+        m = active_mask(w.arr("np2"), w.np)
+        uz[m] = 0.999 * uz[m]
 
     def expected(self):
         """step the oracle through the same schedule -> [(kind, it, values)]"""
