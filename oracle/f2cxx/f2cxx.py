@@ -394,6 +394,8 @@ def parse_type(spec, where):
         return "type:" + m.group(1)
     if s in ("character(kind=c_char)", "character(c_char)"):
         return "cchar"
+    if re.fullmatch(r"character\(len=\d+\)", s):
+        return "cchar"         # a fixed-length character LOCAL is accepted as a declaration (a driver's file-name buffer); any use of it is not
     raise TranslateError(f"{where}: unsupported type {spec!r}")
 
 

@@ -214,3 +214,162 @@ SETUPS = [("weibel", 3), ("weibel", 2), ("reconnection", 3), ("reconnection", 2)
 if __name__ == "__main__":
     for s_, d_ in SETUPS:
         print(build(s_, d_, force="--force" in sys.argv))
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# the WHOLE driver behind load_config: init() and app__main, verbatim, on top of the shim (Weibel)
+# ------------------------------------------------------------------------------------------------------------------------------
+def _standin_from_call(stmt, name, real_names=(), array_real=("up", "gp", "uf", "q", "r"), array_int=("np2", "cumcnt")):
+    """a do-nothing harness procedure with the dummy list of the driver's own `call name(...)` statement (kinds by actual name)"""
+    m = re.search(rf"call\s+{name}\s*\((.*)\)", stmt, re.S)
+    acts = [a.strip() for a in m.group(1).replace("&", " ").split(",") if a.strip()]
+    dums, decl = [], []
+    for k, a in enumerate(acts):
+        d = f"d{k + 1}"
+        dums.append(d)
+        if a in array_real:
+            decl.append(f"    real(8) :: {d}(*)")
+        elif a in array_int:
+            decl.append(f"    integer :: {d}(*)")
+        elif a in real_names:
+            decl.append(f"    real(8) :: {d}")
+        else:
+            decl.append(f"    integer :: {d}")
+    return f"  subroutine {name}({', '.join(dums)})\n" + "\n".join(decl) + f"\n  end subroutine {name}\n"
+
+
+def _statement(text, first):
+    """the (continued) statement starting at the first line matching `first`"""
+    lines = text.splitlines()
+    i = next(k for k, l in enumerate(lines) if re.search(first, l))
+    j = i
+    while lines[j].rstrip().endswith("&") or (j + 1 < len(lines) and lines[j + 1].lstrip().startswith("&")):
+        j += 1
+    return "\n".join(lines[i:j + 1])
+
+
+def assemble_full(dim):
+    """module app of {dim}d/proj/weibel: the driver's init(), set_initial_condition, set_particle_ids, get_global_cumsum,
+    energy_history and app__main (from `call init()` on) VERBATIM from the patched file; the declarations (app_harness's), the
+    configuration entry, the I/O procedures and mpi_set__init by the harness"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, HERE)
+    import make_reference_patch as mp
+    import app_harness as ah
+    a = ah.APPS[f"weibel{dim}d"]
+    rel = a["file"]
+    patched = mp.edit_app(open(os.path.join(REF, rel)).read(), dim, resident=True)
+    lines = patched.splitlines()
+    i = next(k for k, l in enumerate(lines) if re.match(r"\s*use boundary_", l))
+    j = i
+    while lines[j].rstrip().endswith("&"):
+        j += 1
+    use_bc = "\n".join(lines[i:j + 1])
+    init = ah.procedure(patched, "init")
+    reals = ("delx", "delt", "c", "wpe", "wpi", "wge", "wgi", "vti", "vte")
+    standins = [_standin_from_call(_statement(init, r"call io__init"), "io__init", reals),
+                _standin_from_call(_statement(init, r"call io__input"), "io__input", reals),
+                _standin_from_call(_statement(init, r"call save_param"), "save_param", reals)]
+    yz = "nys = nygs; nye = nyge" + ("; nzs = nzgs; nze = nzge; nrank_j = 0; nrank_k = 0" if dim == 3 else "")
+    mpi_args = "a1,a2,a3,a4,a5,a6,a7" if dim == 3 else "a1,a2,a3"
+    cfg = [c for c, _ in a["config"]]
+    ints = [c for c, t in a["config"] if t == "i"]
+    main = ah.procedure(patched, "app__main").splitlines()
+    k0 = next(k for k, l in enumerate(main) if re.match(r"\s*call init\(\)", l))
+    momin = ":,nxgs:nxge,nys:nye,nzs:nze,:" if dim == 3 else ":,nxgs:nxge,nys:nye,:"
+    jk = "j, k" if dim == 3 else "j"
+    psum = _pencil_loops(dim, "      do ii = 1, np2(@P)\n        s = s + up(1,ii,@P) + 3d0*up(ndim-1,ii,@P)\n      enddo")
+    out = [f"! ASSEMBLED by oracle/f2cxx/mainloop_harness.py (assemble_full) from {rel}, patched by tools/make_reference_patch.py --resident:",
+           "! init(), the loaders, energy_history and app__main are the driver's text; declarations, configuration and I/O by the harness",
+           "module app", "  use particle", "  use field", "  use sort", "  use mom_calc", "  use wuming_b200_c", use_bc, "  implicit none",
+           a["decl"],
+           "  integer :: mnpi = 4, jup = 0, jdown = 0, kup = 0, kdown = 0, nup = 0, ndown = 0, nstat(6)",
+           "  integer :: max_it, intvl_ptcl, intvl_orb, intvl_mom, verbose",
+           "  integer :: restart_file = 0, hunit = 10, datadir = 0, param = 0",
+           "  logical :: restart = .false.", "  real(8) :: max_elapsed", "contains", "",
+           f"  subroutine harness__configure({', '.join(c + '_in' for c in cfg)}, {', '.join(r + '_in' for r in a['rank'])})",
+           f"    integer, intent(in) :: {', '.join(c + '_in' for c in ints + a['rank'])}",
+           f"    real(8), intent(in) :: {', '.join(c + '_in' for c, t in a['config'] if t == 'r')}"]
+    out += [f"    {c} = {c}_in" for c in cfg + a["rank"]]
+    out.append(ah.block(open(os.path.join(REF, rel)).read(), a["sizes"][1], a["sizes"][2], inside=a["sizes"][0]))
+    out += ["  end subroutine harness__configure", "",
+            f"  subroutine mpi_set__init({mpi_args})          ! one rank: the whole box, every neighbour is this rank",
+            f"    integer, intent(in) :: {mpi_args}", f"    {yz}; nrank = 0", "  end subroutine mpi_set__init", "",
+            "  subroutine init_random_seed()", "  end subroutine init_random_seed", ""] + standins + [f"""
+  function get_etime() result(t)
+    real(8) :: t
+    t = 0d0
+  end function get_etime
+
+  function particle_checksum() result(s)
+    real(8) :: s
+    integer :: isp, {jk}, ii
+    s = 0d0
+{psum}  end function particle_checksum
+
+  subroutine io__ptcl(a, b, c_, it)
+    real(8), intent(in) :: a(*), b(*)
+    integer, intent(in) :: c_(*), it
+    write(hunit,*) {MAGIC:.3e}_8, 1d0, 1d0*it, 3d0, 1d0*sum(np2), sum(uf), particle_checksum()
+  end subroutine io__ptcl
+
+  subroutine io__orb(a, b, c_, it)
+    real(8), intent(in) :: a(*), b(*)
+    integer, intent(in) :: c_(*), it
+    write(hunit,*) {MAGIC:.3e}_8, 2d0, 1d0*it, 3d0, 1d0*sum(np2), sum(uf), particle_checksum()
+  end subroutine io__orb
+
+  subroutine io__mom(a, b, it)
+    real(8), intent(in) :: a(*), b(*)
+    integer, intent(in) :: it
+    write(hunit,*) {MAGIC:.3e}_8, 3d0, 1d0*it, 2d0, sum(mom({momin})), sum(uf)
+  end subroutine io__mom
+
+  subroutine save_restart(a, b, c_, n1, n2, it, fname)
+    real(8), intent(in) :: a(*), b(*)
+    integer, intent(in) :: c_(*), n1, n2, it, fname
+    write(hunit,*) {MAGIC:.3e}_8, 5d0, 1d0*it, 3d0, 1d0*sum(np2), sum(uf), particle_checksum()
+  end subroutine save_restart
+
+  subroutine finalize()
+  end subroutine finalize
+""", init]
+    for p_ in ("set_initial_condition", "set_particle_ids", "get_global_cumsum", "energy_history"):
+        out.append(ah.procedure(patched, p_))
+    out += ["  subroutine harness__main()", "    integer :: it", "    real(8) :: etime, etime0"] + main[k0:-1] + \
+           ["  end subroutine harness__main", "end module app"]
+    return "\n".join(out) + "\n"
+
+
+def build_full(dim, force=False):
+    """-> path of oracle/_ref/libwuming_full_weibel{dim}d.so (None without /root/reference and without a prebuilt library)"""
+    lib = os.path.join(OUT, f"libwuming_full_weibel{dim}d.so")
+    ref_file = os.path.join(REF, f"{dim}d", "proj", "weibel", "app.f90")
+    if not os.path.exists(ref_file):
+        return lib if os.path.exists(lib) else None
+    os.makedirs(OUT, exist_ok=True)
+    shim = [os.path.join(ROOT, "fortran", "wuming_b200_c.f90"), os.path.join(ROOT, "fortran", f"wuming_b200_shim{dim}d.f90")]
+    deps = shim + [ref_file, os.path.join(ROOT, "tools", "make_reference_patch.py")] + \
+        [os.path.join(HERE, f) for f in ("f2cxx.py", "f90rt.h", "f90rt.cpp", "shim_rt.cpp", "mainloop_harness.py", "app_harness.py")]
+    h = hashlib.sha1(b"full")
+    for f in deps:
+        h.update(open(f, "rb").read())
+    stamp_file = lib + ".stamp"
+    if not force and os.path.exists(lib) and os.path.exists(stamp_file) and open(stamp_file).read().strip() == h.hexdigest():
+        return lib
+    sys.path.insert(0, HERE)
+    import f2cxx
+    src = assemble_full(dim)
+    with open(os.path.join(OUT, f"full_weibel{dim}d.f90"), "w") as f:
+        f.write(src)
+    files = [(os.path.relpath(f, ROOT), open(f).read()) for f in shim] + [(f"full_weibel{dim}d.f90 <- {dim}d/proj/weibel/app.f90", src)]
+    cpp = os.path.join(OUT, f"full_weibel{dim}d.cpp")
+    with open(cpp, "w") as f:
+        f.write(f2cxx.translate(files, skip=("wm_check",)))
+    r = subprocess.run([CXX, "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-DF90_BOUNDS", "-I", HERE, "-o", lib, cpp,
+                        os.path.join(HERE, "f90rt.cpp"), os.path.join(HERE, "shim_rt.cpp")], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed on the translated driver:\n" + r.stderr[-4000:])
+    with open(stamp_file, "w") as f:
+        f.write(h.hexdigest())
+    return lib

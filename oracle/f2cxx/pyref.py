@@ -354,9 +354,11 @@ class RefApp:
     inputs (`uniform_rand`, `normal_rand`, `shuffle` of utils/wuming_utils.f90) are handed out IN CALL ORDER from the sequences
     given to feed(); running out of values raises."""
 
-    def __init__(self, name):
+    def __init__(self, name, path=None):
+        """path: another library assembled around the same driver (mainloop_harness.build_full: the whole init() + main loop on top
+        of the ISO_C_BINDING shim) -- same module `app`, same configuration and random-input hooks"""
         from . import app_harness
-        path = app_harness.build(name)
+        path = path or app_harness.build(name)
         if path is None:
             raise RuntimeError("the translated driver procedures are not built and /root/reference is absent")
         self.name, self.cfg = name, app_harness.APPS[name]

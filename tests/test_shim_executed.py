@@ -318,3 +318,99 @@ def test_patched_main_loop_of_every_driver(setup, dim):
         # steps with an output: 3 4 5 6 8 9 10 12 -> eight downloads, and the final save_restart finds the host current; ONE upload
         assert names.count("wm_download") == 8 and names.count("wm_upload") == 1
     assert names.count("wm_mom_calc") == 4
+
+
+# ---- the whole Weibel driver behind load_config: init() + app__main, the reference's text, on top of the shim ------------------------
+def full_driver(dim, nz=4, max_it=10):
+    """configured like 3d/proj/weibel/config_sample.json (small): harness__configure = the "parameter" section + the size block of
+    load_config; the random inputs of the loader are the oracle's keyed draws for the same particles; -> (RefApp, oracle world)"""
+    from oracle.f2cxx import mainloop_harness
+    from tests.test_ref_driver_procs import SEED, WEIBEL_CFG, rows_of
+    lib = mainloop_harness.build_full(dim)
+    if lib is None:
+        pytest.skip("the full-driver library is not built and /root/reference is absent")
+    cfg = dict(WEIBEL_CFG)
+    if dim == 3:
+        cfg.update(num_process_j=1, n_z=nz)
+    A = pyref.RefApp(f"weibel{dim}d", path=lib)
+    nx, ny, n0 = cfg["n_x"], cfg["n_y"], cfg["n_ppc"]
+    A.configure([0, 2, ny + 1] if dim == 2 else [0, 2, ny + 1, 2, nz + 1, 0, 0], **cfg)
+    for k, v in dict(max_it=max_it, intvl_ptcl=4, intvl_orb=1000, intvl_mom=3, verbose=0).items():
+        A.scalar(k, C.c_int).value = v
+    A.scalar("max_elapsed", C.c_double).value = 1e30
+    uni, nrm = [], {1: [], 2: []}
+    for j, k, row in rows_of(dim, ny, nz):
+        for ii in range(1, n0 * nx + 1):
+            a, b = pyoracle.philox_uniform2(SEED, row, ii, 0)
+            uni += [a] if dim == 2 else [a, b]
+            for isp in (1, 2):
+                nrm[isp] += list(pyoracle.keyed_normals(SEED, row, ii, isp, 0))
+    A.feed(uniform=uni, normal=nrm[1] + nrm[2])
+    q, r, b0 = pyoracle.weibel_constants(n0, mass_ratio=cfg["mass_ratio"], sigma_e=cfg["sigma_e"], omega_pe=cfg["omega_pe"])
+    from oracle.pyoracle import World2, World3
+    npcap = n0 * nx * (5 if dim == 2 else 3)
+    w = World3(nx, ny, nz, npcap, q=q, r=r) if dim == 3 else World2(nx, ny, npcap, q=q, r=r)
+    w.load_weibel(n0, v_thi=cfg["v_thi"], v_the=cfg["v_the"], t_ani=cfg["t_ani"], b0=b0, seed=SEED)
+    return A, w, cfg
+
+
+@pytest.mark.parametrize("dim", [3, 2])
+def test_the_whole_weibel_driver_behind_load_config(dim):
+    """init() -- mpi_set__init, the patch's wm_shim_comm_init, allocation, constants, the module __init calls in the driver's order,
+    set_initial_condition + set_particle_ids, energy_history, gp = up -- and app__main's loop, all the reference's text (patched
+    --resident), on top of the shim: the device context appears inside the LAST __init with the driver's numbers, the load is the
+    oracle's load, and every output of 10 steps is the oracle's state of its step"""
+    from tests.mainloop_util import assert_records_match
+    from oracle.f2cxx import mainloop_harness as mh
+    D = StubDevice()
+    A, w, cfg = full_driver(dim)
+    A.call("harness__main")
+    assert A.leftover() == (0, 0, 0)                     # the loader consumed exactly the random inputs of its particles
+    names = D.names()
+    assert names[0] == "wm_create" and "wm_comm_init" not in names          # one rank: wm_shim_comm_init only recorded the grid
+    f = D.log[0][1]
+    nx, ny, n0 = cfg["n_x"], cfg["n_y"], cfg["n_ppc"]
+    assert (f["dim"], f["np"], f["nxgs"], f["nxge"], f["nygs"], f["nyge"]) == (dim, n0 * nx * (5 if dim == 2 else 3), 2, nx + 1, 2, ny + 1)
+    assert (f["nproc_j"], f["nproc_k"], f["rank_j"], f["rank_k"], f["bc_kind"]) == (1, 1, 0, 0, 0)
+    assert f["q"] == pytest.approx(list(w.q), rel=3e-16) and f["r"] == list(w.r) and f["gfac"] == 0.501 and f["delt"] == 1.0
+    # the records: MAGIC-framed ones from the output stand-ins; energy_history is the driver's own (its energy.dat records are unframed)
+    buf = (C.c_double * 100000)()
+    A.L.f90rt_captured.argtypes = [C.POINTER(C.c_double), C.c_int]
+    n = A.L.f90rt_captured(buf, len(buf))
+    v, got, i, energy = list(buf[:n]), [], 0, []
+    while i < n:
+        if v[i] != mh.MAGIC:
+            energy.append(v[i])
+            i += 1
+            continue
+        got.append((mh.KINDS[int(v[i + 1])], int(v[i + 2]), v[i + 4:i + 4 + int(v[i + 3])]))
+        i += 4 + int(v[i + 3])
+    # the oracle through the same schedule
+    from tests.util import active_mask
+
+    def sums():
+        up, m = w.arr("up"), active_mask(w.arr("np2"), w.np)
+        return [float(w.arr("np2").sum()), float(w.arr("uf").sum()), float((up[m][:, 0] + 3.0 * up[m][:, w.ndim - 2]).sum())]
+    want, e_want = [], [list(w.energy())]
+    interior = (slice(None),) + (slice(1, -1),) * dim
+    for it in range(1, 11):
+        w.step()
+        if it % 4 == 0:
+            want.append(("io__ptcl", it, sums()))
+        if it % 3 == 0:
+            w.mom_calc()
+            want.append(("io__mom", it, [float(w.arr("mom")[interior].sum()), float(w.arr("uf").sum())]))
+            e_want.append(list(w.energy()))
+    want.append(("save_restart", 11, sums()))
+    assert_records_match(got, want)
+    # energy_history ran on the host arrays at it0 and at every moment cadence: energy.dat records = (t, kinetic..., E, B, total)
+    rec = 6 if dim == 3 else 5
+    # the driver also `write`s the restart file name (one number, the step) before the final save_restart: the trailing value
+    assert len(energy) == rec * len(e_want) + 1 and energy[-1] == 11.0
+    for k, e in enumerate(e_want):
+        r_ = energy[rec * k:rec * (k + 1)]
+        tot = ((e[0] + e[1]) + e[2]) + e[3]
+        ref = [e[0], e[1], e[2], e[3], tot] if dim == 3 else [e[0] + e[1], e[2], e[3], tot]
+        assert r_[0] == 3.0 * k and r_[1:] == pytest.approx(ref, rel=1e-12)
+    # ONE upload (the first push); downloads at the output steps 3 4 6 8 9 and for the final save_restart after step 10
+    assert names.count("wm_upload") == 1 and names.count("wm_download") == 6

@@ -150,3 +150,48 @@ def test_patched_main_loop_on_the_gpu(real_backend, setup, dim):
         if ctx.value:
             real_backend[0].wm_destroy(ctx)
             ctx.value = None
+
+
+def test_the_whole_weibel_driver_on_the_gpu(real_backend):
+    """init() + app__main of 3d/proj/weibel/app.f90 -- the reference's text, patched --resident, translated -- on top of the shim and
+    the real library: the driver's own loader fills the host arrays (random inputs = the oracle's keyed draws), the context is created
+    inside its last __init, 10 steps run device-resident, and the outputs at the driver's cadences are the oracle's states of those steps
+    (CPU twin: tests/test_shim_executed.py::test_the_whole_weibel_driver_behind_load_config)"""
+    from oracle.f2cxx import mainloop_harness as mh
+    from tests.mainloop_util import assert_records_match
+    from tests.test_shim_executed import full_driver
+    A, w, cfg = full_driver(3)
+    try:
+        A.call("harness__main")
+        assert A.leftover() == (0, 0, 0)
+        buf = (C.c_double * 100000)()
+        A.L.f90rt_captured.argtypes = [C.POINTER(C.c_double), C.c_int]
+        n = A.L.f90rt_captured(buf, len(buf))
+        v, got, i = list(buf[:n]), [], 0
+        while i < n:
+            if v[i] != mh.MAGIC:
+                i += 1
+                continue
+            got.append((mh.KINDS[int(v[i + 1])], int(v[i + 2]), v[i + 4:i + 4 + int(v[i + 3])]))
+            i += 4 + int(v[i + 3])
+
+        def sums():
+            up, m = w.arr("up"), active_mask(w.arr("np2"), w.np)
+            return [float(w.arr("np2").sum()), float(w.arr("uf").sum()), float((up[m][:, 0] + 3.0 * up[m][:, w.ndim - 2]).sum())]
+        want = []
+        for it in range(1, 11):
+            w.step()
+            if it % 4 == 0:
+                want.append(("io__ptcl", it, sums()))
+            if it % 3 == 0:
+                w.mom_calc()
+                want.append(("io__mom", it, [float(w.arr("mom")[:, 1:-1, 1:-1, 1:-1].sum()), float(w.arr("uf").sum())]))
+        want.append(("save_restart", 11, sums()))
+        assert_records_match(got, want, rtol=1e-7)
+    finally:
+        f = A.L.f2cxx_modvar__wuming_b200_c__ctx
+        f.restype = C.c_void_p
+        ctx = C.c_void_p.from_address(f())
+        if ctx.value:
+            real_backend[0].wm_destroy(ctx)
+            ctx.value = None
