@@ -414,3 +414,38 @@ def test_the_whole_weibel_driver_behind_load_config(dim):
         assert r_[0] == 3.0 * k and r_[1:] == pytest.approx(ref, rel=1e-12)
     # ONE upload (the first push); downloads at the output steps 3 4 6 8 9 and for the final save_restart after step 10
     assert names.count("wm_upload") == 1 and names.count("wm_download") == 6
+
+
+@pytest.mark.parametrize("dim", [3, 2])
+def test_sort_outside_the_time_loop_is_done_on_the_host(dim):
+    """the drivers call sort__bucket once BEFORE the first push -- on the freshly loaded set (proj/reconnection/app.f90 init:
+    `call sort__bucket(gp, up, ...); up = gp`) and on a restarted one (every driver: `io__input(gp, ...); sort__bucket(up, gp, ...)`).
+    No pushed set exists on the device then; the shim sorts the host arrays itself (the reference's rule: key int(x), stable,
+    cumcnt = exclusive prefix) and the result travels with the first particle__solv"""
+    w = make_world3(NX, NY, NZ, N0) if dim == 3 else make_world2(NX, NY, N0)
+    D, R = shim_world(dim, w)
+    rng = np.random.default_rng(7)
+    # scramble every pencil of the loaded set (what a loader that draws x at random leaves behind), same on both sides
+    up, np2 = w.arr("up"), w.arr("np2")
+    for idx in np.ndindex(np2.shape):
+        n = np2[idx]
+        up[idx][:n] = up[idx][rng.permutation(n)]
+    R.arr("up")[...] = up
+    R.arr("cumcnt")[...] = -7                              # intent(out): whatever was there is replaced
+    w.arr("gp")[...] = up                                  # the oracle's sort__bucket reads gp and writes up
+    w.sort_bucket()
+    del D.log[:]
+    R.ranks[0].call("sort__bucket", R.arr("gp"), R.arr("up"), R.arr("cumcnt"), R.arr("np2"), R.nxs, R.nxe)
+    assert D.log == []                                     # nothing on the device
+    m = active_mask(np2, w.np)
+    assert np.array_equal(R.arr("cumcnt"), w.arr("cumcnt"))
+    assert np.array_equal(R.arr("gp")[m].view(np.int64), w.arr("up")[m].view(np.int64))      # same order too (stable)
+    # the driver's `up = gp`, then the time loop: the first push uploads the sorted set
+    R.arr("up")[...] = R.arr("gp")
+    R.ranks[0].call("wm_shim_set_mode", 1)
+    for _ in range(2):
+        w.step()
+        R.step()
+    assert D.names().count("wm_upload") == 1 and D.names().count("wm_sort_bucket") == 2          # in the loop: on the device
+    R.ranks[0].call("wm_shim_sync_to_host", R.arr("up"), R.arr("uf"), R.arr("np2"), R.arr("cumcnt"))
+    same_state(R, w, "two steps after the host-side sort")
