@@ -248,15 +248,16 @@ def _statement(text, first):
     return "\n".join(lines[i:j + 1])
 
 
-def assemble_full(dim):
-    """module app of {dim}d/proj/weibel: the driver's init(), set_initial_condition, set_particle_ids, get_global_cumsum,
-    energy_history and app__main (from `call init()` on) VERBATIM from the patched file; the declarations (app_harness's), the
-    configuration entry, the I/O procedures and mpi_set__init by the harness"""
+def assemble_full(dim, setup="weibel"):
+    """module app of {dim}d/proj/<setup>: the driver's init(), its loaders and particle source (set_initial_condition,
+    set_particle_ids, get_global_cumsum, energy_history / inject, relocate, vprofile) and app__main VERBATIM from the patched file;
+    the declarations (app_harness's), the configuration entry, the I/O procedures and mpi_set__init by the harness.  harness__main =
+    app__main from `call init()` on; harness__loop = the same without that line (init() is an entry point of its own)"""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     sys.path.insert(0, HERE)
     import make_reference_patch as mp
     import app_harness as ah
-    a = ah.APPS[f"weibel{dim}d"]
+    a = ah.APPS[f"{setup}{dim}d"]
     rel = a["file"]
     patched = mp.edit_app(open(os.path.join(REF, rel)).read(), dim, resident=True)
     lines = patched.splitlines()
@@ -284,7 +285,7 @@ def assemble_full(dim):
            "module app", "  use particle", "  use field", "  use sort", "  use mom_calc", "  use wuming_b200_c", use_bc, "  implicit none",
            a["decl"],
            "  integer :: mnpi = 4, jup = 0, jdown = 0, kup = 0, kdown = 0, nup = 0, ndown = 0, nstat(6)",
-           "  integer :: max_it, intvl_ptcl, intvl_orb, intvl_mom, verbose",
+           "  integer :: max_it, intvl_ptcl, intvl_orb, intvl_mom, intvl_expand, verbose",
            "  integer :: restart_file = 0, hunit = 10, datadir = 0, param = 0",
            "  logical :: restart = .false.", "  real(8) :: max_elapsed", "contains", "",
            f"  subroutine harness__configure({', '.join(c + '_in' for c in cfg)}, {', '.join(r + '_in' for r in a['rank'])})",
@@ -334,24 +335,25 @@ def assemble_full(dim):
   subroutine finalize()
   end subroutine finalize
 """, init]
-    for p_ in ("set_initial_condition", "set_particle_ids", "get_global_cumsum", "energy_history"):
+    for p_ in a["procs"]:
         out.append(ah.procedure(patched, p_))
-    out += ["  subroutine harness__main()", "    integer :: it", "    real(8) :: etime, etime0"] + main[k0:-1] + \
-           ["  end subroutine harness__main", "end module app"]
+    for nm, first in (("harness__main", k0), ("harness__loop", k0 + 1)):
+        out += [f"  subroutine {nm}()", "    integer :: it", "    real(8) :: etime, etime0"] + main[first:-1] + [f"  end subroutine {nm}", ""]
+    out.append("end module app")
     return "\n".join(out) + "\n"
 
 
-def build_full(dim, force=False):
-    """-> path of oracle/_ref/libwuming_full_weibel{dim}d.so (None without /root/reference and without a prebuilt library)"""
-    lib = os.path.join(OUT, f"libwuming_full_weibel{dim}d.so")
-    ref_file = os.path.join(REF, f"{dim}d", "proj", "weibel", "app.f90")
+def build_full(dim, setup="weibel", force=False):
+    """-> path of oracle/_ref/libwuming_full_<setup>{dim}d.so (None without /root/reference and without a prebuilt library)"""
+    lib = os.path.join(OUT, f"libwuming_full_{setup}{dim}d.so")
+    ref_file = os.path.join(REF, f"{dim}d", "proj", setup, "app.f90")
     if not os.path.exists(ref_file):
         return lib if os.path.exists(lib) else None
     os.makedirs(OUT, exist_ok=True)
     shim = [os.path.join(ROOT, "fortran", "wuming_b200_c.f90"), os.path.join(ROOT, "fortran", f"wuming_b200_shim{dim}d.f90")]
     deps = shim + [ref_file, os.path.join(ROOT, "tools", "make_reference_patch.py")] + \
         [os.path.join(HERE, f) for f in ("f2cxx.py", "f90rt.h", "f90rt.cpp", "shim_rt.cpp", "mainloop_harness.py", "app_harness.py")]
-    h = hashlib.sha1(b"full")
+    h = hashlib.sha1(b"full" + setup.encode())
     for f in deps:
         h.update(open(f, "rb").read())
     stamp_file = lib + ".stamp"
@@ -359,11 +361,11 @@ def build_full(dim, force=False):
         return lib
     sys.path.insert(0, HERE)
     import f2cxx
-    src = assemble_full(dim)
-    with open(os.path.join(OUT, f"full_weibel{dim}d.f90"), "w") as f:
+    src = assemble_full(dim, setup)
+    with open(os.path.join(OUT, f"full_{setup}{dim}d.f90"), "w") as f:
         f.write(src)
-    files = [(os.path.relpath(f, ROOT), open(f).read()) for f in shim] + [(f"full_weibel{dim}d.f90 <- {dim}d/proj/weibel/app.f90", src)]
-    cpp = os.path.join(OUT, f"full_weibel{dim}d.cpp")
+    files = [(os.path.relpath(f, ROOT), open(f).read()) for f in shim] + [(f"full_{setup}{dim}d.f90 <- {dim}d/proj/{setup}/app.f90", src)]
+    cpp = os.path.join(OUT, f"full_{setup}{dim}d.cpp")
     with open(cpp, "w") as f:
         f.write(f2cxx.translate(files, skip=("wm_check",)))
     r = subprocess.run([CXX, "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-DF90_BOUNDS", "-I", HERE, "-o", lib, cpp,

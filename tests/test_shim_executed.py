@@ -449,3 +449,36 @@ def test_sort_outside_the_time_loop_is_done_on_the_host(dim):
     assert D.names().count("wm_upload") == 1 and D.names().count("wm_sort_bucket") == 2          # in the loop: on the device
     R.ranks[0].call("wm_shim_sync_to_host", R.arr("up"), R.arr("uf"), R.arr("np2"), R.arr("cumcnt"))
     same_state(R, w, "two steps after the host-side sort")
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_the_whole_reconnection_driver(dim):
+    """{2d,3d}/proj/reconnection/app.f90, patched --resident: init() -- constants, the Harris-sheet loader with its statement
+    functions, the one-off sort__bucket of the load (host side in the shim), `up = gp`, energy_history -- then 10 steps of its loop
+    (reflecting walls before the field solve, cfl 0.5) on top of the shim, against an oracle world started from the loaded state"""
+    from tests.mainloop_util import whole_reconnection
+    D = StubDevice()
+
+    def after_init(A):
+        assert D.names() == ["wm_create"] and D.log[0][1]["bc_kind"] == 1 and D.log[0][1]["delt"] == 0.5
+    whole_reconnection(dim, after_init=after_init)
+    names = D.names()
+    assert names.count("wm_upload") == 1 and names.count("wm_bc_particle_x") == 10 and names.count("wm_sort_bucket") == 10
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_the_whole_shock_driver(dim):
+    """{2d,3d}/proj/shock/app.f90, patched --resident: init() (cold upstream load, nominal cumcnt), then 8 steps of its loop with the
+    driver's OWN inject() and relocate() -- host-side procedures that edit up, np2, cumcnt, uf and nxe every step, bracketed by the
+    patch's sync / host_modified calls -- on top of the shim, the box growing; against the oracle's loop with its particle source
+    (the random inputs of inject / relocate are the oracle's keyed draws, as in tests/test_ref_driver_procs.py)"""
+    from tests.mainloop_util import whole_shock
+    D = StubDevice()
+
+    def after_init(A):
+        assert D.names() == ["wm_create"] and D.log[0][1]["bc_kind"] == 2
+    A, steps = whole_shock(dim, after_init=after_init)
+    names = D.names()
+    # one download per step (in front of inject()); uploads: the load, then once behind each step's edits when something on the
+    # device follows (the pushes of steps 2 .. 8 and the moment block of step 8)
+    assert names.count("wm_bc_injection") == steps and names.count("wm_download") == steps and names.count("wm_upload") == steps + 1

@@ -195,3 +195,21 @@ def test_the_whole_weibel_driver_on_the_gpu(real_backend):
         if ctx.value:
             real_backend[0].wm_destroy(ctx)
             ctx.value = None
+
+
+def test_the_whole_reconnection_driver_on_the_gpu(real_backend):
+    """3d/proj/reconnection/app.f90 -- init() with the Harris-sheet loader and the one-off host-side sort, then 10 steps of its loop
+    (reflecting walls, cfl 0.5), the reference's text patched --resident -- on top of the shim and the real library (CPU twin:
+    tests/test_shim_executed.py::test_the_whole_reconnection_driver)"""
+    from tests.mainloop_util import whole_reconnection
+    made = []
+    try:
+        whole_reconnection(3, rtol=1e-7, after_init=made.append)
+    finally:
+        for A in made:
+            f = A.L.f2cxx_modvar__wuming_b200_c__ctx
+            f.restype = C.c_void_p
+            ctx = C.c_void_p.from_address(f())
+            if ctx.value:
+                real_backend[0].wm_destroy(ctx)
+                ctx.value = None
