@@ -189,9 +189,9 @@ def build(name, force=False):
     sys.path.insert(0, HERE)
     import f2cxx
     src = assemble(name)
-    f90 = os.path.join(OUT, f"app_{name}.f90")
-    with open(f90, "w") as f:
-        f.write(src)
+    if os.environ.get("WM_KEEP_F90"):              # debugging aid only: the assembled text holds the reference's procedures verbatim,
+        with open(os.path.join(OUT, f"app_{name}.f90"), "w") as f:       # so it is not kept (only the generated C++ and the library are)
+            f.write(src)
     cpp = os.path.join(OUT, f"app_{name}.cpp")
     with open(cpp, "w") as f:
         f.write(f2cxx.translate([(f"app_{name}.f90 <- {APPS[name]['file']}", src)]))

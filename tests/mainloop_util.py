@@ -21,8 +21,8 @@ class MainLoop:
         self.R = R = pyref._Rank(dim, lib)
         # one driver (2d/proj/reconnection) ends without a final save_restart after the loop: read it off the assembled text
         import os
-        src = os.path.join(os.path.dirname(lib), f"main_{setup}{dim}d.f90")
-        self.final_save = open(src).read().count("call save_restart(") >= 2 if os.path.exists(src) else not (setup == "reconnection" and dim == 2)
+        meta = os.path.join(os.path.dirname(lib), f"main_{setup}{dim}d.meta")
+        self.final_save = open(meta).read().split()[1] == "1" if os.path.exists(meta) else not (setup == "reconnection" and dim == 2)
         nx, ny, nz = w.nx, w.ny, (w.nz if dim == 3 else 1)
         ndim = w.ndim
         geom = [2, nx + 1, 2, ny + 1] + ([2, nz + 1] if dim == 3 else []) + [2, ny + 1] + ([2, nz + 1] if dim == 3 else [])
