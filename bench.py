@@ -170,6 +170,27 @@ def host_memory_available():
     return avail
 
 
+def host_threads():
+    """host threads this job may really use: the affinity mask, capped by a cgroup CPU quota where one is set (a container that sees 64
+    CPUs but may burn 16 CPU-seconds per second would only throttle a 64-thread team)"""
+    n = len(os.sched_getaffinity(0))
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            quota, period = open(path).read().split()[:2]
+            if quota != "max":
+                n = max(1, min(n, int(-(-int(quota) // int(period)))))
+        except (OSError, ValueError):
+            pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        p_ = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0 and p_ > 0:
+            n = max(1, min(n, -(-q // p_)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def rank_grid(cores, ny, nz):
     """nproc_j x nproc_k for a flat-MPI run with one rank per host thread: y first (what every shipped 3-D sample does,
     3d/proj/*/config_sample.json), z as well once the y-slabs would get thinner than 2 cells -- the two ghost layers of the
@@ -191,7 +212,7 @@ def cpu_port(args, steps=2, warmup=1):
     nx, ny, nz, n0 = args.nx, args.ny, args.cpu_nz, args.ppc
     # every host thread this process may use -- set explicitly: launchers (torch.distributed.run) export OMP_NUM_THREADS=1 and
     # the OpenMP runtime obeys it.  `cores` below is the team a parallel region of the oracle library REALLY gets.
-    want = len(os.sched_getaffinity(0))
+    want = host_threads()
     team = pyoracle.set_num_threads(want, fast=True)
     if team != want or pyoracle.num_threads(fast=True) != want:
         raise RuntimeError(f"oracle OpenMP team is {team} threads, {want} host threads are available: refusing to report a CPU baseline")
@@ -227,7 +248,7 @@ def cpu_reference(args, steps=2, warmup=1):
     from oracle.pyoracle import World3, weibel_constants
     import numpy as np
     nx, ny, nz, n0 = args.nx, args.ny, args.cpu_nz, args.ppc
-    cores = len(os.sched_getaffinity(0))
+    cores = host_threads()
     nj, nk = rank_grid(cores, ny, nz)
     q, r, _ = weibel_constants(n0)
     cap = int(n0 * nx * 1.5)

@@ -79,10 +79,11 @@ def test_reference_arm_uses_all_host_threads_under_a_launcher():
                        capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
-    cores = len(os.sched_getaffinity(0))
+    sys.path.insert(0, ROOT)
+    import bench
+    cores = bench.host_threads()
+    assert 1 <= cores <= len(os.sched_getaffinity(0))
     if d["cpu_baseline"]["kind"] == "reference":
-        sys.path.insert(0, ROOT)
-        import bench
         nj, nk = bench.rank_grid(cores, 16, 4)
         assert d["cpu_baseline"]["cores"] == nj * nk and d["config"]["parallelism"] == f"mpi{nj}x{nk}"
         assert d["cpu_baseline"]["port"]["cores"] == cores and d["cpu_baseline"]["port"]["parallelism"] == f"openmp{cores}"
