@@ -54,8 +54,14 @@ void f90rt_mpi_barrier(int*, int* ierr) {
 static void need_one_rank(const char* what) {
   if (g_sr) throw std::runtime_error(std::string(what) + " is implemented for one rank only");
 }
-void f90rt_mpi_bcast(void*, int*, int*, int*, int*, int* ierr) {
-  need_one_rank("MPI_BCAST");
+static f90rt_bcast_fn g_bc = nullptr;
+void f90rt_set_bcast(f90rt_bcast_fn bc) { g_bc = bc; }
+// MPI_BCAST(buffer, count, datatype, root, comm, ierr)
+void f90rt_mpi_bcast(void* buf, int* count, int* type, int* root, int*, int* ierr) {
+  if (g_bc)
+    g_bc(buf, *count * *type, *root);
+  else
+    need_one_rank("MPI_BCAST");
   if (ierr) *ierr = 0;
 }
 void f90rt_mpi_allgather(const void* sbuf, int* scount, int* stype, void* rbuf, int*, int*, int*, int* ierr) {

@@ -264,6 +264,8 @@ extern "C" {
 typedef void (*f90rt_sendrecv_fn)(const void* sbuf, int sbytes, int dest, int stag, void* rbuf, int rbytes, int src, int rtag);
 typedef void (*f90rt_allreduce_fn)(const void* sbuf, void* rbuf, int count, int type, int op);
 void f90rt_set_transport(f90rt_sendrecv_fn sr, f90rt_allreduce_fn ar);
+typedef void (*f90rt_bcast_fn)(void* buf, int bytes, int root);
+void f90rt_set_bcast(f90rt_bcast_fn bc);          // MPI_BCAST of a multi-rank run (the shim hands the NCCL id round with it)
 void f90rt_mpi_sendrecv(const void* sbuf, int* scount, int* stype, int* dest, int* stag, void* rbuf, int* rcount, int* rtype,
                         int* src, int* rtag, int* comm, int* status, int* ierr);
 void f90rt_mpi_allreduce(const void* sbuf, void* rbuf, int* count, int* type, int* op, int* comm, int* ierr);

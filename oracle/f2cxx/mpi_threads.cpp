@@ -53,6 +53,9 @@ struct Hub {
   alignas(64) std::atomic<long> generation{0};
   std::atomic<bool> aborted{false};
   std::atomic<long> n_sendrecv{0}, n_allreduce{0}, bytes{0};
+  std::vector<char> bc_buf;         // MPI_BCAST
+  alignas(64) std::atomic<int> bc_arrived{0};
+  alignas(64) std::atomic<long> bc_generation{0};
   explicit Hub(int nranks) : n(nranks), inbox((size_t)nranks), slot((size_t)nranks) {}
 };
 
@@ -151,6 +154,25 @@ void f2mpi_sendrecv(const void* sbuf, int sbytes, int dest, int stag, void* rbuf
   }, "MPI_SENDRECV");
   if ((long)in.size() > (long)rbytes) throw std::runtime_error("MPI_SENDRECV: message longer than the receive buffer");
   if (!in.empty()) std::memcpy(rbuf, in.data(), in.size());
+}
+
+// f90rt_bcast_fn: the root's bytes reach every rank (two barriers around one shared buffer)
+void f2mpi_bcast(void* buf, int bytes, int root) {
+  Hub& h = hub();
+  if (root < 0 || root >= h.n || bytes < 0) throw std::runtime_error("MPI_BCAST: bad root or count");
+  auto barrier = [&](const char* what) {
+    const long gen = h.bc_generation.load(std::memory_order_acquire);
+    if (h.bc_arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == h.n) {
+      h.bc_arrived.store(0, std::memory_order_relaxed);
+      h.bc_generation.store(gen + 1, std::memory_order_release);
+    } else {
+      wait(h, [&] { return h.bc_generation.load(std::memory_order_acquire) != gen; }, what);
+    }
+  };
+  if (t_rank == root) h.bc_buf.assign((const char*)buf, (const char*)buf + bytes);
+  barrier("MPI_BCAST");                        // the root's data is in place
+  if (t_rank != root) std::memcpy(buf, h.bc_buf.data(), (size_t)bytes);
+  barrier("MPI_BCAST");                        // everybody has copied: the buffer may be reused
 }
 
 // f90rt_allreduce_fn: doubles, MPI_SUM (what cgm uses); the sum runs in rank order on the last rank to arrive

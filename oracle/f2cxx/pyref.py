@@ -80,7 +80,7 @@ class RefWorld:
     numpy sees them in C order with the index order reversed, exactly like oracle.pyoracle.World2 / World3."""
 
     def __init__(self, dim, nx, ny, nz, np_cap, nproc_j=1, nproc_k=1, delx=1.0, delt=1.0, c=1.0, gfac=0.501, q=(1.0, -1.0),
-                 r=(1.0, 1.0), bc=0, bounds=False, fast=False, native_mpi=False, lib=None):
+                 r=(1.0, 1.0), bc=0, bounds=False, fast=False, native_mpi=False, lib=None, before_init=None):
         """fast: the -O3 -march=native build of the same generated C++ (timing only, never parity).  native_mpi: the ranks'
         MPI_SENDRECV / MPI_ALLREDUCE rendezvous in mpi_threads.cpp instead of Python callbacks (same semantics, no interpreter
         lock on the communication path: what a timed flat-MPI run with one rank per host thread needs)"""
@@ -125,6 +125,8 @@ class RefWorld:
             self.a.append(a)
         if self.nranks > 1:
             self._install_transport()
+        if before_init is not None:          # what a driver does between mpi_set__init and the __init calls (the shim's
+            self._all(lambda rk: before_init(rk, self.ranks[rk]))          # wm_shim_comm_init), on every rank
         self._init_modules()
 
     # ---- the MPI library of the emulated ranks ---------------------------------------------------------------------
@@ -147,6 +149,8 @@ class RefWorld:
             for R in self.ranks:
                 R.L.f90rt_set_transport.argtypes = [C.c_void_p, C.c_void_p]
                 R.L.f90rt_set_transport(C.cast(M.f2mpi_sendrecv, C.c_void_p), C.cast(M.f2mpi_allreduce, C.c_void_p))
+                R.L.f90rt_set_bcast.argtypes = [C.c_void_p]
+                R.L.f90rt_set_bcast(C.cast(M.f2mpi_bcast, C.c_void_p))
             return
         SR = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int)
         AR = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int)
@@ -220,8 +224,10 @@ class RefWorld:
         return [self.nxgs, self.nxge, self.nygs, self.nyge, g["nys"], g["nye"]]
 
     def _init_modules(self):
-        nstat = np.zeros(6, np.int32)
-        for rk, R in enumerate(self.ranks):
+        """every rank on its own thread, like ranks of an MPI job: the reference's __init procedures are local, but the shim's last
+        __init creates the device context and connects the communicator -- a collective (MPI_BCAST of the NCCL id)"""
+        def one(rk):
+            R, nstat = self.ranks[rk], np.zeros(6, np.int32)
             g, head = self.g[rk], [self.ndim, self.np, self.nsp] + self._geom_args(rk)
             nb = [g["jup"], g["jdown"], g["kup"], g["kdown"]] if self.dim == 3 else [g["jup"], g["jdown"]]
             # bc__init(..., jup, jdown, kup, kdown, mnpi, mnpr, ncomw, nerr, nstat, delx, delt, c) + the hidden extent of nstat(:)
@@ -231,6 +237,7 @@ class RefWorld:
             R.call("field__init", *head, MPI_DOUBLE, 0, MPI_SUM, 0, self.delx, self.delt, self.c, self.q, self.r, self.gfac)
             R.call("sort__init", *head)
             R.call("mom_calc__init", *head, self.delx, self.delt, self.c, self.q, self.r)
+        self._all(one)
 
     def arr(self, which, rank=0):
         return self.a[rank][which]

@@ -170,3 +170,85 @@ class StubDevice:
 
     def names(self):
         return [e[0] for e in self.log]
+
+
+class MultiRankStubDevice(StubDevice):
+    """N fake devices behind one callback: ONE oracle world with N emulated ranks plays all of them.  Uploads and downloads touch
+    the calling rank's arrays; a compute call is collective -- it waits until every rank has made it (each from its own thread,
+    like ranks of an MPI job), then the oracle does the work once."""
+
+    def __init__(self, nranks):
+        import threading
+        super().__init__()
+        self.nranks, self.barrier, self.lock = nranks, threading.Barrier(nranks), threading.Lock()
+        self.w, self.rank_of, self.logs, self.ids = None, {}, [[] for _ in range(nranks)], {}
+
+    def collective(self, fn):
+        if self.barrier.wait(timeout=60) == 0:
+            # the OpenMP team size is a per-thread setting: the oracle must run serially HERE (a rank's thread) for bit-exact sums
+            from oracle import pyoracle
+            pyoracle.set_num_threads(1)
+            fn()
+        self.barrier.wait(timeout=60)
+
+    def do_wm_create(self, p, i, d):
+        prm = C.cast(p[0], C.POINTER(_Params)).contents
+        f = {k: getattr(prm, k) for k, _ in _Params._fields_ if k not in ("q", "r")}
+        f["q"], f["r"] = list(prm.q), list(prm.r)
+        rank = f["rank_j"] * f["nproc_k"] + f["rank_k"]
+        with self.lock:
+            if self.w is None:
+                nx, ny, nz = f["nxge"] - f["nxgs"] + 1, f["nyge"] - f["nygs"] + 1, f["nzge"] - f["nzgs"] + 1
+                kw = dict(delx=f["delx"], delt=f["delt"], c=f["c"], gfac=f["gfac"], q=f["q"], r=f["r"], bc=f["bc_kind"])
+                self.w = World3(nx, ny, nz, f["np"], nproc_j=f["nproc_j"], nproc_k=f["nproc_k"], **kw) if f["dim"] == 3 else \
+                    World2(nx, ny, f["np"], nproc=f["nproc_j"], **kw)
+            self.rank_of[p[1]] = rank
+            self.prm[rank] = f
+        self.logs[rank].append(("wm_create",))
+        return 0
+
+    def _r(self, handle):
+        return self.rank_of[handle]
+
+    def do_wm_upload(self, p, i, d):
+        rk = self._r(p[0])
+        for k, which in enumerate(("up", "np2", "cumcnt", "uf"), 1):
+            if p[k]:
+                self.w.arr(which, rk)[...] = self.view(p[k], self.w.arr(which, rk))
+        self.logs[rk].append(("wm_upload",))
+        return 0
+
+    def do_wm_download(self, p, i, d):
+        rk = self._r(p[0])
+        for k, which in enumerate(("up", "np2", "cumcnt", "uf", "gp"), 1):
+            if p[k]:
+                self.view(p[k], self.w.arr(which, rk))[...] = self.w.arr(which, rk)
+        self.logs[rk].append(("wm_download",))
+        return 0
+
+    def _ranged(self, name, p, i, fn):
+        rk = self._r(p[0])
+        self.logs[rk].append((name, int(i[0]), int(i[1])))
+
+        def work():
+            self.w.set_xrange(int(i[0]), int(i[1]))
+            fn(self.w)
+        self.collective(work)
+        return 4 if self.w.error() else 0
+
+    def do_wm_bc_particle_yz(self, p, i, d):
+        rk = self._r(p[0])
+        self.logs[rk].append(("wm_bc_particle_yz",))
+        self.collective(lambda: (self.w.bc_particle_yz if isinstance(self.w, World3) else self.w.bc_particle_y)())
+        return 4 if self.w.error() else 0
+
+    def do_wm_comm_unique_id(self, p, i, d):
+        C.memmove(p[0], bytes(range(1, 129)), 128)               # what rank 0 draws; the shim hands it round with MPI_BCAST
+        self.logs[0].append(("wm_comm_unique_id",))
+        return 0
+
+    def do_wm_comm_init(self, p, i, d):
+        rk = self._r(p[0])
+        self.ids[rk] = C.string_at(p[1], 128)
+        self.logs[rk].append(("wm_comm_init", int(i[0]), int(i[1])))
+        return 0

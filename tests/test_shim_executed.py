@@ -482,3 +482,37 @@ def test_the_whole_shock_driver(dim):
     # one download per step (in front of inject()); uploads: the load, then once behind each step's edits when something on the
     # device follows (the pushes of steps 2 .. 8 and the moment block of step 8)
     assert names.count("wm_bc_injection") == steps and names.count("wm_download") == steps and names.count("wm_upload") == steps + 1
+
+
+@pytest.mark.parametrize("nproc_j,nproc_k", [(2, 1), (1, 2)], ids=["y-slabs", "z-slabs"])
+def test_two_ranks_through_the_shim(nproc_j, nproc_k):
+    """two ranks of a driver, each with its private copy of the shim (module state = one rank), on two threads: wm_shim_comm_init after
+    mpi_set__init, the context of every rank created by its last __init with its OWN slab bounds and rank coordinates, the NCCL id
+    drawn on rank 0 and handed round with MPI_BCAST, then the time loop with every rank's host arrays (lower bounds nys / nzs that
+    are not the global ones) -- against the oracle's two-rank world, bit for bit"""
+    from tests.shim_stub import MultiRankStubDevice
+    w = make_world3(NX, 8, 6, N0, nproc_j=nproc_j, nproc_k=nproc_k)
+    D = MultiRankStubDevice(2)
+    R = pyref.RefWorld(3, NX, 8, 6, w.np, nproc_j=nproc_j, nproc_k=nproc_k, q=w.q, r=w.r, lib=shim_harness.build(3), native_mpi=True,
+                       before_init=lambda rk, L: L.call("wm_shim_comm_init", 2, nproc_j, nproc_k, rk, 0))
+    for rk in range(2):
+        g, f = w.geom(rk), D.prm[rk]
+        assert (f["nproc_j"], f["nproc_k"], f["rank_j"], f["rank_k"]) == (nproc_j, nproc_k, rk // nproc_k, rk % nproc_k)
+        assert (f["nys"], f["nye"], f["nzs"], f["nze"]) == (g["nys"], g["nye"], g["nzs"], g["nze"])
+        assert (f["nygs"], f["nyge"], f["nzgs"], f["nzge"]) == (2, 9, 2, 7)
+    assert [e[0] for e in D.logs[0]] == ["wm_create", "wm_comm_unique_id", "wm_comm_init"] and D.logs[0][2] == ("wm_comm_init", 2, 0)
+    assert [e[0] for e in D.logs[1]] == ["wm_create", "wm_comm_init"] and D.logs[1][1] == ("wm_comm_init", 2, 1)
+    assert D.ids[0] == D.ids[1] == bytes(range(1, 129))                       # the id rank 0 drew reached rank 1
+    for rk in range(2):
+        for k in ("up", "gp", "uf", "np2", "cumcnt"):
+            R.arr(k, rk)[...] = w.arr(k, rk)
+    for it in range(3):
+        w.step()
+        R.step()
+        assert w.error() == 0
+        for rk in range(2):
+            for k in ("np2", "cumcnt", "uf"):
+                assert np.array_equal(R.arr(k, rk), w.arr(k, rk)), (it, rk, k)
+            m = active_mask(w.arr("np2", rk), w.np)
+            assert np.array_equal(R.arr("up", rk)[m].view(np.int64), w.arr("up", rk)[m].view(np.int64)), (it, rk)
+    R.close()
