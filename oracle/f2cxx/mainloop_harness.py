@@ -15,7 +15,7 @@ translated together with fortran/wuming_b200_c.f90 + wuming_b200_shim{2,3}d.f90 
     oracle/_ref/libwuming_main_<setup><dim>d.so        (undefined wm_* symbols, like the shim library)
 
 and run over the recording stub with the oracle as the device (tests/test_shim_executed.py) and over libwuming_b200.so on a GPU
-(tests/test_zzzz_gpu_shim.py): every output a patched driver writes must be the state of that step, although nothing but those
+(tests/gpu_shim_cases.py): every output a patched driver writes must be the state of that step, although nothing but those
 outputs ever leaves the device.
 """
 import hashlib
